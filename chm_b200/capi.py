@@ -1,0 +1,285 @@
+"""ctypes binding of include/pbsm3d.h (libpbsm3d_b200.so).  Plumbing only: no arithmetic happens here.
+
+This is the Python twin of the cgo/JNI-style stub INTEGRATION.md shows for CHM's C++ adaptor: it declares
+exactly the symbols the header declares and fails loudly when the CUDA library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+from .mesh import TriMesh
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpbsm3d_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+c_uint8_p = C.POINTER(C.c_uint8)
+
+SOLVER_AUTO, SOLVER_LINE, SOLVER_BICGSTAB = 0, 1, 2
+ERR_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "NOCONVERGE"}
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("nLayer", C.c_int), ("do_fixed_settling", C.c_int), ("settling_velocity", C.c_double),
+        ("do_sublimation", C.c_int), ("do_lateral_diff", C.c_int), ("smooth_coeff", C.c_double),
+        ("min_sd_trans", C.c_double), ("cutoff", C.c_double), ("snow_diffusion_const", C.c_double),
+        ("rouault_diffusion_coef", C.c_int), ("enable_veg", C.c_int), ("iterative_subl", C.c_int),
+        ("use_exp_fetch", C.c_int), ("use_tanh_fetch", C.c_int), ("use_PomLi_probability", C.c_int),
+        ("z0_ustar_coupling", C.c_int), ("use_subgrid_topo", C.c_int), ("use_subgrid_topo_V2", C.c_int),
+        ("use_R94_lambda", C.c_int), ("debug_output", C.c_int),
+        ("tolerance", C.c_double), ("max_iterations", C.c_int), ("solver", C.c_int),
+    ]
+
+
+class Mesh(C.Structure):
+    _fields_ = [
+        ("n_global", C.c_int64), ("n_local", C.c_int32), ("n_ghost", C.c_int32),
+        ("global_id", c_int64_p), ("ghost_owner", c_int32_p), ("neigh", c_int32_p), ("vertices", c_double_p),
+        ("area", c_double_p), ("canopy_height", c_double_p), ("lai", c_double_p), ("stalk_number", c_double_p),
+        ("stalk_diameter", c_double_p), ("is_water", c_uint8_p),
+    ]
+
+
+class Comm(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("n_ranks", C.c_int32), ("nccl_unique_id", C.c_void_p)]
+
+
+class Forcing(C.Structure):
+    _fields_ = [(n, c_double_p) for n in ("U_R", "U_2m_above_srf", "snowdepthavg", "swe", "t", "rh", "vw_dir", "fetch")]
+
+
+class Outputs(C.Structure):
+    _fields_ = [(n, c_double_p) for n in ("Qsalt", "Qsusp", "Qsubl", "Qsubl_mass", "sum_subl", "drift_mass", "sum_drift",
+                                          "pbsm_more_than_avail")]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("suspension_present", C.c_int32), ("deposition_present", C.c_int32), ("suspension_iterations", C.c_int32),
+        ("deposition_iterations", C.c_int32), ("suspension_solver_used", C.c_int32), ("reserved", C.c_int32),
+        ("suspension_residual", C.c_double), ("deposition_residual", C.c_double), ("suspension_rhs_max", C.c_double),
+        ("deposition_rhs_max", C.c_double), ("ms_assembly", C.c_float), ("ms_suspension_solve", C.c_float),
+        ("ms_flux_and_halo", C.c_float), ("ms_deposition", C.c_float), ("ms_total", C.c_float), ("reserved2", C.c_float),
+    ]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
+
+
+FORCING_NAMES = [n for n, _ in Forcing._fields_]
+OUTPUT_NAMES = [n for n, _ in Outputs._fields_]
+
+# every symbol include/pbsm3d.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "pbsm3d_abi_version": (C.c_int, []),
+    "pbsm3d_last_error": (C.c_char_p, []),
+    "pbsm3d_config_defaults": (None, [C.POINTER(Config)]),
+    "pbsm3d_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "pbsm3d_create": (C.c_int, [C.POINTER(Config), C.POINTER(Mesh), C.c_int, C.POINTER(Comm), C.POINTER(C.c_void_p)]),
+    "pbsm3d_destroy": (None, [C.c_void_p]),
+    "pbsm3d_step": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(Forcing), C.POINTER(Outputs), C.POINTER(Stats)]),
+    "pbsm3d_step_device": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(Forcing), C.POINTER(Outputs), C.POINTER(Stats)]),
+    "pbsm3d_get_state": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
+    "pbsm3d_set_state": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
+    "pbsm3d_get_geometry": (C.c_int, [C.c_void_p] + [c_double_p] * 8),
+    "pbsm3d_get_solution": (C.c_int, [C.c_void_p, c_double_p]),
+    "pbsm3d_get_suspension_system": (C.c_int, [C.c_void_p] + [c_double_p] * 8 + [c_uint8_p]),
+    "pbsm3d_get_deposition_system": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
+    "pbsm3d_time_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+class Pbsm3dError(RuntimeError):
+    """What the CHM adaptor raises as module_error."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{ERR_NAMES.get(code, code)}] {msg}")
+        self.code = code
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the CUDA library.  There is no fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(f"{p} not found: build it with `python -m chm_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pbsm3d_abi_version() != 1:
+        raise ImportError("pbsm3d ABI version mismatch")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _dp(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def _check(lib, rc: int):
+    if rc != 0:
+        raise Pbsm3dError(rc, lib.pbsm3d_last_error().decode())
+
+
+def default_config(**overrides) -> Config:
+    lib = load_library()
+    cfg = Config()
+    lib.pbsm3d_config_defaults(C.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise KeyError(f"unknown PBSM3D config key {k}")
+        setattr(cfg, k, type(getattr(cfg, k))(v))
+    return cfg
+
+
+def nccl_unique_id() -> bytes:
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    _check(lib, lib.pbsm3d_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Handle:
+    """Owns one pbsm3d_handle (one rank, one GPU)."""
+
+    def __init__(self, cfg: Config, mesh: TriMesh, device: int = 0, rank: int = 0, n_ranks: int = 1,
+                 unique_id: Optional[bytes] = None, is_water: Optional[np.ndarray] = None):
+        self.lib = load_library()
+        self.T = mesh.n_local
+        self.L = int(cfg.nLayer)
+        self._keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            self._keep.append(a)
+            return a
+
+        m = Mesh()
+        m.n_global = mesh.n_global
+        m.n_local = mesh.n_local
+        m.n_ghost = mesh.n_ghost
+        m.global_id = arr(mesh.global_id, np.int64).ctypes.data_as(c_int64_p)
+        m.ghost_owner = arr(mesh.ghost_owner, np.int32).ctypes.data_as(c_int32_p) if mesh.n_ghost else None
+        m.neigh = arr(mesh.neigh, np.int32).ctypes.data_as(c_int32_p)
+        m.vertices = _dp(arr(mesh.face_vertices(), np.float64))
+        p = mesh.params
+        m.area = _dp(arr(p["area"], np.float64)) if "area" in p else None
+        m.canopy_height = _dp(arr(p["CanopyHeight"], np.float64)) if "CanopyHeight" in p else None
+        m.lai = _dp(arr(p["LAI"], np.float64)) if "LAI" in p else None
+        m.stalk_number = _dp(arr(p["stalk_number"], np.float64)) if "stalk_number" in p else None
+        m.stalk_diameter = _dp(arr(p["stalk_diameter"], np.float64)) if "stalk_diameter" in p else None
+        m.is_water = arr(is_water, np.uint8).ctypes.data_as(c_uint8_p) if is_water is not None else None
+        comm = None
+        if n_ranks > 1:
+            self._uid = C.create_string_buffer(unique_id, 128)
+            comm = Comm(rank, n_ranks, C.cast(self._uid, C.c_void_p))
+        h = C.c_void_p()
+        _check(self.lib, self.lib.pbsm3d_create(C.byref(cfg), C.byref(m), device, C.byref(comm) if comm else None, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pbsm3d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ stepping
+    def step(self, dt: float, forcing: Dict[str, np.ndarray], want=OUTPUT_NAMES):
+        """Host-buffer entry point (what the CHM adaptor calls).  Returns (outputs dict, stats dict)."""
+        f = Forcing()
+        keep = []
+        for n in FORCING_NAMES:
+            if n in forcing and forcing[n] is not None:
+                a = np.ascontiguousarray(forcing[n], dtype=np.float64)
+                if a.shape != (self.T,):
+                    raise ValueError(f"forcing {n} must be [{self.T}]")
+                keep.append(a)
+                setattr(f, n, _dp(a))
+        o = Outputs()
+        outs = {n: np.empty(self.T) for n in want}
+        for n, a in outs.items():
+            setattr(o, n, _dp(a))
+        st = Stats()
+        _check(self.lib, self.lib.pbsm3d_step(self.h, dt, C.byref(f), C.byref(o), C.byref(st)))
+        return outs, st.asdict()
+
+    def step_ptr(self, dt: float, forcing_ptrs: Dict[str, int], output_ptrs: Dict[str, int], device: bool):
+        """Raw-pointer entry (pinned host buffers or device buffers owned by the caller, e.g. torch tensors)."""
+        f = Forcing()
+        for n, p in forcing_ptrs.items():
+            setattr(f, n, C.cast(C.c_void_p(p), c_double_p))
+        o = Outputs()
+        for n, p in output_ptrs.items():
+            setattr(o, n, C.cast(C.c_void_p(p), c_double_p))
+        st = Stats()
+        fn = self.lib.pbsm3d_step_device if device else self.lib.pbsm3d_step
+        _check(self.lib, fn(self.h, dt, C.byref(f), C.byref(o), C.byref(st)))
+        return st.asdict()
+
+    # ------------------------------------------------------------------ inspection
+    def geometry(self):
+        T = self.T
+        g = {k: np.empty((3, T)) for k in ("nx", "ny", "elen", "dx")}
+        g.update({k: np.empty(T) for k in ("area", "cx", "cy", "cz")})
+        _check(self.lib, self.lib.pbsm3d_get_geometry(self.h, _dp(g["nx"]), _dp(g["ny"]), _dp(g["elen"]), _dp(g["area"]),
+                                                      _dp(g["dx"]), _dp(g["cx"]), _dp(g["cy"]), _dp(g["cz"])))
+        return g
+
+    def solution(self) -> np.ndarray:
+        x = np.empty((self.L, self.T))
+        _check(self.lib, self.lib.pbsm3d_get_solution(self.h, _dp(x)))
+        return x
+
+    def suspension_system(self):
+        L, T = self.L, self.T
+        s = {k: np.empty((L, T)) for k in ("diag", "below", "above", "u_z", "csubl")}
+        s["lat"] = np.empty((3, L, T))
+        s["rhs0"] = np.empty(T)
+        s["c_salt"] = np.empty(T)
+        s["saltation"] = np.empty(T, dtype=np.uint8)
+        _check(self.lib, self.lib.pbsm3d_get_suspension_system(
+            self.h, _dp(s["diag"]), _dp(s["lat"]), _dp(s["below"]), _dp(s["above"]), _dp(s["rhs0"]), _dp(s["u_z"]),
+            _dp(s["csubl"]), _dp(s["c_salt"]), s["saltation"].ctypes.data_as(c_uint8_p)))
+        return s
+
+    def deposition_system(self):
+        T = self.T
+        d = {"diag": np.empty(T), "off": np.empty((3, T)), "rhs": np.empty(T), "q": np.empty(T)}
+        _check(self.lib, self.lib.pbsm3d_get_deposition_system(self.h, _dp(d["diag"]), _dp(d["off"]), _dp(d["rhs"]), _dp(d["q"])))
+        return d
+
+    def get_state(self):
+        T = self.T
+        s = {k: np.empty(T) for k in ("sum_drift", "sum_subl", "drift_mass", "pbsm_more_than_avail")}
+        _check(self.lib, self.lib.pbsm3d_get_state(self.h, _dp(s["sum_drift"]), _dp(s["sum_subl"]), _dp(s["drift_mass"]),
+                                                   _dp(s["pbsm_more_than_avail"])))
+        return s
+
+    def set_state(self, sum_drift=None, sum_subl=None, drift_mass=None, pbsm_more_than_avail=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+                for a in (sum_drift, sum_subl, drift_mass, pbsm_more_than_avail)]
+        _check(self.lib, self.lib.pbsm3d_set_state(self.h, *[_dp(a) for a in arrs]))
+
+    def time_kernel(self, kernel: int, reps: int = 20) -> float:
+        ms = C.c_float()
+        _check(self.lib, self.lib.pbsm3d_time_kernel(self.h, kernel, reps, C.byref(ms)))
+        return float(ms.value)

@@ -1,0 +1,907 @@
+// libpbsm3d_b200.so — C-ABI (include/pbsm3d.h) and host orchestration of one PBSM3D timestep on one B200.
+// One process per GPU; NCCL carries the ghost-face halos and the global reductions.  No CPU fallback.
+#include "../../include/pbsm3d.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pbsm3d_kernels.cuh"
+
+using namespace pbsm3d;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(PBSM3D_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                             std::to_string(__LINE__) + ")");                                \
+    } while (0)
+#define NC(call)                                                                                             \
+    do {                                                                                                     \
+        ncclResult_t e_ = (call);                                                                            \
+        if (e_ != ncclSuccess)                                                                               \
+            return fail(PBSM3D_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                             std::to_string(__LINE__) + ")");                                \
+    } while (0)
+#define TRY(call)              \
+    do {                       \
+        int rc_ = (call);      \
+        if (rc_) return rc_;   \
+    } while (0)
+
+inline int cdiv(size_t a, int b) { return (int)((a + b - 1) / b); }
+
+struct Partner {
+    int rank;
+    int send_off, send_cnt;  // into the concatenated send list
+    int recv_off, recv_cnt;  // ghost block [recv_off, recv_off+recv_cnt)
+};
+
+}  // namespace
+
+struct pbsm3d_handle {
+    pbsm3d_config cfg;
+    DevConfig dc;
+    DevMesh dm;
+    SuspSystem ss;
+    int device = 0;
+    int T = 0, nG = 0, L = 0;
+    int64_t G = 0, gstart_id = 0;
+    size_t N = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+
+    // mesh / static
+    int *neigh = nullptr, *gstart = nullptr, *gcnt = nullptr;
+    double *nx = nullptr, *ny = nullptr, *elen = nullptr, *area = nullptr, *cx = nullptr, *cy = nullptr, *cz = nullptr, *dx = nullptr;
+    double *canopy = nullptr, *lai = nullptr, *stalk_n = nullptr, *stalk_dv = nullptr;
+    unsigned char* water = nullptr;
+    double *ddiag = nullptr, *doff = nullptr, *dinv = nullptr;
+    // forcing (own device copies for the host-pointer entry point)
+    double* forcing_buf[8] = {nullptr};
+    DevForcing last_forcing{};
+    double last_dt = 0.0;
+    // solution / work
+    double *xa = nullptr, *xb = nullptr, *xga = nullptr, *xgb = nullptr, *xcur = nullptr;
+    double* kry[7] = {nullptr};  // r, rhat, p, v, ph, sh, t (allocated on first Krylov use)
+    double* kry_g = nullptr;     // ghost values of the preconditioned vector
+    // per-face outputs and deposition work
+    double *Qsusp = nullptr, *Qsubl = nullptr, *Qsubl_mass = nullptr, *sum_subl = nullptr, *drift_mass = nullptr,
+           *sum_drift = nullptr, *more_avail = nullptr;
+    double *drhs = nullptr, *q = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_Ap = nullptr, *qg = nullptr, *pg = nullptr,
+           *q2 = nullptr;
+    // reductions
+    double *partial = nullptr, *red = nullptr;
+    Scalars* sc = nullptr;
+    Scalars* h_sc = nullptr;   // pinned
+    double* h_red = nullptr;   // pinned [8]
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    std::vector<Partner> partners;
+    int n_send = 0;
+    int *send_idx = nullptr, *send_boff = nullptr, *send_cnt = nullptr, *send_pos = nullptr;
+    double* sendbuf = nullptr;
+    // timing
+    cudaEvent_t ev[6] = {nullptr};
+    bool have_system = false;
+
+    template <typename U>
+    int alloc(U** p, size_t n) {
+        if (n == 0) n = 1;
+        void* q_ = nullptr;
+        CU(cudaMalloc(&q_, n * sizeof(U)));
+        allocs.push_back(q_);
+        *p = (U*)q_;
+        return 0;
+    }
+};
+
+namespace {
+
+int upload(pbsm3d_handle* h, void* dst, const void* src, size_t bytes) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+// ---- reductions ------------------------------------------------------------------------------------
+// fold `nvals` partial arrays into h->red[0..nvals) and make them global (NCCL) when partitioned.
+int fold(pbsm3d_handle* h, int nblocks, int nvals, int op) {
+    fold_kernel<<<1, 256, 0, h->stream>>>(nblocks, nvals, kRedBlocks, h->partial, h->red, op);
+    if (h->n_ranks > 1) NC(ncclAllReduce(h->red, h->red, nvals, ncclDouble, op ? ncclMax : ncclSum, h->comm, h->stream));
+    return 0;
+}
+int read_red(pbsm3d_handle* h, int nvals) {
+    CU(cudaMemcpyAsync(h->h_red, h->red, nvals * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int read_scalars(pbsm3d_handle* h) {
+    CU(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- halo (reference: triangulation::ghost_neighbors_communicate_variable, triangulation.cpp:1976-2079) -------
+// v is [nl][T] on the device; ghost values land in `ghost` as per-owner blocks [nl][cnt].
+int halo_exchange(pbsm3d_handle* h, const double* v, int nl, double* ghost) {
+    if (h->n_ranks == 1 || h->partners.empty()) return 0;
+    if (h->n_send > 0) {
+        size_t total = (size_t)h->n_send * nl;
+        int blocks = std::min(cdiv(total, 256), 148 * 8);
+        halo_pack_kernel<<<blocks, 256, 0, h->stream>>>(h->n_send, nl, h->T, h->send_idx, h->send_boff, h->send_cnt,
+                                                        h->send_pos, v, h->sendbuf);
+    }
+    NC(ncclGroupStart());
+    for (const Partner& p : h->partners) {
+        if (p.send_cnt > 0)
+            NC(ncclSend(h->sendbuf + (size_t)p.send_off * nl, (size_t)p.send_cnt * nl, ncclDouble, p.rank, h->comm, h->stream));
+        if (p.recv_cnt > 0)
+            NC(ncclRecv(ghost + (size_t)p.recv_off * nl, (size_t)p.recv_cnt * nl, ncclDouble, p.rank, h->comm, h->stream));
+    }
+    NC(ncclGroupEnd());
+    return 0;
+}
+
+int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* comm) {
+    const int P = h->n_ranks, me = h->rank, nG = h->nG;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(&id, comm->nccl_unique_id, sizeof(id));
+    NC(ncclCommInitRank(&h->comm, P, id, me));
+
+    // ghost blocks per owner (ghosts are sorted by global id ⇒ contiguous per owner, triangulation.cpp:1784-1829)
+    std::vector<int> need_cnt(P, 0), need_off(P, 0);
+    for (int g = 0; g < nG; ++g) {
+        int o = mesh->ghost_owner[g];
+        if (o < 0 || o >= P || o == me) return fail(PBSM3D_ERR_INVALID, "ghost_owner out of range");
+        if (g > 0 && mesh->ghost_owner[g] < mesh->ghost_owner[g - 1])
+            return fail(PBSM3D_ERR_INVALID, "ghost faces must be sorted by global id (owner blocks contiguous)");
+        need_cnt[o]++;
+    }
+    for (int q = 1; q < P; ++q) need_off[q] = need_off[q - 1] + need_cnt[q - 1];
+    // everyone learns the P×P matrix of needs: M[r][q] = ghosts rank r needs from rank q
+    int* d_cnt = nullptr;
+    int* d_all = nullptr;
+    TRY(h->alloc(&d_cnt, P));
+    TRY(h->alloc(&d_all, (size_t)P * P));
+    TRY(upload(h, d_cnt, need_cnt.data(), P * sizeof(int)));
+    NC(ncclAllGather(d_cnt, d_all, P, ncclInt32, h->comm, h->stream));
+    std::vector<int> M((size_t)P * P);
+    CU(cudaMemcpyAsync(M.data(), d_all, M.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    // tell each owner which of its faces we need (setup_nearest_neighbor_communication, triangulation.cpp:1845-1945)
+    int n_send = 0;
+    for (int r = 0; r < P; ++r) n_send += M[(size_t)r * P + me];
+    h->n_send = n_send;
+    long long *d_need = nullptr, *d_give = nullptr;
+    TRY(h->alloc(&d_need, (size_t)nG));
+    TRY(h->alloc(&d_give, (size_t)n_send));
+    std::vector<long long> need_ids(nG);
+    for (int g = 0; g < nG; ++g) need_ids[g] = mesh->global_id[h->T + g];
+    TRY(upload(h, d_need, need_ids.data(), nG * sizeof(long long)));
+    NC(ncclGroupStart());
+    int soff = 0;
+    for (int r = 0; r < P; ++r) {
+        if (r == me) continue;
+        int sc_ = M[(size_t)r * P + me], rc_ = need_cnt[r];
+        if (rc_ > 0) NC(ncclSend(d_need + need_off[r], rc_, ncclInt64, r, h->comm, h->stream));
+        if (sc_ > 0) NC(ncclRecv(d_give + soff, sc_, ncclInt64, r, h->comm, h->stream));
+        if (sc_ > 0 || rc_ > 0) h->partners.push_back({r, soff, sc_, need_off[r], rc_});
+        soff += sc_;
+    }
+    NC(ncclGroupEnd());
+    std::vector<long long> give(n_send);
+    CU(cudaMemcpyAsync(give.data(), d_give, n_send * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<int> sidx(n_send), sboff(n_send), scnt(n_send), spos(n_send);
+    for (const Partner& p : h->partners)
+        for (int k = 0; k < p.send_cnt; ++k) {
+            long long loc = give[p.send_off + k] - h->gstart_id;
+            if (loc < 0 || loc >= h->T) return fail(PBSM3D_ERR_INVALID, "a partner asked for a face this rank does not own");
+            sidx[p.send_off + k] = (int)loc;
+            sboff[p.send_off + k] = p.send_off;
+            scnt[p.send_off + k] = p.send_cnt;
+            spos[p.send_off + k] = k;
+        }
+    TRY(h->alloc(&h->send_idx, n_send));
+    TRY(h->alloc(&h->send_boff, n_send));
+    TRY(h->alloc(&h->send_cnt, n_send));
+    TRY(h->alloc(&h->send_pos, n_send));
+    TRY(upload(h, h->send_idx, sidx.data(), n_send * sizeof(int)));
+    TRY(upload(h, h->send_boff, sboff.data(), n_send * sizeof(int)));
+    TRY(upload(h, h->send_cnt, scnt.data(), n_send * sizeof(int)));
+    TRY(upload(h, h->send_pos, spos.data(), n_send * sizeof(int)));
+    TRY(h->alloc(&h->sendbuf, (size_t)n_send * std::max(h->L, 2)));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- suspension solve ------------------------------------------------------------------------------
+template <int LT>
+void launch_sweep(pbsm3d_handle* h, const double* xo, const double* xgo, double* xn) {
+    line_sweep_kernel<LT><<<cdiv(h->T, 128), 128, 0, h->stream>>>(h->ss, h->dm, h->L, xo, xgo, xn, nullptr);
+}
+void sweep(pbsm3d_handle* h, const double* xo, const double* xgo, double* xn) {
+    switch (h->L) {
+        case 5: launch_sweep<5>(h, xo, xgo, xn); break;
+        case 10: launch_sweep<10>(h, xo, xgo, xn); break;
+        case 15: launch_sweep<15>(h, xo, xgo, xn); break;
+        case 20: launch_sweep<20>(h, xo, xgo, xn); break;
+        default: launch_sweep<0>(h, xo, xgo, xn); break;
+    }
+}
+
+inline int red_grid(size_t n) { return std::max(1, std::min(kRedBlocks, cdiv(n, kRedThreads))); }
+
+// ||b - A x||^2 into h_red[0]  (x's ghost values must be current in xg)
+int residual_norm2(pbsm3d_handle* h, const double* x, const double* xg) {
+    int g = red_grid(h->N);
+    spmv_kernel<1><<<g, kRedThreads, 0, h->stream>>>(h->ss, h->dm, h->L, x, xg, nullptr, nullptr, nullptr, 1, h->partial,
+                                                    kRedBlocks, nullptr);
+    fold_kernel<<<1, 256, 0, h->stream>>>(g, 1, kRedBlocks, h->partial + kRedBlocks, h->red, 0);
+    if (h->n_ranks > 1) NC(ncclAllReduce(h->red, h->red, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    return read_red(h, 1);
+}
+
+// Stationary line relaxation.  Returns 0 and sets *converged; iterations/residual in stats.
+int solve_line(pbsm3d_handle* h, double bnorm2, pbsm3d_stats* st, bool* converged, bool allow_bail) {
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    CU(cudaMemsetAsync(h->xa, 0, h->N * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->xga, 0, (size_t)h->L * std::max(h->nG, 1) * sizeof(double), h->stream));
+    double *xo = h->xa, *xn = h->xb, *xgo = h->xga, *xgn = h->xgb;
+    int it = 0, next_check = 8, checks = 0;
+    double prev_rr = bnorm2;
+    int prev_it = 0;
+    *converged = false;
+    const int maxit = h->cfg.max_iterations;
+    while (it < maxit) {
+        int target = std::min(next_check, maxit);
+        for (; it < target; ++it) {
+            sweep(h, xo, xgo, xn);
+            std::swap(xo, xn);
+            TRY(halo_exchange(h, xo, h->L, xgn));
+            std::swap(xgo, xgn);
+        }
+        TRY(residual_norm2(h, xo, xgo));
+        double rr = h->h_red[0];
+        ++checks;
+        st->suspension_residual = std::sqrt(rr / bnorm2);
+        if (rr <= tol2 * bnorm2) { *converged = true; break; }
+        if (!std::isfinite(rr)) break;
+        // geometric convergence: predict the sweeps still needed from the observed rate
+        double rate = std::pow(rr / prev_rr, 0.5 / (double)(it - prev_it));  // per-sweep factor on ||r||
+        int step = 8;
+        if (rate < 1.0 && rate > 0.0) {
+            double need = 0.5 * std::log(tol2 * bnorm2 / rr) / std::log(rate);
+            step = (int)std::ceil(need);
+            step = std::max(1, std::min(step, 128));
+        } else if (allow_bail && checks >= 2) {
+            break;  // not contracting: hand over to the Krylov path
+        }
+        if (allow_bail && checks >= 3 && rate > 0.97 && it >= 64) break;  // crawling: Krylov is the better tool
+        prev_rr = rr;
+        prev_it = it;
+        next_check = it + step;
+    }
+    h->xcur = xo;
+    st->suspension_iterations = it;
+    st->suspension_solver_used = PBSM3D_SOLVER_LINE;
+    return 0;
+}
+
+int ensure_krylov(pbsm3d_handle* h) {
+    if (h->kry[0]) return 0;
+    for (int k = 0; k < 7; ++k) TRY(h->alloc(&h->kry[k], h->N));
+    TRY(h->alloc(&h->kry_g, (size_t)h->L * std::max(h->nG, 1)));
+    return 0;
+}
+
+// Right-preconditioned BiCGStab with the column-tridiagonal preconditioner (the Krylov path).
+int solve_bicgstab(pbsm3d_handle* h, pbsm3d_stats* st, bool* converged) {
+    TRY(ensure_krylov(h));
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    double *x = h->xa, *r = h->kry[0], *rhat = h->kry[1], *p = h->kry[2], *v = h->kry[3], *ph = h->kry[4], *sh = h->kry[5],
+           *t = h->kry[6];
+    const size_t N = h->N;
+    const int g = red_grid(N), gt = cdiv(h->T, 128);
+    cudaStream_t s = h->stream;
+    const int* done = &h->sc->done;
+    bicg_init_kernel<<<g, kRedThreads, 0, s>>>(h->T, h->L, h->ss.rhs0, x, r, rhat, p, v, h->partial);
+    TRY(fold(h, g, 1, 0));
+    bicg_scalar_kernel<<<1, 1, 0, s>>>(0, h->sc, h->red, tol2);
+    *converged = false;
+    const int maxit = h->cfg.max_iterations;
+    int it = 0;
+    while (it < maxit) {
+        int target = std::min(it + 4, maxit);
+        for (; it < target; ++it) {
+            bicg_p_kernel<<<g, kRedThreads, 0, s>>>(N, h->sc, r, v, p);
+            thomas_kernel<<<gt, 128, 0, s>>>(h->ss, h->T, h->L, p, ph, done);
+            TRY(halo_exchange(h, ph, h->L, h->kry_g));
+            spmv_kernel<0><<<g, kRedThreads, 0, s>>>(h->ss, h->dm, h->L, ph, h->kry_g, v, rhat, nullptr, 0, h->partial, kRedBlocks, done);
+            TRY(fold(h, g, 1, 0));
+            bicg_scalar_kernel<<<1, 1, 0, s>>>(1, h->sc, h->red, tol2);
+            bicg_s_kernel<<<g, kRedThreads, 0, s>>>(N, h->sc, r, v, h->partial);
+            thomas_kernel<<<gt, 128, 0, s>>>(h->ss, h->T, h->L, r, sh, done);
+            TRY(halo_exchange(h, sh, h->L, h->kry_g));
+            spmv_kernel<0><<<g, kRedThreads, 0, s>>>(h->ss, h->dm, h->L, sh, h->kry_g, t, r, nullptr, 1, h->partial, kRedBlocks, done);
+            TRY(fold(h, g, 2, 0));
+            bicg_scalar_kernel<<<1, 1, 0, s>>>(3, h->sc, h->red, tol2);
+            bicg_xr_kernel<<<g, kRedThreads, 0, s>>>(N, h->sc, x, r, ph, sh, t, rhat, h->partial, kRedBlocks);
+            TRY(fold(h, g, 2, 0));
+            bicg_scalar_kernel<<<1, 1, 0, s>>>(4, h->sc, h->red, tol2);
+        }
+        TRY(read_scalars(h));
+        if (h->h_sc->done) break;
+    }
+    *converged = (h->h_sc->done == 1);
+    st->suspension_iterations = h->h_sc->iters;
+    st->suspension_residual = std::sqrt(h->h_sc->rr / h->h_sc->bnorm2);
+    st->suspension_solver_used = PBSM3D_SOLVER_BICGSTAB;
+    h->xcur = x;
+    return 0;
+}
+
+// Jacobi-preconditioned CG on the deposition system.
+int solve_deposition(pbsm3d_handle* h, pbsm3d_stats* st, bool* converged) {
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    const int T = h->T;
+    const int g = red_grid(T);
+    cudaStream_t s = h->stream;
+    cg_init_kernel<<<g, kRedThreads, 0, s>>>(T, h->drhs, h->dinv, h->q, h->cg_r, h->cg_p, h->partial, kRedBlocks);
+    TRY(fold(h, g, 2, 0));
+    cg_scalar_kernel<<<1, 1, 0, s>>>(0, h->sc, h->red, tol2);
+    const int maxit = h->cfg.max_iterations;
+    int it = 0;
+    *converged = false;
+    while (it < maxit) {
+        int target = std::min(it + 16, maxit);
+        for (; it < target; ++it) {
+            TRY(halo_exchange(h, h->cg_p, 1, h->pg));
+            cg_spmv_kernel<<<g, kRedThreads, 0, s>>>(h->dm, h->ddiag, h->doff, h->cg_p, h->pg, h->cg_Ap, h->partial, h->sc);
+            TRY(fold(h, g, 1, 0));
+            cg_scalar_kernel<<<1, 1, 0, s>>>(1, h->sc, h->red, tol2);
+            cg_update_kernel<<<g, kRedThreads, 0, s>>>(T, h->sc, h->dinv, h->cg_p, h->cg_Ap, h->q, h->cg_r, h->partial, kRedBlocks);
+            TRY(fold(h, g, 2, 0));
+            cg_scalar_kernel<<<1, 1, 0, s>>>(2, h->sc, h->red, tol2);
+            cg_p_kernel<<<g, kRedThreads, 0, s>>>(T, h->sc, h->dinv, h->cg_r, h->cg_p);
+        }
+        TRY(read_scalars(h));
+        if (h->h_sc->done) break;
+    }
+    *converged = (h->h_sc->done == 1);
+    st->deposition_iterations = h->h_sc->iters;
+    st->deposition_residual = std::sqrt(h->h_sc->rr / h->h_sc->bnorm2);
+    return 0;
+}
+
+void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt) {
+    assemble_kernel<<<cdiv(h->T, 128), 128, 0, h->stream>>>(h->dc, h->dm, f, h->ss, dt);
+}
+
+// One PBSM3D::run with device-resident forcing (reference PBSM3D.cpp:400-1748, phases A–I of SURVEY §3.2).
+int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, pbsm3d_stats* st) {
+    cudaStream_t s = h->stream;
+    const int T = h->T;
+    std::memset(st, 0, sizeof(*st));
+    h->last_forcing = f;
+    h->last_dt = dt;
+    CU(cudaEventRecord(h->ev[0], s));
+    // A+B: zeroSystem is implicit (every coefficient is overwritten); saltation + suspension assembly
+    launch_assembly(h, f, dt);
+    h->have_system = true;
+    // C: suspension_present = ||rhs||_inf > 1e-12 (PBSM3D.cpp:1424-1427); also ||b||_2^2 for the stopping rule
+    {
+        int g = red_grid(T);
+        absmax_kernel<<<g, kRedThreads, 0, s>>>(T, h->ss.rhs0, h->partial);
+        fold_kernel<<<1, 256, 0, s>>>(g, 1, kRedBlocks, h->partial, h->red, 1);
+        sumsq_kernel<<<g, kRedThreads, 0, s>>>(T, h->ss.rhs0, h->partial + kRedBlocks);
+        fold_kernel<<<1, 256, 0, s>>>(g, 1, kRedBlocks, h->partial + kRedBlocks, h->red + 1, 0);
+        if (h->n_ranks > 1) {
+            NC(ncclAllReduce(h->red, h->red, 1, ncclDouble, ncclMax, h->comm, s));
+            NC(ncclAllReduce(h->red + 1, h->red + 1, 1, ncclDouble, ncclSum, h->comm, s));
+        }
+    }
+    CU(cudaEventRecord(h->ev[1], s));
+    TRY(read_red(h, 2));
+    st->suspension_rhs_max = h->h_red[0];
+    const double bnorm2 = h->h_red[1];
+    const bool susp = st->suspension_rhs_max > 1e-12;
+    st->suspension_present = susp ? 1 : 0;
+    // D: suspension solve
+    if (susp) {
+        bool conv = false;
+        int solver = h->cfg.solver;
+        if (solver == PBSM3D_SOLVER_AUTO || solver == PBSM3D_SOLVER_LINE)
+            TRY(solve_line(h, bnorm2, st, &conv, solver == PBSM3D_SOLVER_AUTO));
+        if (!conv && solver != PBSM3D_SOLVER_LINE) TRY(solve_bicgstab(h, st, &conv));
+        if (!conv) return fail(PBSM3D_ERR_NOCONVERGE, "suspension solver failed to converge");
+    } else {
+        CU(cudaMemsetAsync(h->xa, 0, h->N * sizeof(double), s));  // solution stays the zero vector (PBSM3D.cpp:1461-1465)
+        h->xcur = h->xa;
+    }
+    CU(cudaEventRecord(h->ev[2], s));
+    // E: flux integration
+    flux_kernel<<<cdiv(T, 256), 256, 0, s>>>(T, h->L, h->dc.dz, dt, h->xcur, h->ss.u_z, h->ss.csubl, h->Qsusp, h->Qsubl,
+                                             h->Qsubl_mass, h->sum_subl);
+    // F: halo of Qsusp, Qsalt (PBSM3D.cpp:1509-1510) — one message per partner carrying both
+    if (h->n_ranks > 1) {
+        CU(cudaMemcpyAsync(h->q2, h->Qsusp, T * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CU(cudaMemcpyAsync(h->q2 + T, h->ss.Qsalt, T * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        TRY(halo_exchange(h, h->q2, 2, h->qg));
+    }
+    // G: deposition RHS (the matrix is static) + H: rhs max
+    {
+        int g = red_grid(T);
+        deposition_rhs_kernel<<<g, 256, 0, s>>>(h->dm, f.vw_dir, h->Qsusp, h->ss.Qsalt, h->qg, h->drhs, h->partial);
+        fold_kernel<<<1, 256, 0, s>>>(g, 1, kRedBlocks, h->partial, h->red, 1);
+        if (h->n_ranks > 1) NC(ncclAllReduce(h->red, h->red, 1, ncclDouble, ncclMax, h->comm, s));
+    }
+    CU(cudaEventRecord(h->ev[3], s));
+    TRY(read_red(h, 1));
+    st->deposition_rhs_max = h->h_red[0];
+    const bool dep = susp && st->deposition_rhs_max > 1e-12;  // PBSM3D.cpp:1661-1664
+    st->deposition_present = dep ? 1 : 0;
+    if (dep) {
+        bool conv = false;
+        TRY(solve_deposition(h, st, &conv));
+        if (!conv) return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver failed to converge");
+        // I: drift update
+        drift_kernel<<<cdiv(T, 256), 256, 0, s>>>(T, dt, h->q, f.swe, h->ss.salt, h->drift_mass, h->sum_drift, h->more_avail);
+    }
+    CU(cudaEventRecord(h->ev[4], s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaEventElapsedTime(&st->ms_assembly, h->ev[0], h->ev[1]));
+    CU(cudaEventElapsedTime(&st->ms_suspension_solve, h->ev[1], h->ev[2]));
+    CU(cudaEventElapsedTime(&st->ms_flux_and_halo, h->ev[2], h->ev[3]));
+    CU(cudaEventElapsedTime(&st->ms_deposition, h->ev[3], h->ev[4]));
+    CU(cudaEventElapsedTime(&st->ms_total, h->ev[0], h->ev[4]));
+    return 0;
+}
+
+int copy_out(pbsm3d_handle* h, double* dst, const double* src, size_t n, cudaMemcpyKind kind) {
+    if (!dst) return 0;
+    CU(cudaMemcpyAsync(dst, src, n * sizeof(double), kind, h->stream));
+    return 0;
+}
+
+int write_outputs(pbsm3d_handle* h, const pbsm3d_outputs* o, cudaMemcpyKind kind) {
+    if (!o) return 0;
+    const size_t T = h->T;
+    TRY(copy_out(h, o->Qsalt, h->ss.Qsalt, T, kind));
+    TRY(copy_out(h, o->Qsusp, h->Qsusp, T, kind));
+    TRY(copy_out(h, o->Qsubl, h->Qsubl, T, kind));
+    TRY(copy_out(h, o->Qsubl_mass, h->Qsubl_mass, T, kind));
+    TRY(copy_out(h, o->sum_subl, h->sum_subl, T, kind));
+    TRY(copy_out(h, o->drift_mass, h->drift_mass, T, kind));
+    TRY(copy_out(h, o->sum_drift, h->sum_drift, T, kind));
+    TRY(copy_out(h, o->pbsm_more_than_avail, h->more_avail, T, kind));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // namespace
+
+// ======================================================================================== C ABI
+extern "C" {
+
+int pbsm3d_abi_version(void) { return PBSM3D_ABI_VERSION; }
+const char* pbsm3d_last_error(void) { return g_last_error.c_str(); }
+
+void pbsm3d_config_defaults(pbsm3d_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->nLayer = 10;             // PBSM3D.cpp:223
+    c->do_fixed_settling = 0;   // :229
+    c->settling_velocity = 0.5; // :233
+    c->do_sublimation = 1;      // :244
+    c->do_lateral_diff = 1;     // :245
+    c->smooth_coeff = 820;      // :246
+    c->min_sd_trans = 0.1;      // :247
+    c->cutoff = 0.3;            // :249
+    c->snow_diffusion_const = 0.3;  // :252
+    c->rouault_diffusion_coef = 0;  // :254
+    c->enable_veg = 1;          // :256
+    c->iterative_subl = 0;      // :258
+    c->use_exp_fetch = 0;       // :123
+    c->use_tanh_fetch = 1;      // :124
+    c->use_PomLi_probability = 0;  // :125
+    c->z0_ustar_coupling = 0;   // :126
+    c->use_subgrid_topo = 0;    // :129
+    c->use_subgrid_topo_V2 = 0; // :130
+    c->use_R94_lambda = 1;      // :141
+    c->debug_output = 0;        // :145
+    c->tolerance = 1e-8;        // LinearAlgebra.cpp:168
+    c->max_iterations = 1000;   // LinearAlgebra.cpp:167
+    c->solver = PBSM3D_SOLVER_AUTO;
+}
+
+int pbsm3d_nccl_unique_id(void* out) {
+    if (!out) return fail(PBSM3D_ERR_INVALID, "null output");
+    ncclUniqueId id;
+    NC(ncclGetUniqueId(&id));
+    std::memcpy(out, &id, sizeof(id));
+    return 0;
+}
+
+void pbsm3d_destroy(pbsm3d_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) ncclCommDestroy(h->comm);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_sc) cudaFreeHost(h->h_sc);
+    if (h->h_red) cudaFreeHost(h->h_red);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_mesh* mesh, int device, const pbsm3d_comm* comm) {
+    // ---- config checks: same errors the reference raises, plus "unsupported" for optional paths
+    if (cfg->use_exp_fetch && cfg->use_tanh_fetch)
+        return fail(PBSM3D_ERR_INVALID, "PBSM3d: Cannot specify both exp_fetch and tanh_fetch");  // PBSM3D.cpp:132-135
+    if (cfg->settling_velocity < 0) return fail(PBSM3D_ERR_INVALID, "PBSM3D settling velocity must be positive");  // :239-242
+    if (cfg->nLayer < 2) return fail(PBSM3D_ERR_INVALID, "nLayer must be >= 2 (top and bottom layers are distinct rows)");
+    if (cfg->iterative_subl) return fail(PBSM3D_ERR_UNSUPPORTED, "iterative_subl is not implemented");
+    if (cfg->use_PomLi_probability) return fail(PBSM3D_ERR_UNSUPPORTED, "use_PomLi_probability is not implemented");
+    if (cfg->z0_ustar_coupling) return fail(PBSM3D_ERR_UNSUPPORTED, "z0_ustar_coupling is not implemented");
+    if (cfg->use_subgrid_topo || cfg->use_subgrid_topo_V2) return fail(PBSM3D_ERR_UNSUPPORTED, "use_subgrid_topo* is not implemented");
+    if (cfg->debug_output) return fail(PBSM3D_ERR_UNSUPPORTED, "debug_output is not implemented");
+    if (!(cfg->tolerance > 0) || cfg->max_iterations < 1) return fail(PBSM3D_ERR_INVALID, "bad solver controls");
+    if (mesh->n_local < 1 || mesh->n_ghost < 0 || !mesh->neigh || !mesh->vertices || !mesh->global_id)
+        return fail(PBSM3D_ERR_INVALID, "mesh arrays missing");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PBSM3D_ERR_CUDA, "no CUDA device: libpbsm3d_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(PBSM3D_ERR_INVALID, "device index out of range");
+    CU(cudaSetDevice(device));
+    h->device = device;
+    h->cfg = *cfg;
+    const int T = h->T = mesh->n_local, nG = h->nG = mesh->n_ghost, L = h->L = cfg->nLayer;
+    h->G = mesh->n_global;
+    h->N = (size_t)T * L;
+    h->rank = comm ? comm->rank : 0;
+    h->n_ranks = comm ? comm->n_ranks : 1;
+    if (h->n_ranks > 1 && !comm->nccl_unique_id) return fail(PBSM3D_ERR_INVALID, "nccl_unique_id missing");
+    if (h->n_ranks == 1 && nG != 0) return fail(PBSM3D_ERR_INVALID, "ghost faces on a single-rank mesh");
+    // owned faces are one contiguous ascending global range (triangulation.cpp:1482-1531)
+    h->gstart_id = mesh->global_id[0];
+    for (int i = 0; i < T; ++i)
+        if (mesh->global_id[i] != h->gstart_id + i)
+            return fail(PBSM3D_ERR_INVALID, "owned faces must be a contiguous ascending range of cell_global_id");
+    for (int g = 1; g < nG; ++g)
+        if (mesh->global_id[T + g] <= mesh->global_id[T + g - 1])
+            return fail(PBSM3D_ERR_INVALID, "ghost faces must be sorted by cell_global_id");
+    if (h->gstart_id < 0 || h->gstart_id + T > h->G) return fail(PBSM3D_ERR_INVALID, "global ids exceed n_global");
+
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) CU(cudaEventCreate(&e));
+    CU(cudaMallocHost((void**)&h->h_sc, sizeof(Scalars)));
+    CU(cudaMallocHost((void**)&h->h_red, 8 * sizeof(double)));
+
+    // ---- neighbour table: AoS [T][3] from the caller -> SoA [3][T]
+    std::vector<int> nb((size_t)3 * T);
+    for (int i = 0; i < T; ++i)
+        for (int j = 0; j < 3; ++j) {
+            int n = mesh->neigh[(size_t)i * 3 + j];
+            if (n < -1 || n >= T + nG) return fail(PBSM3D_ERR_INVALID, "Face " + std::to_string(i) + " has out of bound neighbors.");
+            nb[(size_t)j * T + i] = n;
+        }
+    TRY(h->alloc(&h->neigh, (size_t)3 * T));
+    TRY(upload(h, h->neigh, nb.data(), nb.size() * sizeof(int)));
+    // ghost owner blocks
+    std::vector<int> gs(std::max(nG, 1), 0), gc(std::max(nG, 1), 0);
+    for (int g = 0; g < nG;) {
+        int e = g;
+        while (e < nG && mesh->ghost_owner && mesh->ghost_owner[e] == mesh->ghost_owner[g]) ++e;
+        if (e == g) return fail(PBSM3D_ERR_INVALID, "ghost_owner missing");
+        for (int k = g; k < e; ++k) { gs[k] = g; gc[k] = e - g; }
+        g = e;
+    }
+    TRY(h->alloc(&h->gstart, nG));
+    TRY(h->alloc(&h->gcnt, nG));
+    TRY(upload(h, h->gstart, gs.data(), std::max(nG, 1) * sizeof(int)));
+    TRY(upload(h, h->gcnt, gc.data(), std::max(nG, 1) * sizeof(int)));
+
+    // ---- geometry on the device
+    const size_t Tall = (size_t)T + nG;
+    double* d_verts = nullptr;
+    double* d_area_param = nullptr;
+    TRY(h->alloc(&d_verts, Tall * 9));
+    TRY(upload(h, d_verts, mesh->vertices, Tall * 9 * sizeof(double)));
+    if (mesh->area) {
+        TRY(h->alloc(&d_area_param, T));
+        TRY(upload(h, d_area_param, mesh->area, T * sizeof(double)));
+    }
+    TRY(h->alloc(&h->nx, (size_t)3 * T));
+    TRY(h->alloc(&h->ny, (size_t)3 * T));
+    TRY(h->alloc(&h->elen, (size_t)3 * T));
+    TRY(h->alloc(&h->dx, (size_t)3 * T));
+    TRY(h->alloc(&h->area, T));
+    TRY(h->alloc(&h->cx, Tall));
+    TRY(h->alloc(&h->cy, Tall));
+    TRY(h->alloc(&h->cz, Tall));
+    geometry_kernel<<<cdiv(Tall, 256), 256, 0, h->stream>>>(T, (int)Tall, d_verts, d_area_param, h->nx, h->ny, h->elen, h->area,
+                                                            h->cx, h->cy, h->cz);
+    TRY(h->alloc(&h->ddiag, T));
+    TRY(h->alloc(&h->doff, (size_t)3 * T));
+    TRY(h->alloc(&h->dinv, T));
+    deposition_matrix_kernel<<<cdiv(T, 256), 256, 0, h->stream>>>(T, cfg->smooth_coeff, h->neigh, h->elen, h->area, h->cx, h->cy,
+                                                                  h->dx, h->ddiag, h->doff, h->dinv);
+    CU(cudaGetLastError());
+
+    // ---- vegetation (PBSM3D.cpp:284-324): no vegetation information => veg off for the whole run
+    bool veg = cfg->enable_veg && mesh->canopy_height != nullptr;
+    if (veg && cfg->use_R94_lambda && !mesh->lai) return fail(PBSM3D_ERR_INVALID, "Parameter LAI does not exist.");
+    if (veg) {
+        TRY(h->alloc(&h->canopy, T));
+        TRY(upload(h, h->canopy, mesh->canopy_height, T * sizeof(double)));
+        if (cfg->use_R94_lambda) {
+            TRY(h->alloc(&h->lai, T));
+            TRY(upload(h, h->lai, mesh->lai, T * sizeof(double)));
+        } else {
+            if (mesh->stalk_number) { TRY(h->alloc(&h->stalk_n, T)); TRY(upload(h, h->stalk_n, mesh->stalk_number, T * sizeof(double))); }
+            if (mesh->stalk_diameter) { TRY(h->alloc(&h->stalk_dv, T)); TRY(upload(h, h->stalk_dv, mesh->stalk_diameter, T * sizeof(double))); }
+        }
+    }
+    if (mesh->is_water) {
+        TRY(h->alloc(&h->water, T));
+        TRY(upload(h, h->water, mesh->is_water, T));
+    }
+
+    // ---- per-step arrays
+    for (auto& b : h->forcing_buf) TRY(h->alloc(&b, T));
+    SuspSystem& ss = h->ss;
+    TRY(h->alloc(&ss.diag, h->N));
+    TRY(h->alloc(&ss.below, h->N));
+    TRY(h->alloc(&ss.above, h->N));
+    TRY(h->alloc(&ss.lat, 3 * h->N));
+    TRY(h->alloc(&ss.cp, h->N));
+    TRY(h->alloc(&ss.inv, h->N));
+    TRY(h->alloc(&ss.u_z, h->N));
+    TRY(h->alloc(&ss.csubl, h->N));
+    TRY(h->alloc(&ss.rhs0, T));
+    TRY(h->alloc(&ss.Qsalt, T));
+    TRY(h->alloc(&ss.c_salt, T));
+    TRY(h->alloc(&ss.salt, T));
+    TRY(h->alloc(&h->xa, h->N));
+    TRY(h->alloc(&h->xb, h->N));
+    TRY(h->alloc(&h->xga, (size_t)L * std::max(nG, 1)));
+    TRY(h->alloc(&h->xgb, (size_t)L * std::max(nG, 1)));
+    double** perface[] = {&h->Qsusp, &h->Qsubl, &h->Qsubl_mass, &h->sum_subl, &h->drift_mass, &h->sum_drift, &h->more_avail,
+                          &h->drhs,  &h->q,     &h->cg_r,       &h->cg_p,     &h->cg_Ap};
+    for (double** p : perface) {
+        TRY(h->alloc(p, T));
+        CU(cudaMemsetAsync(*p, 0, T * sizeof(double), h->stream));
+    }
+    TRY(h->alloc(&h->q2, (size_t)2 * T));
+    TRY(h->alloc(&h->qg, (size_t)2 * std::max(nG, 1)));
+    TRY(h->alloc(&h->pg, std::max(nG, 1)));
+    CU(cudaMemsetAsync(h->xa, 0, h->N * sizeof(double), h->stream));
+    h->xcur = h->xa;
+    // drift_mass is a face variable that is -9999 until first written (variablestorage default)
+    fill_kernel<<<cdiv(T, 256), 256, 0, h->stream>>>(T, h->drift_mass, -9999.0);
+    TRY(h->alloc(&h->partial, (size_t)kRedBlocks * 4));
+    TRY(h->alloc(&h->red, 8));
+    TRY(h->alloc(&h->sc, 1));
+    CU(cudaMemsetAsync(h->sc, 0, sizeof(Scalars), h->stream));
+
+    DevConfig& dc = h->dc;
+    dc.L = L;
+    dc.do_fixed_settling = cfg->do_fixed_settling;
+    dc.do_sublimation = cfg->do_sublimation;
+    dc.do_lateral_diff = cfg->do_lateral_diff;
+    dc.rouault = cfg->rouault_diffusion_coef;
+    dc.enable_veg = veg ? 1 : 0;
+    dc.use_exp_fetch = cfg->use_exp_fetch;
+    dc.use_tanh_fetch = cfg->use_tanh_fetch;
+    dc.use_R94_lambda = cfg->use_R94_lambda;
+    dc.settling_velocity = cfg->settling_velocity;
+    dc.eps = cfg->smooth_coeff;
+    dc.min_sd_trans = cfg->min_sd_trans;
+    dc.cutoff = cfg->cutoff;
+    dc.snow_diffusion_const = cfg->snow_diffusion_const;
+    dc.dz = 5.0 / (double)L;  // susp_depth / nLayer
+    dc.l_max = 40.0;
+    DevMesh& dm = h->dm;
+    dm.T = T;
+    dm.n_ghost = nG;
+    dm.neigh = h->neigh;
+    dm.nx = h->nx;
+    dm.ny = h->ny;
+    dm.elen = h->elen;
+    dm.area = h->area;
+    dm.zc = h->cz;
+    dm.canopy = h->canopy;
+    dm.lai = h->lai;
+    dm.stalk_n = h->stalk_n;
+    dm.stalk_dv = h->stalk_dv;
+    dm.water = h->water;
+    dm.gstart = h->gstart;
+    dm.gcnt = h->gcnt;
+
+    if (h->n_ranks > 1) TRY(setup_comm(h, mesh, comm));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pbsm3d_create(const pbsm3d_config* cfg, const pbsm3d_mesh* mesh, int device, const pbsm3d_comm* comm, pbsm3d_handle** out) {
+    if (!cfg || !mesh || !out) return fail(PBSM3D_ERR_INVALID, "null argument");
+    *out = nullptr;
+    pbsm3d_handle* h = new pbsm3d_handle();
+    int rc = create_impl(h, cfg, mesh, device, comm);
+    if (rc) {
+        std::string keep = g_last_error;
+        pbsm3d_destroy(h);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+int pbsm3d_step_device(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm3d_outputs* out, pbsm3d_stats* stats) {
+    if (!h || !f) return fail(PBSM3D_ERR_INVALID, "null argument");
+    if (!f->U_R || !f->U_2m_above_srf || !f->snowdepthavg || !f->swe || !f->t || !f->rh || !f->vw_dir)
+        return fail(PBSM3D_ERR_INVALID, "forcing array missing");
+    CU(cudaSetDevice(h->device));
+    pbsm3d_stats local;
+    if (!stats) stats = &local;
+    DevForcing df{f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch};
+    TRY(step_impl(h, dt, df, stats));
+    return write_outputs(h, out, cudaMemcpyDeviceToDevice);
+}
+
+int pbsm3d_step(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm3d_outputs* out, pbsm3d_stats* stats) {
+    if (!h || !f) return fail(PBSM3D_ERR_INVALID, "null argument");
+    if (!f->U_R || !f->U_2m_above_srf || !f->snowdepthavg || !f->swe || !f->t || !f->rh || !f->vw_dir)
+        return fail(PBSM3D_ERR_INVALID, "forcing array missing");
+    CU(cudaSetDevice(h->device));
+    pbsm3d_stats local;
+    if (!stats) stats = &local;
+    const double* src[8] = {f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch};
+    for (int k = 0; k < 8; ++k)
+        if (src[k]) TRY(upload(h, h->forcing_buf[k], src[k], (size_t)h->T * sizeof(double)));
+    DevForcing df{h->forcing_buf[0], h->forcing_buf[1], h->forcing_buf[2], h->forcing_buf[3], h->forcing_buf[4],
+                  h->forcing_buf[5], h->forcing_buf[6], f->fetch ? h->forcing_buf[7] : nullptr};
+    TRY(step_impl(h, dt, df, stats));
+    return write_outputs(h, out, cudaMemcpyDeviceToHost);
+}
+
+int pbsm3d_get_state(pbsm3d_handle* h, double* sum_drift, double* sum_subl, double* drift_mass, double* more) {
+    if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    TRY(copy_out(h, sum_drift, h->sum_drift, h->T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, sum_subl, h->sum_subl, h->T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, drift_mass, h->drift_mass, h->T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, more, h->more_avail, h->T, cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pbsm3d_set_state(pbsm3d_handle* h, const double* sum_drift, const double* sum_subl, const double* drift_mass, const double* more) {
+    if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    const size_t b = (size_t)h->T * sizeof(double);
+    if (sum_drift) TRY(upload(h, h->sum_drift, sum_drift, b));
+    if (sum_subl) TRY(upload(h, h->sum_subl, sum_subl, b));
+    if (drift_mass) TRY(upload(h, h->drift_mass, drift_mass, b));
+    if (more) TRY(upload(h, h->more_avail, more, b));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pbsm3d_get_geometry(pbsm3d_handle* h, double* nx, double* ny, double* el, double* area, double* dx, double* cx, double* cy, double* cz) {
+    if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    const size_t T = h->T;
+    TRY(copy_out(h, nx, h->nx, 3 * T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, ny, h->ny, 3 * T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, el, h->elen, 3 * T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, area, h->area, T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, dx, h->dx, 3 * T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, cx, h->cx, T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, cy, h->cy, T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, cz, h->cz, T, cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pbsm3d_get_solution(pbsm3d_handle* h, double* x) {
+    if (!h || !x) return fail(PBSM3D_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    TRY(copy_out(h, x, h->xcur, h->N, cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pbsm3d_get_suspension_system(pbsm3d_handle* h, double* diag, double* lat, double* below, double* above, double* rhs0,
+                                 double* u_z, double* csubl, double* c_salt, uint8_t* saltation) {
+    if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
+    if (!h->have_system) return fail(PBSM3D_ERR_INVALID, "no system assembled yet");
+    CU(cudaSetDevice(h->device));
+    const size_t N = h->N, T = h->T;
+    TRY(copy_out(h, diag, h->ss.diag, N, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, lat, h->ss.lat, 3 * N, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, below, h->ss.below, N, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, above, h->ss.above, N, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, rhs0, h->ss.rhs0, T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, u_z, h->ss.u_z, N, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, csubl, h->ss.csubl, N, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, c_salt, h->ss.c_salt, T, cudaMemcpyDeviceToHost));
+    if (saltation) CU(cudaMemcpyAsync(saltation, h->ss.salt, T, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pbsm3d_get_deposition_system(pbsm3d_handle* h, double* diag, double* off, double* rhs, double* q) {
+    if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    const size_t T = h->T;
+    TRY(copy_out(h, diag, h->ddiag, T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, off, h->doff, 3 * T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, rhs, h->drhs, T, cudaMemcpyDeviceToHost));
+    TRY(copy_out(h, q, h->q, T, cudaMemcpyDeviceToHost));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms) {
+    if (!h || !ms || reps < 1) return fail(PBSM3D_ERR_INVALID, "bad argument");
+    if (!h->have_system) return fail(PBSM3D_ERR_INVALID, "run a step first");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    double *xo = h->xcur, *xn = (h->xcur == h->xa) ? h->xb : h->xa;
+    // one untimed launch, then `reps` timed ones
+    for (int pass = 0; pass < 2; ++pass) {
+        int n = pass == 0 ? 1 : reps;
+        if (pass == 1) CU(cudaEventRecord(h->ev[0], s));
+        for (int k = 0; k < n; ++k) {
+            switch (kernel) {
+                case 0: sweep(h, xo, h->xga, xn); break;
+                case 1:
+                    spmv_kernel<1><<<red_grid(h->N), kRedThreads, 0, s>>>(h->ss, h->dm, h->L, xo, h->xga, nullptr, nullptr, nullptr,
+                                                                         1, h->partial, kRedBlocks, nullptr);
+                    break;
+                case 2: launch_assembly(h, h->last_forcing, h->last_dt); break;
+                case 3:
+                    cg_spmv_kernel<<<red_grid(h->T), kRedThreads, 0, s>>>(h->dm, h->ddiag, h->doff, h->cg_p, h->pg, h->cg_Ap,
+                                                                         h->partial, nullptr);
+                    break;
+                default: return fail(PBSM3D_ERR_INVALID, "unknown kernel id");
+            }
+        }
+        if (pass == 1) CU(cudaEventRecord(h->ev[1], s));
+    }
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+    *ms = t / reps;
+    if (kernel == 2) {
+        // the assembly rewrote the factors with the same values; nothing else to restore
+    }
+    return 0;
+}
+
+}  // extern "C"

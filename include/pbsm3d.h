@@ -1,0 +1,204 @@
+/*
+ * pbsm3d.h — C-ABI of the B200-native PBSM3D hot path (libpbsm3d_b200.so).
+ *
+ * This is the boundary a CHM adaptor module binds.  It replaces, for one
+ * MPI rank / one GPU, everything `PBSM3D::init` and `PBSM3D::run` do between reading the per-face
+ * variable store and writing it back:
+ *
+ *   reference interface                                         replaced by
+ *   ----------------------------------------------------------  -------------------------
+ *   PBSM3D::PBSM3D(config_file)        PBSM3D.cpp:103-219       pbsm3d_config_defaults + pbsm3d_config
+ *   PBSM3D::init(mesh&)                PBSM3D.cpp:221-398       pbsm3d_create
+ *   NearestNeighborProblem ctor        LinearAlgebra.cpp:31-197 pbsm3d_create (static sparsity = mesh adjacency)
+ *   PBSM3D::run(mesh&)                 PBSM3D.cpp:400-1748      pbsm3d_step / pbsm3d_step_device
+ *   NearestNeighborProblem::Solve      LinearAlgebra.cpp:228-252  (inside pbsm3d_step)
+ *   ghost_neighbors_communicate_variable  triangulation.cpp:1976-2079  (inside pbsm3d_step, NCCL)
+ *   getSolutionView                    LinearAlgebra.cpp:272-275  pbsm3d_get_solution
+ *   writeSystemMatrixMarket (debug)    LinearAlgebra.cpp:277-287  pbsm3d_get_suspension_system / _deposition_system
+ *   PBSM3D::checkpoint/load_checkpoint PBSM3D.cpp:1753-1773     pbsm3d_get_state / pbsm3d_set_state
+ *   ~PBSM3D                                                     pbsm3d_destroy
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
+ * code on failure with a message available from pbsm3d_last_error() (the adaptor turns it into
+ * CHM's module_error).  The caller owns all host buffers; the library owns all device memory.
+ * A handle is bound to one CUDA device and is not re-entrant.  All floating point is fp64.
+ * There is no CPU fallback: without a CUDA device pbsm3d_create fails.
+ */
+#ifndef PBSM3D_B200_H
+#define PBSM3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBSM3D_ABI_VERSION 1
+
+enum {
+    PBSM3D_OK = 0,
+    PBSM3D_ERR_INVALID = 1,     /* bad argument / inconsistent mesh */
+    PBSM3D_ERR_UNSUPPORTED = 2, /* optional reference path that is not implemented (never silently ignored) */
+    PBSM3D_ERR_CUDA = 3,
+    PBSM3D_ERR_NCCL = 4,
+    PBSM3D_ERR_NOCONVERGE = 5   /* "Belos solver failed to converge", LinearAlgebra.cpp:236-243 */
+};
+
+enum {
+    PBSM3D_SOLVER_AUTO = 0,     /* line relaxation, falling back to BiCGStab if it stagnates */
+    PBSM3D_SOLVER_LINE = 1,     /* stationary column-block-Jacobi sweeps (exact vertical tridiagonal solve) */
+    PBSM3D_SOLVER_BICGSTAB = 2  /* right-preconditioned BiCGStab, column-tridiagonal preconditioner */
+};
+
+/* PBSM3D config keys, same names and defaults as the reference reads with cfg.get()
+ * (PBSM3D.cpp:123-145 and :223-258).  Booleans are int 0/1. */
+typedef struct pbsm3d_config {
+    int nLayer;                   /* 10 */
+    int do_fixed_settling;        /* false */
+    double settling_velocity;     /* 0.5 */
+    int do_sublimation;           /* true */
+    int do_lateral_diff;          /* true */
+    double smooth_coeff;          /* 820 */
+    double min_sd_trans;          /* 0.1 */
+    double cutoff;                /* 0.3 */
+    double snow_diffusion_const;  /* 0.3 */
+    int rouault_diffusion_coef;   /* false */
+    int enable_veg;               /* true */
+    int iterative_subl;           /* false — unsupported if true */
+    int use_exp_fetch;            /* false */
+    int use_tanh_fetch;           /* true */
+    int use_PomLi_probability;    /* false — unsupported if true */
+    int z0_ustar_coupling;        /* false — unsupported if true */
+    int use_subgrid_topo;         /* false — unsupported if true */
+    int use_subgrid_topo_V2;      /* false — unsupported if true */
+    int use_R94_lambda;           /* true */
+    int debug_output;             /* false — unsupported if true */
+    /* Solver controls.  The reference hard-codes these (LinearAlgebra.cpp:164-168). */
+    double tolerance;             /* 1e-8: ||b-Ax||2/||b||2, x0 = 0 */
+    int max_iterations;           /* 1000 */
+    int solver;                   /* PBSM3D_SOLVER_AUTO */
+} pbsm3d_config;
+
+/* One rank's share of the mesh, flattened from CHM's triangulation in CHM's own face order.
+ * Faces [0,n_local) are the owned faces `domain->face(i)` (ascending cell_global_id, one contiguous
+ * global range per rank: triangulation.cpp:1482-1531); faces [n_local, n_local+n_ghost) are the
+ * NEIGH ghosts sorted by cell_global_id (triangulation.cpp:1721-1770). */
+typedef struct pbsm3d_mesh {
+    int64_t n_global;             /* domain->size_global_faces() */
+    int32_t n_local;              /* domain->size_faces() */
+    int32_t n_ghost;
+    const int64_t* global_id;     /* [n_local+n_ghost] cell_global_id */
+    const int32_t* ghost_owner;   /* [n_ghost] owning rank (face->owner); may be NULL when n_ghost==0 */
+    const int32_t* neigh;         /* [n_local][3] face->neighbor(j) as a local index; -1 = nullptr */
+    const double* vertices;       /* [n_local+n_ghost][3 vertices][x,y,z] */
+    const double* area;           /* [n_local] face->get_area() when the mesh has an "area" parameter, else NULL */
+    const double* canopy_height;  /* [n_local] veg_attribute("CanopyHeight"), NULL = no vegetation info
+                                     (then enable_veg turns off, PBSM3D.cpp:317-324) */
+    const double* lai;            /* [n_local] veg_attribute("LAI") (use_R94_lambda), may be NULL otherwise */
+    const double* stalk_number;   /* [n_local] or NULL -> 1   (PBSM3D.cpp:303-312) */
+    const double* stalk_diameter; /* [n_local] or NULL -> 0.8 */
+    const uint8_t* is_water;      /* [n_local] module_base::is_water(face), NULL = none */
+} pbsm3d_mesh;
+
+/* Multi-GPU: one process per GPU.  NULL or n_ranks==1 means a single-rank run. */
+typedef struct pbsm3d_comm {
+    int32_t rank;
+    int32_t n_ranks;
+    const void* nccl_unique_id;   /* 128 bytes from pbsm3d_nccl_unique_id() on rank 0, broadcast by the host */
+} pbsm3d_comm;
+
+/* Per-face inputs of one timestep, the variables PBSM3D::run reads from the face store
+ * (PBSM3D.cpp:436-449,468,670,880,927).  Each is [n_local]; -9999 / NaN mean "missing" as in CHM. */
+typedef struct pbsm3d_forcing {
+    const double* U_R;
+    const double* U_2m_above_srf;
+    const double* snowdepthavg;
+    const double* swe;
+    const double* t;
+    const double* rh;
+    const double* vw_dir;
+    const double* fetch;          /* may be NULL when neither fetch option is on (1000 m is used) */
+} pbsm3d_forcing;
+
+/* Per-face outputs PBSM3D::run writes back (provides(), PBSM3D.cpp:194-202).  Each [n_local];
+ * any pointer may be NULL to skip that copy. */
+typedef struct pbsm3d_outputs {
+    double* Qsalt;
+    double* Qsusp;
+    double* Qsubl;
+    double* Qsubl_mass;
+    double* sum_subl;
+    double* drift_mass;           /* unchanged from the previous step when no deposition solve ran */
+    double* sum_drift;
+    double* pbsm_more_than_avail; /* sticky 0/1 flag */
+} pbsm3d_outputs;
+
+typedef struct pbsm3d_stats {
+    int32_t suspension_present;
+    int32_t deposition_present;
+    int32_t suspension_iterations;   /* sweeps (line) or matvec pairs (BiCGStab) */
+    int32_t deposition_iterations;
+    int32_t suspension_solver_used;  /* PBSM3D_SOLVER_LINE / _BICGSTAB */
+    int32_t reserved;
+    double suspension_residual;      /* achieved ||b-Ax||2/||b||2 */
+    double deposition_residual;
+    double suspension_rhs_max;
+    double deposition_rhs_max;
+    float ms_assembly;               /* CUDA-event times of the phases of this step */
+    float ms_suspension_solve;
+    float ms_flux_and_halo;
+    float ms_deposition;
+    float ms_total;
+    float reserved2;
+} pbsm3d_stats;
+
+typedef struct pbsm3d_handle pbsm3d_handle;
+
+int pbsm3d_abi_version(void);
+const char* pbsm3d_last_error(void);
+void pbsm3d_config_defaults(pbsm3d_config* cfg);
+
+/* rank 0 calls this, the host broadcasts the 128 bytes, every rank passes them in pbsm3d_comm. */
+int pbsm3d_nccl_unique_id(void* out_128_bytes);
+
+int pbsm3d_create(const pbsm3d_config* cfg, const pbsm3d_mesh* mesh, int device, const pbsm3d_comm* comm,
+                  pbsm3d_handle** out);
+void pbsm3d_destroy(pbsm3d_handle* h);
+
+/* One PBSM3D::run.  Host buffers; H2D of the forcing and D2H of the outputs are part of the call. */
+int pbsm3d_step(pbsm3d_handle* h, double dt, const pbsm3d_forcing* forcing, const pbsm3d_outputs* out,
+                pbsm3d_stats* stats);
+/* Same with DEVICE pointers (forcing already resident, outputs left on the device). */
+int pbsm3d_step_device(pbsm3d_handle* h, double dt, const pbsm3d_forcing* forcing_dev, const pbsm3d_outputs* out_dev,
+                       pbsm3d_stats* stats);
+
+/* Checkpoint state (PBSM3D.cpp:1753-1773 persists sum_drift; sum_subl, drift_mass and the sticky flag
+ * are the other values that survive between steps).  Each [n_local]; NULL = skip. */
+int pbsm3d_get_state(pbsm3d_handle* h, double* sum_drift, double* sum_subl, double* drift_mass, double* more_than_avail);
+int pbsm3d_set_state(pbsm3d_handle* h, const double* sum_drift, const double* sum_subl, const double* drift_mass,
+                     const double* more_than_avail);
+
+/* ---- inspection (parity tests; mirrors the reference's commented-out MatrixMarket dump hooks) ---- */
+
+/* Device-computed face geometry, each [3][n_local] or [n_local] (NULL = skip). */
+int pbsm3d_get_geometry(pbsm3d_handle* h, double* nx, double* ny, double* edge_length, double* area, double* dx,
+                        double* cx, double* cy, double* cz);
+/* Suspended concentration of the last step, layout x[z*n_local + local_id] (LinearAlgebra.cpp:81). */
+int pbsm3d_get_solution(pbsm3d_handle* h, double* x);
+/* Last assembled suspension system in extruded-ELL form, each [nLayer][n_local] except lat [3][nLayer][n_local]
+ * and rhs0/c_salt [n_local] (the RHS is non-zero only in layer 0); saltation is [n_local] 0/1. */
+int pbsm3d_get_suspension_system(pbsm3d_handle* h, double* diag, double* lat, double* below, double* above,
+                                 double* rhs0, double* u_z, double* csubl, double* c_salt, uint8_t* saltation);
+/* Last deposition system: diag [n_local], off [3][n_local], rhs [n_local], solution q [n_local]. */
+int pbsm3d_get_deposition_system(pbsm3d_handle* h, double* diag, double* off, double* rhs, double* q);
+
+/* Stand-alone kernels for measurement (bench.py roofline line, ncu): run `reps` launches of the named kernel on
+ * the last assembled system and return the mean CUDA-event time per launch in milliseconds.
+ * kernel: 0 = line sweep, 1 = SpMV/residual, 2 = assembly, 3 = deposition SpMV. */
+int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBSM3D_B200_H */
