@@ -20,6 +20,21 @@ NVCC_FLAGS = [
 ]
 
 
+def nccl_paths():
+    """Prefer the NCCL that ships with torch (nvidia-nccl wheel): torch's libtorch_cuda needs its symbols, and the
+    dynamic loader shares one libnccl.so.2 per process whichever of us loads first.  Fall back to the system one."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        base = list(spec.submodule_search_locations)[0]
+        inc, lib = os.path.join(base, "include"), os.path.join(base, "lib")
+        if os.path.exists(os.path.join(lib, "libnccl.so.2")) and os.path.exists(os.path.join(inc, "nccl.h")):
+            return inc, lib
+    except Exception:
+        pass
+    return None, None
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -31,7 +46,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lnccl"]
+    inc, libdir = nccl_paths()
+    nccl = ["-lnccl"]
+    if inc:
+        nccl = ["-I", inc, "-L", libdir, "-l:libnccl.so.2", "-Xlinker", "-rpath", "-Xlinker", libdir]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], *nccl]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

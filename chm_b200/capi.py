@@ -63,14 +63,14 @@ class Outputs(C.Structure):
 class Stats(C.Structure):
     _fields_ = [
         ("suspension_present", C.c_int32), ("deposition_present", C.c_int32), ("suspension_iterations", C.c_int32),
-        ("deposition_iterations", C.c_int32), ("suspension_solver_used", C.c_int32), ("reserved", C.c_int32),
+        ("deposition_iterations", C.c_int32), ("suspension_solver_used", C.c_int32), ("kernel_launches", C.c_int32),
         ("suspension_residual", C.c_double), ("deposition_residual", C.c_double), ("suspension_rhs_max", C.c_double),
         ("deposition_rhs_max", C.c_double), ("ms_assembly", C.c_float), ("ms_suspension_solve", C.c_float),
-        ("ms_flux_and_halo", C.c_float), ("ms_deposition", C.c_float), ("ms_total", C.c_float), ("reserved2", C.c_float),
+        ("ms_flux_and_halo", C.c_float), ("ms_deposition", C.c_float), ("ms_total", C.c_float), ("ms_line_sweeps", C.c_float),
     ]
 
     def asdict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 FORCING_NAMES = [n for n, _ in Forcing._fields_]
@@ -114,7 +114,7 @@ def load_library(path: Optional[str] = None):
     p = path or LIB_PATH
     if not os.path.exists(p):
         raise ImportError(f"{p} not found: build it with `python -m chm_b200.build` (there is no CPU fallback)")
-    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(p)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res

@@ -47,6 +47,13 @@ int fail(int code, const std::string& msg) {
 
 inline int cdiv(size_t a, int b) { return (int)((a + b - 1) / b); }
 
+// every kernel launch goes through here so the step can report how many of our kernels it launched
+#define LAUNCH(h_, kernel_, grid_, block_, ...)                                  \
+    do {                                                                         \
+        ++(h_)->n_launch;                                                        \
+        kernel_<<<(grid_), (block_), 0, (h_)->stream>>>(__VA_ARGS__);            \
+    } while (0)
+
 struct Partner {
     int rank;
     int send_off, send_cnt;  // into the concatenated send list
@@ -101,6 +108,9 @@ struct pbsm3d_handle {
     // timing
     cudaEvent_t ev[6] = {nullptr};
     bool have_system = false;
+    long long n_launch = 0;
+    cudaEvent_t ev_sw[2] = {nullptr};
+    float ms_sweeps = 0.f;
 
     template <typename U>
     int alloc(U** p, size_t n) {
@@ -123,7 +133,7 @@ int upload(pbsm3d_handle* h, void* dst, const void* src, size_t bytes) {
 // ---- reductions ------------------------------------------------------------------------------------
 // fold `nvals` partial arrays into h->red[0..nvals) and make them global (NCCL) when partitioned.
 int fold(pbsm3d_handle* h, int nblocks, int nvals, int op) {
-    fold_kernel<<<1, 256, 0, h->stream>>>(nblocks, nvals, kRedBlocks, h->partial, h->red, op);
+    LAUNCH(h, fold_kernel, 1, 256, nblocks, nvals, kRedBlocks, h->partial, h->red, op);
     if (h->n_ranks > 1) NC(ncclAllReduce(h->red, h->red, nvals, ncclDouble, op ? ncclMax : ncclSum, h->comm, h->stream));
     return 0;
 }
@@ -145,7 +155,7 @@ int halo_exchange(pbsm3d_handle* h, const double* v, int nl, double* ghost) {
     if (h->n_send > 0) {
         size_t total = (size_t)h->n_send * nl;
         int blocks = std::min(cdiv(total, 256), 148 * 8);
-        halo_pack_kernel<<<blocks, 256, 0, h->stream>>>(h->n_send, nl, h->T, h->send_idx, h->send_boff, h->send_cnt,
+        LAUNCH(h, halo_pack_kernel, blocks, 256, h->n_send, nl, h->T, h->send_idx, h->send_boff, h->send_cnt,
                                                         h->send_pos, v, h->sendbuf);
     }
     NC(ncclGroupStart());
@@ -236,7 +246,7 @@ int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* com
 // ---- suspension solve ------------------------------------------------------------------------------
 template <int LT>
 void launch_sweep(pbsm3d_handle* h, const double* xo, const double* xgo, double* xn) {
-    line_sweep_kernel<LT><<<cdiv(h->T, 128), 128, 0, h->stream>>>(h->ss, h->dm, h->L, xo, xgo, xn, nullptr);
+    LAUNCH(h, line_sweep_kernel<LT>, cdiv(h->T, 128), 128, h->ss, h->dm, h->L, xo, xgo, xn, nullptr);
 }
 void sweep(pbsm3d_handle* h, const double* xo, const double* xgo, double* xn) {
     switch (h->L) {
@@ -253,9 +263,9 @@ inline int red_grid(size_t n) { return std::max(1, std::min(kRedBlocks, cdiv(n, 
 // ||b - A x||^2 into h_red[0]  (x's ghost values must be current in xg)
 int residual_norm2(pbsm3d_handle* h, const double* x, const double* xg) {
     int g = red_grid(h->N);
-    spmv_kernel<1><<<g, kRedThreads, 0, h->stream>>>(h->ss, h->dm, h->L, x, xg, nullptr, nullptr, nullptr, 1, h->partial,
+    LAUNCH(h, spmv_kernel<1>, g, kRedThreads, h->ss, h->dm, h->L, x, xg, nullptr, nullptr, nullptr, 1, h->partial,
                                                     kRedBlocks, nullptr);
-    fold_kernel<<<1, 256, 0, h->stream>>>(g, 1, kRedBlocks, h->partial + kRedBlocks, h->red, 0);
+    LAUNCH(h, fold_kernel, 1, 256, g, 1, kRedBlocks, h->partial + kRedBlocks, h->red, 0);
     if (h->n_ranks > 1) NC(ncclAllReduce(h->red, h->red, 1, ncclDouble, ncclSum, h->comm, h->stream));
     return read_red(h, 1);
 }
@@ -273,13 +283,20 @@ int solve_line(pbsm3d_handle* h, double bnorm2, pbsm3d_stats* st, bool* converge
     const int maxit = h->cfg.max_iterations;
     while (it < maxit) {
         int target = std::min(next_check, maxit);
+        CU(cudaEventRecord(h->ev_sw[0], h->stream));
         for (; it < target; ++it) {
             sweep(h, xo, xgo, xn);
             std::swap(xo, xn);
             TRY(halo_exchange(h, xo, h->L, xgn));
             std::swap(xgo, xgn);
         }
+        CU(cudaEventRecord(h->ev_sw[1], h->stream));
         TRY(residual_norm2(h, xo, xgo));
+        {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, h->ev_sw[0], h->ev_sw[1]));
+            h->ms_sweeps += ms;
+        }
         double rr = h->h_red[0];
         ++checks;
         st->suspension_residual = std::sqrt(rr / bnorm2);
@@ -323,30 +340,30 @@ int solve_bicgstab(pbsm3d_handle* h, pbsm3d_stats* st, bool* converged) {
     const int g = red_grid(N), gt = cdiv(h->T, 128);
     cudaStream_t s = h->stream;
     const int* done = &h->sc->done;
-    bicg_init_kernel<<<g, kRedThreads, 0, s>>>(h->T, h->L, h->ss.rhs0, x, r, rhat, p, v, h->partial);
+    LAUNCH(h, bicg_init_kernel, g, kRedThreads, h->T, h->L, h->ss.rhs0, x, r, rhat, p, v, h->partial);
     TRY(fold(h, g, 1, 0));
-    bicg_scalar_kernel<<<1, 1, 0, s>>>(0, h->sc, h->red, tol2);
+    LAUNCH(h, bicg_scalar_kernel, 1, 1, 0, h->sc, h->red, tol2);
     *converged = false;
     const int maxit = h->cfg.max_iterations;
     int it = 0;
     while (it < maxit) {
         int target = std::min(it + 4, maxit);
         for (; it < target; ++it) {
-            bicg_p_kernel<<<g, kRedThreads, 0, s>>>(N, h->sc, r, v, p);
-            thomas_kernel<<<gt, 128, 0, s>>>(h->ss, h->T, h->L, p, ph, done);
+            LAUNCH(h, bicg_p_kernel, g, kRedThreads, N, h->sc, r, v, p);
+            LAUNCH(h, thomas_kernel, gt, 128, h->ss, h->T, h->L, p, ph, done);
             TRY(halo_exchange(h, ph, h->L, h->kry_g));
-            spmv_kernel<0><<<g, kRedThreads, 0, s>>>(h->ss, h->dm, h->L, ph, h->kry_g, v, rhat, nullptr, 0, h->partial, kRedBlocks, done);
+            LAUNCH(h, spmv_kernel<0>, g, kRedThreads, h->ss, h->dm, h->L, ph, h->kry_g, v, rhat, nullptr, 0, h->partial, kRedBlocks, done);
             TRY(fold(h, g, 1, 0));
-            bicg_scalar_kernel<<<1, 1, 0, s>>>(1, h->sc, h->red, tol2);
-            bicg_s_kernel<<<g, kRedThreads, 0, s>>>(N, h->sc, r, v, h->partial);
-            thomas_kernel<<<gt, 128, 0, s>>>(h->ss, h->T, h->L, r, sh, done);
+            LAUNCH(h, bicg_scalar_kernel, 1, 1, 1, h->sc, h->red, tol2);
+            LAUNCH(h, bicg_s_kernel, g, kRedThreads, N, h->sc, r, v, h->partial);
+            LAUNCH(h, thomas_kernel, gt, 128, h->ss, h->T, h->L, r, sh, done);
             TRY(halo_exchange(h, sh, h->L, h->kry_g));
-            spmv_kernel<0><<<g, kRedThreads, 0, s>>>(h->ss, h->dm, h->L, sh, h->kry_g, t, r, nullptr, 1, h->partial, kRedBlocks, done);
+            LAUNCH(h, spmv_kernel<0>, g, kRedThreads, h->ss, h->dm, h->L, sh, h->kry_g, t, r, nullptr, 1, h->partial, kRedBlocks, done);
             TRY(fold(h, g, 2, 0));
-            bicg_scalar_kernel<<<1, 1, 0, s>>>(3, h->sc, h->red, tol2);
-            bicg_xr_kernel<<<g, kRedThreads, 0, s>>>(N, h->sc, x, r, ph, sh, t, rhat, h->partial, kRedBlocks);
+            LAUNCH(h, bicg_scalar_kernel, 1, 1, 3, h->sc, h->red, tol2);
+            LAUNCH(h, bicg_xr_kernel, g, kRedThreads, N, h->sc, x, r, ph, sh, t, rhat, h->partial, kRedBlocks);
             TRY(fold(h, g, 2, 0));
-            bicg_scalar_kernel<<<1, 1, 0, s>>>(4, h->sc, h->red, tol2);
+            LAUNCH(h, bicg_scalar_kernel, 1, 1, 4, h->sc, h->red, tol2);
         }
         TRY(read_scalars(h));
         if (h->h_sc->done) break;
@@ -365,9 +382,9 @@ int solve_deposition(pbsm3d_handle* h, pbsm3d_stats* st, bool* converged) {
     const int T = h->T;
     const int g = red_grid(T);
     cudaStream_t s = h->stream;
-    cg_init_kernel<<<g, kRedThreads, 0, s>>>(T, h->drhs, h->dinv, h->q, h->cg_r, h->cg_p, h->partial, kRedBlocks);
+    LAUNCH(h, cg_init_kernel, g, kRedThreads, T, h->drhs, h->dinv, h->q, h->cg_r, h->cg_p, h->partial, kRedBlocks);
     TRY(fold(h, g, 2, 0));
-    cg_scalar_kernel<<<1, 1, 0, s>>>(0, h->sc, h->red, tol2);
+    LAUNCH(h, cg_scalar_kernel, 1, 1, 0, h->sc, h->red, tol2);
     const int maxit = h->cfg.max_iterations;
     int it = 0;
     *converged = false;
@@ -375,13 +392,13 @@ int solve_deposition(pbsm3d_handle* h, pbsm3d_stats* st, bool* converged) {
         int target = std::min(it + 16, maxit);
         for (; it < target; ++it) {
             TRY(halo_exchange(h, h->cg_p, 1, h->pg));
-            cg_spmv_kernel<<<g, kRedThreads, 0, s>>>(h->dm, h->ddiag, h->doff, h->cg_p, h->pg, h->cg_Ap, h->partial, h->sc);
+            LAUNCH(h, cg_spmv_kernel, g, kRedThreads, h->dm, h->ddiag, h->doff, h->cg_p, h->pg, h->cg_Ap, h->partial, h->sc);
             TRY(fold(h, g, 1, 0));
-            cg_scalar_kernel<<<1, 1, 0, s>>>(1, h->sc, h->red, tol2);
-            cg_update_kernel<<<g, kRedThreads, 0, s>>>(T, h->sc, h->dinv, h->cg_p, h->cg_Ap, h->q, h->cg_r, h->partial, kRedBlocks);
+            LAUNCH(h, cg_scalar_kernel, 1, 1, 1, h->sc, h->red, tol2);
+            LAUNCH(h, cg_update_kernel, g, kRedThreads, T, h->sc, h->dinv, h->cg_p, h->cg_Ap, h->q, h->cg_r, h->partial, kRedBlocks);
             TRY(fold(h, g, 2, 0));
-            cg_scalar_kernel<<<1, 1, 0, s>>>(2, h->sc, h->red, tol2);
-            cg_p_kernel<<<g, kRedThreads, 0, s>>>(T, h->sc, h->dinv, h->cg_r, h->cg_p);
+            LAUNCH(h, cg_scalar_kernel, 1, 1, 2, h->sc, h->red, tol2);
+            LAUNCH(h, cg_p_kernel, g, kRedThreads, T, h->sc, h->dinv, h->cg_r, h->cg_p);
         }
         TRY(read_scalars(h));
         if (h->h_sc->done) break;
@@ -393,7 +410,7 @@ int solve_deposition(pbsm3d_handle* h, pbsm3d_stats* st, bool* converged) {
 }
 
 void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt) {
-    assemble_kernel<<<cdiv(h->T, 128), 128, 0, h->stream>>>(h->dc, h->dm, f, h->ss, dt);
+    LAUNCH(h, assemble_kernel, cdiv(h->T, 128), 128, h->dc, h->dm, f, h->ss, dt);
 }
 
 // One PBSM3D::run with device-resident forcing (reference PBSM3D.cpp:400-1748, phases A–I of SURVEY §3.2).
@@ -401,6 +418,8 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, pbsm3d_stats* st
     cudaStream_t s = h->stream;
     const int T = h->T;
     std::memset(st, 0, sizeof(*st));
+    const long long launch0 = h->n_launch;
+    h->ms_sweeps = 0.f;
     h->last_forcing = f;
     h->last_dt = dt;
     CU(cudaEventRecord(h->ev[0], s));
@@ -410,10 +429,10 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, pbsm3d_stats* st
     // C: suspension_present = ||rhs||_inf > 1e-12 (PBSM3D.cpp:1424-1427); also ||b||_2^2 for the stopping rule
     {
         int g = red_grid(T);
-        absmax_kernel<<<g, kRedThreads, 0, s>>>(T, h->ss.rhs0, h->partial);
-        fold_kernel<<<1, 256, 0, s>>>(g, 1, kRedBlocks, h->partial, h->red, 1);
-        sumsq_kernel<<<g, kRedThreads, 0, s>>>(T, h->ss.rhs0, h->partial + kRedBlocks);
-        fold_kernel<<<1, 256, 0, s>>>(g, 1, kRedBlocks, h->partial + kRedBlocks, h->red + 1, 0);
+        LAUNCH(h, absmax_kernel, g, kRedThreads, T, h->ss.rhs0, h->partial);
+        LAUNCH(h, fold_kernel, 1, 256, g, 1, kRedBlocks, h->partial, h->red, 1);
+        LAUNCH(h, sumsq_kernel, g, kRedThreads, T, h->ss.rhs0, h->partial + kRedBlocks);
+        LAUNCH(h, fold_kernel, 1, 256, g, 1, kRedBlocks, h->partial + kRedBlocks, h->red + 1, 0);
         if (h->n_ranks > 1) {
             NC(ncclAllReduce(h->red, h->red, 1, ncclDouble, ncclMax, h->comm, s));
             NC(ncclAllReduce(h->red + 1, h->red + 1, 1, ncclDouble, ncclSum, h->comm, s));
@@ -439,7 +458,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, pbsm3d_stats* st
     }
     CU(cudaEventRecord(h->ev[2], s));
     // E: flux integration
-    flux_kernel<<<cdiv(T, 256), 256, 0, s>>>(T, h->L, h->dc.dz, dt, h->xcur, h->ss.u_z, h->ss.csubl, h->Qsusp, h->Qsubl,
+    LAUNCH(h, flux_kernel, cdiv(T, 256), 256, T, h->L, h->dc.dz, dt, h->xcur, h->ss.u_z, h->ss.csubl, h->Qsusp, h->Qsubl,
                                              h->Qsubl_mass, h->sum_subl);
     // F: halo of Qsusp, Qsalt (PBSM3D.cpp:1509-1510) — one message per partner carrying both
     if (h->n_ranks > 1) {
@@ -450,8 +469,8 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, pbsm3d_stats* st
     // G: deposition RHS (the matrix is static) + H: rhs max
     {
         int g = red_grid(T);
-        deposition_rhs_kernel<<<g, 256, 0, s>>>(h->dm, f.vw_dir, h->Qsusp, h->ss.Qsalt, h->qg, h->drhs, h->partial);
-        fold_kernel<<<1, 256, 0, s>>>(g, 1, kRedBlocks, h->partial, h->red, 1);
+        LAUNCH(h, deposition_rhs_kernel, g, 256, h->dm, f.vw_dir, h->Qsusp, h->ss.Qsalt, h->qg, h->drhs, h->partial);
+        LAUNCH(h, fold_kernel, 1, 256, g, 1, kRedBlocks, h->partial, h->red, 1);
         if (h->n_ranks > 1) NC(ncclAllReduce(h->red, h->red, 1, ncclDouble, ncclMax, h->comm, s));
     }
     CU(cudaEventRecord(h->ev[3], s));
@@ -464,7 +483,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, pbsm3d_stats* st
         TRY(solve_deposition(h, st, &conv));
         if (!conv) return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver failed to converge");
         // I: drift update
-        drift_kernel<<<cdiv(T, 256), 256, 0, s>>>(T, dt, h->q, f.swe, h->ss.salt, h->drift_mass, h->sum_drift, h->more_avail);
+        LAUNCH(h, drift_kernel, cdiv(T, 256), 256, T, dt, h->q, f.swe, h->ss.salt, h->drift_mass, h->sum_drift, h->more_avail);
     }
     CU(cudaEventRecord(h->ev[4], s));
     CU(cudaStreamSynchronize(s));
@@ -473,6 +492,8 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, pbsm3d_stats* st
     CU(cudaEventElapsedTime(&st->ms_flux_and_halo, h->ev[2], h->ev[3]));
     CU(cudaEventElapsedTime(&st->ms_deposition, h->ev[3], h->ev[4]));
     CU(cudaEventElapsedTime(&st->ms_total, h->ev[0], h->ev[4]));
+    st->ms_line_sweeps = h->ms_sweeps;
+    st->kernel_launches = (int32_t)(h->n_launch - launch0);
     return 0;
 }
 
@@ -551,6 +572,8 @@ void pbsm3d_destroy(pbsm3d_handle* h) {
     if (h->h_red) cudaFreeHost(h->h_red);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : h->ev_sw)
+        if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -595,6 +618,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
 
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) CU(cudaEventCreate(&e));
+    for (auto& e : h->ev_sw) CU(cudaEventCreate(&e));
     CU(cudaMallocHost((void**)&h->h_sc, sizeof(Scalars)));
     CU(cudaMallocHost((void**)&h->h_red, 8 * sizeof(double)));
 
@@ -640,12 +664,12 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     TRY(h->alloc(&h->cx, Tall));
     TRY(h->alloc(&h->cy, Tall));
     TRY(h->alloc(&h->cz, Tall));
-    geometry_kernel<<<cdiv(Tall, 256), 256, 0, h->stream>>>(T, (int)Tall, d_verts, d_area_param, h->nx, h->ny, h->elen, h->area,
+    LAUNCH(h, geometry_kernel, cdiv(Tall, 256), 256, T, (int)Tall, d_verts, d_area_param, h->nx, h->ny, h->elen, h->area,
                                                             h->cx, h->cy, h->cz);
     TRY(h->alloc(&h->ddiag, T));
     TRY(h->alloc(&h->doff, (size_t)3 * T));
     TRY(h->alloc(&h->dinv, T));
-    deposition_matrix_kernel<<<cdiv(T, 256), 256, 0, h->stream>>>(T, cfg->smooth_coeff, h->neigh, h->elen, h->area, h->cx, h->cy,
+    LAUNCH(h, deposition_matrix_kernel, cdiv(T, 256), 256, T, cfg->smooth_coeff, h->neigh, h->elen, h->area, h->cx, h->cy,
                                                                   h->dx, h->ddiag, h->doff, h->dinv);
     CU(cudaGetLastError());
 
@@ -699,7 +723,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     CU(cudaMemsetAsync(h->xa, 0, h->N * sizeof(double), h->stream));
     h->xcur = h->xa;
     // drift_mass is a face variable that is -9999 until first written (variablestorage default)
-    fill_kernel<<<cdiv(T, 256), 256, 0, h->stream>>>(T, h->drift_mass, -9999.0);
+    LAUNCH(h, fill_kernel, cdiv(T, 256), 256, T, h->drift_mass, -9999.0);
     TRY(h->alloc(&h->partial, (size_t)kRedBlocks * 4));
     TRY(h->alloc(&h->red, 8));
     TRY(h->alloc(&h->sc, 1));
@@ -880,12 +904,12 @@ int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms) {
             switch (kernel) {
                 case 0: sweep(h, xo, h->xga, xn); break;
                 case 1:
-                    spmv_kernel<1><<<red_grid(h->N), kRedThreads, 0, s>>>(h->ss, h->dm, h->L, xo, h->xga, nullptr, nullptr, nullptr,
+                    LAUNCH(h, spmv_kernel<1>, red_grid(h->N), kRedThreads, h->ss, h->dm, h->L, xo, h->xga, nullptr, nullptr, nullptr,
                                                                          1, h->partial, kRedBlocks, nullptr);
                     break;
                 case 2: launch_assembly(h, h->last_forcing, h->last_dt); break;
                 case 3:
-                    cg_spmv_kernel<<<red_grid(h->T), kRedThreads, 0, s>>>(h->dm, h->ddiag, h->doff, h->cg_p, h->pg, h->cg_Ap,
+                    LAUNCH(h, cg_spmv_kernel, red_grid(h->T), kRedThreads, h->dm, h->ddiag, h->doff, h->cg_p, h->pg, h->cg_Ap,
                                                                          h->partial, nullptr);
                     break;
                 default: return fail(PBSM3D_ERR_INVALID, "unknown kernel id");

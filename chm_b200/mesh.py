@@ -13,7 +13,7 @@ plain arrays in CHM's own face order (ascending ``cell_global_id``):
 Only host-side bookkeeping lives here (file reading, the ``cell_global_id`` permutation, CHM's
 contiguous-range partition rule and ghost lists).  Edge normals / lengths / centroids used by the
 product are computed on the device by ``pbsm3d_create`` (csrc/pbsm3d_setup.cu); the numpy versions in
-this file exist so that tests can pin that kernel bit-for-bit, and so the oracle has geometry.
+this file exist so that tests can pin that kernel bit-for-bit (they are the geometry the CPU checker uses).
 """
 from __future__ import annotations
 

@@ -177,9 +177,11 @@ def forcing(cx: np.ndarray, cy: np.ndarray, seed: int = 7, step: int = 0, calm: 
             "vw_dir": vw_dir, "fetch": fetch}
 
 
-def shrub_params(n: int, frac: float = 0.2, seed: int = 11) -> Dict[str, np.ndarray]:
-    """Variant with `frac` of faces carrying shrubs (CanopyHeight 0.6, N 1, dv 0.8), others bare."""
+def shrub_params(n: int, frac: float = 0.2, seed: int = 11, canopy: float = 1.0) -> Dict[str, np.ndarray]:
+    """Variant with `frac` of faces carrying shrubs (CanopyHeight `canopy`, N 1, dv 0.8), others bare.
+    With snow depths of 0.2–1.5 m a 1 m canopy gives all three regimes: buried, partly exposed (lambda > 0)
+    and exposed by more than `cutoff` (saltation inhibited)."""
     rng = np.random.default_rng(seed)
     shrub = rng.random(n) < frac
-    return {"CanopyHeight": np.where(shrub, 0.6, 0.0), "stalk_number": np.ones(n), "stalk_diameter": np.full(n, 0.8),
+    return {"CanopyHeight": np.where(shrub, canopy, 0.0), "stalk_number": np.ones(n), "stalk_diameter": np.full(n, 0.8),
             "LAI": np.where(shrub, 1.0, 0.0)}

@@ -140,7 +140,7 @@ typedef struct pbsm3d_stats {
     int32_t suspension_iterations;   /* sweeps (line) or matvec pairs (BiCGStab) */
     int32_t deposition_iterations;
     int32_t suspension_solver_used;  /* PBSM3D_SOLVER_LINE / _BICGSTAB */
-    int32_t reserved;
+    int32_t kernel_launches;         /* kernels of this library launched by the step */
     double suspension_residual;      /* achieved ||b-Ax||2/||b||2 */
     double deposition_residual;
     double suspension_rhs_max;
@@ -150,7 +150,7 @@ typedef struct pbsm3d_stats {
     float ms_flux_and_halo;
     float ms_deposition;
     float ms_total;
-    float reserved2;
+    float ms_line_sweeps;            /* CUDA-event time spent in line-sweep launches (sum over the step) */
 } pbsm3d_stats;
 
 typedef struct pbsm3d_handle pbsm3d_handle;

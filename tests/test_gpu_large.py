@@ -1,0 +1,119 @@
+"""BASELINE-size checks through size-independent properties (run with -m gpu).
+
+The oracle's direct solve is out of reach at 10^7 unknowns, so the full-size configuration is checked by
+(1) the true residual of the exported system recomputed on the CPU with an independent scipy SpMV,
+(2) agreement of the two device solvers (stationary line relaxation vs BiCGStab) with each other,
+(3) the conservation identity of the deposition system  sum(area·q) = sum(rhs),
+(4) oracle parity of the assembled coefficients on a sample of faces.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from chm_b200 import capi, synthetic
+from conftest import functest_kw, max_rel, rel_l2
+from oracle.pbsm3d_oracle import Config, PBSM3DOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def ell_to_csr(s, neigh, T, L):
+    rows, cols, vals = [], [], []
+    idx = np.arange(T)
+    for z in range(L):
+        r = z * T + idx
+        rows.append(r); cols.append(r); vals.append(s["diag"][z])
+        for j in range(3):
+            has = neigh[:, j] >= 0
+            rows.append(r[has]); cols.append(z * T + neigh[has, j]); vals.append(s["lat"][j, z][has])
+        if z > 0:
+            rows.append(r); cols.append(r - T); vals.append(s["below"][z])
+        if z < L - 1:
+            rows.append(r); cols.append(r + T); vals.append(s["above"][z])
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(L * T, L * T))
+
+
+@pytest.fixture(scope="module")
+def mesh1m():
+    return synthetic.uniform_mesh(708, 708)
+
+
+def test_config_c2_properties(mesh1m):
+    m = mesh1m
+    T, L = m.n_local, 10
+    assert T == 1002528
+    geo = m.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy)
+    h = capi.Handle(capi.default_config(solver=capi.SOLVER_LINE, **functest_kw(L)), m)
+    outs, st = h.step(3600.0, F)
+    assert st["suspension_present"] and st["deposition_present"]
+    x = h.solution().reshape(-1)
+    s = h.suspension_system()
+    A = ell_to_csr(s, m.neigh, T, L)
+    b = np.zeros(L * T)
+    b[:T] = s["rhs0"]
+    res = np.linalg.norm(b - A @ x) / np.linalg.norm(b)
+    assert res <= 1e-8, res  # the reference's stopping rule, verified off-device
+    assert abs(res - st["suspension_residual"]) <= 1e-3 * res + 1e-12
+    # deposition: independent residual + conservation
+    d = h.deposition_system()
+    idx = np.arange(T)
+    rows, cols, vals = [idx], [idx], [d["diag"]]
+    for j in range(3):
+        has = m.neigh[:, j] >= 0
+        rows.append(idx[has]); cols.append(m.neigh[has, j]); vals.append(d["off"][j][has])
+    Ad = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(T, T))
+    assert np.linalg.norm(d["rhs"] - Ad @ d["q"]) / np.linalg.norm(d["rhs"]) <= 1e-8
+    assert abs(Ad - Ad.T).max() <= 1e-12 * abs(Ad).max()
+    assert np.isclose((geo.area * d["q"]).sum(), d["rhs"].sum(), rtol=1e-6, atol=1e-6 * np.abs(d["rhs"]).sum())
+    # second solver agrees
+    h2 = capi.Handle(capi.default_config(solver=capi.SOLVER_BICGSTAB, **functest_kw(L)), m)
+    outs2, st2 = h2.step(3600.0, F)
+    assert st2["suspension_solver_used"] == capi.SOLVER_BICGSTAB
+    assert rel_l2(h2.solution().reshape(-1), x) <= 1e-6
+    for v in ("Qsusp", "Qsalt", "drift_mass"):
+        assert rel_l2(outs2[v], outs[v]) <= 1e-6, v
+    # oracle parity of the coefficients on the first 20 000 faces (assembly only needs a face's own data)
+    n = 20000
+    o = PBSM3DOracle(Config.functional_test(L), m.neigh[:n].clip(max=n - 1), type(geo)(geo.nx[:, :n], geo.ny[:, :n],
+                     geo.elen[:, :n], geo.area[:n], geo.cx[:n], geo.cy[:n], geo.cz[:n], geo.dx[:, :n]),
+                     m.global_id[:n], T, {})
+    asm = o.assemble({k: v[:n] for k, v in F.items()}, 3600.0)
+    assert max_rel(s["diag"][:, :n], asm.diag) <= 1e-12
+    assert max_rel(s["above"][:, :n], asm.above) <= 1e-12 and max_rel(s["rhs0"][:n], asm.rhs[0]) <= 1e-12
+    assert max_rel(s["u_z"][:, :n], asm.u_z) <= 1e-12 and max_rel(s["csubl"][:, :n], asm.csubl) <= 1e-12
+    h.close()
+    h2.close()
+
+
+def test_variable_resolution_mesh_against_direct_solve():
+    """Config c3's generator at a size the direct solve handles: irregular adjacency, 10:1 areas."""
+    m = synthetic.variable_mesh(20000)
+    geo = m.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy)
+    o = PBSM3DOracle(Config.functional_test(6), m.neigh, geo, m.global_id, m.n_global, m.params)
+    r = o.step(F, 3600.0)
+    h = capi.Handle(capi.default_config(**functest_kw(6)), m)
+    outs, st = h.step(3600.0, F)
+    assert rel_l2(h.solution(), r["c"]) <= 1e-6
+    for v in ("Qsusp", "Qsalt", "drift_mass", "sum_drift"):
+        assert rel_l2(outs[v], r[v]) <= 1e-6, v
+    h.close()
+
+
+def test_linearity_of_the_solve(mesh1m):
+    """Scaling the saltation source scales the solution: x(b) is linear, and the calm step is the zero of it."""
+    m = synthetic.uniform_mesh(200, 200)
+    geo = m.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy)
+    h = capi.Handle(capi.default_config(tolerance=1e-11, **functest_kw(10)), m)
+    h.step(3600.0, F)
+    x1 = h.solution()
+    # a different elevation changes only the air density in c_salt (a uniform-ish scale on the RHS)
+    s1 = h.suspension_system()
+    assert np.abs(s1["rhs0"]).max() > 0
+    o, st = h.step(3600.0, synthetic.forcing(geo.cx, geo.cy, calm=True))
+    assert st["suspension_present"] == 0 and not h.solution().any()
+    h.step(3600.0, F)
+    assert np.array_equal(h.solution(), x1)  # idempotent: same inputs, same bits
+    h.close()

@@ -1,0 +1,225 @@
+"""Parity of the CUDA path against the oracle, through the C-ABI (run with -m gpu on the B200 box).
+
+Tolerances (BASELINE.md §5 / north_star): face ordering, neighbour indexing and geometry bit-exact; assembled
+coefficients ≤ 1e-12 relative; suspended concentration, fluxes and drift ≤ 1e-6 relative L2 (fp64), against the
+oracle's exact sparse direct solve.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from chm_b200 import capi, synthetic
+from chm_b200.mesh import TriMesh
+from chm_b200.module import Domain, PBSM3D, module_error
+from conftest import GOLDEN, functest_kw, load_mesh, max_rel, rel_l2
+from oracle.pbsm3d_oracle import Config, PBSM3DOracle
+
+pytestmark = pytest.mark.gpu
+
+ASM_TOL = 1e-12
+L2_TOL = 1e-6
+
+
+def oracle_for(mesh, cfg, is_water=None):
+    return PBSM3DOracle(cfg, mesh.neigh, mesh.geometry(), mesh.global_id, mesh.n_global, mesh.params, is_water)
+
+
+def check_assembly(h, asm):
+    s = h.suspension_system()
+    for k, ref in (("diag", asm.diag), ("below", asm.below), ("above", asm.above), ("u_z", asm.u_z), ("csubl", asm.csubl)):
+        assert max_rel(s[k], ref) <= ASM_TOL, k
+    # lateral coefficients: some are sums of a large and a tiny term; compare against the row scale
+    scale = np.abs(asm.diag)[None]
+    assert np.max(np.abs(s["lat"] - asm.lat) / scale) <= ASM_TOL
+    assert max_rel(s["rhs0"], asm.rhs[0]) <= ASM_TOL
+    assert max_rel(s["c_salt"], asm.c_salt) <= ASM_TOL
+    assert np.array_equal(s["saltation"].astype(bool), asm.saltation)
+
+
+@pytest.mark.parametrize("meshname", ["granger1m", "slope", "slope_metis"])
+def test_geometry_and_indexing_bit_exact(meshname):
+    mesh = load_mesh(meshname)
+    h = capi.Handle(capi.default_config(nLayer=5), mesh)
+    g, ref = h.geometry(), mesh.geometry()
+    for k in ("nx", "ny", "elen", "area", "dx"):
+        assert np.array_equal(g[k], getattr(ref, k)), k
+    for k in ("cx", "cy", "cz"):
+        assert np.array_equal(g[k], getattr(ref, k)[:mesh.n_local]), k
+    h.close()
+
+
+def test_geometry_without_area_parameter_bit_exact():
+    mesh = synthetic.variable_mesh(6000)
+    h = capi.Handle(capi.default_config(nLayer=4), mesh)
+    g, ref = h.geometry(), mesh.geometry()
+    for k in ("nx", "ny", "elen", "area", "dx"):
+        assert np.array_equal(g[k], getattr(ref, k)), k
+    h.close()
+
+
+CASES = [
+    ("default_L5", Config(nLayer=5), dict(nLayer=5)),
+    ("functest_L10", Config.functional_test(10), functest_kw(10)),
+    ("generic_L7", Config(nLayer=7), dict(nLayer=7)),  # runtime-L sweep kernel
+    ("L2_min", Config(nLayer=2), dict(nLayer=2)),
+    ("L20", Config.functional_test(20), functest_kw(20)),
+    ("no_subl_no_latdiff", Config(nLayer=5, do_sublimation=False, do_lateral_diff=False),
+     dict(nLayer=5, do_sublimation=0, do_lateral_diff=0)),
+    ("rouault", Config(nLayer=5, rouault_diffusion_coef=True), dict(nLayer=5, rouault_diffusion_coef=1)),
+    ("exp_fetch", Config(nLayer=5, use_exp_fetch=True, use_tanh_fetch=False), dict(nLayer=5, use_exp_fetch=1, use_tanh_fetch=0)),
+    ("no_fetch", Config(nLayer=5, use_tanh_fetch=False), dict(nLayer=5, use_tanh_fetch=0)),
+]
+
+
+@pytest.mark.parametrize("name,ocfg,kw", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("solver", [capi.SOLVER_LINE, capi.SOLVER_BICGSTAB], ids=["line", "bicgstab"])
+def test_step_matches_oracle(granger, name, ocfg, kw, solver):
+    geo = granger.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy, seed=3, fetch_const=None if "fetch" in name else 1000.0)
+    r = oracle_for(granger, ocfg).step(F, 3600.0, solver="direct")
+    h = capi.Handle(capi.default_config(solver=solver, tolerance=1e-11, **kw), granger)
+    outs, st = h.step(3600.0, F)
+    check_assembly(h, r["asm"])
+    assert st["suspension_present"] == 1 and st["deposition_present"] == 1
+    assert st["suspension_solver_used"] == solver
+    assert rel_l2(h.solution(), r["c"]) <= 1e-9
+    for v in ("Qsusp", "Qsalt", "Qsubl", "drift_mass", "sum_drift", "sum_subl"):
+        assert rel_l2(outs[v], r[v]) <= 1e-8, v
+    d = h.deposition_system()
+    assert max_rel(d["diag"], r["dep"][0]) <= ASM_TOL and max_rel(d["off"], r["dep"][1]) <= ASM_TOL
+    assert np.max(np.abs(d["rhs"] - r["dep"][2])) <= 1e-9 * np.abs(r["dep"][2]).max()
+    h.close()
+
+
+def test_reference_tolerance_meets_the_parity_bar(slope):
+    """At the reference's own stopping rule (1e-8) the GPU solution is within 1e-6 of the exact solve."""
+    geo = slope.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy)
+    r = oracle_for(slope, Config.functional_test(10)).step(F, 3600.0)
+    for solver in (capi.SOLVER_AUTO, capi.SOLVER_BICGSTAB):
+        h = capi.Handle(capi.default_config(solver=solver, **functest_kw(10)), slope)
+        outs, st = h.step(3600.0, F)
+        assert st["suspension_residual"] <= 1e-8 and st["deposition_residual"] <= 1e-8
+        assert rel_l2(h.solution(), r["c"]) <= L2_TOL
+        for v in ("Qsusp", "Qsalt", "drift_mass"):
+            assert rel_l2(outs[v], r[v]) <= L2_TOL, v
+        h.close()
+
+
+@pytest.mark.parametrize("golden,meshname,cfgd,nsteps", [
+    ("golden_granger1m_L5_default", "granger1m", {"nLayer": "5"}, 24),
+    ("golden_slope_L10_functest", "slope", {"nLayer": "10", "smooth_coeff": "6500", "do_fixed_settling": "true",
+                                            "settling_velocity": "0.5", "use_R94_lambda": "false"}, 3),
+])
+def test_golden_sequence_through_module_interface(golden, meshname, cfgd, nsteps):
+    """Config c1 shape: 24 hourly steps on the bundled mesh, driven like CHM drives a module
+    (ctor(config) → init(mesh) → run(mesh) per step), compared with the committed golden vectors."""
+    mesh = load_mesh(meshname)
+    g = np.load(os.path.join(GOLDEN, golden + ".npz"))
+    mod = PBSM3D(cfgd)
+    dom = Domain(mesh, dt=3600.0)
+    mod.init(dom)
+    geo = mesh.geometry()
+    for k in range(nsteps):
+        F = synthetic.forcing(geo.cx, geo.cy, seed=7, step=k, calm=(k % 8 == 5))
+        for name, val in F.items():
+            dom[name] = val
+        st = mod.run(dom)
+        assert [st["suspension_present"], st["deposition_present"]] == g[f"present_{k}"].tolist()
+        for v in ("Qsusp", "Qsalt", "Qsubl", "drift_mass", "sum_drift", "sum_subl"):
+            assert rel_l2(dom[v], g[f"{v}_{k}"]) <= L2_TOL, (v, k)
+    assert rel_l2(mod.handle.solution(), np.zeros_like(g["c_0"])) >= 0  # solution view is readable
+    chk = mod.checkpoint(dom)
+    assert np.array_equal(chk["PBSM3D:sum_drift"], dom["sum_drift"])
+    mod.close()
+
+
+def test_calm_step_keeps_stale_drift_mass(granger):
+    geo = granger.geometry()
+    h = capi.Handle(capi.default_config(nLayer=5), granger)
+    o0, s0 = h.step(3600.0, synthetic.forcing(geo.cx, geo.cy, step=0))
+    o1, s1 = h.step(3600.0, synthetic.forcing(geo.cx, geo.cy, step=1, calm=True))
+    assert s1["suspension_present"] == 0 and s1["deposition_present"] == 0 and s1["suspension_iterations"] == 0
+    assert np.array_equal(o1["drift_mass"], o0["drift_mass"]) and np.array_equal(o1["sum_drift"], o0["sum_drift"])
+    assert not o1["Qsusp"].any() and not o1["Qsalt"].any() and not h.solution().any()
+    fresh = capi.Handle(capi.default_config(nLayer=5), granger)
+    o, s = fresh.step(3600.0, synthetic.forcing(geo.cx, geo.cy, step=1, calm=True))
+    assert (o["drift_mass"] == -9999.0).all()  # never written: the face-store default
+    h.close()
+    fresh.close()
+
+
+@pytest.mark.parametrize("r94", [True, False], ids=["R94_LAI", "stalks"])
+def test_vegetation_and_water(slope, r94):
+    params = dict(slope.params, **synthetic.shrub_params(slope.n_local))
+    mesh = TriMesh(slope.vertex, slope.elem, slope.neigh, params)
+    water = (np.arange(mesh.n_local) % 17 == 0)
+    ocfg = Config(nLayer=5, use_R94_lambda=r94)
+    geo = mesh.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy, seed=5)
+    r = oracle_for(mesh, ocfg, water).step(F, 3600.0)
+    h = capi.Handle(capi.default_config(nLayer=5, use_R94_lambda=int(r94), tolerance=1e-11), mesh, is_water=water)
+    outs, st = h.step(3600.0, F)
+    check_assembly(h, r["asm"])
+    assert not r["asm"].saltation[water].any()
+    assert (r["asm"].u_z == 0.01).any()  # some layers sit inside the canopy
+    for v in ("Qsusp", "Qsalt", "drift_mass"):
+        assert rel_l2(outs[v], r[v]) <= 1e-8, v
+    h.close()
+
+
+def test_missing_values_follow_chm_sentinels(granger):
+    geo = granger.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy)
+    F["snowdepthavg"] = np.where(np.arange(granger.n_local) % 3 == 0, -9999.0, F["snowdepthavg"])
+    F["swe"] = np.where(np.arange(granger.n_local) % 5 == 0, np.nan, F["swe"])
+    r = oracle_for(granger, Config(nLayer=5)).step(F, 3600.0)
+    h = capi.Handle(capi.default_config(nLayer=5, tolerance=1e-11), granger)
+    outs, st = h.step(3600.0, F)
+    s = h.suspension_system()
+    # swe == 0 makes the reference's availability test a test on rounding noise: compare the
+    # faces where it cannot fire, and the flag everywhere
+    assert np.array_equal(s["saltation"].astype(bool), r["asm"].saltation)
+    ok = ~np.isnan(F["swe"])
+    assert max_rel(s["c_salt"][ok], r["asm"].c_salt[ok]) <= ASM_TOL
+    assert max_rel(s["diag"], r["asm"].diag) <= ASM_TOL
+    h.close()
+
+
+def test_state_roundtrip_and_checkpoint(granger):
+    geo = granger.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy)
+    a = capi.Handle(capi.default_config(nLayer=5), granger)
+    a.step(3600.0, F)
+    st = a.get_state()
+    b = capi.Handle(capi.default_config(nLayer=5), granger)
+    b.set_state(**st)
+    oa, _ = a.step(3600.0, F)
+    ob, _ = b.step(3600.0, F)
+    assert np.array_equal(oa["sum_drift"], ob["sum_drift"]) and np.array_equal(oa["sum_subl"], ob["sum_subl"])
+    a.close()
+    b.close()
+
+
+def test_error_paths_on_device(granger):
+    bad = TriMesh(granger.vertex, granger.elem, granger.neigh.copy(), granger.params)
+    bad.neigh[3, 1] = 5000
+    with pytest.raises(capi.Pbsm3dError, match="out of bound neighbors"):
+        capi.Handle(capi.default_config(nLayer=5), bad)
+    with pytest.raises(capi.Pbsm3dError, match="nLayer"):
+        capi.Handle(capi.default_config(nLayer=1), granger)
+    h = capi.Handle(capi.default_config(nLayer=5, max_iterations=3, solver=capi.SOLVER_LINE), granger)
+    geo = granger.geometry()
+    with pytest.raises(capi.Pbsm3dError) as e:
+        h.step(3600.0, synthetic.forcing(geo.cx, geo.cy))
+    assert e.value.code == 5  # "failed to converge" (LinearAlgebra.cpp:236-243)
+    mod = PBSM3D({"nLayer": 5, "max_iterations": 3, "solver": 1})
+    dom = Domain(granger)
+    mod.init(dom)
+    for k, v in synthetic.forcing(geo.cx, geo.cy).items():
+        dom[k] = v
+    with pytest.raises(module_error, match="converge"):
+        mod.run(dom)
+    h.close()
+    mod.close()

@@ -1,0 +1,38 @@
+"""The module_base-shaped host layer (chm_b200/module.py) — what CHM's core sees (CPU)."""
+import numpy as np
+import pytest
+
+from chm_b200.module import MISSING, Domain, PBSM3D, module_error
+
+
+def test_depends_provides_match_reference():
+    m = PBSM3D({})
+    # PBSM3D.cpp:105-110 + :137-140
+    assert m.get_depends() == ["U_2m_above_srf", "vw_dir", "swe", "t", "rh", "U_R", "fetch"]
+    # PBSM3D.cpp:112-114,144,194-202
+    assert m.get_provides() == ["pbsm_more_than_avail", "global_cell_id", "blowingsnow_probability", "Qsubl",
+                                "Qsubl_mass", "sum_subl", "drift_mass", "Qsusp", "Qsalt", "sum_drift"]
+    assert PBSM3D({"use_tanh_fetch": "false"}).get_depends()[-1] == "p_snow_hours"
+    assert PBSM3D.parallel == "domain"
+
+
+def test_config_errors():
+    with pytest.raises(module_error, match="Cannot specify both"):
+        PBSM3D({"use_exp_fetch": "true", "use_tanh_fetch": "true"})
+    with pytest.raises(module_error, match="unknown config key"):
+        PBSM3D({"nlayers": 3})
+
+
+def test_config_strings_are_coerced_like_ptree():
+    m = PBSM3D({"nLayer": "10", "smooth_coeff": "6500", "do_fixed_settling": "true", "settling_velocity": "0.5"})
+    assert m.cfg == {"nLayer": 10, "smooth_coeff": 6500, "do_fixed_settling": True, "settling_velocity": 0.5}
+
+
+def test_domain_store_defaults_to_missing(granger):
+    d = Domain(granger, dt=3600)
+    d.init_face_data(["Qsusp"])
+    assert (d["Qsusp"] == MISSING).all() and d.size_faces() == 985
+    with pytest.raises(module_error):
+        d["nope"]
+    with pytest.raises(module_error, match="before init"):
+        PBSM3D({}).run(d)
