@@ -1,0 +1,64 @@
+"""Worker for tests/test_gpu_multi.py: one rank per GPU under torch.distributed.run.
+
+Each rank partitions the global mesh by CHM's rule, runs `nsteps` PBSM3D steps through the C-ABI with NCCL halos
+and reductions, and rank 0 gathers the per-face outputs in global order into an npz."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from chm_b200 import capi, synthetic
+    from chm_b200.mesh import partition_mesh
+    from conftest import functest_kw, load_mesh
+
+    out_path, meshname, L, solver, nsteps = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    uid = bytes(buf.cpu().numpy().tobytes())
+    if meshname.startswith("uniform"):
+        n = int(meshname[7:])
+        gmesh = synthetic.uniform_mesh(n, n)
+    else:
+        gmesh = load_mesh(meshname)
+    ggeo = gmesh.geometry()
+    p = partition_mesh(gmesh, rank, world)
+    T = p.n_local
+    s = int(p.global_id[0])
+    h = capi.Handle(capi.default_config(solver=solver, tolerance=1e-10, **functest_kw(L)), p, device=local, rank=rank,
+                    n_ranks=world, unique_id=uid)
+    gathered = {}
+    for k in range(nsteps):
+        Fg = synthetic.forcing(ggeo.cx, ggeo.cy, seed=7, step=k, calm=(k == 1))
+        F = {n: v[s:s + T] for n, v in Fg.items()}
+        outs, st = h.step(3600.0, F)
+        x = h.solution()
+        pieces = dict(outs, **{f"c{z}": x[z] for z in range(L)})
+        for name, a in pieces.items():
+            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([T], dtype=torch.int64, device="cuda"))
+            parts = [torch.zeros(int(n_.item()), dtype=torch.float64, device="cuda") for n_ in sizes]
+            dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(a)).cuda())
+            gathered[f"{name}_{k}"] = torch.cat(parts).cpu().numpy()
+        gathered[f"iters_{k}"] = np.array([st["suspension_iterations"], st["deposition_iterations"], st["suspension_present"],
+                                           st["deposition_present"]])
+    if rank == 0:
+        np.savez(out_path, **gathered)
+    h.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,70 @@
+"""Multi-GPU parity (needs >= 2 GPUs; run with -m gpu under `gpurun --gpus 2`): the partitioned run over NCCL must
+reproduce the single-GPU run and the oracle on the same global mesh (the preconditioner is per column,
+so results are independent of the GPU count up to reduction-order rounding)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from chm_b200 import capi, synthetic
+from conftest import ROOT, functest_kw, load_mesh, rel_l2
+from oracle.pbsm3d_oracle import Config, PBSM3DOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_ranks(tmp_path, world, meshname, L, solver, nsteps):
+    out = str(tmp_path / f"mp_{meshname}_{world}_{solver}.npz")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(ROOT, "tests", "mp_worker.py"), out, meshname, str(L), str(solver), str(nsteps)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    return np.load(out)
+
+
+@pytest.mark.parametrize("solver", [capi.SOLVER_LINE, capi.SOLVER_BICGSTAB], ids=["line", "bicgstab"])
+def test_two_ranks_match_oracle_and_single_gpu(tmp_path, solver):
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    L = 6
+    mesh = load_mesh("slope_metis")
+    geo = mesh.geometry()
+    g = run_ranks(tmp_path, 2, "slope_metis", L, solver, 3)
+    o = PBSM3DOracle(Config.functional_test(L), mesh.neigh, geo, mesh.global_id, mesh.n_global, mesh.params)
+    h = capi.Handle(capi.default_config(solver=solver, tolerance=1e-10, **functest_kw(L)), mesh)
+    for k in range(3):
+        F = synthetic.forcing(geo.cx, geo.cy, seed=7, step=k, calm=(k == 1))
+        r = o.step(F, 3600.0)
+        outs, st = h.step(3600.0, F)
+        assert g[f"iters_{k}"][2] == int(r["suspension_present"]) and g[f"iters_{k}"][3] == int(r["deposition_present"])
+        c = np.stack([g[f"c{z}_{k}"] for z in range(L)])
+        assert rel_l2(c, r["c"]) <= 1e-6 and rel_l2(c, h.solution()) <= 1e-7
+        for v in ("Qsusp", "Qsalt", "Qsubl", "drift_mass", "sum_drift", "sum_subl"):
+            assert rel_l2(g[f"{v}_{k}"], r[v]) <= 1e-6, (v, k)
+            assert rel_l2(g[f"{v}_{k}"], outs[v]) <= 1e-7, (v, k)
+    h.close()
+
+
+def test_max_ranks_on_uniform_mesh(tmp_path):
+    n = ngpus()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    L = 10
+    g = run_ranks(tmp_path, world, "uniform120", L, capi.SOLVER_AUTO, 1)
+    mesh = synthetic.uniform_mesh(120, 120)
+    geo = mesh.geometry()
+    h = capi.Handle(capi.default_config(tolerance=1e-10, **functest_kw(L)), mesh)
+    outs, st = h.step(3600.0, synthetic.forcing(geo.cx, geo.cy, seed=7, step=0))
+    c = np.stack([g[f"c{z}_0"] for z in range(L)])
+    assert rel_l2(c, h.solution()) <= 1e-7
+    for v in ("Qsusp", "Qsalt", "drift_mass"):
+        assert rel_l2(g[f"{v}_0"], outs[v]) <= 1e-7, v
+    h.close()

@@ -88,7 +88,7 @@ def test_step_matches_oracle(granger, name, ocfg, kw, solver):
         assert rel_l2(outs[v], r[v]) <= 1e-8, v
     d = h.deposition_system()
     assert max_rel(d["diag"], r["dep"][0]) <= ASM_TOL and max_rel(d["off"], r["dep"][1]) <= ASM_TOL
-    assert np.max(np.abs(d["rhs"] - r["dep"][2])) <= 1e-9 * np.abs(r["dep"][2]).max()
+    assert np.max(np.abs(d["rhs"] - r["dep"][2])) <= 1e-7 * np.abs(r["dep"][2]).max()  # carries the solve error of Qsusp
     h.close()
 
 
