@@ -98,10 +98,10 @@ def measured_peak_gbs():
 
 
 def sweep_bytes_per_row(L: int) -> float:
-    """Algorithmic HBM bytes of one line-relaxation sweep per unknown row:
-    3 lateral coefficients + below + inv + cp (6×8) + x_old read + x_new write (2×8) = 64 B/row,
-    plus per face 3 int32 neighbour ids + rhs0 (20 B) amortised over L layers."""
-    return 64.0 + 20.0 / L
+    """Algorithmic HBM bytes of one full line Gauss-Seidel sweep per unknown row:
+    3 row-scaled lateral coefficients + scaled sub-diagonal + cp (5×8) + x read once + x written once (2×8)
+    = 56 B/row, plus per face 3 int32 neighbour slots + the scaled rhs (20 B) amortised over L layers."""
+    return 56.0 + 20.0 / L
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
@@ -249,7 +249,7 @@ def main():
         ev_ms += st["ms_total"]
         launches += st["kernel_launches"]
         sweep_ms += st["ms_line_sweeps"]
-        sweeps += st["suspension_iterations"] if st["suspension_solver_used"] == capi.SOLVER_LINE else 0
+        sweeps += st["sweeps_timed"]
         for k in phases:
             phases[k] += st[k]
     barrier()
@@ -291,7 +291,7 @@ def main():
             "config": {"workload": f"BASELINE c2 generator: {side}x{side} squares of 30 m -> {G} triangles x nLayer {NLAYER} "
                                    f"({total_rows} unknowns), Morton order, functional-test PBSM3D block, tol 1e-8"
                                    + ("" if world == 1 else f", {world} ranks by CHM contiguous global-id partition"),
-                       "triangles": G, "nLayer": NLAYER, "solver": "line relaxation (auto)",
+                       "triangles": G, "nLayer": NLAYER, "solver": "multicolour line Gauss-Seidel (auto)", "colours": st["n_colours"],
                        "suspension_iterations": st["suspension_iterations"], "deposition_iterations": st["deposition_iterations"],
                        "suspension_residual": st["suspension_residual"],
                        "l2_policy": "working set of one step (~1 GB of coefficient streams per rank) exceeds the 126 MB L2; no flush needed",
@@ -299,7 +299,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * 8 * T * world,
                     "d2h_bytes_per_step": 8 * 8 * T * world},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "line_sweep_kernel<10>", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "gs_sweep_kernel<10> (one full sweep = all colour passes)", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": sweep_bytes_per_row(NLAYER) * T * NLAYER, "avg_launch_ms": avg_sweep_ms,
                          "launches_timed": int(sweeps), "share_of_step": sweep_ms / max(ev_ms, 1e-9)},

@@ -67,6 +67,7 @@ class Stats(C.Structure):
         ("suspension_residual", C.c_double), ("deposition_residual", C.c_double), ("suspension_rhs_max", C.c_double),
         ("deposition_rhs_max", C.c_double), ("ms_assembly", C.c_float), ("ms_suspension_solve", C.c_float),
         ("ms_flux_and_halo", C.c_float), ("ms_deposition", C.c_float), ("ms_total", C.c_float), ("ms_line_sweeps", C.c_float),
+        ("sweeps_timed", C.c_int32), ("n_colours", C.c_int32),
     ]
 
     def asdict(self):
@@ -89,6 +90,7 @@ SYMBOLS = {
     "pbsm3d_get_state": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
     "pbsm3d_set_state": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
     "pbsm3d_get_geometry": (C.c_int, [C.c_void_p] + [c_double_p] * 8),
+    "pbsm3d_get_layout": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
     "pbsm3d_get_solution": (C.c_int, [C.c_void_p, c_double_p]),
     "pbsm3d_get_suspension_system": (C.c_int, [C.c_void_p] + [c_double_p] * 8 + [c_uint8_p]),
     "pbsm3d_get_deposition_system": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
@@ -243,6 +245,15 @@ class Handle:
         _check(self.lib, self.lib.pbsm3d_get_geometry(self.h, _dp(g["nx"]), _dp(g["ny"]), _dp(g["elen"]), _dp(g["area"]),
                                                       _dp(g["dx"]), _dp(g["cx"]), _dp(g["cy"]), _dp(g["cz"])))
         return g
+
+    def layout(self):
+        """(n_colours, n_slots, slot_of_face[T], colour_of_face[T]) of the colour-major device order."""
+        nc, ns = C.c_int32(), C.c_int32()
+        slot = np.empty(self.T, dtype=np.int32)
+        colour = np.empty(self.T, dtype=np.int32)
+        _check(self.lib, self.lib.pbsm3d_get_layout(self.h, C.byref(nc), C.byref(ns), slot.ctypes.data_as(c_int32_p),
+                                                    colour.ctypes.data_as(c_int32_p)))
+        return int(nc.value), int(ns.value), slot, colour
 
     def solution(self) -> np.ndarray:
         x = np.empty((self.L, self.T))

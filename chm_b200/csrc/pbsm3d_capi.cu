@@ -1,5 +1,11 @@
 // libpbsm3d_b200.so — C-ABI (include/pbsm3d.h) and host orchestration of one PBSM3D timestep on one B200.
 // One process per GPU; NCCL carries the ghost-face halos and the global reductions.  No CPU fallback.
+//
+// A step is enqueued optimistically: assembly, a predicted number of line-relaxation sweeps with residual
+// checks, flux integration, the deposition right-hand side, a predicted number of CG iterations, the drift
+// update and the export to CHM order all go onto one stream, each kernel guarded by device-resident flags
+// (suspension converged? deposition present? CG converged?), and the host synchronises ONCE at the end.  Only
+// when a prediction was too short does the host add more sweeps / iterations and re-enqueue the tail.
 #include "../../include/pbsm3d.h"
 
 #include <cuda_runtime.h>
@@ -46,6 +52,7 @@ int fail(int code, const std::string& msg) {
     } while (0)
 
 inline int cdiv(size_t a, int b) { return (int)((a + b - 1) / b); }
+inline int align_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // every kernel launch goes through here so the step can report how many of our kernels it launched
 #define LAUNCH(h_, kernel_, grid_, block_, ...)                                  \
@@ -60,6 +67,8 @@ struct Partner {
     int recv_off, recv_cnt;  // ghost block [recv_off, recv_off+recv_cnt)
 };
 
+constexpr int kMaxColours = 8;
+
 }  // namespace
 
 struct pbsm3d_handle {
@@ -68,49 +77,55 @@ struct pbsm3d_handle {
     DevMesh dm;
     SuspSystem ss;
     int device = 0;
-    int T = 0, nG = 0, L = 0;
+    int T = 0, Tp = 0, S = 0, nG = 0, L = 0;
     int64_t G = 0, gstart_id = 0;
-    size_t N = 0;
+    size_t N = 0;   // L * Tp coefficient rows
+    size_t NS = 0;  // L * S   ghost-extended vector length
+    int n_colours = 0;
+    int cstart[kMaxColours] = {0}, ccount[kMaxColours] = {0};
     cudaStream_t stream = nullptr;
     std::vector<void*> allocs;
 
-    // mesh / static
-    int *neigh = nullptr, *gstart = nullptr, *gcnt = nullptr;
+    // mesh / static (slot order)
+    int *perm = nullptr, *iperm = nullptr, *nbs = nullptr, *gstart = nullptr, *gcnt = nullptr;
     double *nx = nullptr, *ny = nullptr, *elen = nullptr, *area = nullptr, *cx = nullptr, *cy = nullptr, *cz = nullptr, *dx = nullptr;
     double *canopy = nullptr, *lai = nullptr, *stalk_n = nullptr, *stalk_dv = nullptr;
     unsigned char* water = nullptr;
     double *ddiag = nullptr, *doff = nullptr, *dinv = nullptr;
-    // forcing (own device copies for the host-pointer entry point)
+    // forcing (own device copies for the host-pointer entry point), CHM order
     double* forcing_buf[8] = {nullptr};
     DevForcing last_forcing{};
     double last_dt = 0.0;
     // solution / work
-    double *xa = nullptr, *xb = nullptr, *xga = nullptr, *xgb = nullptr, *xcur = nullptr;
-    double* kry[7] = {nullptr};  // r, rhat, p, v, ph, sh, t (allocated on first Krylov use)
-    double* kry_g = nullptr;     // ghost values of the preconditioned vector
-    // per-face outputs and deposition work
-    double *Qsusp = nullptr, *Qsubl = nullptr, *Qsubl_mass = nullptr, *sum_subl = nullptr, *drift_mass = nullptr,
+    double* x = nullptr;         // [L][S] suspended concentration, ghost-extended
+    double* kry[7] = {nullptr};  // r, rhat, p, v, ph, sh, t (allocated on first Krylov use), each [L][S]
+    // per-face outputs and deposition work (slot order)
+    double *Qsusp = nullptr /*[S]*/, *Qsubl = nullptr, *Qsubl_mass = nullptr, *sum_subl = nullptr, *drift_mass = nullptr,
            *sum_drift = nullptr, *more_avail = nullptr;
-    double *drhs = nullptr, *q = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_Ap = nullptr, *qg = nullptr, *pg = nullptr,
-           *q2 = nullptr;
+    double *drhs = nullptr, *q = nullptr, *cg_r = nullptr, *cg_p = nullptr /*[S]*/, *cg_Ap = nullptr;
+    double* out_stage = nullptr;  // [8][T] CHM-ordered outputs on their way to host buffers
+    double* scratch = nullptr;    // inspection getters
+    size_t scratch_n = 0;
     // reductions
     double *partial = nullptr, *red = nullptr;
     Scalars* sc = nullptr;
-    Scalars* h_sc = nullptr;   // pinned
-    double* h_red = nullptr;   // pinned [8]
+    Scalars* h_sc = nullptr;  // pinned
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, n_ranks = 1;
     std::vector<Partner> partners;
     int n_send = 0;
-    int *send_idx = nullptr, *send_boff = nullptr, *send_cnt = nullptr, *send_pos = nullptr;
-    double* sendbuf = nullptr;
+    int *send_slot = nullptr, *send_boff = nullptr, *send_cnt = nullptr, *send_pos = nullptr;
+    double *sendbuf = nullptr, *recvbuf = nullptr;
+    // predictions carried from step to step (iteration counts only; every solve still starts from x0 = 0)
+    int pred_sweeps = 0, pred_cg = 0;
+    double sweep_rate2 = 0.0;  // observed per-sweep contraction of ||r||^2
     // timing
     cudaEvent_t ev[6] = {nullptr};
+    cudaEvent_t ev_sw[2] = {nullptr};
+    int sweeps_timed = 0;
     bool have_system = false;
     long long n_launch = 0;
-    cudaEvent_t ev_sw[2] = {nullptr};
-    float ms_sweeps = 0.f;
 
     template <typename U>
     int alloc(U** p, size_t n) {
@@ -121,6 +136,17 @@ struct pbsm3d_handle {
         *p = (U*)q_;
         return 0;
     }
+    template <typename U>
+    int alloc_zero(U** p, size_t n) {
+        TRY(alloc(p, n));
+        CU(cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(U), stream));
+        return 0;
+    }
+    void release(void* p) {
+        for (size_t k = 0; k < allocs.size(); ++k)
+            if (allocs[k] == p) { allocs.erase(allocs.begin() + k); break; }
+        cudaFree(p);
+    }
 };
 
 namespace {
@@ -129,17 +155,11 @@ int upload(pbsm3d_handle* h, void* dst, const void* src, size_t bytes) {
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
     return 0;
 }
+inline int red_grid(size_t n) { return std::max(1, std::min(kRedBlocks, cdiv(n, kRedThreads))); }
+inline bool fused(const pbsm3d_handle* h) { return h->n_ranks == 1; }
 
-// ---- reductions ------------------------------------------------------------------------------------
-// fold `nvals` partial arrays into h->red[0..nvals) and make them global (NCCL) when partitioned.
-int fold(pbsm3d_handle* h, int nblocks, int nvals, int op) {
-    LAUNCH(h, fold_kernel, 1, 256, nblocks, nvals, kRedBlocks, h->partial, h->red, op);
-    if (h->n_ranks > 1) NC(ncclAllReduce(h->red, h->red, nvals, ncclDouble, op ? ncclMax : ncclSum, h->comm, h->stream));
-    return 0;
-}
-int read_red(pbsm3d_handle* h, int nvals) {
-    CU(cudaMemcpyAsync(h->h_red, h->red, nvals * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+int allreduce(pbsm3d_handle* h, double* buf, int n, bool is_max) {
+    if (h->n_ranks > 1) NC(ncclAllReduce(buf, buf, n, ncclDouble, is_max ? ncclMax : ncclSum, h->comm, h->stream));
     return 0;
 }
 int read_scalars(pbsm3d_handle* h) {
@@ -148,28 +168,71 @@ int read_scalars(pbsm3d_handle* h) {
     return 0;
 }
 
+// ---- colouring (host, once): a proper colouring of the owned faces' edge-adjacency graph ---------------------
+// 2 colours when the dual graph is bipartite (every structured/alternating-diagonal mesh, many others), else
+// greedy first-fit in CHM order, which needs at most 4 colours on a graph of maximum degree 3.
+void colour_faces(int T, const int32_t* neigh, std::vector<int>& colour, int& n_colours) {
+    colour.assign(T, -1);
+    bool bipartite = true;
+    std::vector<int> stack;
+    for (int s = 0; s < T && bipartite; ++s) {
+        if (colour[s] >= 0) continue;
+        colour[s] = 0;
+        stack.push_back(s);
+        while (!stack.empty() && bipartite) {
+            int i = stack.back();
+            stack.pop_back();
+            for (int j = 0; j < 3; ++j) {
+                int n = neigh[(size_t)i * 3 + j];
+                if (n < 0 || n >= T) continue;
+                if (colour[n] < 0) { colour[n] = 1 - colour[i]; stack.push_back(n); }
+                else if (colour[n] == colour[i]) { bipartite = false; break; }
+            }
+        }
+    }
+    if (bipartite) { n_colours = T > 1 ? 2 : 1; return; }
+    colour.assign(T, -1);
+    n_colours = 0;
+    for (int i = 0; i < T; ++i) {
+        unsigned used = 0;
+        for (int j = 0; j < 3; ++j) {
+            int n = neigh[(size_t)i * 3 + j];
+            if (n >= 0 && n < T && colour[n] >= 0) used |= 1u << colour[n];
+        }
+        int c = 0;
+        while (used & (1u << c)) ++c;
+        colour[i] = c;
+        n_colours = std::max(n_colours, c + 1);
+    }
+}
+
 // ---- halo (reference: triangulation::ghost_neighbors_communicate_variable, triangulation.cpp:1976-2079) -------
-// v is [nl][T] on the device; ghost values land in `ghost` as per-owner blocks [nl][cnt].
-int halo_exchange(pbsm3d_handle* h, const double* v, int nl, double* ghost) {
+// v is a ghost-extended [nl][S] vector on the device; the ghost tails v[z*S + Tp + g] are refreshed in place.
+int halo_exchange(pbsm3d_handle* h, double* v, int nl) {
     if (h->n_ranks == 1 || h->partners.empty()) return 0;
     if (h->n_send > 0) {
         size_t total = (size_t)h->n_send * nl;
         int blocks = std::min(cdiv(total, 256), 148 * 8);
-        LAUNCH(h, halo_pack_kernel, blocks, 256, h->n_send, nl, h->T, h->send_idx, h->send_boff, h->send_cnt,
-                                                        h->send_pos, v, h->sendbuf);
+        LAUNCH(h, halo_pack_kernel, blocks, 256, h->n_send, nl, h->S, h->send_slot, h->send_boff, h->send_cnt, h->send_pos, v,
+               h->sendbuf);
     }
     NC(ncclGroupStart());
     for (const Partner& p : h->partners) {
         if (p.send_cnt > 0)
             NC(ncclSend(h->sendbuf + (size_t)p.send_off * nl, (size_t)p.send_cnt * nl, ncclDouble, p.rank, h->comm, h->stream));
         if (p.recv_cnt > 0)
-            NC(ncclRecv(ghost + (size_t)p.recv_off * nl, (size_t)p.recv_cnt * nl, ncclDouble, p.rank, h->comm, h->stream));
+            NC(ncclRecv(h->recvbuf + (size_t)p.recv_off * nl, (size_t)p.recv_cnt * nl, ncclDouble, p.rank, h->comm, h->stream));
     }
     NC(ncclGroupEnd());
+    if (h->nG > 0) {
+        size_t total = (size_t)h->nG * nl;
+        int blocks = std::min(cdiv(total, 256), 148 * 8);
+        LAUNCH(h, halo_unpack_kernel, blocks, 256, h->nG, nl, h->Tp, h->S, h->gstart, h->gcnt, h->recvbuf, v);
+    }
     return 0;
 }
 
-int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* comm) {
+int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* comm, const std::vector<int>& iperm) {
     const int P = h->n_ranks, me = h->rank, nG = h->nG;
     ncclUniqueId id;
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
@@ -220,128 +283,148 @@ int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* com
     std::vector<long long> give(n_send);
     CU(cudaMemcpyAsync(give.data(), d_give, n_send * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    std::vector<int> sidx(n_send), sboff(n_send), scnt(n_send), spos(n_send);
+    std::vector<int> sslot(n_send), sboff(n_send), scnt(n_send), spos(n_send);
     for (const Partner& p : h->partners)
         for (int k = 0; k < p.send_cnt; ++k) {
             long long loc = give[p.send_off + k] - h->gstart_id;
             if (loc < 0 || loc >= h->T) return fail(PBSM3D_ERR_INVALID, "a partner asked for a face this rank does not own");
-            sidx[p.send_off + k] = (int)loc;
+            sslot[p.send_off + k] = iperm[(int)loc];
             sboff[p.send_off + k] = p.send_off;
             scnt[p.send_off + k] = p.send_cnt;
             spos[p.send_off + k] = k;
         }
-    TRY(h->alloc(&h->send_idx, n_send));
+    TRY(h->alloc(&h->send_slot, n_send));
     TRY(h->alloc(&h->send_boff, n_send));
     TRY(h->alloc(&h->send_cnt, n_send));
     TRY(h->alloc(&h->send_pos, n_send));
-    TRY(upload(h, h->send_idx, sidx.data(), n_send * sizeof(int)));
+    TRY(upload(h, h->send_slot, sslot.data(), n_send * sizeof(int)));
     TRY(upload(h, h->send_boff, sboff.data(), n_send * sizeof(int)));
     TRY(upload(h, h->send_cnt, scnt.data(), n_send * sizeof(int)));
     TRY(upload(h, h->send_pos, spos.data(), n_send * sizeof(int)));
-    TRY(h->alloc(&h->sendbuf, (size_t)n_send * std::max(h->L, 2)));
+    TRY(h->alloc(&h->sendbuf, (size_t)n_send * h->L));
+    TRY(h->alloc(&h->recvbuf, (size_t)std::max(nG, 1) * h->L));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
-// ---- suspension solve ------------------------------------------------------------------------------
+// ---- suspension solve: multicolour line Gauss–Seidel ---------------------------------------------------------
 template <int LT>
-void launch_sweep(pbsm3d_handle* h, const double* xo, const double* xgo, double* xn) {
-    LAUNCH(h, line_sweep_kernel<LT>, cdiv(h->T, 128), 128, h->ss, h->dm, h->L, xo, xgo, xn, nullptr);
+void launch_colour(pbsm3d_handle* h, int c) {
+    const int p0 = h->cstart[c], p1 = p0 + h->ccount[c];
+    LAUNCH(h, gs_sweep_kernel<LT>, cdiv(h->ccount[c], 128), 128, h->ss, h->dm, h->L, p0, p1, h->x, h->sc);
 }
-void sweep(pbsm3d_handle* h, const double* xo, const double* xgo, double* xn) {
-    switch (h->L) {
-        case 5: launch_sweep<5>(h, xo, xgo, xn); break;
-        case 10: launch_sweep<10>(h, xo, xgo, xn); break;
-        case 15: launch_sweep<15>(h, xo, xgo, xn); break;
-        case 20: launch_sweep<20>(h, xo, xgo, xn); break;
-        default: launch_sweep<0>(h, xo, xgo, xn); break;
+int enqueue_sweeps(pbsm3d_handle* h, int n) {
+    for (int k = 0; k < n; ++k) {
+        for (int c = 0; c < h->n_colours; ++c) {
+            if (h->ccount[c] == 0) continue;
+            switch (h->L) {
+                case 5: launch_colour<5>(h, c); break;
+                case 10: launch_colour<10>(h, c); break;
+                case 15: launch_colour<15>(h, c); break;
+                case 20: launch_colour<20>(h, c); break;
+                default: launch_colour<0>(h, c); break;
+            }
+        }
+        TRY(halo_exchange(h, h->x, h->L));
     }
+    return 0;
 }
-
-inline int red_grid(size_t n) { return std::max(1, std::min(kRedBlocks, cdiv(n, kRedThreads))); }
-
-// ||b - A x||^2 into h_red[0]  (x's ghost values must be current in xg)
-int residual_norm2(pbsm3d_handle* h, const double* x, const double* xg) {
-    int g = red_grid(h->N);
-    LAUNCH(h, spmv_kernel<1>, g, kRedThreads, h->ss, h->dm, h->L, x, xg, nullptr, nullptr, nullptr, 1, h->partial,
-                                                    kRedBlocks, nullptr);
-    LAUNCH(h, fold_kernel, 1, 256, g, 1, kRedBlocks, h->partial + kRedBlocks, h->red, 0);
-    if (h->n_ranks > 1) NC(ncclAllReduce(h->red, h->red, 1, ncclDouble, ncclSum, h->comm, h->stream));
-    return read_red(h, 1);
-}
-
-// Stationary line relaxation.  Returns 0 and sets *converged; iterations/residual in stats.
-int solve_line(pbsm3d_handle* h, double bnorm2, pbsm3d_stats* st, bool* converged, bool allow_bail) {
+// ||b - A x||^2 against tol^2 ||b||^2, decided on the device (x's ghost tails must be current)
+int enqueue_check(pbsm3d_handle* h, int it_now) {
     const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
-    CU(cudaMemsetAsync(h->xa, 0, h->N * sizeof(double), h->stream));
-    CU(cudaMemsetAsync(h->xga, 0, (size_t)h->L * std::max(h->nG, 1) * sizeof(double), h->stream));
-    double *xo = h->xa, *xn = h->xb, *xgo = h->xga, *xgn = h->xgb;
-    int it = 0, next_check = 8, checks = 0;
-    double prev_rr = bnorm2;
-    int prev_it = 0;
-    *converged = false;
-    const int maxit = h->cfg.max_iterations;
-    while (it < maxit) {
-        int target = std::min(next_check, maxit);
-        CU(cudaEventRecord(h->ev_sw[0], h->stream));
-        for (; it < target; ++it) {
-            sweep(h, xo, xgo, xn);
-            std::swap(xo, xn);
-            TRY(halo_exchange(h, xo, h->L, xgn));
-            std::swap(xgo, xgn);
-        }
-        CU(cudaEventRecord(h->ev_sw[1], h->stream));
-        TRY(residual_norm2(h, xo, xgo));
-        {
-            float ms = 0.f;
-            CU(cudaEventElapsedTime(&ms, h->ev_sw[0], h->ev_sw[1]));
-            h->ms_sweeps += ms;
-        }
-        double rr = h->h_red[0];
-        ++checks;
-        st->suspension_residual = std::sqrt(rr / bnorm2);
-        if (rr <= tol2 * bnorm2) { *converged = true; break; }
-        if (!std::isfinite(rr)) break;
-        // geometric convergence: predict the sweeps still needed from the observed rate
-        double rate = std::pow(rr / prev_rr, 0.5 / (double)(it - prev_it));  // per-sweep factor on ||r||
-        int step = 8;
-        if (rate < 1.0 && rate > 0.0) {
-            double need = 0.5 * std::log(tol2 * bnorm2 / rr) / std::log(rate);
-            step = (int)std::ceil(need);
-            step = std::max(1, std::min(step, 128));
-        } else if (allow_bail && checks >= 2) {
-            break;  // not contracting: hand over to the Krylov path
-        }
-        if (allow_bail && checks >= 3 && rate > 0.97 && it >= 64) break;  // crawling: Krylov is the better tool
-        prev_rr = rr;
-        prev_it = it;
-        next_check = it + step;
+    LAUNCH(h, residual_kernel, red_grid(h->N), kRedThreads, h->ss, h->dm, h->L, h->x, h->partial, kRedBlocks, h->sc, h->red, it_now,
+           tol2, fused(h) ? 1 : 0);
+    if (!fused(h)) {
+        TRY(allreduce(h, h->red, 1, false));
+        LAUNCH(h, flags_kernel, 1, 1, FLAGS_SUSP_CHECK, h->sc, h->red, it_now, tol2);
     }
-    h->xcur = xo;
-    st->suspension_iterations = it;
-    st->suspension_solver_used = PBSM3D_SOLVER_LINE;
+    return 0;
+}
+
+// Optimistic part: a predicted number of sweeps, a check, and a few short speculative rounds (no-ops once converged).
+int line_enqueue_initial(pbsm3d_handle* h, int* total_out) {
+    const int maxit = h->cfg.max_iterations;
+    int total = 0;
+    const bool known = h->pred_sweeps > 0;
+    int first = std::min(known ? h->pred_sweeps : 8, maxit);
+    CU(cudaEventRecord(h->ev_sw[0], h->stream));
+    TRY(enqueue_sweeps(h, first));
+    CU(cudaEventRecord(h->ev_sw[1], h->stream));
+    h->sweeps_timed = first;
+    total = first;
+    TRY(enqueue_check(h, total));
+    const int spec_known[3] = {1, 1, 2}, spec_unknown[3] = {8, 8, 8};
+    for (int k = 0; k < 3 && total < maxit; ++k) {
+        int step = std::min(known ? spec_known[k] : spec_unknown[k], maxit - total);
+        TRY(enqueue_sweeps(h, step));
+        total += step;
+        TRY(enqueue_check(h, total));
+    }
+    *total_out = total;
+    return 0;
+}
+
+// Slow path: the optimistic rounds did not reach the tolerance.  Predict the sweeps still needed from the observed
+// geometric rate, run them, look again.  Returns with *converged set; stagnation hands over to the Krylov path.
+int line_continue(pbsm3d_handle* h, int total, bool allow_bail, bool* converged) {
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    const int maxit = h->cfg.max_iterations;
+    *converged = false;
+    const Scalars& s = *h->h_sc;
+    double prev_rr = s.susp_bnorm2;
+    int prev_it = 0;
+    int nh = std::min(s.n_checks, 16);
+    if (nh >= 2) { prev_rr = s.rr_hist[nh - 2]; prev_it = s.it_hist[nh - 2]; }
+    double rr = s.susp_rr;
+    int it = total, slow = 0;
+    while (it < maxit) {
+        if (!std::isfinite(rr)) return 0;
+        int step = 8;
+        double rate = (rr > 0 && prev_rr > 0 && it > prev_it) ? std::pow(rr / prev_rr, 0.5 / (double)(it - prev_it)) : 2.0;
+        if (rate < 1.0 && rate > 0.0) {
+            double need = 0.5 * std::log(tol2 * s.susp_bnorm2 / rr) / std::log(rate);
+            step = std::max(1, std::min((int)std::ceil(need), 256));
+            if (rate > 0.97 && it >= 64) ++slow;
+        } else {
+            ++slow;
+        }
+        if (allow_bail && slow >= 2) return 0;  // not contracting / crawling: the Krylov path is the better tool
+        step = std::min(step, maxit - it);
+        TRY(enqueue_sweeps(h, step));
+        it += step;
+        TRY(enqueue_check(h, it));
+        prev_rr = rr;
+        prev_it = it - step;
+        TRY(read_scalars(h));
+        rr = h->h_sc->susp_rr;
+        if (h->h_sc->susp_done) { *converged = true; return 0; }
+    }
     return 0;
 }
 
 int ensure_krylov(pbsm3d_handle* h) {
     if (h->kry[0]) return 0;
-    for (int k = 0; k < 7; ++k) TRY(h->alloc(&h->kry[k], h->N));
-    TRY(h->alloc(&h->kry_g, (size_t)h->L * std::max(h->nG, 1)));
+    for (int k = 0; k < 7; ++k) TRY(h->alloc_zero(&h->kry[k], h->NS));
     return 0;
 }
 
-// Right-preconditioned BiCGStab with the column-tridiagonal preconditioner (the Krylov path).
-int solve_bicgstab(pbsm3d_handle* h, pbsm3d_stats* st, bool* converged) {
+int fold(pbsm3d_handle* h, int nblocks, int nvals) {
+    LAUNCH(h, fold_kernel, 1, 256, nblocks, nvals, kRedBlocks, h->partial, h->red, 0);
+    return allreduce(h, h->red, nvals, false);
+}
+
+// Right-preconditioned BiCGStab with the column-tridiagonal preconditioner (fallback and cross-check solver;
+// host-paced in batches of 4 iterations).
+int solve_bicgstab(pbsm3d_handle* h, bool* converged) {
     TRY(ensure_krylov(h));
     const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
-    double *x = h->xa, *r = h->kry[0], *rhat = h->kry[1], *p = h->kry[2], *v = h->kry[3], *ph = h->kry[4], *sh = h->kry[5],
+    double *x = h->x, *r = h->kry[0], *rhat = h->kry[1], *p = h->kry[2], *v = h->kry[3], *ph = h->kry[4], *sh = h->kry[5],
            *t = h->kry[6];
-    const size_t N = h->N;
-    const int g = red_grid(N), gt = cdiv(h->T, 128);
-    cudaStream_t s = h->stream;
+    const size_t NS = h->NS;
+    const int g = red_grid(h->N), gv = red_grid(NS), gt = cdiv(h->Tp, 128);
     const int* done = &h->sc->done;
-    LAUNCH(h, bicg_init_kernel, g, kRedThreads, h->T, h->L, h->ss.rhs0, x, r, rhat, p, v, h->partial);
-    TRY(fold(h, g, 1, 0));
+    LAUNCH(h, bicg_init_kernel, gv, 256, h->Tp, h->S, h->L, h->ss.rhs0, x, r, rhat, p, v, h->partial);
+    TRY(fold(h, gv, 1));
     LAUNCH(h, bicg_scalar_kernel, 1, 1, 0, h->sc, h->red, tol2);
     *converged = false;
     const int maxit = h->cfg.max_iterations;
@@ -349,172 +432,271 @@ int solve_bicgstab(pbsm3d_handle* h, pbsm3d_stats* st, bool* converged) {
     while (it < maxit) {
         int target = std::min(it + 4, maxit);
         for (; it < target; ++it) {
-            LAUNCH(h, bicg_p_kernel, g, kRedThreads, N, h->sc, r, v, p);
-            LAUNCH(h, thomas_kernel, gt, 128, h->ss, h->T, h->L, p, ph, done);
-            TRY(halo_exchange(h, ph, h->L, h->kry_g));
-            LAUNCH(h, spmv_kernel<0>, g, kRedThreads, h->ss, h->dm, h->L, ph, h->kry_g, v, rhat, nullptr, 0, h->partial, kRedBlocks, done);
-            TRY(fold(h, g, 1, 0));
+            LAUNCH(h, bicg_p_kernel, gv, 256, NS, h->sc, r, v, p);
+            LAUNCH(h, thomas_kernel, gt, 128, h->ss, h->Tp, h->S, h->L, p, ph, done);
+            TRY(halo_exchange(h, ph, h->L));
+            LAUNCH(h, spmv_kernel, g, kRedThreads, h->ss, h->dm, h->L, ph, v, rhat, nullptr, 0, h->partial, kRedBlocks, done);
+            TRY(fold(h, g, 1));
             LAUNCH(h, bicg_scalar_kernel, 1, 1, 1, h->sc, h->red, tol2);
-            LAUNCH(h, bicg_s_kernel, g, kRedThreads, N, h->sc, r, v, h->partial);
-            LAUNCH(h, thomas_kernel, gt, 128, h->ss, h->T, h->L, r, sh, done);
-            TRY(halo_exchange(h, sh, h->L, h->kry_g));
-            LAUNCH(h, spmv_kernel<0>, g, kRedThreads, h->ss, h->dm, h->L, sh, h->kry_g, t, r, nullptr, 1, h->partial, kRedBlocks, done);
-            TRY(fold(h, g, 2, 0));
+            LAUNCH(h, bicg_s_kernel, gv, 256, NS, h->sc, r, v, h->partial);
+            LAUNCH(h, thomas_kernel, gt, 128, h->ss, h->Tp, h->S, h->L, r, sh, done);
+            TRY(halo_exchange(h, sh, h->L));
+            LAUNCH(h, spmv_kernel, g, kRedThreads, h->ss, h->dm, h->L, sh, t, r, nullptr, 1, h->partial, kRedBlocks, done);
+            TRY(fold(h, g, 2));
             LAUNCH(h, bicg_scalar_kernel, 1, 1, 3, h->sc, h->red, tol2);
-            LAUNCH(h, bicg_xr_kernel, g, kRedThreads, N, h->sc, x, r, ph, sh, t, rhat, h->partial, kRedBlocks);
-            TRY(fold(h, g, 2, 0));
+            LAUNCH(h, bicg_xr_kernel, gv, 256, NS, h->sc, x, r, ph, sh, t, rhat, h->partial, kRedBlocks);
+            TRY(fold(h, gv, 2));
             LAUNCH(h, bicg_scalar_kernel, 1, 1, 4, h->sc, h->red, tol2);
         }
         TRY(read_scalars(h));
         if (h->h_sc->done) break;
     }
     *converged = (h->h_sc->done == 1);
-    st->suspension_iterations = h->h_sc->iters;
-    st->suspension_residual = std::sqrt(h->h_sc->rr / h->h_sc->bnorm2);
-    st->suspension_solver_used = PBSM3D_SOLVER_BICGSTAB;
-    h->xcur = x;
     return 0;
 }
 
-// Jacobi-preconditioned CG on the deposition system.
-int solve_deposition(pbsm3d_handle* h, pbsm3d_stats* st, bool* converged) {
+// ---- deposition: Jacobi-preconditioned CG, three launches per iteration on one rank -------------------------
+int enqueue_cg_iterations(pbsm3d_handle* h, int n) {
     const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
-    const int T = h->T;
-    const int g = red_grid(T);
-    cudaStream_t s = h->stream;
-    LAUNCH(h, cg_init_kernel, g, kRedThreads, T, h->drhs, h->dinv, h->q, h->cg_r, h->cg_p, h->partial, kRedBlocks);
-    TRY(fold(h, g, 2, 0));
-    LAUNCH(h, cg_scalar_kernel, 1, 1, 0, h->sc, h->red, tol2);
-    const int maxit = h->cfg.max_iterations;
-    int it = 0;
-    *converged = false;
-    while (it < maxit) {
-        int target = std::min(it + 16, maxit);
-        for (; it < target; ++it) {
-            TRY(halo_exchange(h, h->cg_p, 1, h->pg));
-            LAUNCH(h, cg_spmv_kernel, g, kRedThreads, h->dm, h->ddiag, h->doff, h->cg_p, h->pg, h->cg_Ap, h->partial, h->sc);
-            TRY(fold(h, g, 1, 0));
+    const int Tp = h->Tp, g = red_grid(Tp), f = fused(h) ? 1 : 0;
+    for (int k = 0; k < n; ++k) {
+        LAUNCH(h, cg_spmv_kernel, g, kRedThreads, h->dm, h->ddiag, h->doff, h->cg_p, h->cg_Ap, h->partial, kRedBlocks, h->sc, h->red,
+               tol2, f);
+        if (!f) {
+            TRY(allreduce(h, h->red, 1, false));
             LAUNCH(h, cg_scalar_kernel, 1, 1, 1, h->sc, h->red, tol2);
-            LAUNCH(h, cg_update_kernel, g, kRedThreads, T, h->sc, h->dinv, h->cg_p, h->cg_Ap, h->q, h->cg_r, h->partial, kRedBlocks);
-            TRY(fold(h, g, 2, 0));
-            LAUNCH(h, cg_scalar_kernel, 1, 1, 2, h->sc, h->red, tol2);
-            LAUNCH(h, cg_p_kernel, g, kRedThreads, T, h->sc, h->dinv, h->cg_r, h->cg_p);
         }
-        TRY(read_scalars(h));
-        if (h->h_sc->done) break;
+        LAUNCH(h, cg_update_kernel, g, kRedThreads, Tp, h->sc, h->dinv, h->cg_p, h->cg_Ap, h->q, h->cg_r, h->partial, kRedBlocks,
+               h->red, tol2, f);
+        if (!f) {
+            TRY(allreduce(h, h->red, 2, false));
+            LAUNCH(h, cg_scalar_kernel, 1, 1, 2, h->sc, h->red, tol2);
+        }
+        LAUNCH(h, cg_p_kernel, g, kRedThreads, Tp, h->sc, h->dinv, h->cg_r, h->cg_p);
+        TRY(halo_exchange(h, h->cg_p, 1));
     }
-    *converged = (h->h_sc->done == 1);
-    st->deposition_iterations = h->h_sc->iters;
-    st->deposition_residual = std::sqrt(h->h_sc->rr / h->h_sc->bnorm2);
+    return 0;
+}
+
+struct OutTargets {
+    double* dst[8];       // where export_kernel writes (device pointers: caller's buffers or out_stage)
+    double* host[8];      // optional host destinations for a following D2H
+};
+
+// E..I of SURVEY §3.2 plus the export: everything after the suspension solve.  Safe to enqueue before the host
+// knows whether the solve converged (device guards), and safe to enqueue again if it had not.
+int enqueue_tail(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTargets* out, int n_cg) {
+    cudaStream_t s = h->stream;
+    const int Tp = h->Tp;
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    // E: flux integration
+    LAUNCH(h, flux_kernel, cdiv(Tp, 256), 256, Tp, h->S, h->L, h->dc.dz, dt, h->perm, h->x, h->ss.u_z, h->ss.csubl, h->Qsusp, h->Qsubl,
+           h->Qsubl_mass, h->sum_subl, h->sc);
+    // F: halo of Qsusp, Qsalt (PBSM3D.cpp:1509-1510)
+    TRY(halo_exchange(h, h->Qsusp, 1));
+    TRY(halo_exchange(h, h->ss.Qsalt, 1));
+    // G: deposition RHS (the matrix is static) + H: rhs max
+    LAUNCH(h, deposition_rhs_kernel, red_grid(Tp), kRedThreads, h->dm, f.vw_dir, h->Qsusp, h->ss.Qsalt, h->drhs, h->partial, kRedBlocks,
+           h->sc, h->red);
+    TRY(allreduce(h, h->red, 1, true));
+    LAUNCH(h, flags_kernel, 1, 1, FLAGS_DEP, h->sc, h->red, 0, tol2);
+    CU(cudaEventRecord(h->ev[3], s));
+    // deposition solve
+    LAUNCH(h, cg_init_kernel, red_grid(Tp), kRedThreads, Tp, h->drhs, h->dinv, h->q, h->cg_r, h->cg_p, h->partial, kRedBlocks, h->sc,
+           h->red, tol2, fused(h) ? 1 : 0);
+    if (!fused(h)) {
+        TRY(allreduce(h, h->red, 2, false));
+        LAUNCH(h, cg_scalar_kernel, 1, 1, 0, h->sc, h->red, tol2);
+    }
+    TRY(halo_exchange(h, h->cg_p, 1));
+    TRY(enqueue_cg_iterations(h, n_cg));
+    return 0;
+}
+
+// I: drift update + export to CHM order (+ D2H when the caller's buffers are on the host)
+int enqueue_finish(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTargets* out) {
+    cudaStream_t s = h->stream;
+    const int Tp = h->Tp, T = h->T;
+    LAUNCH(h, drift_kernel, cdiv(Tp, 256), 256, Tp, dt, h->perm, h->q, f.swe, h->ss.salt, h->drift_mass, h->sum_drift, h->more_avail,
+           h->sc);
+    LAUNCH(h, drift_done_kernel, 1, 1, h->sc);
+    if (out) {
+        ExportPtrs e;
+        const double* src[8] = {h->ss.Qsalt, h->Qsusp, h->Qsubl, h->Qsubl_mass, h->sum_subl, h->drift_mass, h->sum_drift, h->more_avail};
+        bool any = false;
+        for (int k = 0; k < 8; ++k) { e.src[k] = src[k]; e.dst[k] = out->dst[k]; any = any || out->dst[k]; }
+        if (any) LAUNCH(h, export_kernel, cdiv(T, 256), 256, T, h->iperm, e);
+    }
+    CU(cudaEventRecord(h->ev[4], s));
+    if (out)
+        for (int k = 0; k < 8; ++k)
+            if (out->host[k]) CU(cudaMemcpyAsync(out->host[k], out->dst[k], (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
     return 0;
 }
 
 void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt) {
-    LAUNCH(h, assemble_kernel, cdiv(h->T, 128), 128, h->dc, h->dm, f, h->ss, dt);
+    const int ntiles = cdiv(h->Tp, 128);
+    LAUNCH(h, assemble_kernel, std::min(ntiles, kRedBlocks), 128, h->dc, h->dm, f, h->ss, dt, h->partial, kRedBlocks, h->sc, h->red);
 }
 
 // One PBSM3D::run with device-resident forcing (reference PBSM3D.cpp:400-1748, phases A–I of SURVEY §3.2).
-int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, pbsm3d_stats* st) {
+int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const OutTargets* out, pbsm3d_stats* st) {
     cudaStream_t s = h->stream;
-    const int T = h->T;
     std::memset(st, 0, sizeof(*st));
     const long long launch0 = h->n_launch;
-    h->ms_sweeps = 0.f;
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    const int maxit = h->cfg.max_iterations;
     h->last_forcing = f;
     h->last_dt = dt;
+    const int solver = h->cfg.solver;
     CU(cudaEventRecord(h->ev[0], s));
-    // A+B: zeroSystem is implicit (every coefficient is overwritten); saltation + suspension assembly
+    // x0 = 0 (Belos starts from the zero vector); ghost tails included
+    CU(cudaMemsetAsync(h->x, 0, h->NS * sizeof(double), s));
+    // A+B: zeroSystem is implicit (every coefficient is overwritten); saltation + suspension assembly,
+    // C: suspension_present = ||rhs||_inf > 1e-12 and ||b||_2^2, reduced inside the assembly kernel
     launch_assembly(h, f, dt);
     h->have_system = true;
-    // C: suspension_present = ||rhs||_inf > 1e-12 (PBSM3D.cpp:1424-1427); also ||b||_2^2 for the stopping rule
-    {
-        int g = red_grid(T);
-        LAUNCH(h, absmax_kernel, g, kRedThreads, T, h->ss.rhs0, h->partial);
-        LAUNCH(h, fold_kernel, 1, 256, g, 1, kRedBlocks, h->partial, h->red, 1);
-        LAUNCH(h, sumsq_kernel, g, kRedThreads, T, h->ss.rhs0, h->partial + kRedBlocks);
-        LAUNCH(h, fold_kernel, 1, 256, g, 1, kRedBlocks, h->partial + kRedBlocks, h->red + 1, 0);
-        if (h->n_ranks > 1) {
-            NC(ncclAllReduce(h->red, h->red, 1, ncclDouble, ncclMax, h->comm, s));
-            NC(ncclAllReduce(h->red + 1, h->red + 1, 1, ncclDouble, ncclSum, h->comm, s));
+    if (h->n_ranks > 1) {
+        TRY(allreduce(h, h->red, 1, true));
+        TRY(allreduce(h, h->red + 1, 1, false));
+    }
+    LAUNCH(h, flags_kernel, 1, 1, FLAGS_SUSP, h->sc, h->red, 0, tol2);
+    CU(cudaEventRecord(h->ev[1], s));
+
+    // D: suspension solve
+    int total = 0;
+    bool line = (solver == PBSM3D_SOLVER_AUTO || solver == PBSM3D_SOLVER_LINE);
+    h->sweeps_timed = 0;
+    if (line) {
+        TRY(line_enqueue_initial(h, &total));
+    } else {
+        TRY(read_scalars(h));
+        if (h->h_sc->susp_present) {
+            bool conv = false;
+            TRY(solve_bicgstab(h, &conv));
+            if (!conv) return fail(PBSM3D_ERR_NOCONVERGE, "suspension solver failed to converge");
+            st->suspension_iterations = h->h_sc->iters;
+            st->suspension_residual = std::sqrt(h->h_sc->rr / h->h_sc->bnorm2);
+            st->suspension_solver_used = PBSM3D_SOLVER_BICGSTAB;
+            LAUNCH(h, flags_kernel, 1, 1, FLAGS_FORCE_SUSP_OK, h->sc, h->red, 0, tol2);
         }
     }
-    CU(cudaEventRecord(h->ev[1], s));
-    TRY(read_red(h, 2));
-    st->suspension_rhs_max = h->h_red[0];
-    const double bnorm2 = h->h_red[1];
-    const bool susp = st->suspension_rhs_max > 1e-12;
-    st->suspension_present = susp ? 1 : 0;
-    // D: suspension solve
-    if (susp) {
-        bool conv = false;
-        int solver = h->cfg.solver;
-        if (solver == PBSM3D_SOLVER_AUTO || solver == PBSM3D_SOLVER_LINE)
-            TRY(solve_line(h, bnorm2, st, &conv, solver == PBSM3D_SOLVER_AUTO));
-        if (!conv && solver != PBSM3D_SOLVER_LINE) TRY(solve_bicgstab(h, st, &conv));
-        if (!conv) return fail(PBSM3D_ERR_NOCONVERGE, "suspension solver failed to converge");
-    } else {
-        CU(cudaMemsetAsync(h->xa, 0, h->N * sizeof(double), s));  // solution stays the zero vector (PBSM3D.cpp:1461-1465)
-        h->xcur = h->xa;
-    }
     CU(cudaEventRecord(h->ev[2], s));
-    // E: flux integration
-    LAUNCH(h, flux_kernel, cdiv(T, 256), 256, T, h->L, h->dc.dz, dt, h->xcur, h->ss.u_z, h->ss.csubl, h->Qsusp, h->Qsubl,
-                                             h->Qsubl_mass, h->sum_subl);
-    // F: halo of Qsusp, Qsalt (PBSM3D.cpp:1509-1510) — one message per partner carrying both
-    if (h->n_ranks > 1) {
-        CU(cudaMemcpyAsync(h->q2, h->Qsusp, T * sizeof(double), cudaMemcpyDeviceToDevice, s));
-        CU(cudaMemcpyAsync(h->q2 + T, h->ss.Qsalt, T * sizeof(double), cudaMemcpyDeviceToDevice, s));
-        TRY(halo_exchange(h, h->q2, 2, h->qg));
-    }
-    // G: deposition RHS (the matrix is static) + H: rhs max
-    {
-        int g = red_grid(T);
-        LAUNCH(h, deposition_rhs_kernel, g, 256, h->dm, f.vw_dir, h->Qsusp, h->ss.Qsalt, h->qg, h->drhs, h->partial);
-        LAUNCH(h, fold_kernel, 1, 256, g, 1, kRedBlocks, h->partial, h->red, 1);
-        if (h->n_ranks > 1) NC(ncclAllReduce(h->red, h->red, 1, ncclDouble, ncclMax, h->comm, s));
-    }
-    CU(cudaEventRecord(h->ev[3], s));
-    TRY(read_red(h, 1));
-    st->deposition_rhs_max = h->h_red[0];
-    const bool dep = susp && st->deposition_rhs_max > 1e-12;  // PBSM3D.cpp:1661-1664
-    st->deposition_present = dep ? 1 : 0;
-    if (dep) {
-        bool conv = false;
-        TRY(solve_deposition(h, st, &conv));
-        if (!conv) return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver failed to converge");
-        // I: drift update
-        LAUNCH(h, drift_kernel, cdiv(T, 256), 256, T, dt, h->q, f.swe, h->ss.salt, h->drift_mass, h->sum_drift, h->more_avail);
-    }
-    CU(cudaEventRecord(h->ev[4], s));
+    // E..I, optimistic
+    int n_cg = std::min(maxit, h->pred_cg > 0 ? h->pred_cg + std::max(4, h->pred_cg / 16) : 64);
+    TRY(enqueue_tail(h, f, dt, out, n_cg));
+    TRY(enqueue_finish(h, f, dt, out));
     CU(cudaStreamSynchronize(s));
+
+    // ---- what actually happened
+    bool redo_tail = false;
+    if (line && h->h_sc->susp_present && !h->h_sc->susp_ok) {
+        bool conv = false;
+        TRY(line_continue(h, total, solver == PBSM3D_SOLVER_AUTO, &conv));
+        if (!conv && solver == PBSM3D_SOLVER_AUTO) {
+            TRY(solve_bicgstab(h, &conv));
+            if (conv) {
+                st->suspension_iterations = h->h_sc->iters;
+                st->suspension_residual = std::sqrt(h->h_sc->rr / h->h_sc->bnorm2);
+                st->suspension_solver_used = PBSM3D_SOLVER_BICGSTAB;
+                LAUNCH(h, flags_kernel, 1, 1, FLAGS_FORCE_SUSP_OK, h->sc, h->red, 0, tol2);
+            }
+        }
+        if (!conv) return fail(PBSM3D_ERR_NOCONVERGE, "suspension solver failed to converge");
+        CU(cudaEventRecord(h->ev[2], s));
+        redo_tail = true;
+    }
+    if (line && h->h_sc->susp_present && st->suspension_solver_used == 0) {
+        const Scalars& c = *h->h_sc;
+        st->suspension_iterations = c.susp_iters;
+        st->suspension_residual = std::sqrt(c.susp_rr / c.susp_bnorm2);
+        st->suspension_solver_used = PBSM3D_SOLVER_LINE;
+        // carry the iteration count (not the solution) to the next step's schedule
+        int nh = std::min(c.n_checks, 16);
+        if (nh >= 2 && c.rr_hist[nh - 1] > 0 && c.rr_hist[nh - 2] > 0 && c.it_hist[nh - 1] > c.it_hist[nh - 2])
+            h->sweep_rate2 = std::pow(c.rr_hist[nh - 1] / c.rr_hist[nh - 2], 1.0 / (c.it_hist[nh - 1] - c.it_hist[nh - 2]));
+        int pred = c.susp_iters;
+        if (c.susp_rr > 0 && h->sweep_rate2 > 0 && h->sweep_rate2 < 1) {
+            // sweeps the detection overshot the tolerance by (the check grid is coarser than one sweep)
+            double over = std::log(tol2 * c.susp_bnorm2 / c.susp_rr) / std::log(h->sweep_rate2);
+            if (over <= -1.0) pred = std::max(1, pred + (int)std::ceil(over + 1e-9));
+        }
+        h->pred_sweeps = pred;
+    }
+    if (redo_tail) {
+        TRY(enqueue_tail(h, f, dt, out, n_cg));
+        TRY(enqueue_finish(h, f, dt, out));
+        CU(cudaStreamSynchronize(s));
+    }
+    // deposition solve still open?
+    while (h->h_sc->tail_done && h->h_sc->dep_present && !h->h_sc->dep_ok) {
+        if (h->h_sc->done == 2 || h->h_sc->iters >= maxit || !std::isfinite(h->h_sc->rr))
+            return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver failed to converge");
+        TRY(enqueue_cg_iterations(h, std::min(64, maxit - h->h_sc->iters)));
+        TRY(enqueue_finish(h, f, dt, out));
+        CU(cudaStreamSynchronize(s));
+    }
+    const Scalars& c = *h->h_sc;
+    st->suspension_present = c.susp_present;
+    st->suspension_rhs_max = c.susp_rhs_max;
+    st->deposition_present = c.dep_present;
+    st->deposition_rhs_max = c.dep_rhs_max;
+    if (c.dep_present) {
+        st->deposition_iterations = c.iters;
+        st->deposition_residual = c.bnorm2 > 0 ? std::sqrt(c.rr / c.bnorm2) : 0.0;
+        h->pred_cg = c.iters;
+    }
     CU(cudaEventElapsedTime(&st->ms_assembly, h->ev[0], h->ev[1]));
     CU(cudaEventElapsedTime(&st->ms_suspension_solve, h->ev[1], h->ev[2]));
     CU(cudaEventElapsedTime(&st->ms_flux_and_halo, h->ev[2], h->ev[3]));
     CU(cudaEventElapsedTime(&st->ms_deposition, h->ev[3], h->ev[4]));
     CU(cudaEventElapsedTime(&st->ms_total, h->ev[0], h->ev[4]));
-    st->ms_line_sweeps = h->ms_sweeps;
+    if (h->sweeps_timed > 0) CU(cudaEventElapsedTime(&st->ms_line_sweeps, h->ev_sw[0], h->ev_sw[1]));
+    st->sweeps_timed = h->sweeps_timed;
+    st->n_colours = h->n_colours;
     st->kernel_launches = (int32_t)(h->n_launch - launch0);
+    CU(cudaGetLastError());
     return 0;
 }
 
-int copy_out(pbsm3d_handle* h, double* dst, const double* src, size_t n, cudaMemcpyKind kind) {
-    if (!dst) return 0;
-    CU(cudaMemcpyAsync(dst, src, n * sizeof(double), kind, h->stream));
+int ensure_scratch(pbsm3d_handle* h, size_t n) {
+    if (h->scratch_n >= n) return 0;
+    if (h->scratch) h->release(h->scratch);
+    h->scratch = nullptr;
+    h->scratch_n = 0;
+    TRY(h->alloc(&h->scratch, n));
+    h->scratch_n = n;
     return 0;
 }
-
-int write_outputs(pbsm3d_handle* h, const pbsm3d_outputs* o, cudaMemcpyKind kind) {
-    if (!o) return 0;
-    const size_t T = h->T;
-    TRY(copy_out(h, o->Qsalt, h->ss.Qsalt, T, kind));
-    TRY(copy_out(h, o->Qsusp, h->Qsusp, T, kind));
-    TRY(copy_out(h, o->Qsubl, h->Qsubl, T, kind));
-    TRY(copy_out(h, o->Qsubl_mass, h->Qsubl_mass, T, kind));
-    TRY(copy_out(h, o->sum_subl, h->sum_subl, T, kind));
-    TRY(copy_out(h, o->drift_mass, h->drift_mass, T, kind));
-    TRY(copy_out(h, o->sum_drift, h->sum_drift, T, kind));
-    TRY(copy_out(h, o->pbsm_more_than_avail, h->more_avail, T, kind));
+// slot-ordered device array(s) -> CHM-ordered host array
+int fetch_chm(pbsm3d_handle* h, double* host_dst, const double* dev_src, int rows, size_t src_stride) {
+    if (!host_dst) return 0;
+    const size_t n = (size_t)rows * h->T;
+    TRY(ensure_scratch(h, n));
+    LAUNCH(h, to_chm_kernel, cdiv(h->T, 256), 256, rows, h->T, src_stride, h->iperm, dev_src, h->scratch);
+    CU(cudaMemcpyAsync(host_dst, h->scratch, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int store_chm(pbsm3d_handle* h, double* dev_dst, const double* host_src) {
+    if (!host_src) return 0;
+    TRY(ensure_scratch(h, h->T));
+    TRY(upload(h, h->scratch, host_src, (size_t)h->T * sizeof(double)));
+    LAUNCH(h, from_chm_kernel, cdiv(h->T, 256), 256, h->T, h->iperm, h->scratch, dev_dst);
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <typename U>
+int slots_from_host(pbsm3d_handle* h, U** dst, const U* host_src, U fill) {
+    U* tmp = nullptr;
+    TRY(h->alloc(&tmp, h->T));
+    TRY(upload(h, tmp, host_src, (size_t)h->T * sizeof(U)));
+    TRY(h->alloc(dst, h->Tp));
+    LAUNCH(h, to_slots_kernel<U>, cdiv(h->Tp, 256), 256, h->Tp, h->perm, tmp, *dst, fill);
+    CU(cudaStreamSynchronize(h->stream));
+    h->release(tmp);
     return 0;
 }
 
@@ -569,7 +751,6 @@ void pbsm3d_destroy(pbsm3d_handle* h) {
     if (h->comm) ncclCommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
-    if (h->h_red) cudaFreeHost(h->h_red);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_sw)
@@ -601,11 +782,11 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     h->cfg = *cfg;
     const int T = h->T = mesh->n_local, nG = h->nG = mesh->n_ghost, L = h->L = cfg->nLayer;
     h->G = mesh->n_global;
-    h->N = (size_t)T * L;
     h->rank = comm ? comm->rank : 0;
     h->n_ranks = comm ? comm->n_ranks : 1;
     if (h->n_ranks > 1 && !comm->nccl_unique_id) return fail(PBSM3D_ERR_INVALID, "nccl_unique_id missing");
     if (h->n_ranks == 1 && nG != 0) return fail(PBSM3D_ERR_INVALID, "ghost faces on a single-rank mesh");
+    if (nG > 0 && !mesh->ghost_owner) return fail(PBSM3D_ERR_INVALID, "ghost_owner missing");
     // owned faces are one contiguous ascending global range (triangulation.cpp:1482-1531)
     h->gstart_id = mesh->global_id[0];
     for (int i = 0; i < T; ++i)
@@ -615,29 +796,60 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
         if (mesh->global_id[T + g] <= mesh->global_id[T + g - 1])
             return fail(PBSM3D_ERR_INVALID, "ghost faces must be sorted by cell_global_id");
     if (h->gstart_id < 0 || h->gstart_id + T > h->G) return fail(PBSM3D_ERR_INVALID, "global ids exceed n_global");
+    for (int i = 0; i < T; ++i)
+        for (int j = 0; j < 3; ++j) {
+            int n = mesh->neigh[(size_t)i * 3 + j];
+            if (n < -1 || n >= T + nG || n == i)
+                return fail(PBSM3D_ERR_INVALID, "Face " + std::to_string(i) + " has out of bound neighbors.");
+        }
 
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) CU(cudaEventCreate(&e));
     for (auto& e : h->ev_sw) CU(cudaEventCreate(&e));
     CU(cudaMallocHost((void**)&h->h_sc, sizeof(Scalars)));
-    CU(cudaMallocHost((void**)&h->h_red, 8 * sizeof(double)));
+    std::memset(h->h_sc, 0, sizeof(Scalars));
 
-    // ---- neighbour table: AoS [T][3] from the caller -> SoA [3][T]
-    std::vector<int> nb((size_t)3 * T);
-    for (int i = 0; i < T; ++i)
-        for (int j = 0; j < 3; ++j) {
-            int n = mesh->neigh[(size_t)i * 3 + j];
-            if (n < -1 || n >= T + nG) return fail(PBSM3D_ERR_INVALID, "Face " + std::to_string(i) + " has out of bound neighbors.");
-            nb[(size_t)j * T + i] = n;
-        }
-    TRY(h->alloc(&h->neigh, (size_t)3 * T));
-    TRY(upload(h, h->neigh, nb.data(), nb.size() * sizeof(int)));
+    // ---- colour-major slot order
+    std::vector<int> colour;
+    colour_faces(T, mesh->neigh, colour, h->n_colours);
+    if (h->n_colours > kMaxColours) return fail(PBSM3D_ERR_INVALID, "face colouring needs too many colours");
+    std::vector<int> count(h->n_colours, 0);
+    for (int i = 0; i < T; ++i) count[colour[i]]++;
+    int Tp = 0;
+    for (int c = 0; c < h->n_colours; ++c) {
+        h->cstart[c] = Tp;
+        h->ccount[c] = count[c];
+        Tp = align_up(Tp + count[c], 32);
+    }
+    h->Tp = Tp;
+    h->S = Tp + align_up(nG, 32);
+    h->N = (size_t)L * Tp;
+    h->NS = (size_t)L * h->S;
+    std::vector<int> perm(Tp, -1), iperm(T), fillpos(h->n_colours);
+    for (int c = 0; c < h->n_colours; ++c) fillpos[c] = h->cstart[c];
+    for (int i = 0; i < T; ++i) {
+        int p = fillpos[colour[i]]++;
+        perm[p] = i;
+        iperm[i] = p;
+    }
+    TRY(h->alloc(&h->perm, Tp));
+    TRY(h->alloc(&h->iperm, T));
+    TRY(upload(h, h->perm, perm.data(), (size_t)Tp * sizeof(int)));
+    TRY(upload(h, h->iperm, iperm.data(), (size_t)T * sizeof(int)));
+    {
+        int* d_neigh = nullptr;
+        TRY(h->alloc(&d_neigh, (size_t)3 * T));
+        TRY(upload(h, d_neigh, mesh->neigh, (size_t)3 * T * sizeof(int)));
+        TRY(h->alloc(&h->nbs, (size_t)3 * Tp));
+        LAUNCH(h, neighbour_slots_kernel, cdiv(Tp, 256), 256, T, Tp, h->perm, h->iperm, d_neigh, h->nbs);
+        CU(cudaStreamSynchronize(h->stream));
+        h->release(d_neigh);
+    }
     // ghost owner blocks
     std::vector<int> gs(std::max(nG, 1), 0), gc(std::max(nG, 1), 0);
     for (int g = 0; g < nG;) {
         int e = g;
-        while (e < nG && mesh->ghost_owner && mesh->ghost_owner[e] == mesh->ghost_owner[g]) ++e;
-        if (e == g) return fail(PBSM3D_ERR_INVALID, "ghost_owner missing");
+        while (e < nG && mesh->ghost_owner[e] == mesh->ghost_owner[g]) ++e;
         for (int k = g; k < e; ++k) { gs[k] = g; gc[k] = e - g; }
         g = e;
     }
@@ -647,87 +859,82 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     TRY(upload(h, h->gcnt, gc.data(), std::max(nG, 1) * sizeof(int)));
 
     // ---- geometry on the device
-    const size_t Tall = (size_t)T + nG;
-    double* d_verts = nullptr;
-    double* d_area_param = nullptr;
-    TRY(h->alloc(&d_verts, Tall * 9));
-    TRY(upload(h, d_verts, mesh->vertices, Tall * 9 * sizeof(double)));
-    if (mesh->area) {
-        TRY(h->alloc(&d_area_param, T));
-        TRY(upload(h, d_area_param, mesh->area, T * sizeof(double)));
+    {
+        const size_t Tall = (size_t)T + nG;
+        double* d_verts = nullptr;
+        double* d_area_param = nullptr;
+        TRY(h->alloc(&d_verts, Tall * 9));
+        TRY(upload(h, d_verts, mesh->vertices, Tall * 9 * sizeof(double)));
+        if (mesh->area) {
+            TRY(h->alloc(&d_area_param, T));
+            TRY(upload(h, d_area_param, mesh->area, T * sizeof(double)));
+        }
+        TRY(h->alloc(&h->nx, (size_t)3 * Tp));
+        TRY(h->alloc(&h->ny, (size_t)3 * Tp));
+        TRY(h->alloc(&h->elen, (size_t)3 * Tp));
+        TRY(h->alloc(&h->dx, (size_t)3 * Tp));
+        TRY(h->alloc(&h->area, Tp));
+        TRY(h->alloc(&h->cx, (size_t)Tp + nG));
+        TRY(h->alloc(&h->cy, (size_t)Tp + nG));
+        TRY(h->alloc(&h->cz, (size_t)Tp + nG));
+        LAUNCH(h, geometry_kernel, cdiv((size_t)Tp + nG, 256), 256, T, Tp, nG, h->perm, d_verts, d_area_param, h->nx, h->ny, h->elen,
+               h->area, h->cx, h->cy, h->cz);
+        TRY(h->alloc(&h->ddiag, Tp));
+        TRY(h->alloc(&h->doff, (size_t)3 * Tp));
+        TRY(h->alloc(&h->dinv, Tp));
+        LAUNCH(h, deposition_matrix_kernel, cdiv(Tp, 256), 256, Tp, cfg->smooth_coeff, h->perm, h->nbs, h->elen, h->area, h->cx, h->cy,
+               h->dx, h->ddiag, h->doff, h->dinv);
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaGetLastError());
+        h->release(d_verts);
+        if (d_area_param) h->release(d_area_param);
     }
-    TRY(h->alloc(&h->nx, (size_t)3 * T));
-    TRY(h->alloc(&h->ny, (size_t)3 * T));
-    TRY(h->alloc(&h->elen, (size_t)3 * T));
-    TRY(h->alloc(&h->dx, (size_t)3 * T));
-    TRY(h->alloc(&h->area, T));
-    TRY(h->alloc(&h->cx, Tall));
-    TRY(h->alloc(&h->cy, Tall));
-    TRY(h->alloc(&h->cz, Tall));
-    LAUNCH(h, geometry_kernel, cdiv(Tall, 256), 256, T, (int)Tall, d_verts, d_area_param, h->nx, h->ny, h->elen, h->area,
-                                                            h->cx, h->cy, h->cz);
-    TRY(h->alloc(&h->ddiag, T));
-    TRY(h->alloc(&h->doff, (size_t)3 * T));
-    TRY(h->alloc(&h->dinv, T));
-    LAUNCH(h, deposition_matrix_kernel, cdiv(T, 256), 256, T, cfg->smooth_coeff, h->neigh, h->elen, h->area, h->cx, h->cy,
-                                                                  h->dx, h->ddiag, h->doff, h->dinv);
-    CU(cudaGetLastError());
 
     // ---- vegetation (PBSM3D.cpp:284-324): no vegetation information => veg off for the whole run
     bool veg = cfg->enable_veg && mesh->canopy_height != nullptr;
     if (veg && cfg->use_R94_lambda && !mesh->lai) return fail(PBSM3D_ERR_INVALID, "Parameter LAI does not exist.");
     if (veg) {
-        TRY(h->alloc(&h->canopy, T));
-        TRY(upload(h, h->canopy, mesh->canopy_height, T * sizeof(double)));
+        TRY(slots_from_host(h, &h->canopy, mesh->canopy_height, 0.0));
         if (cfg->use_R94_lambda) {
-            TRY(h->alloc(&h->lai, T));
-            TRY(upload(h, h->lai, mesh->lai, T * sizeof(double)));
+            TRY(slots_from_host(h, &h->lai, mesh->lai, 0.0));
         } else {
-            if (mesh->stalk_number) { TRY(h->alloc(&h->stalk_n, T)); TRY(upload(h, h->stalk_n, mesh->stalk_number, T * sizeof(double))); }
-            if (mesh->stalk_diameter) { TRY(h->alloc(&h->stalk_dv, T)); TRY(upload(h, h->stalk_dv, mesh->stalk_diameter, T * sizeof(double))); }
+            if (mesh->stalk_number) TRY(slots_from_host(h, &h->stalk_n, mesh->stalk_number, 1.0));
+            if (mesh->stalk_diameter) TRY(slots_from_host(h, &h->stalk_dv, mesh->stalk_diameter, 0.8));
         }
     }
-    if (mesh->is_water) {
-        TRY(h->alloc(&h->water, T));
-        TRY(upload(h, h->water, mesh->is_water, T));
-    }
+    if (mesh->is_water) TRY(slots_from_host<unsigned char>(h, &h->water, mesh->is_water, (unsigned char)0));
 
     // ---- per-step arrays
     for (auto& b : h->forcing_buf) TRY(h->alloc(&b, T));
     SuspSystem& ss = h->ss;
-    TRY(h->alloc(&ss.diag, h->N));
-    TRY(h->alloc(&ss.below, h->N));
-    TRY(h->alloc(&ss.above, h->N));
-    TRY(h->alloc(&ss.lat, 3 * h->N));
-    TRY(h->alloc(&ss.cp, h->N));
-    TRY(h->alloc(&ss.inv, h->N));
-    TRY(h->alloc(&ss.u_z, h->N));
-    TRY(h->alloc(&ss.csubl, h->N));
-    TRY(h->alloc(&ss.rhs0, T));
-    TRY(h->alloc(&ss.Qsalt, T));
-    TRY(h->alloc(&ss.c_salt, T));
-    TRY(h->alloc(&ss.salt, T));
-    TRY(h->alloc(&h->xa, h->N));
-    TRY(h->alloc(&h->xb, h->N));
-    TRY(h->alloc(&h->xga, (size_t)L * std::max(nG, 1)));
-    TRY(h->alloc(&h->xgb, (size_t)L * std::max(nG, 1)));
-    double** perface[] = {&h->Qsusp, &h->Qsubl, &h->Qsubl_mass, &h->sum_subl, &h->drift_mass, &h->sum_drift, &h->more_avail,
-                          &h->drhs,  &h->q,     &h->cg_r,       &h->cg_p,     &h->cg_Ap};
-    for (double** p : perface) {
-        TRY(h->alloc(p, T));
-        CU(cudaMemsetAsync(*p, 0, T * sizeof(double), h->stream));
-    }
-    TRY(h->alloc(&h->q2, (size_t)2 * T));
-    TRY(h->alloc(&h->qg, (size_t)2 * std::max(nG, 1)));
-    TRY(h->alloc(&h->pg, std::max(nG, 1)));
-    CU(cudaMemsetAsync(h->xa, 0, h->N * sizeof(double), h->stream));
-    h->xcur = h->xa;
+    const size_t N = h->N;
+    TRY(h->alloc(&ss.diag, N));
+    TRY(h->alloc(&ss.below, N));
+    TRY(h->alloc(&ss.above, N));
+    TRY(h->alloc(&ss.lat, 3 * N));
+    TRY(h->alloc(&ss.cp, N));
+    TRY(h->alloc(&ss.inv, N));
+    TRY(h->alloc(&ss.latS, 3 * N));
+    TRY(h->alloc(&ss.belowS, N));
+    TRY(h->alloc(&ss.u_z, N));
+    TRY(h->alloc(&ss.csubl, N));
+    TRY(h->alloc(&ss.rhs0, Tp));
+    TRY(h->alloc(&ss.rhsS0, Tp));
+    TRY(h->alloc_zero(&ss.Qsalt, h->S));
+    TRY(h->alloc(&ss.c_salt, Tp));
+    TRY(h->alloc(&ss.salt, Tp));
+    TRY(h->alloc_zero(&h->x, h->NS));
+    TRY(h->alloc_zero(&h->Qsusp, h->S));
+    TRY(h->alloc_zero(&h->cg_p, h->S));
+    double** perslot[] = {&h->Qsubl, &h->Qsubl_mass, &h->sum_subl, &h->drift_mass, &h->sum_drift, &h->more_avail,
+                          &h->drhs,  &h->q,          &h->cg_r,     &h->cg_Ap};
+    for (double** p : perslot) TRY(h->alloc_zero(p, Tp));
+    TRY(h->alloc(&h->out_stage, (size_t)8 * T));
     // drift_mass is a face variable that is -9999 until first written (variablestorage default)
-    LAUNCH(h, fill_kernel, cdiv(T, 256), 256, T, h->drift_mass, -9999.0);
-    TRY(h->alloc(&h->partial, (size_t)kRedBlocks * 4));
-    TRY(h->alloc(&h->red, 8));
-    TRY(h->alloc(&h->sc, 1));
-    CU(cudaMemsetAsync(h->sc, 0, sizeof(Scalars), h->stream));
+    LAUNCH(h, fill_slots_kernel, cdiv(Tp, 256), 256, Tp, h->perm, h->drift_mass, -9999.0);
+    TRY(h->alloc_zero(&h->partial, (size_t)kRedBlocks * 4));
+    TRY(h->alloc_zero(&h->red, 8));
+    TRY(h->alloc_zero(&h->sc, 1));
 
     DevConfig& dc = h->dc;
     dc.L = L;
@@ -748,8 +955,11 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     dc.l_max = 40.0;
     DevMesh& dm = h->dm;
     dm.T = T;
-    dm.n_ghost = nG;
-    dm.neigh = h->neigh;
+    dm.Tp = Tp;
+    dm.S = h->S;
+    dm.nG = nG;
+    dm.perm = h->perm;
+    dm.nbs = h->nbs;
     dm.nx = h->nx;
     dm.ny = h->ny;
     dm.elen = h->elen;
@@ -760,10 +970,8 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     dm.stalk_n = h->stalk_n;
     dm.stalk_dv = h->stalk_dv;
     dm.water = h->water;
-    dm.gstart = h->gstart;
-    dm.gcnt = h->gcnt;
 
-    if (h->n_ranks > 1) TRY(setup_comm(h, mesh, comm));
+    if (h->n_ranks > 1) TRY(setup_comm(h, mesh, comm, iperm));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     return 0;
@@ -784,22 +992,29 @@ int pbsm3d_create(const pbsm3d_config* cfg, const pbsm3d_mesh* mesh, int device,
     return 0;
 }
 
+static bool forcing_complete(const pbsm3d_forcing* f) {
+    return f->U_R && f->U_2m_above_srf && f->snowdepthavg && f->swe && f->t && f->rh && f->vw_dir;
+}
+static void out_pointers(const pbsm3d_outputs* o, double* p[8]) {
+    p[0] = o->Qsalt; p[1] = o->Qsusp; p[2] = o->Qsubl; p[3] = o->Qsubl_mass; p[4] = o->sum_subl; p[5] = o->drift_mass;
+    p[6] = o->sum_drift; p[7] = o->pbsm_more_than_avail;
+}
+
 int pbsm3d_step_device(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm3d_outputs* out, pbsm3d_stats* stats) {
     if (!h || !f) return fail(PBSM3D_ERR_INVALID, "null argument");
-    if (!f->U_R || !f->U_2m_above_srf || !f->snowdepthavg || !f->swe || !f->t || !f->rh || !f->vw_dir)
-        return fail(PBSM3D_ERR_INVALID, "forcing array missing");
+    if (!forcing_complete(f)) return fail(PBSM3D_ERR_INVALID, "forcing array missing");
     CU(cudaSetDevice(h->device));
     pbsm3d_stats local;
     if (!stats) stats = &local;
     DevForcing df{f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch};
-    TRY(step_impl(h, dt, df, stats));
-    return write_outputs(h, out, cudaMemcpyDeviceToDevice);
+    OutTargets ot{};
+    if (out) out_pointers(out, ot.dst);
+    return step_impl(h, dt, df, out ? &ot : nullptr, stats);
 }
 
 int pbsm3d_step(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm3d_outputs* out, pbsm3d_stats* stats) {
     if (!h || !f) return fail(PBSM3D_ERR_INVALID, "null argument");
-    if (!f->U_R || !f->U_2m_above_srf || !f->snowdepthavg || !f->swe || !f->t || !f->rh || !f->vw_dir)
-        return fail(PBSM3D_ERR_INVALID, "forcing array missing");
+    if (!forcing_complete(f)) return fail(PBSM3D_ERR_INVALID, "forcing array missing");
     CU(cudaSetDevice(h->device));
     pbsm3d_stats local;
     if (!stats) stats = &local;
@@ -808,55 +1023,74 @@ int pbsm3d_step(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm
         if (src[k]) TRY(upload(h, h->forcing_buf[k], src[k], (size_t)h->T * sizeof(double)));
     DevForcing df{h->forcing_buf[0], h->forcing_buf[1], h->forcing_buf[2], h->forcing_buf[3], h->forcing_buf[4],
                   h->forcing_buf[5], h->forcing_buf[6], f->fetch ? h->forcing_buf[7] : nullptr};
-    TRY(step_impl(h, dt, df, stats));
-    return write_outputs(h, out, cudaMemcpyDeviceToHost);
+    OutTargets ot{};
+    if (out) {
+        out_pointers(out, ot.host);
+        for (int k = 0; k < 8; ++k) ot.dst[k] = ot.host[k] ? h->out_stage + (size_t)k * h->T : nullptr;
+    }
+    return step_impl(h, dt, df, out ? &ot : nullptr, stats);
 }
 
 int pbsm3d_get_state(pbsm3d_handle* h, double* sum_drift, double* sum_subl, double* drift_mass, double* more) {
     if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
-    TRY(copy_out(h, sum_drift, h->sum_drift, h->T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, sum_subl, h->sum_subl, h->T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, drift_mass, h->drift_mass, h->T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, more, h->more_avail, h->T, cudaMemcpyDeviceToHost));
-    CU(cudaStreamSynchronize(h->stream));
+    TRY(fetch_chm(h, sum_drift, h->sum_drift, 1, h->Tp));
+    TRY(fetch_chm(h, sum_subl, h->sum_subl, 1, h->Tp));
+    TRY(fetch_chm(h, drift_mass, h->drift_mass, 1, h->Tp));
+    TRY(fetch_chm(h, more, h->more_avail, 1, h->Tp));
     return 0;
 }
 
 int pbsm3d_set_state(pbsm3d_handle* h, const double* sum_drift, const double* sum_subl, const double* drift_mass, const double* more) {
     if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
-    const size_t b = (size_t)h->T * sizeof(double);
-    if (sum_drift) TRY(upload(h, h->sum_drift, sum_drift, b));
-    if (sum_subl) TRY(upload(h, h->sum_subl, sum_subl, b));
-    if (drift_mass) TRY(upload(h, h->drift_mass, drift_mass, b));
-    if (more) TRY(upload(h, h->more_avail, more, b));
-    CU(cudaStreamSynchronize(h->stream));
+    TRY(store_chm(h, h->sum_drift, sum_drift));
+    TRY(store_chm(h, h->sum_subl, sum_subl));
+    TRY(store_chm(h, h->drift_mass, drift_mass));
+    TRY(store_chm(h, h->more_avail, more));
     return 0;
 }
 
 int pbsm3d_get_geometry(pbsm3d_handle* h, double* nx, double* ny, double* el, double* area, double* dx, double* cx, double* cy, double* cz) {
     if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
-    const size_t T = h->T;
-    TRY(copy_out(h, nx, h->nx, 3 * T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, ny, h->ny, 3 * T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, el, h->elen, 3 * T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, area, h->area, T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, dx, h->dx, 3 * T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, cx, h->cx, T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, cy, h->cy, T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, cz, h->cz, T, cudaMemcpyDeviceToHost));
-    CU(cudaStreamSynchronize(h->stream));
+    const size_t Tp = h->Tp;
+    TRY(fetch_chm(h, nx, h->nx, 3, Tp));
+    TRY(fetch_chm(h, ny, h->ny, 3, Tp));
+    TRY(fetch_chm(h, el, h->elen, 3, Tp));
+    TRY(fetch_chm(h, area, h->area, 1, Tp));
+    TRY(fetch_chm(h, dx, h->dx, 3, Tp));
+    TRY(fetch_chm(h, cx, h->cx, 1, Tp));
+    TRY(fetch_chm(h, cy, h->cy, 1, Tp));
+    TRY(fetch_chm(h, cz, h->cz, 1, Tp));
+    return 0;
+}
+
+int pbsm3d_get_layout(pbsm3d_handle* h, int32_t* n_colours, int32_t* n_slots, int32_t* slot_of_face, int32_t* colour_of_face) {
+    if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    if (n_colours) *n_colours = h->n_colours;
+    if (n_slots) *n_slots = h->Tp;
+    if (slot_of_face || colour_of_face) {
+        std::vector<int> slot(h->T);
+        CU(cudaMemcpyAsync(slot.data(), h->iperm, (size_t)h->T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < h->T; ++i) {
+            if (slot_of_face) slot_of_face[i] = slot[i];
+            if (colour_of_face) {
+                int c = 0;
+                while (c + 1 < h->n_colours && slot[i] >= h->cstart[c + 1]) ++c;
+                colour_of_face[i] = c;
+            }
+        }
+    }
     return 0;
 }
 
 int pbsm3d_get_solution(pbsm3d_handle* h, double* x) {
     if (!h || !x) return fail(PBSM3D_ERR_INVALID, "null argument");
     CU(cudaSetDevice(h->device));
-    TRY(copy_out(h, x, h->xcur, h->N, cudaMemcpyDeviceToHost));
-    CU(cudaStreamSynchronize(h->stream));
-    return 0;
+    return fetch_chm(h, x, h->x, h->L, h->S);
 }
 
 int pbsm3d_get_suspension_system(pbsm3d_handle* h, double* diag, double* lat, double* below, double* above, double* rhs0,
@@ -864,29 +1098,34 @@ int pbsm3d_get_suspension_system(pbsm3d_handle* h, double* diag, double* lat, do
     if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
     if (!h->have_system) return fail(PBSM3D_ERR_INVALID, "no system assembled yet");
     CU(cudaSetDevice(h->device));
-    const size_t N = h->N, T = h->T;
-    TRY(copy_out(h, diag, h->ss.diag, N, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, lat, h->ss.lat, 3 * N, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, below, h->ss.below, N, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, above, h->ss.above, N, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, rhs0, h->ss.rhs0, T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, u_z, h->ss.u_z, N, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, csubl, h->ss.csubl, N, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, c_salt, h->ss.c_salt, T, cudaMemcpyDeviceToHost));
-    if (saltation) CU(cudaMemcpyAsync(saltation, h->ss.salt, T, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    const size_t Tp = h->Tp;
+    const int L = h->L;
+    TRY(fetch_chm(h, diag, h->ss.diag, L, Tp));
+    TRY(fetch_chm(h, lat, h->ss.lat, 3 * L, Tp));
+    TRY(fetch_chm(h, below, h->ss.below, L, Tp));
+    TRY(fetch_chm(h, above, h->ss.above, L, Tp));
+    TRY(fetch_chm(h, rhs0, h->ss.rhs0, 1, Tp));
+    TRY(fetch_chm(h, u_z, h->ss.u_z, L, Tp));
+    TRY(fetch_chm(h, csubl, h->ss.csubl, L, Tp));
+    TRY(fetch_chm(h, c_salt, h->ss.c_salt, 1, Tp));
+    if (saltation) {
+        TRY(ensure_scratch(h, h->T));
+        unsigned char* tmp = (unsigned char*)h->scratch;
+        LAUNCH(h, to_chm_u8_kernel, cdiv(h->T, 256), 256, h->T, h->iperm, h->ss.salt, tmp);
+        CU(cudaMemcpyAsync(saltation, tmp, h->T, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     return 0;
 }
 
 int pbsm3d_get_deposition_system(pbsm3d_handle* h, double* diag, double* off, double* rhs, double* q) {
     if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
-    const size_t T = h->T;
-    TRY(copy_out(h, diag, h->ddiag, T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, off, h->doff, 3 * T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, rhs, h->drhs, T, cudaMemcpyDeviceToHost));
-    TRY(copy_out(h, q, h->q, T, cudaMemcpyDeviceToHost));
-    CU(cudaStreamSynchronize(h->stream));
+    const size_t Tp = h->Tp;
+    TRY(fetch_chm(h, diag, h->ddiag, 1, Tp));
+    TRY(fetch_chm(h, off, h->doff, 3, Tp));
+    TRY(fetch_chm(h, rhs, h->drhs, 1, Tp));
+    TRY(fetch_chm(h, q, h->q, 1, Tp));
     return 0;
 }
 
@@ -895,36 +1134,35 @@ int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms) {
     if (!h->have_system) return fail(PBSM3D_ERR_INVALID, "run a step first");
     CU(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
-    double *xo = h->xcur, *xn = (h->xcur == h->xa) ? h->xb : h->xa;
-    // one untimed launch, then `reps` timed ones
-    for (int pass = 0; pass < 2; ++pass) {
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    // the sweep and residual kernels idle once the solve has converged: reopen it for the measurement
+    CU(cudaMemsetAsync(&h->sc->susp_done, 0, sizeof(int), s));
+    for (int pass = 0; pass < 2; ++pass) {  // one untimed launch, then `reps` timed ones
         int n = pass == 0 ? 1 : reps;
         if (pass == 1) CU(cudaEventRecord(h->ev[0], s));
         for (int k = 0; k < n; ++k) {
             switch (kernel) {
-                case 0: sweep(h, xo, h->xga, xn); break;
+                case 0: TRY(enqueue_sweeps(h, 1)); break;
                 case 1:
-                    LAUNCH(h, spmv_kernel<1>, red_grid(h->N), kRedThreads, h->ss, h->dm, h->L, xo, h->xga, nullptr, nullptr, nullptr,
-                                                                         1, h->partial, kRedBlocks, nullptr);
+                    LAUNCH(h, residual_kernel, red_grid(h->N), kRedThreads, h->ss, h->dm, h->L, h->x, h->partial, kRedBlocks, h->sc,
+                           h->red, 0, tol2, 0);
                     break;
                 case 2: launch_assembly(h, h->last_forcing, h->last_dt); break;
                 case 3:
-                    LAUNCH(h, cg_spmv_kernel, red_grid(h->T), kRedThreads, h->dm, h->ddiag, h->doff, h->cg_p, h->pg, h->cg_Ap,
-                                                                         h->partial, nullptr);
+                    LAUNCH(h, cg_spmv_kernel, red_grid(h->Tp), kRedThreads, h->dm, h->ddiag, h->doff, h->cg_p, h->cg_Ap, h->partial,
+                           kRedBlocks, nullptr, h->red, tol2, 0);
                     break;
                 default: return fail(PBSM3D_ERR_INVALID, "unknown kernel id");
             }
         }
         if (pass == 1) CU(cudaEventRecord(h->ev[1], s));
     }
+    LAUNCH(h, flags_kernel, 1, 1, FLAGS_FORCE_SUSP_OK, h->sc, h->red, 0, tol2);
     CU(cudaStreamSynchronize(s));
     CU(cudaGetLastError());
     float t = 0;
     CU(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
     *ms = t / reps;
-    if (kernel == 2) {
-        // the assembly rewrote the factors with the same values; nothing else to restore
-    }
     return 0;
 }
 

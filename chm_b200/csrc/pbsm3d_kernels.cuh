@@ -1,14 +1,20 @@
 // sm_100a kernels of the PBSM3D hot path.  All arithmetic is fp64; the path is sparse and HBM-bound
 // (≈0.15 flop/B), so there are no tensor-core instructions here: the rules that matter are coalesced
-// layer-major SoA streams, one pass over each array, L2-resident neighbour gathers and grids that fill
-// the 148 SMs.
+// layer-major SoA streams, one pass over each array, L2-resident neighbour gathers, enough independent
+// loads in flight per thread to cover HBM latency, and grids that fill the 148 SMs.
 //
-// Data layout (all device arrays, T = owned faces of this rank, L = nLayer):
-//   per face        a[i]                      i in [0,T)
-//   per face-edge   a[j*T + i]                j in 0..2   (edge j is shared with neighbour j)
-//   per row         a[z*T + i]                the reference's local unknown numbering (LinearAlgebra.cpp:81)
-//   ghosts          xg[nl*gstart[g] + z*gcnt[g] + (g - gstart[g])]   g = neigh - T; ghosts are sorted by global id, so
-//                   each owner's ghosts are one contiguous block [gstart, gstart+gcnt), received as [nl][gcnt]
+// INTERNAL FACE ORDER.  CHM's face order (ascending cell_global_id) is the order of every array that crosses
+// the C-ABI.  Inside the library faces are stored colour-major: the owned faces are coloured so that no two
+// edge-neighbours share a colour (2 colours when the dual graph is bipartite, else greedy ≤ 4), each colour
+// class keeps CHM's order internally and starts on a 32-face (256-byte) boundary.  slot p -> CHM face perm[p]
+// (-1 = padding slot, assembled as the identity row), CHM face i -> slot iperm[i].
+//
+// Data layout (device arrays; Tp = padded slots, S = Tp + padded ghost count, L = nLayer):
+//   per slot        a[p]                      p in [0,Tp)
+//   per slot-edge   a[j*Tp + p]               j in 0..2   (edge j is shared with neighbour j)
+//   coefficients    a[z*Tp + p]               one stream per coefficient, layer-major
+//   vectors         v[z*S + p]                ghost-extended: v[z*S + Tp + g] is ghost face g of layer z,
+//                                             so a neighbour gather is x[z*S + nbs] with no owned/ghost branch
 #pragma once
 #include <cuda_runtime.h>
 #include "pbsm3d_physics.cuh"
@@ -25,47 +31,119 @@ struct DevConfig {
 };
 
 struct DevMesh {
-    int T, n_ghost;
-    const int* neigh;      // [3][T] local ids, -1 none, >=T ghost
-    const double* nx;      // [3][T]
-    const double* ny;      // [3][T]
-    const double* elen;    // [3][T]
-    const double* area;    // [T]
-    const double* zc;      // [T] centroid elevation (face->get_z())
-    const double* canopy;  // [T] or null
-    const double* lai;     // [T] or null
-    const double* stalk_n; // [T] or null
+    int T, Tp, S, nG;
+    const int* perm;       // [Tp] slot -> CHM local face, -1 = pad
+    const int* nbs;        // [3][Tp] neighbour slot (ghost g -> Tp+g); own slot when there is no neighbour
+    const double* nx;      // [3][Tp]
+    const double* ny;      // [3][Tp]
+    const double* elen;    // [3][Tp]
+    const double* area;    // [Tp]
+    const double* zc;      // [Tp] centroid elevation (face->get_z())
+    const double* canopy;  // [Tp] or null
+    const double* lai;     // [Tp] or null
+    const double* stalk_n; // [Tp] or null
     const double* stalk_dv;
-    const unsigned char* water;  // [T] or null
-    const int* gstart;     // [n_ghost] first ghost of the owner block this ghost belongs to
-    const int* gcnt;       // [n_ghost] size of that block
+    const unsigned char* water;  // [Tp] or null
 };
 
-struct DevForcing {
+struct DevForcing {  // CHM order, [T]
     const double *U_R, *u2, *sd, *swe, *t, *rh, *vw_dir, *fetch;
 };
 
 struct SuspSystem {
-    double *diag, *below, *above;  // [L][T]
-    double* lat;                   // [3][L][T]
-    double *cp, *inv;              // [L][T] Thomas factors of the column blocks
-    double* rhs0;                  // [T]
-    double *u_z, *csubl;           // [L][T]
-    double *Qsalt, *c_salt;        // [T]
-    unsigned char* salt;           // [T]
+    double *diag, *below, *above;  // [L][Tp]   the assembled rows (reference values)
+    double* lat;                   // [3][L][Tp]
+    double *cp, *inv;              // [L][Tp]   Thomas factors of the vertical (column) blocks
+    double* latS;                  // [3][L][Tp] lat * inv   } the row-scaled copies the line sweep streams
+    double* belowS;                // [L][Tp]   below * inv  }
+    double* rhs0;                  // [Tp]      b of layer 0 (all other layers are 0)
+    double* rhsS0;                 // [Tp]      rhs0 * inv[0]
+    double *u_z, *csubl;           // [L][Tp]
+    double *Qsalt, *c_salt;        // [Tp]
+    unsigned char* salt;           // [Tp]
+};
+
+// Device-resident control block: recurrence scalars, convergence flags and the tickets of the fused
+// "last block folds" reductions.  The host reads it once per step (or per batch while a solve is still open).
+struct Scalars {
+    double rho, alpha, omega, beta;   // BiCGStab / CG recurrences
+    double rr, bnorm2;                // ||r||^2, ||b||^2 of the solve in flight
+    double tmp[4];
+    double susp_rhs_max, dep_rhs_max;
+    double susp_bnorm2, susp_rr;      // line solver: ||b||^2 and the last checked ||b-Ax||^2
+    double rr_hist[16];               // ||b-Ax||^2 at the residual checks of this step
+    int it_hist[16];
+    int n_checks;
+    int done;                         // Krylov solve in flight: 1 = converged, 2 = breakdown
+    int iters;
+    int susp_present, dep_present;
+    int susp_done, susp_iters;        // line solver: converged flag and the sweep count at detection
+    int susp_ok;                      // suspension phase finished (converged, or nothing to solve)
+    int dep_ok;                       // deposition solve finished (converged)
+    int tail_done;                    // flux/deposition-rhs ran on a finished suspension solve
+    int drift_done;
+    unsigned ticket[4];
 };
 
 // ---------------------------------------------------------------------------------------------- setup
+// Neighbour table in slot numbering.  neigh_chm is [T][3] with -1 = none and >= T = ghost (T + g).
+__global__ void neighbour_slots_kernel(int T, int Tp, const int* __restrict__ perm, const int* __restrict__ iperm,
+                                       const int* __restrict__ neigh_chm, int* __restrict__ nbs) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp) return;
+    const int i = perm[p];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        int s = p;
+        if (i >= 0) {
+            const int n = neigh_chm[(size_t)i * 3 + j];
+            if (n >= T) s = Tp + (n - T);
+            else if (n >= 0) s = iperm[n];
+        }
+        nbs[(size_t)j * Tp + p] = s;
+    }
+}
+
+// dst[p] = src[perm[p]] (pad -> fill): brings a CHM-ordered per-face array into slot order.
+template <typename U>
+__global__ void to_slots_kernel(int Tp, const int* __restrict__ perm, const U* __restrict__ src, U* __restrict__ dst, U fill) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp) return;
+    const int i = perm[p];
+    dst[p] = i >= 0 ? src[i] : fill;
+}
+// dst[r*T + i] = src[r*src_stride + iperm[i]]: slot order -> CHM order for `rows` stacked arrays.
+__global__ void to_chm_kernel(int rows, int T, size_t src_stride, const int* __restrict__ iperm, const double* __restrict__ src,
+                              double* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const int p = iperm[i];
+    for (int r = 0; r < rows; ++r) dst[(size_t)r * T + i] = src[(size_t)r * src_stride + p];
+}
+__global__ void to_chm_u8_kernel(int T, const int* __restrict__ iperm, const unsigned char* __restrict__ src,
+                                 unsigned char* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T) dst[i] = src[iperm[i]];
+}
+
 // Face geometry from the three vertices of each face (reference: mesh/triangulation.hpp:1443-1475
 // edge_unit_normal/edge, :1491-1498 edge_length, :1577-1589 center, :1830-1856 get_area).
 // Runs once in pbsm3d_create.  Products and sums use the __d*_rn intrinsics, which nvcc never contracts
 // into FMAs, so every value is bit-identical to the plain IEEE fp64 evaluation the reference (and numpy) do.
-__global__ void geometry_kernel(int T, int Tall, const double* __restrict__ verts, const double* __restrict__ area_param,
-                                double* __restrict__ nx, double* __restrict__ ny, double* __restrict__ elen,
-                                double* __restrict__ area, double* __restrict__ cx, double* __restrict__ cy,
-                                double* __restrict__ cz) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Tall) return;
+// Slots [0,Tp) are owned faces (or pads), slots [Tp, Tp+nG) the ghosts (centroid only).
+__global__ void geometry_kernel(int T, int Tp, int nG, const int* __restrict__ perm, const double* __restrict__ verts,
+                                const double* __restrict__ area_param, double* __restrict__ nx, double* __restrict__ ny,
+                                double* __restrict__ elen, double* __restrict__ area, double* __restrict__ cx,
+                                double* __restrict__ cy, double* __restrict__ cz) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp + nG) return;
+    const int i = p < Tp ? perm[p] : T + (p - Tp);
+    if (i < 0) {  // pad: a harmless unit triangle
+        cx[p] = cy[p] = cz[p] = 0.0;
+        for (int k = 0; k < 3; ++k) { nx[(size_t)k * Tp + p] = 1.0; ny[(size_t)k * Tp + p] = 0.0; elen[(size_t)k * Tp + p] = 1.0; }
+        area[p] = 1.0;
+        return;
+    }
     double px[3], py[3], pz[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -73,10 +151,10 @@ __global__ void geometry_kernel(int T, int Tall, const double* __restrict__ vert
         py[k] = verts[(size_t)i * 9 + k * 3 + 1];
         pz[k] = verts[(size_t)i * 9 + k * 3 + 2];
     }
-    cx[i] = __ddiv_rn(__dadd_rn(__dadd_rn(px[0], px[1]), px[2]), 3.0);
-    cy[i] = __ddiv_rn(__dadd_rn(__dadd_rn(py[0], py[1]), py[2]), 3.0);
-    cz[i] = __ddiv_rn(__dadd_rn(__dadd_rn(pz[0], pz[1]), pz[2]), 3.0);
-    if (i >= T) return;  // ghosts only need a centroid
+    cx[p] = __ddiv_rn(__dadd_rn(__dadd_rn(px[0], px[1]), px[2]), 3.0);
+    cy[p] = __ddiv_rn(__dadd_rn(__dadd_rn(py[0], py[1]), py[2]), 3.0);
+    cz[p] = __ddiv_rn(__dadd_rn(__dadd_rn(pz[0], pz[1]), pz[2]), 3.0);
+    if (p >= Tp) return;  // ghosts only need a centroid
     double ex[3], ey[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {  // edge(k) = v[cw(k)] - v[ccw(k)]
@@ -91,231 +169,45 @@ __global__ void geometry_kernel(int T, int Tall, const double* __restrict__ vert
         double D = __dadd_rn(__dmul_rn(ex[k1], n_x), __dmul_rn(ey[k1], n_y));
         if (D > 0) { n_x = -n_x; n_y = -n_y; }
         double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(n_x, n_x), __dmul_rn(n_y, n_y)));
-        nx[(size_t)k * T + i] = __ddiv_rn(n_x, nrm);
-        ny[(size_t)k * T + i] = __ddiv_rn(n_y, nrm);
-        elen[(size_t)k * T + i] = __dsqrt_rn(__dadd_rn(__dmul_rn(ex[k], ex[k]), __dmul_rn(ey[k], ey[k])));
+        nx[(size_t)k * Tp + p] = __ddiv_rn(n_x, nrm);
+        ny[(size_t)k * Tp + p] = __ddiv_rn(n_y, nrm);
+        elen[(size_t)k * Tp + p] = __dsqrt_rn(__dadd_rn(__dmul_rn(ex[k], ex[k]), __dmul_rn(ey[k], ey[k])));
     }
     if (area_param) {
-        area[i] = area_param[i];
+        area[p] = area_param[i];
     } else {
         double v1x = __dsub_rn(px[1], px[0]), v1y = __dsub_rn(py[1], py[0]);
         double v2x = __dsub_rn(px[2], px[0]), v2y = __dsub_rn(py[2], py[0]);
-        area[i] = __ddiv_rn(__dsub_rn(__dmul_rn(v1x, v2y), __dmul_rn(v1y, v2x)), 2.0);
+        area[p] = __ddiv_rn(__dsub_rn(__dmul_rn(v1x, v2y), __dmul_rn(v1y, v2x)), 2.0);
     }
 }
 
 // Static part of the deposition system (reference re-derives it every step, PBSM3D.cpp:1546,1609-1628):
 // diag = area + sum eps*E_j/dx_j, off_j = -eps*E_j/dx_j, dx_j = 2-D centroid distance (coordinates.cpp:100-106).
-// cx/cy are [T + n_ghost], so a neighbour that is a ghost face resolves like any other.
-__global__ void deposition_matrix_kernel(int T, double eps, const int* __restrict__ neigh, const double* __restrict__ elen,
-                                         const double* __restrict__ area, const double* __restrict__ cx,
-                                         const double* __restrict__ cy, double* __restrict__ dx, double* __restrict__ ddiag,
-                                         double* __restrict__ doff, double* __restrict__ dinv) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
-    double d = area[i];
+// cx/cy are [Tp + nG], so a neighbour that is a ghost face resolves like any other.
+__global__ void deposition_matrix_kernel(int Tp, double eps, const int* __restrict__ perm, const int* __restrict__ nbs,
+                                         const double* __restrict__ elen, const double* __restrict__ area,
+                                         const double* __restrict__ cx, const double* __restrict__ cy, double* __restrict__ dx,
+                                         double* __restrict__ ddiag, double* __restrict__ doff, double* __restrict__ dinv) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp) return;
+    double d = area[p];
+    const bool pad = perm[p] < 0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        int n = neigh[(size_t)j * T + i];
+        int n = nbs[(size_t)j * Tp + p];
         double dist = 2.0, c = 0.0;  // dx[] default 2.0, PBSM3D.cpp:1534
-        if (n >= 0) {
-            double ddx = __dsub_rn(cx[i], cx[n]), ddy = __dsub_rn(cy[i], cy[n]);
+        if (n != p && !pad) {
+            double ddx = __dsub_rn(cx[p], cx[n]), ddy = __dsub_rn(cy[p], cy[n]);
             dist = __dsqrt_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
-            c = __ddiv_rn(__dmul_rn(eps, elen[(size_t)j * T + i]), dist);
+            c = __ddiv_rn(__dmul_rn(eps, elen[(size_t)j * Tp + p]), dist);
         }
-        dx[(size_t)j * T + i] = dist;
+        dx[(size_t)j * Tp + p] = dist;
         d = __dadd_rn(d, c);
-        doff[(size_t)j * T + i] = -c;
+        doff[(size_t)j * Tp + p] = -c;
     }
-    ddiag[i] = d;
-    dinv[i] = 1.0 / d;
-}
-
-// ------------------------------------------------------------------------------------------- assembly
-// HOT LOOP 1: saltation + every layer of one face column (reference PBSM3D.cpp:436-1406), fused with the
-// forward elimination of that column's tridiagonal block (the preconditioner / line solver factor).
-// One thread per face; for each layer the 32 lanes of a warp write 32 consecutive doubles of every
-// output stream.  Replaces ≈11 Tpetra sumIntoGlobalValues hash lookups per row by direct ELL stores.
-__global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt) {
-    const int T = m.T;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
-
-    double fetch = 1000.0;
-    if ((c.use_exp_fetch || c.use_tanh_fetch) && f.fetch) fetch = f.fetch[i];
-    const double uref = f.U_R[i];
-    double sd = f.sd[i];
-    sd = chm_is_nan(sd) ? 0.0 : sd;
-    const double u2 = f.u2[i];
-    double swe = f.swe[i];
-    swe = chm_is_nan(swe) ? 0.0 : swe;
-    const double Tc = f.t[i];
-    const double phi = f.vw_dir[i];
-    const double area = m.area[i];
-    double nxj[3], nyj[3], Ej[3];
-    int nb[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        nxj[j] = m.nx[(size_t)j * T + i];
-        nyj[j] = m.ny[(size_t)j * T + i];
-        Ej[j] = m.elen[(size_t)j * T + i];
-        nb[j] = m.neigh[(size_t)j * T + i];
-    }
-
-    double height_diff = 0.0, LAI = 0.0, Nst = 0.0, dv = 0.0;
-    if (c.enable_veg) {
-        height_diff = fmax(0.0, m.canopy[i] - sd);
-        if (c.use_R94_lambda) LAI = m.lai[i];
-        else { Nst = m.stalk_n ? m.stalk_n[i] : 1.0; dv = m.stalk_dv ? m.stalk_dv[i] : 0.8; }
-    }
-    const bool water = m.water ? (m.water[i] != 0) : false;
-    const double ust_th = 0.35 + (1.0 / 150.0) * Tc + (1.0 / 8200.0) * Tc * Tc;
-
-    bool salt = false;
-    double lambda = 0.0, ustar = 1.3;
-    if (height_diff <= c.cutoff && sd >= c.min_sd_trans && !water) {
-        lambda = c.use_R94_lambda ? 0.5 * LAI * height_diff : Nst * dv * height_diff;
-        ustar = u2 * kKappa / log(2.0 / 0.0002);
-        if (ustar >= ust_th) salt = true;
-    }
-    double z0 = kZ0Snow;
-    if (!salt) ustar = fmax(0.01, kKappa * uref / log(kZUR / z0));
-    z0 = fmax(kZ0Snow, z0);
-    ustar = fmax(0.01, ustar);
-    const double hs = salt ? 0.08436 * pow(ustar, 1.27) : 0.0;
-
-    const double t = Tc + 273.15;
-    double vx, vy;
-    wind_unit_vector(phi, vx, vy);
-    double Qsalt = 0.0, c_salt = 0.0;
-    if (salt) {
-        const double rho_f = std_dry_air_density(m.zc[i], t);
-        const double mB = 0.16 * 202.0;
-        const double tau_n_ratio = (mB * lambda) / (1.0 + mB * lambda);
-        c_salt = rho_f / (3.29 * ustar) * (1.0 - tau_n_ratio - (ust_th * ust_th) / (ustar * ustar));
-        if (c_salt < 0 || isnan(c_salt)) { c_salt = 0.0; salt = false; }
-        if (c.use_exp_fetch && fetch < 500.0) {
-            c_salt *= 1.0 - exp(-3.0 * fetch / 500.0);
-        } else if (c.use_tanh_fetch && fetch <= 300.0) {
-            const double Lc = 0.5 * tanh(0.1333333333e-1 * 300.0 - 2.0) + 0.5;  // fetch_ref inside tanh, as the reference
-            c_salt *= Lc;
-        }
-        const double uhs = 2.8 * ust_th;
-        Qsalt = c_salt * uhs * hs;
-        double mass = 0.0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            double udotm = vx * nxj[j] + vy * nyj[j];
-            mass += -Ej[j] * Qsalt * udotm;
-        }
-        mass = mass / area * dt;
-        if (mass < 0 && fabs(mass) > swe) { c_salt = 0.0; Qsalt = c_salt * uhs * hs; }  // saltation flag survives
-    }
-    s.Qsalt[i] = Qsalt;
-    s.c_salt[i] = c_salt;
-    s.salt[i] = salt ? 1 : 0;
-
-    const double rh = f.rh[i] / 100.0;
-    const double es = saturated_vapour_pressure(t);
-    const double dz = c.dz;
-    const double nrm = sqrt(vx * vx + vy * vy);
-    // layer-independent pieces of the sublimation model (same expressions as inside the reference's z loop)
-    const double D = 2.06e-5 * pow(t / 273.15, 1.75);
-    const double lambda_t = 0.000063 * t + 0.00673;
-    const double Ls = 2.838e6, Mw = 18.01, Rg = 8313.0;
-    const double rho_sat = (Mw * es) / (Rg * t);
-    const double ulog_den = log((kZUR - (sd + z0)) / z0);
-    double Aj[3], alphaj[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        Aj[j] = Ej[j] * dz;
-        alphaj[j] = c.do_lateral_diff ? Aj[j] * 0.00001 : 0.0;
-    }
-
-    double cp_prev = 0.0;
-    const int L = c.L;
-    for (int z = 0; z < L; ++z) {
-        const size_t r = (size_t)z * T + i;
-        const double cz = z * dz + hs + dz / 2.0;
-        const double hz = cz + sd;
-        double u_z;
-        if (salt && cz < height_diff) u_z = 2.8 * ust_th;
-        else if (cz < height_diff) u_z = 0.01;
-        else if (hz < kZUR) u_z = fmax(0.01, uref * log((hz - (sd + z0)) / z0) / ulog_den);
-        else u_z = fmax(0.01, uref);
-        s.u_z[r] = u_z;
-
-        const double rm = 4.6e-5 * pow(cz, -0.258);
-        const double mm_alpha = 4.08 + 12.6 * cz;
-        const double mm = 4.0 / 3.0 * kPi * kRhoIce * rm * rm * rm * (1.0 + 3.0 / mm_alpha + 2.0 / (mm_alpha * mm_alpha));
-        const double r_z = pow((3.0 * mm) / (4 * kPi * kRhoIce), 0.3333333);
-        const double xrz = 0.005 * pow(u_z, 1.36);
-        const double omega = c.do_fixed_settling ? c.settling_velocity : 1.1e7 * pow(r_z, 1.8);
-        const double Vr = omega + 3.0 * xrz * cos(kPi / 4.0);
-        const double Re = 2.0 * r_z * Vr / 1.88e-5;
-        const double Nu = 1.79 + 0.606 * sqrt(Re);
-        const double Sh = Nu;
-        const double sigma = (rh - 1.0) * (1.019 + 0.027 * log(cz));
-        const double Qr = 0.9 * kPi * rm * rm * 120.0;
-        const double dmdtz = Sh * rho_sat * D * (6.283185308 * Nu * Rg * r_z * sigma * t * t * lambda_t - Ls * Mw * Qr + Qr * Rg * t) /
-                             (D * Ls * Sh * (Ls * Mw - Rg * t) * rho_sat + lambda_t * t * t * Nu * Rg);
-        double csubl = dmdtz / mm;
-        if (!c.do_sublimation) csubl = 0.0;
-        s.csubl[r] = csubl;
-
-        const double lmix = kKappa * (cz + z0) * c.l_max / (kKappa * (cz + z0) + c.l_max);
-        const double w = omega;
-        double diffusion_coeff = c.snow_diffusion_const;
-        if (c.rouault) diffusion_coeff = 1.0 / (1.0 + (1.0 * w * w) / (1.56 * ustar * ustar));
-        const double K = diffusion_coeff * ustar * lmix;
-        const double alpha3 = area * K / dz;
-        const double alpha4 = area * K / dz;
-        const double sc = u_z / nrm;
-        const double ux = vx * sc, uy = vy * sc;
-        const double udotm3 = -w, udotm4 = w;
-        const double Vc = (area * dz / 5.0) * csubl;
-
-        double d = 0.0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const double udotm = ux * nxj[j] + uy * nyj[j];
-            double off = 0.0;
-            if (udotm > 0) {
-                if (nb[j] >= 0) { d += Vc - Aj[j] * udotm - alphaj[j]; off = alphaj[j]; }
-                else d += -0.1e-1 * alphaj[j] - 1.0 * Aj[j] * udotm + Vc;
-            } else {
-                if (nb[j] >= 0) { d += Vc - alphaj[j]; off = -Aj[j] * udotm + alphaj[j]; }
-                else d += -0.1e-1 * alphaj[j] - 0.99 * Aj[j] * udotm + Vc;
-            }
-            s.lat[((size_t)j * L + z) * T + i] = off;
-        }
-        double lo = 0.0, up = 0.0;
-        if (z == 0) {
-            const double alpha4p = area * K / (hs / 2.0 + dz / 2.0);
-            d += Vc - area * udotm4 - alpha4p;
-            s.rhs0[i] = -alpha4p * c_salt;
-            if (udotm3 > 0) { d += Vc - area * udotm3 - alpha3; up = alpha3; }
-            else { d += Vc - alpha3; up = -area * udotm3 + alpha3; }
-        } else if (z == L - 1) {
-            if (udotm3 > 0) d += Vc - area * udotm3 - alpha3;
-            else d += Vc - alpha3;
-            if (udotm4 > 0) { d += Vc - area * udotm4 - alpha4; lo = alpha4; }
-            else { d += Vc - alpha4; lo = -area * udotm4 + alpha4; }
-        } else {
-            if (udotm3 > 0) { d += Vc - area * udotm3 - alpha3; up = alpha3; }
-            else { d += Vc - alpha3; up = -area * udotm3 + alpha3; }
-            if (udotm4 > 0) { d += Vc - area * udotm4 - alpha4; lo = alpha4; }
-            else { d += Vc - alpha4; lo = -area * udotm4 + alpha4; }
-        }
-        s.diag[r] = d;
-        s.below[r] = lo;
-        s.above[r] = up;
-        // forward elimination of the column block (Thomas): den_z = d_z - lo_z * cp_{z-1}
-        const double inv = 1.0 / (d - lo * cp_prev);
-        cp_prev = up * inv;
-        s.inv[r] = inv;
-        s.cp[r] = cp_prev;
-    }
+    ddiag[p] = d;
+    dinv[p] = 1.0 / d;
 }
 
 // -------------------------------------------------------------------------------------- reductions
@@ -329,7 +221,7 @@ __device__ __forceinline__ double warp_max(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// Block-wide sum staged through shared memory; result valid in thread 0.
+// Block-wide reductions staged through shared memory; result valid in thread 0 (warp 0).
 __device__ __forceinline__ double block_sum(double v) {
     __shared__ double sm[32];
     __syncthreads();  // protect sm reuse across consecutive calls
@@ -355,94 +247,424 @@ __device__ __forceinline__ double block_max(double v) {
     return v;
 }
 
-constexpr int kRedBlocks = 148 * 4;  // partial-sum slots: a multiple of the SM count
+constexpr int kRedBlocks = 148 * 8;  // partial-sum slots: a multiple of the SM count
 constexpr int kRedThreads = 256;
 
-// ||v||_inf partials (NearestNeighborProblem::getRhsMax, LinearAlgebra.cpp:264-270)
-__global__ void __launch_bounds__(kRedThreads) absmax_kernel(size_t n, const double* __restrict__ v, double* __restrict__ partial) {
-    double m = 0.0;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
-        m = fmax(m, fabs(v[k]));
-    m = block_max(m);
-    if (threadIdx.x == 0) partial[blockIdx.x] = m;
-}
-
-// sum v^2 partials (||b||_2^2 for the relative-residual stopping rule)
-__global__ void __launch_bounds__(kRedThreads) sumsq_kernel(size_t n, const double* __restrict__ v, double* __restrict__ partial) {
-    double a = 0.0;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) a += v[k] * v[k];
-    a = block_sum(a);
-    if (threadIdx.x == 0) partial[blockIdx.x] = a;
-}
-
-// Scalar slots shared by the solver kernels (device resident; the host only reads `status` now and then).
-struct Scalars {
-    double rho, alpha, omega, beta;   // BiCGStab / CG recurrences
-    double rr, bnorm2;                // ||r||^2, ||b||^2
-    double tmp[4];
-    int done;                         // 1 = converged, 2 = breakdown
-    int iters;
-};
-
-// Final stage of every fused reduction: one block folds `nvals` interleaved partial arrays
-// (partial[v*stride + b]) into out[v].  op 0 = sum, 1 = max.
-__global__ void __launch_bounds__(256) fold_kernel(int nblocks, int nvals, int stride, const double* __restrict__ partial,
-                                                   double* __restrict__ out, int op) {
-    for (int v = 0; v < nvals; ++v) {
-        double a = 0.0;
-        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
-            double p = partial[(size_t)v * stride + b];
-            a = op ? fmax(a, p) : a + p;
+// Fused grid reduction.  Every block publishes up to two partials; the block that draws the last ticket folds
+// them IN INDEX ORDER (so the result does not depend on which block finished last) and returns true in all of
+// its threads with the totals in out0/out1 (thread 0).  op: 0 = sum, 1 = max.
+template <int NV>
+__device__ __forceinline__ bool grid_fold(double v0, double v1, int op0, int op1, double* __restrict__ partial, int stride,
+                                          unsigned* ticket, double& out0, double& out1) {
+    __shared__ bool last;
+    v0 = op0 ? block_max(v0) : block_sum(v0);
+    if (NV > 1) v1 = op1 ? block_max(v1) : block_sum(v1);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = v0;
+        if (NV > 1) partial[stride + blockIdx.x] = v1;
+        __threadfence();
+        unsigned t = atomicInc(ticket, gridDim.x - 1);  // wraps to 0 after the last block: self-resetting
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+    double a0 = 0.0, a1 = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        double q0 = __ldcg(&partial[b]);
+        a0 = op0 ? fmax(a0, q0) : a0 + q0;
+        if (NV > 1) {
+            double q1 = __ldcg(&partial[stride + b]);
+            a1 = op1 ? fmax(a1, q1) : a1 + q1;
         }
-        a = op ? block_max(a) : block_sum(a);
-        if (threadIdx.x == 0) out[v] = a;
+    }
+    out0 = op0 ? block_max(a0) : block_sum(a0);
+    if (NV > 1) out1 = op1 ? block_max(a1) : block_sum(a1);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------- assembly
+// HOT LOOP 1: saltation + every layer of one face column (reference PBSM3D.cpp:436-1406), fused with the
+// forward elimination of that column's tridiagonal block (the line-solver factor), the row scaling the sweep
+// streams, and the two global facts the step needs next: max|b| (suspension_present, PBSM3D.cpp:1424-1427)
+// and ||b||^2 (the stopping rule of LinearAlgebra.cpp:168).
+// One thread per slot; for each layer the 32 lanes of a warp write 32 consecutive doubles of every output
+// stream.  Replaces ≈11 Tpetra sumIntoGlobalValues hash lookups per row by direct ELL stores.
+__device__ __forceinline__ double assemble_column(const DevConfig& c, const DevMesh& m, const DevForcing& f, const SuspSystem& s,
+                                                   double dt, int p) {
+    const int Tp = m.Tp;
+    const int i = m.perm[p];
+    const int L = c.L;
+    double b0 = 0.0;
+    if (i < 0) {  // padding slot: identity rows, zero right-hand side
+        s.Qsalt[p] = 0.0; s.c_salt[p] = 0.0; s.salt[p] = 0; s.rhs0[p] = 0.0; s.rhsS0[p] = 0.0;
+        for (int z = 0; z < L; ++z) {
+            const size_t r = (size_t)z * Tp + p;
+            s.diag[r] = 1.0; s.below[r] = 0.0; s.above[r] = 0.0; s.inv[r] = 1.0; s.cp[r] = 0.0; s.belowS[r] = 0.0;
+            s.u_z[r] = 0.0; s.csubl[r] = 0.0;
+            for (int j = 0; j < 3; ++j) { s.lat[((size_t)j * L + z) * Tp + p] = 0.0; s.latS[((size_t)j * L + z) * Tp + p] = 0.0; }
+        }
+    } else {
+        double fetch = 1000.0;
+        if ((c.use_exp_fetch || c.use_tanh_fetch) && f.fetch) fetch = f.fetch[i];
+        const double uref = f.U_R[i];
+        double sd = f.sd[i];
+        sd = chm_is_nan(sd) ? 0.0 : sd;
+        const double u2 = f.u2[i];
+        double swe = f.swe[i];
+        swe = chm_is_nan(swe) ? 0.0 : swe;
+        const double Tc = f.t[i];
+        const double phi = f.vw_dir[i];
+        const double area = m.area[p];
+        double nxj[3], nyj[3], Ej[3];
+        bool has[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            nxj[j] = m.nx[(size_t)j * Tp + p];
+            nyj[j] = m.ny[(size_t)j * Tp + p];
+            Ej[j] = m.elen[(size_t)j * Tp + p];
+            has[j] = m.nbs[(size_t)j * Tp + p] != p;
+        }
+
+        double height_diff = 0.0, LAI = 0.0, Nst = 0.0, dv = 0.0;
+        if (c.enable_veg) {
+            height_diff = fmax(0.0, m.canopy[p] - sd);
+            if (c.use_R94_lambda) LAI = m.lai[p];
+            else { Nst = m.stalk_n ? m.stalk_n[p] : 1.0; dv = m.stalk_dv ? m.stalk_dv[p] : 0.8; }
+        }
+        const bool water = m.water ? (m.water[p] != 0) : false;
+        const double ust_th = 0.35 + (1.0 / 150.0) * Tc + (1.0 / 8200.0) * Tc * Tc;
+
+        bool salt = false;
+        double lambda = 0.0, ustar = 1.3;
+        if (height_diff <= c.cutoff && sd >= c.min_sd_trans && !water) {
+            lambda = c.use_R94_lambda ? 0.5 * LAI * height_diff : Nst * dv * height_diff;
+            ustar = u2 * kKappa / log(2.0 / 0.0002);
+            if (ustar >= ust_th) salt = true;
+        }
+        double z0 = kZ0Snow;
+        if (!salt) ustar = fmax(0.01, kKappa * uref / log(kZUR / z0));
+        z0 = fmax(kZ0Snow, z0);
+        ustar = fmax(0.01, ustar);
+        const double hs = salt ? 0.08436 * pow(ustar, 1.27) : 0.0;
+
+        const double t = Tc + 273.15;
+        double vx, vy;
+        wind_unit_vector(phi, vx, vy);
+        double Qsalt = 0.0, c_salt = 0.0;
+        if (salt) {
+            const double rho_f = std_dry_air_density(m.zc[p], t);
+            const double mB = 0.16 * 202.0;
+            const double tau_n_ratio = (mB * lambda) / (1.0 + mB * lambda);
+            c_salt = rho_f / (3.29 * ustar) * (1.0 - tau_n_ratio - (ust_th * ust_th) / (ustar * ustar));
+            if (c_salt < 0 || isnan(c_salt)) { c_salt = 0.0; salt = false; }
+            if (c.use_exp_fetch && fetch < 500.0) {
+                c_salt *= 1.0 - exp(-3.0 * fetch / 500.0);
+            } else if (c.use_tanh_fetch && fetch <= 300.0) {
+                const double Lc = 0.5 * tanh(0.1333333333e-1 * 300.0 - 2.0) + 0.5;  // fetch_ref inside tanh, as the reference
+                c_salt *= Lc;
+            }
+            const double uhs = 2.8 * ust_th;
+            Qsalt = c_salt * uhs * hs;
+            double mass = 0.0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                double udotm = vx * nxj[j] + vy * nyj[j];
+                mass += -Ej[j] * Qsalt * udotm;
+            }
+            mass = mass / area * dt;
+            if (mass < 0 && fabs(mass) > swe) { c_salt = 0.0; Qsalt = c_salt * uhs * hs; }  // saltation flag survives
+        }
+        s.Qsalt[p] = Qsalt;
+        s.c_salt[p] = c_salt;
+        s.salt[p] = salt ? 1 : 0;
+
+        const double rh = f.rh[i] / 100.0;
+        const double es = saturated_vapour_pressure(t);
+        const double dz = c.dz;
+        const double nrm = sqrt(vx * vx + vy * vy);
+        // layer-independent pieces of the sublimation model (same expressions as inside the reference's z loop)
+        const double D = 2.06e-5 * pow(t / 273.15, 1.75);
+        const double lambda_t = 0.000063 * t + 0.00673;
+        const double Ls = 2.838e6, Mw = 18.01, Rg = 8313.0;
+        const double rho_sat = (Mw * es) / (Rg * t);
+        const double ulog_den = log((kZUR - (sd + z0)) / z0);
+        double Aj[3], alphaj[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            Aj[j] = Ej[j] * dz;
+            alphaj[j] = c.do_lateral_diff ? Aj[j] * 0.00001 : 0.0;
+        }
+
+        double cp_prev = 0.0;
+        for (int z = 0; z < L; ++z) {
+            const size_t r = (size_t)z * Tp + p;
+            const double cz = z * dz + hs + dz / 2.0;
+            const double hz = cz + sd;
+            double u_z;
+            if (salt && cz < height_diff) u_z = 2.8 * ust_th;
+            else if (cz < height_diff) u_z = 0.01;
+            else if (hz < kZUR) u_z = fmax(0.01, uref * log((hz - (sd + z0)) / z0) / ulog_den);
+            else u_z = fmax(0.01, uref);
+            s.u_z[r] = u_z;
+
+            const double rm = 4.6e-5 * pow(cz, -0.258);
+            const double mm_alpha = 4.08 + 12.6 * cz;
+            const double mm = 4.0 / 3.0 * kPi * kRhoIce * rm * rm * rm * (1.0 + 3.0 / mm_alpha + 2.0 / (mm_alpha * mm_alpha));
+            const double r_z = pow((3.0 * mm) / (4 * kPi * kRhoIce), 0.3333333);
+            const double xrz = 0.005 * pow(u_z, 1.36);
+            const double omega = c.do_fixed_settling ? c.settling_velocity : 1.1e7 * pow(r_z, 1.8);
+            const double Vr = omega + 3.0 * xrz * cos(kPi / 4.0);
+            const double Re = 2.0 * r_z * Vr / 1.88e-5;
+            const double Nu = 1.79 + 0.606 * sqrt(Re);
+            const double Sh = Nu;
+            const double sigma = (rh - 1.0) * (1.019 + 0.027 * log(cz));
+            const double Qr = 0.9 * kPi * rm * rm * 120.0;
+            const double dmdtz = Sh * rho_sat * D * (6.283185308 * Nu * Rg * r_z * sigma * t * t * lambda_t - Ls * Mw * Qr + Qr * Rg * t) /
+                                 (D * Ls * Sh * (Ls * Mw - Rg * t) * rho_sat + lambda_t * t * t * Nu * Rg);
+            double csubl = dmdtz / mm;
+            if (!c.do_sublimation) csubl = 0.0;
+            s.csubl[r] = csubl;
+
+            const double lmix = kKappa * (cz + z0) * c.l_max / (kKappa * (cz + z0) + c.l_max);
+            const double w = omega;
+            double diffusion_coeff = c.snow_diffusion_const;
+            if (c.rouault) diffusion_coeff = 1.0 / (1.0 + (1.0 * w * w) / (1.56 * ustar * ustar));
+            const double K = diffusion_coeff * ustar * lmix;
+            const double alpha3 = area * K / dz;
+            const double alpha4 = area * K / dz;
+            const double scl = u_z / nrm;
+            const double ux = vx * scl, uy = vy * scl;
+            const double udotm3 = -w, udotm4 = w;
+            const double Vc = (area * dz / 5.0) * csubl;
+
+            double d = 0.0;
+            double offj[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double udotm = ux * nxj[j] + uy * nyj[j];
+                double off = 0.0;
+                if (udotm > 0) {
+                    if (has[j]) { d += Vc - Aj[j] * udotm - alphaj[j]; off = alphaj[j]; }
+                    else d += -0.1e-1 * alphaj[j] - 1.0 * Aj[j] * udotm + Vc;
+                } else {
+                    if (has[j]) { d += Vc - alphaj[j]; off = -Aj[j] * udotm + alphaj[j]; }
+                    else d += -0.1e-1 * alphaj[j] - 0.99 * Aj[j] * udotm + Vc;
+                }
+                offj[j] = off;
+                s.lat[((size_t)j * L + z) * Tp + p] = off;
+            }
+            double lo = 0.0, up = 0.0, rhs = 0.0;
+            if (z == 0) {
+                const double alpha4p = area * K / (hs / 2.0 + dz / 2.0);
+                d += Vc - area * udotm4 - alpha4p;
+                rhs = -alpha4p * c_salt;
+                b0 = rhs;
+                s.rhs0[p] = rhs;
+                if (udotm3 > 0) { d += Vc - area * udotm3 - alpha3; up = alpha3; }
+                else { d += Vc - alpha3; up = -area * udotm3 + alpha3; }
+            } else if (z == L - 1) {
+                if (udotm3 > 0) d += Vc - area * udotm3 - alpha3;
+                else d += Vc - alpha3;
+                if (udotm4 > 0) { d += Vc - area * udotm4 - alpha4; lo = alpha4; }
+                else { d += Vc - alpha4; lo = -area * udotm4 + alpha4; }
+            } else {
+                if (udotm3 > 0) { d += Vc - area * udotm3 - alpha3; up = alpha3; }
+                else { d += Vc - alpha3; up = -area * udotm3 + alpha3; }
+                if (udotm4 > 0) { d += Vc - area * udotm4 - alpha4; lo = alpha4; }
+                else { d += Vc - alpha4; lo = -area * udotm4 + alpha4; }
+            }
+            s.diag[r] = d;
+            s.below[r] = lo;
+            s.above[r] = up;
+            // forward elimination of the column block (Thomas): den_z = d_z - lo_z * cp_{z-1}
+            const double inv = 1.0 / (d - lo * cp_prev);
+            cp_prev = up * inv;
+            s.inv[r] = inv;
+            s.cp[r] = cp_prev;
+            s.belowS[r] = lo * inv;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) s.latS[((size_t)j * L + z) * Tp + p] = offj[j] * inv;
+            if (z == 0) s.rhsS0[p] = rhs * inv;
+        }
+    }
+    return b0;
+}
+
+// Persistent-style grid (a multiple of the SM count, each block walks 128-slot tiles) so the fused reduction
+// folds a bounded number of partials.  red[0] = max|b|, red[1] = sum b^2 (this rank).
+__global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt,
+                                                       double* __restrict__ partial, int pstride, Scalars* sc,
+                                                       double* __restrict__ red) {
+    double mx = 0.0, ss = 0.0;
+    const int ntiles = (m.Tp + 127) / 128;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p = tile * 128 + threadIdx.x;
+        if (p < m.Tp) {
+            const double b0 = assemble_column(c, m, f, s, dt, p);
+            mx = fmax(mx, fabs(b0));
+            ss += b0 * b0;
+        }
+    }
+    double o0, o1;
+    if (grid_fold<2>(mx, ss, 1, 0, partial, pstride, &sc->ticket[0], o0, o1)) {
+        if (threadIdx.x == 0) { red[0] = o0; red[1] = o1; }
+    }
+}
+
+
+// -------------------------------------------------------------------------------------- step control
+// One-thread bookkeeping between phases.  `red` holds the (already globally reduced) values of the kernel before.
+enum { FLAGS_SUSP = 0, FLAGS_SUSP_CHECK = 1, FLAGS_DEP = 2, FLAGS_FORCE_SUSP_OK = 3 };
+
+__device__ __forceinline__ void susp_check(Scalars* sc, double rr, int it_now, double tol2) {
+    sc->susp_rr = rr;
+    const int k = sc->n_checks;
+    if (k < 16) { sc->rr_hist[k] = rr; sc->it_hist[k] = it_now; }
+    sc->n_checks = k + 1;
+    if (rr <= tol2 * sc->susp_bnorm2) { sc->susp_done = 1; sc->susp_iters = it_now; sc->susp_ok = 1; }
+}
+
+__global__ void flags_kernel(int stage, Scalars* sc, const double* __restrict__ red, int it_now, double tol2) {
+    switch (stage) {
+        case FLAGS_SUSP: {  // after assembly: suspension_present = ||b||_inf > 1e-12 (PBSM3D.cpp:1424-1427)
+            sc->susp_rhs_max = red[0];
+            sc->susp_bnorm2 = red[1];
+            const int present = red[0] > 1e-12;
+            sc->susp_present = present;
+            sc->susp_done = present ? 0 : 1;  // nothing to solve: the solution stays the zero vector (:1461-1465)
+            sc->susp_ok = present ? 0 : 1;
+            sc->susp_iters = 0;
+            sc->susp_rr = 0.0;
+            sc->n_checks = 0;
+            sc->dep_present = 0; sc->dep_ok = 0; sc->tail_done = 0; sc->drift_done = 0;
+            sc->done = 0; sc->iters = 0; sc->dep_rhs_max = 0.0; sc->rr = 0.0; sc->bnorm2 = 0.0;
+        } break;
+        case FLAGS_SUSP_CHECK:
+            if (!sc->susp_done) susp_check(sc, red[0], it_now, tol2);
+            break;
+        case FLAGS_DEP:  // deposition solve iff suspension_present && ||rhs||_inf > 1e-12 (PBSM3D.cpp:1661-1664)
+            if (!sc->susp_ok || sc->tail_done) break;
+            sc->dep_rhs_max = red[0];
+            sc->dep_present = (sc->susp_present && red[0] > 1e-12) ? 1 : 0;
+            sc->tail_done = 1;
+            break;
+        case FLAGS_FORCE_SUSP_OK:  // the host-driven Krylov path converged
+            sc->susp_ok = 1; sc->susp_done = 1;
+            break;
+    }
+}
+
+// ---------------------------------------------------------------------------------- line relaxation
+// HOT LOOP 2: one colour pass of the multicolour line Gauss–Seidel iteration
+//     x_c  <-  T_c^{-1} (b_c - A_lat[c,:] x)          (in place; T = vertical tridiagonal blocks, factored at assembly)
+// Faces of one colour are never edge-neighbours, so a pass only reads columns of other colours (or ghosts) and
+// writes its own: no races, no second x array, and the result is independent of scheduling.
+// One thread per face column.  Every coefficient stream (3 scaled lateral, scaled sub-diagonal, cp) is read
+// exactly once, coalesced, with the evict-first hint so the streams do not push x out of the 126 MB L2; the
+// 3·L gathers x[z*S + nbs] are branch-free and hit L1/L2.  All loads of a column are independent of the
+// Thomas recurrence, so they are issued up front and the dependent chain runs on registers.
+// LT > 0: compile-time layer count; LT == 0: any L (the own column of x is the scratch for the forward pass).
+template <int LT>
+__global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh m, int Lrt, int p0, int p1, double* x,
+                                                          const Scalars* __restrict__ sc) {
+    if (sc->susp_done) return;
+    const int Tp = m.Tp, S = m.S;
+    const int L = LT > 0 ? LT : Lrt;
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
+    const double* __restrict__ l0 = s.latS;
+    const double* __restrict__ l1 = s.latS + (size_t)L * Tp;
+    const double* __restrict__ l2 = s.latS + (size_t)2 * L * Tp;
+    if (LT > 0) {
+        double g[LT > 0 ? LT : 1];
+#pragma unroll
+        for (int z = 0; z < LT; ++z) {
+            const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
+            g[z] = -(__ldcs(l0 + r) * x[xr + n0] + __ldcs(l1 + r) * x[xr + n1] + __ldcs(l2 + r) * x[xr + n2]);
+        }
+        double bl[LT > 0 ? LT : 1], cu[LT > 0 ? LT : 1];
+#pragma unroll
+        for (int z = 0; z < LT; ++z) {
+            bl[z] = __ldcs(s.belowS + (size_t)z * Tp + p);
+            cu[z] = __ldcs(s.cp + (size_t)z * Tp + p);
+        }
+        double y = g[0] + s.rhsS0[p];
+        g[0] = y;
+#pragma unroll
+        for (int z = 1; z < LT; ++z) { y = g[z] - bl[z] * y; g[z] = y; }
+        x[(size_t)(LT - 1) * S + p] = y;
+#pragma unroll
+        for (int z = LT - 2; z >= 0; --z) { y = g[z] - cu[z] * y; x[(size_t)z * S + p] = y; }
+    } else {
+        double y = 0.0;
+        for (int z = 0; z < L; ++z) {
+            const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
+            double g = -(__ldcs(l0 + r) * x[xr + n0] + __ldcs(l1 + r) * x[xr + n1] + __ldcs(l2 + r) * x[xr + n2]);
+            if (z == 0) g += s.rhsS0[p];
+            y = g - __ldcs(s.belowS + r) * y;
+            x[xr + p] = y;
+        }
+        for (int z = L - 2; z >= 0; --z) {
+            y = x[(size_t)z * S + p] - __ldcs(s.cp + (size_t)z * Tp + p) * y;
+            x[(size_t)z * S + p] = y;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------ SpMV / residual
-__device__ __forceinline__ double gather_x(const double* __restrict__ x, const double* __restrict__ xg, const DevMesh& m,
-                                           int L, int n, int z) {
-    if (n < m.T) return x[(size_t)z * m.T + n];
-    const int g = n - m.T, gs = m.gstart[g];
-    return xg[(size_t)L * gs + (size_t)z * m.gcnt[g] + (g - gs)];
-}
-
-// Row of A·x in the extruded-ELL layout: lateral gathers x[z*T + neigh_j], vertical x[(z±1)*T + i].
-__device__ __forceinline__ double spmv_row(const SuspSystem& s, const DevMesh& m, int L, const double* __restrict__ x,
-                                           const double* __restrict__ xg, int z, int i) {
-    const int T = m.T;
-    const size_t r = (size_t)z * T + i;
-    double acc = s.diag[r] * x[r];
+// Row of A·x in the extruded-ELL layout: lateral gathers x[z*S + nbs_j], vertical x[(z±1)*S + p].
+__device__ __forceinline__ double spmv_row(const SuspSystem& s, const DevMesh& m, int L, const double* __restrict__ x, int z, int p) {
+    const int Tp = m.Tp, S = m.S;
+    const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
+    double acc = s.diag[r] * x[xr + p];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        int n = m.neigh[(size_t)j * T + i];
-        if (n >= 0) acc += s.lat[((size_t)j * L + z) * T + i] * gather_x(x, xg, m, L, n, z);
-    }
-    if (z > 0) acc += s.below[r] * x[r - T];
-    if (z < L - 1) acc += s.above[r] * x[r + T];
+    for (int j = 0; j < 3; ++j) acc += s.lat[((size_t)j * L + z) * Tp + p] * x[xr + m.nbs[(size_t)j * Tp + p]];
+    if (z > 0) acc += s.below[r] * x[xr - S + p];
+    if (z < L - 1) acc += s.above[r] * x[xr + S + p];
     return acc;
 }
 
-// mode 0: y = A x.   mode 1: y = b - A x (b is non-zero only in layer 0).  Optionally accumulates up to two
-// dot products with the freshly produced y: partial[b] = <y, d0>, partial[stride+b] = <y, d1 or y>.
-// Grid-stride over rows with a grid that is a multiple of the SM count; partials make the sums deterministic.
-template <int MODE>
-__global__ void __launch_bounds__(256) spmv_kernel(SuspSystem s, DevMesh m, int L, const double* __restrict__ x,
-                                                   const double* __restrict__ xg, double* __restrict__ y,
-                                                   const double* __restrict__ d0, const double* __restrict__ d1,
-                                                   int self_dot, double* __restrict__ partial, int stride,
-                                                   const int* __restrict__ done) {
+// True residual of the line solver: ||b - A x||_2^2 of this rank into red[0]; with `fused` (single rank) the
+// last block also applies the stopping rule ||b-Ax|| <= tol ||b|| (LinearAlgebra.cpp:168, x0 = 0).
+__global__ void __launch_bounds__(kRedThreads) residual_kernel(SuspSystem s, DevMesh m, int L, const double* __restrict__ x,
+                                                               double* __restrict__ partial, int pstride, Scalars* sc,
+                                                               double* __restrict__ red, int it_now, double tol2, int fused) {
+    if (sc->susp_done) return;
+    const int Tp = m.Tp;
+    const size_t N = (size_t)L * Tp;
+    double a = 0.0;
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (size_t)gridDim.x * blockDim.x) {
+        const int z = (int)(r / Tp), p = (int)(r - (size_t)z * Tp);
+        const double v = ((z == 0) ? s.rhs0[p] : 0.0) - spmv_row(s, m, L, x, z, p);
+        a += v * v;
+    }
+    double rr, unused;
+    if (grid_fold<1>(a, 0.0, 0, 0, partial, pstride, &sc->ticket[1], rr, unused)) {
+        if (threadIdx.x == 0) {
+            red[0] = rr;
+            if (fused) susp_check(sc, rr, it_now, tol2);
+        }
+    }
+}
+
+// y = A x on ghost-extended vectors (Krylov path), optionally with <y,d0> and <y,d1|y> partials.
+__global__ void __launch_bounds__(kRedThreads) spmv_kernel(SuspSystem s, DevMesh m, int L, const double* __restrict__ x,
+                                                           double* __restrict__ y, const double* __restrict__ d0,
+                                                           const double* __restrict__ d1, int self_dot,
+                                                           double* __restrict__ partial, int stride, const int* __restrict__ done) {
     if (done && *done) return;
-    const int T = m.T;
-    const size_t N = (size_t)L * T;
+    const int Tp = m.Tp, S = m.S;
+    const size_t N = (size_t)L * Tp;
     double a0 = 0.0, a1 = 0.0;
     for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (size_t)gridDim.x * blockDim.x) {
-        int z = (int)(r / T), i = (int)(r - (size_t)z * T);
-        double v = spmv_row(s, m, L, x, xg, z, i);
-        if (MODE == 1) v = ((z == 0) ? s.rhs0[i] : 0.0) - v;
-        if (y) y[r] = v;
-        if (d0) a0 += v * d0[r];
-        if (d1) a1 += v * d1[r];
+        const int z = (int)(r / Tp), p = (int)(r - (size_t)z * Tp);
+        const size_t e = (size_t)z * S + p;
+        const double v = spmv_row(s, m, L, x, z, p);
+        if (y) y[e] = v;
+        if (d0) a0 += v * d0[e];
+        if (d1) a1 += v * d1[e];
         else if (self_dot) a1 += v * v;
     }
     if (partial) {
@@ -451,78 +673,49 @@ __global__ void __launch_bounds__(256) spmv_kernel(SuspSystem s, DevMesh m, int 
     }
 }
 
-// ---------------------------------------------------------------------------------- line relaxation
-// One sweep of the stationary column-block-Jacobi iteration  x_new = T^{-1} (b - A_lat x_old):
-// T = the vertical tridiagonal blocks (factored in assemble_kernel), A_lat = the three lateral couplings.
-// One thread per face column; every stream is read exactly once, coalesced; x_old gathers hit L2.
-// LT > 0: compile-time layer count (the forward-substitution column stays in registers);
-// LT == 0: any L, the column is staged through x_new.
-template <int LT>
-__global__ void __launch_bounds__(128) line_sweep_kernel(SuspSystem s, DevMesh m, int Lrt, const double* __restrict__ x_old,
-                                                         const double* __restrict__ xg_old, double* __restrict__ x_new,
-                                                         const int* __restrict__ done) {
-    if (done && *done) return;
-    const int T = m.T;
-    const int L = LT > 0 ? LT : Lrt;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
-    int nb[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) nb[j] = m.neigh[(size_t)j * T + i];
-    double dp[LT > 0 ? LT : 1];
-    double prev = 0.0;
-#pragma unroll
-    for (int z = 0; z < L; ++z) {
-        const size_t r = (size_t)z * T + i;
-        double g = (z == 0) ? s.rhs0[i] : 0.0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            if (nb[j] >= 0) g -= s.lat[((size_t)j * L + z) * T + i] * gather_x(x_old, xg_old, m, L, nb[j], z);
-        prev = (g - s.below[r] * prev) * s.inv[r];
-        if (LT > 0) dp[z] = prev;
-        else x_new[r] = prev;
-    }
-    double xn = prev;
-    x_new[(size_t)(L - 1) * T + i] = xn;
-#pragma unroll
-    for (int z = L - 2; z >= 0; --z) {
-        const size_t r = (size_t)z * T + i;
-        const double d = (LT > 0) ? dp[z] : x_new[r];
-        xn = d - s.cp[r] * xn;
-        x_new[r] = xn;
+// Final stage of the unfused reductions (Krylov path): one block folds `nvals` partial arrays into out[v].
+__global__ void __launch_bounds__(256) fold_kernel(int nblocks, int nvals, int stride, const double* __restrict__ partial,
+                                                   double* __restrict__ out, int op) {
+    for (int v = 0; v < nvals; ++v) {
+        double a = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+            double q = partial[(size_t)v * stride + b];
+            a = op ? fmax(a, q) : a + q;
+        }
+        a = op ? block_max(a) : block_sum(a);
+        if (threadIdx.x == 0) out[v] = a;
     }
 }
 
 // Column-tridiagonal preconditioner apply y = T^{-1} v (right preconditioner of the Krylov path).
-__global__ void __launch_bounds__(128) thomas_kernel(SuspSystem s, int T, int L, const double* __restrict__ v,
+__global__ void __launch_bounds__(128) thomas_kernel(SuspSystem s, int Tp, int S, int L, const double* __restrict__ v,
                                                      double* __restrict__ y, const int* __restrict__ done) {
     if (done && *done) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp) return;
     double prev = 0.0;
     for (int z = 0; z < L; ++z) {
-        const size_t r = (size_t)z * T + i;
-        prev = (v[r] - s.below[r] * prev) * s.inv[r];
-        y[r] = prev;
+        const size_t r = (size_t)z * Tp + p;
+        prev = (v[(size_t)z * S + p] - s.below[r] * prev) * s.inv[r];
+        y[(size_t)z * S + p] = prev;
     }
     double xn = prev;
     for (int z = L - 2; z >= 0; --z) {
-        const size_t r = (size_t)z * T + i;
-        xn = y[r] - s.cp[r] * xn;
-        y[r] = xn;
+        xn = y[(size_t)z * S + p] - s.cp[(size_t)z * Tp + p] * xn;
+        y[(size_t)z * S + p] = xn;
     }
 }
 
 // ------------------------------------------------------------------------------------------ BiCGStab
-// Right-preconditioned BiCGStab, all recurrence scalars on the device (no host round trip per iteration).
-// init: r = b (x0 = 0), rhat = r, p = v = 0, rho = alpha = omega = 1; partial <- ||b||^2.
-__global__ void __launch_bounds__(256) bicg_init_kernel(int T, int L, const double* __restrict__ rhs0, double* __restrict__ x,
+// Right-preconditioned BiCGStab (fallback / cross-check solver), recurrence scalars on the device.  Vectors are
+// ghost-extended [L][S]; r, rhat, p, v, t keep zero ghost tails, so flat dot products over L*S are exact.
+__global__ void __launch_bounds__(256) bicg_init_kernel(int Tp, int S, int L, const double* __restrict__ rhs0, double* __restrict__ x,
                                                         double* __restrict__ r, double* __restrict__ rhat, double* __restrict__ p,
                                                         double* __restrict__ v, double* __restrict__ partial) {
-    const size_t N = (size_t)L * T;
+    const size_t N = (size_t)L * S;
     double a = 0.0;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
-        double b = (k < (size_t)T) ? rhs0[k] : 0.0;
+        double b = (k < (size_t)Tp) ? rhs0[k] : 0.0;
         x[k] = 0.0; r[k] = b; rhat[k] = b; p[k] = 0.0; v[k] = 0.0;
         a += b * b;
     }
@@ -571,17 +764,11 @@ __global__ void __launch_bounds__(256) bicg_xr_kernel(size_t N, const Scalars* _
     a1 = block_sum(a1);
     if (threadIdx.x == 0) partial[stride + blockIdx.x] = a1;
 }
-// x += alpha ph (early exit of the half step)
-__global__ void __launch_bounds__(256) axpy_scalar_kernel(size_t N, const double* __restrict__ a, const double* __restrict__ p,
-                                                          double* __restrict__ x) {
-    const double al = *a;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) x[k] += al * p[k];
-}
 
 // Scalar updates (one thread).  `red` holds the globally reduced dot products of the preceding kernel.
 // stage 0: after init            red[0] = ||b||^2
 // stage 1: after v = A ph        red[0] = <rhat, v>           -> alpha
-// stage 2: after s               red[0] = ||s||^2             -> half-step convergence
+// stage 2: after s               red[0] = ||s||^2             -> half-step residual
 // stage 3: after t = A sh        red[0] = <t,s>, red[1]=<t,t> -> omega
 // stage 4: after x,r update      red[0] = <rhat,r>, red[1] = ||r||^2 -> beta, rho, convergence
 __global__ void bicg_scalar_kernel(int stage, Scalars* sc, const double* __restrict__ red, double tol2) {
@@ -599,7 +786,7 @@ __global__ void bicg_scalar_kernel(int stage, Scalars* sc, const double* __restr
             sc->alpha = sc->rho / den;
         } break;
         case 2:
-            sc->tmp[0] = red[0];  // ||s||^2 (reported if we stop at the half step)
+            sc->tmp[0] = red[0];
             break;
         case 3: {
             double tt = red[1];
@@ -620,191 +807,238 @@ __global__ void bicg_scalar_kernel(int stage, Scalars* sc, const double* __restr
 
 // ------------------------------------------------------------------------------------ flux integration
 // reference PBSM3D.cpp:1467-1503: c = max(0,x) (NaN -> 0); Qsusp = sum c u_z dz; Qsubl = sum csubl c dz.
-__global__ void __launch_bounds__(256) flux_kernel(int T, int L, double dz, double dt, const double* __restrict__ x,
-                                                   const double* __restrict__ u_z, const double* __restrict__ csubl,
-                                                   double* __restrict__ Qsusp, double* __restrict__ Qsubl,
-                                                   double* __restrict__ Qsubl_mass, double* __restrict__ sum_subl) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
+__global__ void __launch_bounds__(256) flux_kernel(int Tp, int S, int L, double dz, double dt, const int* __restrict__ perm,
+                                                   const double* __restrict__ x, const double* __restrict__ u_z,
+                                                   const double* __restrict__ csubl, double* __restrict__ Qsusp,
+                                                   double* __restrict__ Qsubl, double* __restrict__ Qsubl_mass,
+                                                   double* __restrict__ sum_subl, const Scalars* __restrict__ sc) {
+    if (!sc->susp_ok || sc->tail_done) return;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp) return;
     double qs = 0.0, ql = 0.0;
     for (int z = 0; z < L; ++z) {
-        const size_t r = (size_t)z * T + i;
-        double c = x[r];
+        const size_t r = (size_t)z * Tp + p;
+        double c = x[(size_t)z * S + p];
         c = (c < 0 || chm_is_nan(c)) ? 0.0 : c;
         qs += c * u_z[r] * dz;
         ql += csubl[r] * c * dz;
     }
-    Qsusp[i] = qs;
-    Qsubl[i] = ql;
+    Qsusp[p] = qs;
+    Qsubl[p] = ql;
     const double qm = ql * dt;
-    Qsubl_mass[i] = qm;
-    sum_subl[i] += qm;
+    Qsubl_mass[p] = qm;
+    sum_subl[p] += qm;
 }
 
 // --------------------------------------------------------------------------------------- deposition
 // RHS of the deposition system with the upwind donor rule (PBSM3D.cpp:1523-1656); the matrix is static.
-// Qsusp/Qsalt of ghost faces come from qg (per owner block [2][gcnt]: Qsusp then Qsalt) after the halo exchange.
+// Qsusp/Qsalt are ghost-extended [S] (tails filled by the halo exchange).  red[0] = max|rhs| of this rank.
 __global__ void __launch_bounds__(256) deposition_rhs_kernel(DevMesh m, const double* __restrict__ vw_dir,
                                                              const double* __restrict__ Qsusp, const double* __restrict__ Qsalt,
-                                                             const double* __restrict__ qg, double* __restrict__ rhs,
-                                                             double* __restrict__ partial) {
-    const int T = m.T;
+                                                             double* __restrict__ rhs, double* __restrict__ partial, int pstride,
+                                                             Scalars* sc, double* __restrict__ red) {
+    if (!sc->susp_ok || sc->tail_done) return;
+    const int Tp = m.Tp;
     double val_abs = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
-        double vx, vy;
-        wind_unit_vector(vw_dir[i], vx, vy);
-        const double own_t = Qsusp[i], own_s = Qsalt[i];
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < Tp; p += gridDim.x * blockDim.x) {
+        const int i = m.perm[p];
         double acc = 0.0;
+        if (i >= 0) {
+            double vx, vy;
+            wind_unit_vector(vw_dir[i], vx, vy);
+            const double own_t = Qsusp[p], own_s = Qsalt[p];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const double udotm = vx * m.nx[(size_t)j * T + i] + vy * m.ny[(size_t)j * T + i];
-            const double E = m.elen[(size_t)j * T + i];
-            const int n = m.neigh[(size_t)j * T + i];
-            double Qt = own_t, Qs = own_s;
-            if (!(udotm > 0) && n >= 0) {
-                if (n < T) { Qt = Qsusp[n]; Qs = Qsalt[n]; }
-                else {
-                    const int g = n - T, gs = m.gstart[g], gc = m.gcnt[g];
-                    Qt = qg[(size_t)2 * gs + (g - gs)];
-                    Qs = qg[(size_t)2 * gs + gc + (g - gs)];
+            for (int j = 0; j < 3; ++j) {
+                const double udotm = vx * m.nx[(size_t)j * Tp + p] + vy * m.ny[(size_t)j * Tp + p];
+                const double E = m.elen[(size_t)j * Tp + p];
+                const int n = m.nbs[(size_t)j * Tp + p];
+                double Qt = own_t, Qs = own_s;
+                if (!(udotm > 0) && n != p) {
+                    Qt = Qsusp[n];
+                    Qs = Qsalt[n];
+                    if (chm_is_nan(Qs)) Qs = 0.0;
                 }
-                if (chm_is_nan(Qs)) Qs = 0.0;
+                acc += -E * (Qt + Qs) * udotm;
             }
-            acc += -E * (Qt + Qs) * udotm;
         }
-        rhs[i] = acc;
+        rhs[p] = acc;
         val_abs = fmax(val_abs, fabs(acc));
     }
-    val_abs = block_max(val_abs);
-    if (threadIdx.x == 0) partial[blockIdx.x] = val_abs;
-}
-
-__device__ __forceinline__ double dep_row(const DevMesh& m, const double* __restrict__ ddiag, const double* __restrict__ doff,
-                                          const double* __restrict__ p, const double* __restrict__ pg, int i) {
-    const int T = m.T;
-    double acc = ddiag[i] * p[i];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        int n = m.neigh[(size_t)j * T + i];
-        if (n >= 0) acc += doff[(size_t)j * T + i] * (n < T ? p[n] : pg[n - T]);
+    double mx, unused;
+    if (grid_fold<1>(val_abs, 0.0, 1, 0, partial, pstride, &sc->ticket[2], mx, unused)) {
+        if (threadIdx.x == 0) red[0] = mx;
     }
-    return acc;
 }
 
-// Jacobi-preconditioned CG on the (SPD) deposition system, scalars on the device.
-// init: x = 0, r = b, z = r/diag, p = z; partials <- <r,z>, <r,r>
-__global__ void __launch_bounds__(256) cg_init_kernel(int T, const double* __restrict__ b, const double* __restrict__ dinv,
-                                                      double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
-                                                      double* __restrict__ partial, int stride) {
+// Jacobi-preconditioned CG on the (SPD) deposition system; q, r, Ap are [Tp], the search direction pv is
+// ghost-extended [S].  Recurrence scalars live on the device; on a single rank the block that folds a dot
+// product also updates them (FUSED), so one iteration is three launches and no host round trip.
+__device__ __forceinline__ void cg_scalars(int stage, Scalars* sc, double r0, double r1, double tol2) {
+    switch (stage) {
+        case 0:
+            sc->rho = r0; sc->bnorm2 = r1; sc->rr = r1;
+            sc->done = (r1 == 0.0) ? 1 : 0; sc->iters = 0; sc->beta = 0.0; sc->alpha = 0.0;
+            if (r1 == 0.0) sc->dep_ok = 1;
+            break;
+        case 1:
+            if (r0 == 0.0 || isnan(r0)) { sc->done = 2; break; }
+            sc->alpha = sc->rho / r0;
+            break;
+        case 2:
+            sc->iters += 1;
+            sc->rr = r1;
+            if (r1 <= tol2 * sc->bnorm2) { sc->done = 1; sc->dep_ok = 1; break; }
+            if (isnan(r0)) { sc->done = 2; break; }
+            sc->beta = r0 / sc->rho;
+            sc->rho = r0;
+            break;
+    }
+}
+__global__ void cg_scalar_kernel(int stage, Scalars* sc, const double* __restrict__ red, double tol2) {
+    if (!sc->tail_done || !sc->dep_present) return;
+    if (stage != 0 && sc->done) return;
+    cg_scalars(stage, sc, red[0], red[1], tol2);
+}
+// init: q = 0, r = b, z = r/diag, p = z; red <- <r,z>, <r,r>
+__global__ void __launch_bounds__(kRedThreads) cg_init_kernel(int Tp, const double* __restrict__ b, const double* __restrict__ dinv,
+                                                              double* __restrict__ q, double* __restrict__ r, double* __restrict__ pv,
+                                                              double* __restrict__ partial, int pstride, Scalars* sc,
+                                                              double* __restrict__ red, double tol2, int fused) {
+    if (!sc->tail_done || !sc->dep_present) return;
     double a0 = 0.0, a1 = 0.0;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < T; k += gridDim.x * blockDim.x) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Tp; k += gridDim.x * blockDim.x) {
         double rv = b[k], zv = rv * dinv[k];
-        x[k] = 0.0; r[k] = rv; p[k] = zv;
+        q[k] = 0.0; r[k] = rv; pv[k] = zv;
         a0 += rv * zv; a1 += rv * rv;
     }
-    a0 = block_sum(a0);
-    if (threadIdx.x == 0) partial[blockIdx.x] = a0;
-    a1 = block_sum(a1);
-    if (threadIdx.x == 0) partial[stride + blockIdx.x] = a1;
-}
-// Ap = A p ; partial <- <p, Ap>
-__global__ void __launch_bounds__(256) cg_spmv_kernel(DevMesh m, const double* __restrict__ ddiag, const double* __restrict__ doff,
-                                                      const double* __restrict__ p, const double* __restrict__ pg,
-                                                      double* __restrict__ Ap, double* __restrict__ partial,
-                                                      const Scalars* __restrict__ sc) {
-    if (sc && sc->done) return;
-    double a = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.T; i += gridDim.x * blockDim.x) {
-        double v = dep_row(m, ddiag, doff, p, pg, i);
-        Ap[i] = v;
-        a += v * p[i];
+    double o0, o1;
+    if (grid_fold<2>(a0, a1, 0, 0, partial, pstride, &sc->ticket[3], o0, o1)) {
+        if (threadIdx.x == 0) { red[0] = o0; red[1] = o1; if (fused) cg_scalars(0, sc, o0, o1, tol2); }
     }
-    if (partial) { a = block_sum(a); if (threadIdx.x == 0) partial[blockIdx.x] = a; }
 }
-// x += alpha p ; r -= alpha Ap ; partials <- <r, r/diag>, <r,r>
-__global__ void __launch_bounds__(256) cg_update_kernel(int T, const Scalars* __restrict__ sc, const double* __restrict__ dinv,
-                                                        const double* __restrict__ p, const double* __restrict__ Ap,
-                                                        double* __restrict__ x, double* __restrict__ r,
-                                                        double* __restrict__ partial, int stride) {
-    if (sc->done) return;
+__device__ __forceinline__ bool cg_idle(const Scalars* sc) { return !sc->tail_done || !sc->dep_present || sc->done; }
+// Ap = A p ; red[0] <- <p, Ap>
+__global__ void __launch_bounds__(kRedThreads) cg_spmv_kernel(DevMesh m, const double* __restrict__ ddiag,
+                                                              const double* __restrict__ doff, const double* __restrict__ pv,
+                                                              double* __restrict__ Ap, double* __restrict__ partial, int pstride,
+                                                              Scalars* sc, double* __restrict__ red, double tol2, int fused) {
+    if (sc && cg_idle(sc)) return;
+    const int Tp = m.Tp;
+    double a = 0.0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < Tp; p += gridDim.x * blockDim.x) {
+        const double pp = pv[p];
+        double v = ddiag[p] * pp;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v += doff[(size_t)j * Tp + p] * pv[m.nbs[(size_t)j * Tp + p]];
+        Ap[p] = v;
+        a += v * pp;
+    }
+    if (!sc) return;
+    double o0, unused;
+    if (grid_fold<1>(a, 0.0, 0, 0, partial, pstride, &sc->ticket[3], o0, unused)) {
+        if (threadIdx.x == 0) { red[0] = o0; red[1] = 0.0; if (fused) cg_scalars(1, sc, o0, 0.0, tol2); }
+    }
+}
+// q += alpha p ; r -= alpha Ap ; red <- <r, r/diag>, <r,r>
+__global__ void __launch_bounds__(kRedThreads) cg_update_kernel(int Tp, Scalars* sc, const double* __restrict__ dinv,
+                                                                const double* __restrict__ pv, const double* __restrict__ Ap,
+                                                                double* __restrict__ q, double* __restrict__ r,
+                                                                double* __restrict__ partial, int pstride, double* __restrict__ red,
+                                                                double tol2, int fused) {
+    if (cg_idle(sc)) return;
     const double alpha = sc->alpha;
     double a0 = 0.0, a1 = 0.0;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < T; k += gridDim.x * blockDim.x) {
-        x[k] += alpha * p[k];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Tp; k += gridDim.x * blockDim.x) {
+        q[k] += alpha * pv[k];
         double rv = r[k] - alpha * Ap[k];
         r[k] = rv;
         a0 += rv * rv * dinv[k];
         a1 += rv * rv;
     }
-    a0 = block_sum(a0);
-    if (threadIdx.x == 0) partial[blockIdx.x] = a0;
-    a1 = block_sum(a1);
-    if (threadIdx.x == 0) partial[stride + blockIdx.x] = a1;
-}
-// p = r/diag + beta p
-__global__ void __launch_bounds__(256) cg_p_kernel(int T, const Scalars* __restrict__ sc, const double* __restrict__ dinv,
-                                                   const double* __restrict__ r, double* __restrict__ p) {
-    if (sc->done) return;
-    const double beta = sc->beta;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < T; k += gridDim.x * blockDim.x) p[k] = r[k] * dinv[k] + beta * p[k];
-}
-// stage 0: after init red = {<r,z>, <r,r>}; stage 1: after spmv red[0] = <p,Ap>; stage 2: after update red = {<r,z>,<r,r>}
-__global__ void cg_scalar_kernel(int stage, Scalars* sc, const double* __restrict__ red, double tol2) {
-    if (stage != 0 && sc->done) return;
-    switch (stage) {
-        case 0:
-            sc->rho = red[0]; sc->bnorm2 = red[1]; sc->rr = red[1];
-            sc->done = (red[1] == 0.0) ? 1 : 0; sc->iters = 0; sc->beta = 0.0; sc->alpha = 0.0;
-            break;
-        case 1: {
-            double den = red[0];
-            if (den == 0.0 || isnan(den)) { sc->done = 2; break; }
-            sc->alpha = sc->rho / den;
-        } break;
-        case 2:
-            sc->iters += 1;
-            sc->rr = red[1];
-            if (red[1] <= tol2 * sc->bnorm2) { sc->done = 1; break; }
-            if (isnan(red[0])) { sc->done = 2; break; }
-            sc->beta = red[0] / sc->rho;
-            sc->rho = red[0];
-            break;
+    double o0, o1;
+    if (grid_fold<2>(a0, a1, 0, 0, partial, pstride, &sc->ticket[3], o0, o1)) {
+        if (threadIdx.x == 0) { red[0] = o0; red[1] = o1; if (fused) cg_scalars(2, sc, o0, o1, tol2); }
     }
 }
+// p = r/diag + beta p
+__global__ void __launch_bounds__(kRedThreads) cg_p_kernel(int Tp, const Scalars* __restrict__ sc, const double* __restrict__ dinv,
+                                                           const double* __restrict__ r, double* __restrict__ pv) {
+    if (cg_idle(sc)) return;
+    const double beta = sc->beta;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Tp; k += gridDim.x * blockDim.x) pv[k] = r[k] * dinv[k] + beta * pv[k];
+}
 
-// Drift update (PBSM3D.cpp:1710-1740).
-__global__ void __launch_bounds__(256) drift_kernel(int T, double dt, const double* __restrict__ q, const double* __restrict__ swe_in,
-                                                    const unsigned char* __restrict__ salt, double* __restrict__ drift_mass,
-                                                    double* __restrict__ sum_drift, double* __restrict__ more_than_avail) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
-    double qdep = q[i];
+// Drift update (PBSM3D.cpp:1710-1740); runs only when the deposition solve happened and converged, otherwise
+// drift_mass keeps its previous value as in the reference.  swe is in CHM order.
+__global__ void __launch_bounds__(256) drift_kernel(int Tp, double dt, const int* __restrict__ perm, const double* __restrict__ q,
+                                                    const double* __restrict__ swe_in, const unsigned char* __restrict__ salt,
+                                                    double* __restrict__ drift_mass, double* __restrict__ sum_drift,
+                                                    double* __restrict__ more_than_avail, const Scalars* __restrict__ sc) {
+    if (!sc->dep_ok || sc->drift_done) return;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp) return;
+    const int i = perm[p];
+    if (i < 0) return;
+    double qdep = q[p];
     qdep = chm_is_nan(qdep) ? 0.0 : qdep;
     double mass = qdep * dt;
     double swe = swe_in[i];
     swe = chm_is_nan(swe) ? 0.0 : swe;
-    if (mass < 0 && fabs(mass) > swe) { more_than_avail[i] = 1.0; mass = -swe; }
-    if (mass < 0 && !salt[i]) mass = 0.0;
-    drift_mass[i] = mass;
-    sum_drift[i] += mass;
+    if (mass < 0 && fabs(mass) > swe) { more_than_avail[p] = 1.0; mass = -swe; }
+    if (mass < 0 && !salt[p]) mass = 0.0;
+    drift_mass[p] = mass;
+    sum_drift[p] += mass;
+}
+__global__ void drift_done_kernel(Scalars* sc) {
+    if (sc->dep_ok) sc->drift_done = 1;
+}
+
+// Outputs back to CHM face order (the order of every array that crosses the C-ABI).
+struct ExportPtrs {
+    const double* src[8];
+    double* dst[8];
+};
+__global__ void __launch_bounds__(256) export_kernel(int T, const int* __restrict__ iperm, ExportPtrs e) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const int p = iperm[i];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (e.dst[k]) e.dst[k][i] = e.src[k][p];
+}
+// dst[iperm[i]] = src[i] (state restore)
+__global__ void from_chm_kernel(int T, const int* __restrict__ iperm, const double* __restrict__ src, double* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T) dst[iperm[i]] = src[i];
 }
 
 // ---------------------------------------------------------------------------------------------- halo
-// Pack the rows of the faces a partner needs into its send block: buf[off_p*nl + z*cnt_p + k] = v[z*T + idx[k]].
-// seg[] maps each packed entry to (partner block offset, count, position) so one launch serves all partners.
-__global__ void __launch_bounds__(256) halo_pack_kernel(int n_send, int nl, int T, const int* __restrict__ send_idx,
+// Pack the rows of the faces a partner needs into its send block: buf[off_p*nl + z*cnt_p + k] = v[z*S + slot[k]].
+__global__ void __launch_bounds__(256) halo_pack_kernel(int n_send, int nl, int S, const int* __restrict__ send_slot,
                                                         const int* __restrict__ send_boff, const int* __restrict__ send_cnt,
                                                         const int* __restrict__ send_pos, const double* __restrict__ v,
                                                         double* __restrict__ buf) {
     size_t total = (size_t)n_send * nl;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         int z = (int)(e / n_send), k = (int)(e - (size_t)z * n_send);
-        buf[(size_t)send_boff[k] * nl + (size_t)z * send_cnt[k] + send_pos[k]] = v[(size_t)z * T + send_idx[k]];
+        buf[(size_t)send_boff[k] * nl + (size_t)z * send_cnt[k] + send_pos[k]] = v[(size_t)z * S + send_slot[k]];
+    }
+}
+// Received blocks (per owner [nl][cnt]) into the ghost tails: v[z*S + Tp + g] = buf[gstart*nl + z*gcnt + (g-gstart)].
+__global__ void __launch_bounds__(256) halo_unpack_kernel(int nG, int nl, int Tp, int S, const int* __restrict__ gstart,
+                                                          const int* __restrict__ gcnt, const double* __restrict__ buf,
+                                                          double* __restrict__ v) {
+    size_t total = (size_t)nG * nl;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int z = (int)(e / nG), g = (int)(e - (size_t)z * nG);
+        const int gs = gstart[g];
+        v[(size_t)z * S + Tp + g] = buf[(size_t)gs * nl + (size_t)z * gcnt[g] + (g - gs)];
     }
 }
 
-__global__ void fill_kernel(size_t n, double* __restrict__ p, double v) {
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) p[k] = v;
+__global__ void fill_slots_kernel(int Tp, const int* __restrict__ perm, double* __restrict__ a, double v) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < Tp) a[p] = perm[p] >= 0 ? v : 0.0;
 }
 
 }  // namespace pbsm3d

@@ -47,7 +47,7 @@ enum {
 
 enum {
     PBSM3D_SOLVER_AUTO = 0,     /* line relaxation, falling back to BiCGStab if it stagnates */
-    PBSM3D_SOLVER_LINE = 1,     /* stationary column-block-Jacobi sweeps (exact vertical tridiagonal solve) */
+    PBSM3D_SOLVER_LINE = 1,     /* multicolour line Gauss-Seidel sweeps (exact vertical tridiagonal solve per face column) */
     PBSM3D_SOLVER_BICGSTAB = 2  /* right-preconditioned BiCGStab, column-tridiagonal preconditioner */
 };
 
@@ -137,7 +137,7 @@ typedef struct pbsm3d_outputs {
 typedef struct pbsm3d_stats {
     int32_t suspension_present;
     int32_t deposition_present;
-    int32_t suspension_iterations;   /* sweeps (line) or matvec pairs (BiCGStab) */
+    int32_t suspension_iterations;   /* full sweeps (line) or matvec pairs (BiCGStab) until the stopping rule held */
     int32_t deposition_iterations;
     int32_t suspension_solver_used;  /* PBSM3D_SOLVER_LINE / _BICGSTAB */
     int32_t kernel_launches;         /* kernels of this library launched by the step */
@@ -150,7 +150,9 @@ typedef struct pbsm3d_stats {
     float ms_flux_and_halo;
     float ms_deposition;
     float ms_total;
-    float ms_line_sweeps;            /* CUDA-event time spent in line-sweep launches (sum over the step) */
+    float ms_line_sweeps;            /* CUDA-event time of the first `sweeps_timed` line sweeps of this step */
+    int32_t sweeps_timed;            /* full sweeps (all colours) inside ms_line_sweeps */
+    int32_t n_colours;               /* colour classes of the internal face order */
 } pbsm3d_stats;
 
 typedef struct pbsm3d_handle pbsm3d_handle;
@@ -184,6 +186,9 @@ int pbsm3d_set_state(pbsm3d_handle* h, const double* sum_drift, const double* su
 /* Device-computed face geometry, each [3][n_local] or [n_local] (NULL = skip). */
 int pbsm3d_get_geometry(pbsm3d_handle* h, double* nx, double* ny, double* edge_length, double* area, double* dx,
                         double* cx, double* cy, double* cz);
+/* Internal layout (tests / diagnostics): number of colour classes, number of padded slots, and for every local
+ * face its slot in the colour-major device order and its colour (each [n_local]; any pointer may be NULL). */
+int pbsm3d_get_layout(pbsm3d_handle* h, int32_t* n_colours, int32_t* n_slots, int32_t* slot_of_face, int32_t* colour_of_face);
 /* Suspended concentration of the last step, layout x[z*n_local + local_id] (LinearAlgebra.cpp:81). */
 int pbsm3d_get_solution(pbsm3d_handle* h, double* x);
 /* Last assembled suspension system in extruded-ELL form, each [nLayer][n_local] except lat [3][nLayer][n_local]
@@ -195,7 +200,7 @@ int pbsm3d_get_deposition_system(pbsm3d_handle* h, double* diag, double* off, do
 
 /* Stand-alone kernels for measurement (bench.py roofline line, ncu): run `reps` launches of the named kernel on
  * the last assembled system and return the mean CUDA-event time per launch in milliseconds.
- * kernel: 0 = line sweep, 1 = SpMV/residual, 2 = assembly, 3 = deposition SpMV. */
+ * kernel: 0 = one full line sweep (all colour passes), 1 = residual (SpMV), 2 = assembly, 3 = deposition SpMV. */
 int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms_per_launch);
 
 #ifdef __cplusplus

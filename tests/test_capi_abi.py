@@ -50,7 +50,7 @@ def test_struct_layouts_match_header(lib):
     # 20 ints/doubles + 3 solver fields; natural alignment, no packing pragmas in the header
     assert C.sizeof(capi.Forcing) == 8 * 8 and C.sizeof(capi.Outputs) == 8 * 8
     assert C.sizeof(capi.Comm) == 16
-    assert C.sizeof(capi.Stats) == 6 * 4 + 4 * 8 + 6 * 4
+    assert C.sizeof(capi.Stats) == 6 * 4 + 4 * 8 + 6 * 4 + 2 * 4
     assert C.sizeof(capi.Mesh) == 8 + 4 + 4 + 10 * 8
 
 

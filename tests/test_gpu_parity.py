@@ -197,7 +197,10 @@ def test_state_roundtrip_and_checkpoint(granger):
     b.set_state(**st)
     oa, _ = a.step(3600.0, F)
     ob, _ = b.step(3600.0, F)
-    assert np.array_equal(oa["sum_drift"], ob["sum_drift"]) and np.array_equal(oa["sum_subl"], ob["sum_subl"])
+    # the restored handle schedules its sweeps without history, so the two runs stop at different (both converged)
+    # iterates: equal to solver tolerance, and exactly equal in the state that was carried over
+    assert rel_l2(oa["sum_drift"], ob["sum_drift"]) <= 1e-7 and rel_l2(oa["sum_subl"], ob["sum_subl"]) <= 1e-7
+    assert np.array_equal(b.get_state()["pbsm_more_than_avail"], a.get_state()["pbsm_more_than_avail"])
     a.close()
     b.close()
 
@@ -223,3 +226,48 @@ def test_error_paths_on_device(granger):
         mod.run(dom)
     h.close()
     mod.close()
+
+
+@pytest.mark.parametrize("which", ["granger1m", "slope_metis", "uniform", "variable"])
+def test_colour_major_layout_is_a_proper_colouring(which):
+    """The device order is a permutation of CHM's faces into colour classes in which no two edge-neighbours share
+    a colour (what makes the in-place line Gauss-Seidel pass race-free); structured meshes need 2 colours."""
+    mesh = {"uniform": lambda: synthetic.uniform_mesh(40, 30), "variable": lambda: synthetic.variable_mesh(5000)}.get(
+        which, lambda: load_mesh(which))()
+    h = capi.Handle(capi.default_config(nLayer=5), mesh)
+    nc, ns, slot, colour = h.layout()
+    T = mesh.n_local
+    assert 1 <= nc <= 4 and ns >= T and ns % 32 == 0
+    assert len(np.unique(slot)) == T and slot.min() >= 0 and slot.max() < ns
+    for j in range(3):
+        nb = mesh.neigh[:, j]
+        has = (nb >= 0) & (nb < T)
+        assert (colour[has] != colour[nb[has]]).all()
+    for c in range(nc):  # CHM order is kept inside a class, classes are contiguous slot ranges
+        s = slot[colour == c]
+        assert (np.diff(s) == 1).all()
+    if which == "uniform":
+        assert nc == 2
+    h.close()
+
+
+def test_iteration_prediction_never_changes_results(slope):
+    """Sweep/CG counts are predicted from the previous step (the solve itself always starts from x0 = 0): a handle
+    that has seen other forcing must return the same fields as a fresh one."""
+    geo = slope.geometry()
+    kw = functest_kw(10)
+    warm = capi.Handle(capi.default_config(**kw), slope)
+    seq = [synthetic.forcing(geo.cx, geo.cy, seed=7, step=k, calm=(k == 2)) for k in range(5)]
+    for F in seq:
+        ow, sw = warm.step(3600.0, F)
+        fresh = capi.Handle(capi.default_config(**kw), slope)
+        of, sf = fresh.step(3600.0, F)
+        assert sw["suspension_present"] == sf["suspension_present"] and sw["deposition_present"] == sf["deposition_present"]
+        if sf["suspension_present"]:
+            assert sw["suspension_residual"] <= 1e-8 and sf["suspension_residual"] <= 1e-8
+        for v in ("Qsusp", "Qsalt", "Qsubl"):
+            assert rel_l2(ow[v], of[v]) <= 1e-7, v
+        if sf["deposition_present"]:
+            assert rel_l2(ow["drift_mass"], of["drift_mass"]) <= 1e-6
+        fresh.close()
+    warm.close()
