@@ -22,6 +22,7 @@ c_int64_p = C.POINTER(C.c_int64)
 c_uint8_p = C.POINTER(C.c_uint8)
 
 SOLVER_AUTO, SOLVER_LINE, SOLVER_BICGSTAB = 0, 1, 2
+DEP_AUTO, DEP_CG, DEP_CHEBYSHEV = 0, 1, 2
 ERR_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "NOCONVERGE"}
 
 
@@ -34,7 +35,7 @@ class Config(C.Structure):
         ("use_exp_fetch", C.c_int), ("use_tanh_fetch", C.c_int), ("use_PomLi_probability", C.c_int),
         ("z0_ustar_coupling", C.c_int), ("use_subgrid_topo", C.c_int), ("use_subgrid_topo_V2", C.c_int),
         ("use_R94_lambda", C.c_int), ("debug_output", C.c_int),
-        ("tolerance", C.c_double), ("max_iterations", C.c_int), ("solver", C.c_int),
+        ("tolerance", C.c_double), ("max_iterations", C.c_int), ("solver", C.c_int), ("deposition_solver", C.c_int),
     ]
 
 
@@ -67,7 +68,7 @@ class Stats(C.Structure):
         ("suspension_residual", C.c_double), ("deposition_residual", C.c_double), ("suspension_rhs_max", C.c_double),
         ("deposition_rhs_max", C.c_double), ("ms_assembly", C.c_float), ("ms_suspension_solve", C.c_float),
         ("ms_flux_and_halo", C.c_float), ("ms_deposition", C.c_float), ("ms_total", C.c_float), ("ms_line_sweeps", C.c_float),
-        ("sweeps_timed", C.c_int32), ("n_colours", C.c_int32),
+        ("sweeps_timed", C.c_int32), ("n_colours", C.c_int32), ("deposition_solver_used", C.c_int32), ("host_syncs", C.c_int32),
     ]
 
     def asdict(self):

@@ -12,8 +12,11 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -60,6 +63,11 @@ inline int align_up(int a, int b) { return (a + b - 1) / b * b; }
         ++(h_)->n_launch;                                                        \
         kernel_<<<(grid_), (block_), 0, (h_)->stream>>>(__VA_ARGS__);            \
     } while (0)
+#define LAUNCH_ON(h_, stream_, kernel_, grid_, block_, ...)                      \
+    do {                                                                         \
+        ++(h_)->n_launch;                                                        \
+        kernel_<<<(grid_), (block_), 0, (stream_)>>>(__VA_ARGS__);               \
+    } while (0)
 
 struct Partner {
     int rank;
@@ -68,6 +76,7 @@ struct Partner {
 };
 
 constexpr int kMaxColours = 8;
+constexpr int kChunks = 4;  // forcing chunks of the host-buffer entry point (H2D of chunk c+1 overlaps assembly of chunk c)
 
 }  // namespace
 
@@ -83,7 +92,9 @@ struct pbsm3d_handle {
     size_t NS = 0;  // L * S   ghost-extended vector length
     int n_colours = 0;
     int cstart[kMaxColours] = {0}, ccount[kMaxColours] = {0};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                  // compute
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D of the forcing / export + D2H of the outputs
+    cudaEvent_t ev_in[kChunks] = {nullptr}, ev_asm = nullptr, ev_flux = nullptr, ev_out = nullptr;
     std::vector<void*> allocs;
 
     // mesh / static (slot order)
@@ -102,7 +113,18 @@ struct pbsm3d_handle {
     // per-face outputs and deposition work (slot order)
     double *Qsusp = nullptr /*[S]*/, *Qsubl = nullptr, *Qsubl_mass = nullptr, *sum_subl = nullptr, *drift_mass = nullptr,
            *sum_drift = nullptr, *more_avail = nullptr;
-    double *drhs = nullptr, *q = nullptr, *cg_r = nullptr, *cg_p = nullptr /*[S]*/, *cg_Ap = nullptr;
+    double *drhs = nullptr, *drhsS = nullptr, *cg_r = nullptr, *cg_p = nullptr /*[S]*/, *cg_Ap = nullptr;
+    double *qA = nullptr, *qB = nullptr;  // [S] deposition iterate (Chebyshev ping-pong; CG uses qA)
+    double *cheb_d = nullptr, *offS = nullptr;
+    // Chebyshev: spectrum bounds of D^-1 A (static matrix, estimated once) and the coefficient sequence
+    bool cheb_ready = false;
+    double cheb_lmin = 0.0, cheb_lmax = 0.0;
+    std::vector<double> cheb_a, cheb_c;
+    int cheb_kest = 0, cheb_enqueued = 0, pred_dep = 0;
+    int lanczos_steps = 0;
+    int n_syncs = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;
+    bool trace = false;
     double* out_stage = nullptr;  // [8][T] CHM-ordered outputs on their way to host buffers
     double* scratch = nullptr;    // inspection getters
     size_t scratch_n = 0;
@@ -162,9 +184,31 @@ int allreduce(pbsm3d_handle* h, double* buf, int n, bool is_max) {
     if (h->n_ranks > 1) NC(ncclAllReduce(buf, buf, n, ncclDouble, is_max ? ncclMax : ncclSum, h->comm, h->stream));
     return 0;
 }
+int sync_stream(pbsm3d_handle* h) {
+    ++h->n_syncs;
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
 int read_scalars(pbsm3d_handle* h) {
     CU(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    return sync_stream(h);
+}
+
+// L2 residency hint for the phase in flight: accesses to [base, base+bytes) are kept in the persisting part of the
+// 126 MB L2 (as much as fits), everything else streams through.  bytes == 0 clears the window.
+int l2_window(pbsm3d_handle* h, const void* base, size_t bytes) {
+    if (h->l2_persist_max == 0) return 0;
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    if (bytes > 0) {
+        const size_t nb = std::min(bytes, h->l2_window_max);
+        attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+        attr.accessPolicyWindow.num_bytes = nb;
+        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, 0.9 * (double)h->l2_persist_max / (double)nb);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    CU(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     return 0;
 }
 
@@ -329,11 +373,25 @@ int enqueue_sweeps(pbsm3d_handle* h, int n) {
     }
     return 0;
 }
+void launch_residual(pbsm3d_handle* h, int it_now, double tol2, int fuse) {
+    const int gcol = std::max(1, std::min(cdiv(h->Tp, 128), kRedBlocks));
+#define RES_COL(LT_)                                                                                                         \
+    LAUNCH(h, residual_col_kernel<LT_>, gcol, 128, h->ss, h->dm, h->x, h->partial, kRedBlocks, h->sc, h->red, it_now, tol2, fuse)
+    switch (h->L) {
+        case 5: RES_COL(5); break;
+        case 10: RES_COL(10); break;
+        case 15: RES_COL(15); break;
+        case 20: RES_COL(20); break;
+        default:
+            LAUNCH(h, residual_kernel, red_grid(h->N), kRedThreads, h->ss, h->dm, h->L, h->x, h->partial, kRedBlocks, h->sc, h->red,
+                   it_now, tol2, fuse);
+    }
+#undef RES_COL
+}
 // ||b - A x||^2 against tol^2 ||b||^2, decided on the device (x's ghost tails must be current)
 int enqueue_check(pbsm3d_handle* h, int it_now) {
     const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
-    LAUNCH(h, residual_kernel, red_grid(h->N), kRedThreads, h->ss, h->dm, h->L, h->x, h->partial, kRedBlocks, h->sc, h->red, it_now,
-           tol2, fused(h) ? 1 : 0);
+    launch_residual(h, it_now, tol2, fused(h) ? 1 : 0);
     if (!fused(h)) {
         TRY(allreduce(h, h->red, 1, false));
         LAUNCH(h, flags_kernel, 1, 1, FLAGS_SUSP_CHECK, h->sc, h->red, it_now, tol2);
@@ -466,7 +524,7 @@ int enqueue_cg_iterations(pbsm3d_handle* h, int n) {
             TRY(allreduce(h, h->red, 1, false));
             LAUNCH(h, cg_scalar_kernel, 1, 1, 1, h->sc, h->red, tol2);
         }
-        LAUNCH(h, cg_update_kernel, g, kRedThreads, Tp, h->sc, h->dinv, h->cg_p, h->cg_Ap, h->q, h->cg_r, h->partial, kRedBlocks,
+        LAUNCH(h, cg_update_kernel, g, kRedThreads, Tp, h->sc, h->dinv, h->cg_p, h->cg_Ap, h->qA, h->cg_r, h->partial, kRedBlocks,
                h->red, tol2, f);
         if (!f) {
             TRY(allreduce(h, h->red, 2, false));
@@ -478,10 +536,181 @@ int enqueue_cg_iterations(pbsm3d_handle* h, int n) {
     return 0;
 }
 
+// ---- deposition: Jacobi-preconditioned Chebyshev iteration (one launch per iteration, no reductions) ---------
+void cheb_coefficients(pbsm3d_handle* h, int upto) {
+    const double theta = 0.5 * (h->cheb_lmax + h->cheb_lmin), delta = 0.5 * (h->cheb_lmax - h->cheb_lmin), sigma1 = theta / delta;
+    if (h->cheb_a.empty()) {
+        h->cheb_a.push_back(0.0);
+        h->cheb_c.push_back(1.0 / theta);
+    }
+    // rho_k is recomputed from the start when the table grows (cheap, and keeps the handle free of hidden state)
+    double rho = 1.0 / sigma1;
+    for (int k = 1; k <= upto; ++k) {
+        const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+        if (k >= (int)h->cheb_a.size()) {
+            h->cheb_a.push_back(rho_new * rho);
+            h->cheb_c.push_back(2.0 * rho_new / delta);
+        }
+        rho = rho_new;
+    }
+}
+// iterations [k0, k1); iterations >= check_from also measure ||b - A q_k|| and apply the stopping rule
+int enqueue_cheb(pbsm3d_handle* h, int k0, int k1, int check_from) {
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    const int g = red_grid(h->Tp), f = fused(h) ? 1 : 0;
+    cheb_coefficients(h, k1);
+    for (int k = k0; k < k1; ++k) {
+        const double* qin = (k & 1) ? h->qB : h->qA;
+        double* qout = (k & 1) ? h->qA : h->qB;
+        if (k >= check_from) {
+            LAUNCH(h, cheb_iter_kernel<1>, g, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
+                   h->cheb_c[k], k, h->partial, kRedBlocks, h->sc, h->red, tol2, f);
+            if (!f) {
+                TRY(allreduce(h, h->red, 1, false));
+                LAUNCH(h, flags_kernel, 1, 1, FLAGS_CHEB_CHECK, h->sc, h->red, k, tol2);
+            }
+        } else {
+            LAUNCH(h, cheb_iter_kernel<0>, g, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
+                   h->cheb_c[k], k, h->partial, kRedBlocks, h->sc, h->red, tol2, f);
+        }
+        TRY(halo_exchange(h, qout, 1));
+    }
+    h->cheb_enqueued = k1;
+    return 0;
+}
+bool use_chebyshev(const pbsm3d_handle* h) { return h->cheb_ready && h->cfg.deposition_solver != PBSM3D_DEP_CG; }
+
+int enqueue_cg_start(pbsm3d_handle* h, int n_cg) {
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    LAUNCH(h, cg_init_kernel, red_grid(h->Tp), kRedThreads, h->Tp, h->drhs, h->dinv, h->qA, h->cg_r, h->cg_p, h->partial, kRedBlocks,
+           h->sc, h->red, tol2, fused(h) ? 1 : 0);
+    if (!fused(h)) {
+        TRY(allreduce(h, h->red, 2, false));
+        LAUNCH(h, cg_scalar_kernel, 1, 1, 0, h->sc, h->red, tol2);
+    }
+    TRY(halo_exchange(h, h->cg_p, 1));
+    return enqueue_cg_iterations(h, n_cg);
+}
+
+// Smallest and largest eigenvalue of a symmetric tridiagonal matrix (diagonal a[0..n), off-diagonal b[0..n-1)) by
+// bisection on the Sturm count.
+void tridiag_extremes(const std::vector<double>& a, const std::vector<double>& b, double* lo_out, double* hi_out) {
+    const int n = (int)a.size();
+    double lo = a[0], hi = a[0];
+    for (int i = 0; i < n; ++i) {
+        double r = (i > 0 ? std::fabs(b[i - 1]) : 0.0) + (i + 1 < n ? std::fabs(b[i]) : 0.0);
+        lo = std::min(lo, a[i] - r);
+        hi = std::max(hi, a[i] + r);
+    }
+    auto count_below = [&](double x) {  // eigenvalues < x
+        int c = 0;
+        double q = a[0] - x;
+        if (q < 0) ++c;
+        for (int i = 1; i < n; ++i) {
+            if (q == 0.0) q = 1e-300;
+            q = a[i] - x - b[i - 1] * b[i - 1] / q;
+            if (q < 0) ++c;
+        }
+        return c;
+    };
+    auto kth = [&](int k) {  // k-th smallest (0-based)
+        double l = lo, r = hi;
+        for (int it = 0; it < 200 && (r - l) > 1e-14 * std::max(std::fabs(l), std::fabs(r)); ++it) {
+            double mid = 0.5 * (l + r);
+            if (count_below(mid) > k) r = mid; else l = mid;
+        }
+        return 0.5 * (l + r);
+    };
+    *lo_out = kth(0);
+    *hi_out = kth(n - 1);
+}
+
+// pbsm3d_create: spectrum bounds of D^-1 A for the Chebyshev iteration.  The deposition matrix depends on the mesh
+// and smooth_coeff only, so this runs once: CG on a fixed pseudo-random right-hand side, its recurrence
+// coefficients give the Lanczos tridiagonal, whose extreme Ritz values converge to the extreme eigenvalues.
+int estimate_spectrum(pbsm3d_handle* h) {
+    const int cap = std::min(512, std::max(8, h->cfg.max_iterations));
+    double *d_la = nullptr, *d_lb = nullptr;
+    TRY(h->alloc_zero(&d_la, cap));
+    TRY(h->alloc_zero(&d_lb, cap));
+    LAUNCH(h, probe_rhs_kernel, cdiv(h->Tp, 256), 256, h->Tp, h->perm, (long long)h->gstart_id, h->drhs);
+    LAUNCH(h, flags_kernel, 1, 1, FLAGS_SETUP_CG, h->sc, h->red, 0, 0.0);
+    CU(cudaMemcpyAsync(&h->sc->log_alpha, &d_la, sizeof(double*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(&h->sc->log_beta, &d_lb, sizeof(double*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(&h->sc->log_cap, &cap, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    const double keep_tol = h->cfg.tolerance;
+    h->cfg.tolerance = 1e-12;  // let the Krylov space grow until the extreme Ritz values have settled
+    TRY(enqueue_cg_start(h, 0));
+    int it = 0;
+    double lmin = 0.0, lmax = 0.0, prev_lmin = -1.0;
+    bool settled = false;
+    std::vector<double> la(cap), lb(cap);
+    while (it < cap && !settled) {
+        const int n = std::min(48, cap - it);
+        TRY(enqueue_cg_iterations(h, n));
+        it += n;
+        TRY(read_scalars(h));
+        const int m = std::min(h->h_sc->log_n, cap);
+        if (m < 2) break;
+        CU(cudaMemcpy(la.data(), d_la, m * sizeof(double), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(lb.data(), d_lb, m * sizeof(double), cudaMemcpyDeviceToHost));
+        std::vector<double> ta(m), tb(m > 1 ? m - 1 : 0);
+        for (int j = 0; j < m; ++j) {
+            ta[j] = 1.0 / la[j] + (j > 0 ? lb[j - 1] / la[j - 1] : 0.0);
+            if (j + 1 < m) tb[j] = std::sqrt(std::max(lb[j], 0.0)) / la[j];
+        }
+        tridiag_extremes(ta, tb, &lmin, &lmax);
+        h->lanczos_steps = m;
+        if (h->h_sc->done) { settled = true; break; }
+        if (prev_lmin > 0 && std::fabs(lmin - prev_lmin) <= 0.01 * lmin) settled = true;
+        prev_lmin = lmin;
+    }
+    h->cfg.tolerance = keep_tol;
+    double* null_ptr = nullptr;
+    CU(cudaMemcpyAsync(&h->sc->log_alpha, &null_ptr, sizeof(double*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(&h->sc->log_beta, &null_ptr, sizeof(double*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->sc, 0, offsetof(Scalars, log_alpha), h->stream));
+    CU(cudaMemsetAsync(h->qA, 0, (size_t)h->S * sizeof(double), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->release(d_la);
+    h->release(d_lb);
+    if (!(lmin > 0) || !(lmax > lmin) || !std::isfinite(lmax)) return 0;  // leave Chebyshev off: CG will be used
+    // Ritz values lie inside the spectrum: widen a little.  D^-1 A of this diagonally dominant M-matrix has its
+    // spectrum in (0, 2) (Gershgorin), so 2 caps the upper bound; an upper bound that is too small would diverge.
+    h->cheb_lmin = (settled ? 0.97 : 0.7) * lmin;
+    h->cheb_lmax = std::min(2.0, 1.01 * lmax + 1e-3);
+    const double kappa = h->cheb_lmax / h->cheb_lmin;
+    const double qf = (std::sqrt(kappa) - 1.0) / (std::sqrt(kappa) + 1.0);
+    h->cheb_kest = qf > 0 ? (int)std::ceil(std::log(h->cfg.tolerance / 2.0) / std::log(qf)) + 2 : 4;
+    h->cheb_ready = true;
+    return 0;
+}
+
 struct OutTargets {
     double* dst[8];       // where export_kernel writes (device pointers: caller's buffers or out_stage)
     double* host[8];      // optional host destinations for a following D2H
 };
+
+// Export of the outputs in `mask` to CHM order on `stream` (+ D2H when the caller's buffers are on the host).
+int enqueue_export(pbsm3d_handle* h, cudaStream_t stream, const OutTargets* out, unsigned mask) {
+    if (!out) return 0;
+    const int T = h->T;
+    ExportPtrs e;
+    const double* src[8] = {h->ss.Qsalt, h->Qsusp, h->Qsubl, h->Qsubl_mass, h->sum_subl, h->drift_mass, h->sum_drift, h->more_avail};
+    bool any = false;
+    for (int k = 0; k < 8; ++k) {
+        e.src[k] = src[k];
+        e.dst[k] = (mask >> k & 1u) ? out->dst[k] : nullptr;
+        any = any || e.dst[k];
+    }
+    if (!any) return 0;
+    LAUNCH_ON(h, stream, export_kernel, cdiv(T, 256), 256, T, h->iperm, e);
+    for (int k = 0; k < 8; ++k)
+        if (e.dst[k] && out->host[k])
+            CU(cudaMemcpyAsync(out->host[k], out->dst[k], (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    return 0;
+}
+constexpr unsigned kOutQsalt = 1u << 0, kOutFlux = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4), kOutDrift = (1u << 5) | (1u << 6) | (1u << 7);
 
 // E..I of SURVEY §3.2 plus the export: everything after the suspension solve.  Safe to enqueue before the host
 // knows whether the solve converged (device guards), and safe to enqueue again if it had not.
@@ -492,61 +721,70 @@ int enqueue_tail(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTarg
     // E: flux integration
     LAUNCH(h, flux_kernel, cdiv(Tp, 256), 256, Tp, h->S, h->L, h->dc.dz, dt, h->perm, h->x, h->ss.u_z, h->ss.csubl, h->Qsusp, h->Qsubl,
            h->Qsubl_mass, h->sum_subl, h->sc);
+    if (out) {  // early export: Qsusp, Qsubl, Qsubl_mass, sum_subl are final from here on
+        CU(cudaEventRecord(h->ev_flux, s));
+        CU(cudaStreamWaitEvent(h->s_out, h->ev_flux, 0));
+        TRY(enqueue_export(h, h->s_out, out, kOutFlux));
+    }
     // F: halo of Qsusp, Qsalt (PBSM3D.cpp:1509-1510)
     TRY(halo_exchange(h, h->Qsusp, 1));
     TRY(halo_exchange(h, h->ss.Qsalt, 1));
     // G: deposition RHS (the matrix is static) + H: rhs max
-    LAUNCH(h, deposition_rhs_kernel, red_grid(Tp), kRedThreads, h->dm, f.vw_dir, h->Qsusp, h->ss.Qsalt, h->drhs, h->partial, kRedBlocks,
-           h->sc, h->red);
-    TRY(allreduce(h, h->red, 1, true));
+    LAUNCH(h, deposition_rhs_kernel, red_grid(Tp), kRedThreads, h->dm, f.vw_dir, h->Qsusp, h->ss.Qsalt, h->dinv, h->drhs, h->drhsS,
+           h->partial, kRedBlocks, h->sc, h->red);
+    if (h->n_ranks > 1) {
+        TRY(allreduce(h, h->red, 1, true));
+        TRY(allreduce(h, h->red + 1, 1, false));
+    }
     LAUNCH(h, flags_kernel, 1, 1, FLAGS_DEP, h->sc, h->red, 0, tol2);
     CU(cudaEventRecord(h->ev[3], s));
-    // deposition solve
-    LAUNCH(h, cg_init_kernel, red_grid(Tp), kRedThreads, Tp, h->drhs, h->dinv, h->q, h->cg_r, h->cg_p, h->partial, kRedBlocks, h->sc,
-           h->red, tol2, fused(h) ? 1 : 0);
-    if (!fused(h)) {
-        TRY(allreduce(h, h->red, 2, false));
-        LAUNCH(h, cg_scalar_kernel, 1, 1, 0, h->sc, h->red, tol2);
+    // deposition solve (x0 = 0)
+    CU(cudaMemsetAsync(h->qA, 0, (size_t)h->S * sizeof(double), s));
+    if (use_chebyshev(h)) {
+        CU(cudaMemsetAsync(h->cheb_d, 0, (size_t)Tp * sizeof(double), s));
+        const int maxit = h->cfg.max_iterations;
+        const bool known = h->pred_dep > 0;
+        const int n = known ? h->pred_dep : h->cheb_kest;
+        const int check_from = known ? std::max(0, n - 3) : std::max(0, n / 2);
+        const int k1 = std::min(maxit, known ? n + 6 : n + n / 4 + 8);
+        TRY(enqueue_cheb(h, 0, k1, check_from));
+    } else {
+        TRY(enqueue_cg_start(h, n_cg));
     }
-    TRY(halo_exchange(h, h->cg_p, 1));
-    TRY(enqueue_cg_iterations(h, n_cg));
     return 0;
 }
 
-// I: drift update + export to CHM order (+ D2H when the caller's buffers are on the host)
-int enqueue_finish(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTargets* out) {
+// I: drift update + export of `mask` (+ the control block) on the compute stream
+int enqueue_finish(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTargets* out, unsigned mask) {
     cudaStream_t s = h->stream;
-    const int Tp = h->Tp, T = h->T;
-    LAUNCH(h, drift_kernel, cdiv(Tp, 256), 256, Tp, dt, h->perm, h->q, f.swe, h->ss.salt, h->drift_mass, h->sum_drift, h->more_avail,
-           h->sc);
+    const int Tp = h->Tp;
+    LAUNCH(h, drift_kernel, cdiv(Tp, 256), 256, Tp, dt, h->perm, h->qA, h->qB, f.swe, h->ss.salt, h->drift_mass, h->sum_drift,
+           h->more_avail, h->sc);
     LAUNCH(h, drift_done_kernel, 1, 1, h->sc);
-    if (out) {
-        ExportPtrs e;
-        const double* src[8] = {h->ss.Qsalt, h->Qsusp, h->Qsubl, h->Qsubl_mass, h->sum_subl, h->drift_mass, h->sum_drift, h->more_avail};
-        bool any = false;
-        for (int k = 0; k < 8; ++k) { e.src[k] = src[k]; e.dst[k] = out->dst[k]; any = any || out->dst[k]; }
-        if (any) LAUNCH(h, export_kernel, cdiv(T, 256), 256, T, h->iperm, e);
-    }
     CU(cudaEventRecord(h->ev[4], s));
-    if (out)
-        for (int k = 0; k < 8; ++k)
-            if (out->host[k]) CU(cudaMemcpyAsync(out->host[k], out->dst[k], (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, s));
+    TRY(enqueue_export(h, s, out, mask));
     CU(cudaMemcpyAsync(h->h_sc, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, s));
     return 0;
 }
 
-void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt) {
-    const int ntiles = cdiv(h->Tp, 128);
-    LAUNCH(h, assemble_kernel, std::min(ntiles, kRedBlocks), 128, h->dc, h->dm, f, h->ss, dt, h->partial, kRedBlocks, h->sc, h->red);
+// Assembly of CHM faces [i0, i1); its {max|b|, sum b^2} go to red[2*chunk ..].
+void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt, int i0, int i1, int chunk) {
+    const int ntiles = cdiv((size_t)(i1 - i0), 128);
+    LAUNCH(h, assemble_kernel, std::max(1, std::min(ntiles, kRedBlocks)), 128, h->dc, h->dm, f, h->ss, dt, i0, i1, h->partial,
+           kRedBlocks, h->sc, h->red + 2 * chunk);
 }
 
 // One PBSM3D::run with device-resident forcing (reference PBSM3D.cpp:400-1748, phases A–I of SURVEY §3.2).
-int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const OutTargets* out, pbsm3d_stats* st) {
+int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const double* const* host_in, const OutTargets* out,
+              pbsm3d_stats* st) {
     cudaStream_t s = h->stream;
+    const int T = h->T;
     std::memset(st, 0, sizeof(*st));
     const long long launch0 = h->n_launch;
     const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
     const int maxit = h->cfg.max_iterations;
+    h->n_syncs = 0;
+    const auto t_host0 = std::chrono::steady_clock::now();
     h->last_forcing = f;
     h->last_dt = dt;
     const int solver = h->cfg.solver;
@@ -555,21 +793,47 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const OutTargets
     CU(cudaMemsetAsync(h->x, 0, h->NS * sizeof(double), s));
     // A+B: zeroSystem is implicit (every coefficient is overwritten); saltation + suspension assembly,
     // C: suspension_present = ||rhs||_inf > 1e-12 and ||b||_2^2, reduced inside the assembly kernel
-    launch_assembly(h, f, dt);
+    // With host buffers the forcing crosses PCIe in chunks on its own stream and each chunk is assembled as it lands.
+    const int nch = host_in ? std::max(1, std::min(kChunks, T / 32768)) : 1;
+    if (host_in)
+        for (int c = 0; c < nch; ++c) {
+            const size_t i0 = (size_t)T * c / nch, i1 = (size_t)T * (c + 1) / nch;
+            for (int k = 0; k < 8; ++k)
+                if (host_in[k])
+                    CU(cudaMemcpyAsync(h->forcing_buf[k] + i0, host_in[k] + i0, (i1 - i0) * sizeof(double), cudaMemcpyHostToDevice,
+                                       h->s_in));
+            CU(cudaEventRecord(h->ev_in[c], h->s_in));
+        }
+    for (int c = 0; c < nch; ++c) {
+        if (host_in) CU(cudaStreamWaitEvent(s, h->ev_in[c], 0));
+        launch_assembly(h, f, dt, (int)((size_t)T * c / nch), (int)((size_t)T * (c + 1) / nch), c);
+    }
     h->have_system = true;
     if (h->n_ranks > 1) {
+        LAUNCH(h, flags_kernel, 1, 1, FLAGS_COMBINE, h->sc, h->red, nch, tol2);
         TRY(allreduce(h, h->red, 1, true));
         TRY(allreduce(h, h->red + 1, 1, false));
+        LAUNCH(h, flags_kernel, 1, 1, FLAGS_SUSP, h->sc, h->red, 1, tol2);
+    } else {
+        LAUNCH(h, flags_kernel, 1, 1, FLAGS_SUSP, h->sc, h->red, nch, tol2);
     }
-    LAUNCH(h, flags_kernel, 1, 1, FLAGS_SUSP, h->sc, h->red, 0, tol2);
     CU(cudaEventRecord(h->ev[1], s));
+    // outputs that are final early leave on their own stream while the solves run (host-buffer entry point)
+    const bool early = out && host_in;
+    if (early) {
+        CU(cudaEventRecord(h->ev_asm, s));
+        CU(cudaStreamWaitEvent(h->s_out, h->ev_asm, 0));
+        TRY(enqueue_export(h, h->s_out, out, kOutQsalt));
+    }
 
     // D: suspension solve
     int total = 0;
     bool line = (solver == PBSM3D_SOLVER_AUTO || solver == PBSM3D_SOLVER_LINE);
     h->sweeps_timed = 0;
     if (line) {
+        TRY(l2_window(h, h->x, h->NS * sizeof(double)));
         TRY(line_enqueue_initial(h, &total));
+        TRY(l2_window(h, nullptr, 0));
     } else {
         TRY(read_scalars(h));
         if (h->h_sc->susp_present) {
@@ -585,9 +849,28 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const OutTargets
     CU(cudaEventRecord(h->ev[2], s));
     // E..I, optimistic
     int n_cg = std::min(maxit, h->pred_cg > 0 ? h->pred_cg + std::max(4, h->pred_cg / 16) : 64);
-    TRY(enqueue_tail(h, f, dt, out, n_cg));
-    TRY(enqueue_finish(h, f, dt, out));
-    CU(cudaStreamSynchronize(s));
+    TRY(enqueue_tail(h, f, dt, early ? out : nullptr, n_cg));
+    TRY(enqueue_finish(h, f, dt, out, early ? kOutDrift : 0xffu));
+    if (early) {
+        CU(cudaEventRecord(h->ev_out, h->s_out));
+        CU(cudaStreamWaitEvent(s, h->ev_out, 0));
+    }
+    const auto t_enq = std::chrono::steady_clock::now();
+    TRY(sync_stream(h));
+    if (h->trace) {  // PBSM3D_TRACE=1: where the step's time went (ms since the first event of the step)
+        const auto t_end = std::chrono::steady_clock::now();
+        auto since = [&](cudaEvent_t e) { float ms = -1.f; cudaEventElapsedTime(&ms, h->ev[0], e); return ms; };
+        fprintf(stderr, "[pbsm3d trace] host enqueue %.3f ms, call-to-sync %.3f ms | assembled %.3f line %.3f dep-rhs %.3f drift %.3f",
+                std::chrono::duration<double, std::milli>(t_enq - t_host0).count(),
+                std::chrono::duration<double, std::milli>(t_end - t_host0).count(), since(h->ev[1]), since(h->ev[2]), since(h->ev[3]),
+                since(h->ev[4]));
+        if (host_in) {
+            fprintf(stderr, " | h2d chunks");
+            for (int c = 0; c < nch; ++c) fprintf(stderr, " %.3f", since(h->ev_in[c]));
+        }
+        if (early) fprintf(stderr, " | qsalt-export-start %.3f flux %.3f early-d2h-done %.3f", since(h->ev_asm), since(h->ev_flux), since(h->ev_out));
+        fprintf(stderr, "\n");
+    }
 
     // ---- what actually happened
     bool redo_tail = false;
@@ -625,17 +908,36 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const OutTargets
         h->pred_sweeps = pred;
     }
     if (redo_tail) {
-        TRY(enqueue_tail(h, f, dt, out, n_cg));
-        TRY(enqueue_finish(h, f, dt, out));
-        CU(cudaStreamSynchronize(s));
+        TRY(enqueue_tail(h, f, dt, nullptr, n_cg));
+        TRY(enqueue_finish(h, f, dt, out, 0xffu));
+        TRY(sync_stream(h));
     }
     // deposition solve still open?
+    bool cheb = use_chebyshev(h);
+    int dep_used = cheb ? PBSM3D_DEP_CHEBYSHEV : PBSM3D_DEP_CG;
     while (h->h_sc->tail_done && h->h_sc->dep_present && !h->h_sc->dep_ok) {
-        if (h->h_sc->done == 2 || h->h_sc->iters >= maxit || !std::isfinite(h->h_sc->rr))
-            return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver failed to converge");
-        TRY(enqueue_cg_iterations(h, std::min(64, maxit - h->h_sc->iters)));
-        TRY(enqueue_finish(h, f, dt, out));
-        CU(cudaStreamSynchronize(s));
+        if (cheb) {
+            const bool gave_up = h->h_sc->done == 2 || h->cheb_enqueued >= std::min(maxit, 4 * h->cheb_kest + 32);
+            if (gave_up && h->cfg.deposition_solver == PBSM3D_DEP_CHEBYSHEV)
+                return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver (Chebyshev) failed to converge");
+            if (gave_up) {  // the spectrum bounds were not good enough for this mesh: CG needs none
+                cheb = false;
+                dep_used = PBSM3D_DEP_CG;
+                h->cheb_ready = false;
+                LAUNCH(h, flags_kernel, 1, 1, FLAGS_DEP_RESTART, h->sc, h->red, 0, tol2);
+                CU(cudaMemsetAsync(h->qA, 0, (size_t)h->S * sizeof(double), s));
+                TRY(enqueue_cg_start(h, n_cg));
+            } else {
+                const int k0 = h->cheb_enqueued;
+                TRY(enqueue_cheb(h, k0, std::min(maxit, k0 + 16), k0));
+            }
+        } else {
+            if (h->h_sc->done == 2 || h->h_sc->iters >= maxit || !std::isfinite(h->h_sc->rr))
+                return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver failed to converge");
+            TRY(enqueue_cg_iterations(h, std::min(64, maxit - h->h_sc->iters)));
+        }
+        TRY(enqueue_finish(h, f, dt, out, 0xffu));
+        TRY(sync_stream(h));
     }
     const Scalars& c = *h->h_sc;
     st->suspension_present = c.susp_present;
@@ -645,8 +947,11 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const OutTargets
     if (c.dep_present) {
         st->deposition_iterations = c.iters;
         st->deposition_residual = c.bnorm2 > 0 ? std::sqrt(c.rr / c.bnorm2) : 0.0;
-        h->pred_cg = c.iters;
+        st->deposition_solver_used = dep_used;
+        if (dep_used == PBSM3D_DEP_CHEBYSHEV) h->pred_dep = c.iters;
+        else h->pred_cg = c.iters;
     }
+    st->host_syncs = h->n_syncs;
     CU(cudaEventElapsedTime(&st->ms_assembly, h->ev[0], h->ev[1]));
     CU(cudaEventElapsedTime(&st->ms_suspension_solve, h->ev[1], h->ev[2]));
     CU(cudaEventElapsedTime(&st->ms_flux_and_halo, h->ev[2], h->ev[3]));
@@ -734,6 +1039,7 @@ void pbsm3d_config_defaults(pbsm3d_config* c) {
     c->tolerance = 1e-8;        // LinearAlgebra.cpp:168
     c->max_iterations = 1000;   // LinearAlgebra.cpp:167
     c->solver = PBSM3D_SOLVER_AUTO;
+    c->deposition_solver = PBSM3D_DEP_AUTO;
 }
 
 int pbsm3d_nccl_unique_id(void* out) {
@@ -748,6 +1054,13 @@ void pbsm3d_destroy(pbsm3d_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->s_in) { cudaStreamSynchronize(h->s_in); cudaStreamDestroy(h->s_in); }
+    if (h->s_out) { cudaStreamSynchronize(h->s_out); cudaStreamDestroy(h->s_out); }
+    for (auto& e : h->ev_in)
+        if (e) cudaEventDestroy(e);
+    if (h->ev_asm) cudaEventDestroy(h->ev_asm);
+    if (h->ev_flux) cudaEventDestroy(h->ev_flux);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->comm) ncclCommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);
@@ -771,6 +1084,8 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     if (cfg->use_subgrid_topo || cfg->use_subgrid_topo_V2) return fail(PBSM3D_ERR_UNSUPPORTED, "use_subgrid_topo* is not implemented");
     if (cfg->debug_output) return fail(PBSM3D_ERR_UNSUPPORTED, "debug_output is not implemented");
     if (!(cfg->tolerance > 0) || cfg->max_iterations < 1) return fail(PBSM3D_ERR_INVALID, "bad solver controls");
+    if (cfg->solver < 0 || cfg->solver > 2 || cfg->deposition_solver < 0 || cfg->deposition_solver > 2)
+        return fail(PBSM3D_ERR_INVALID, "unknown solver id");
     if (mesh->n_local < 1 || mesh->n_ghost < 0 || !mesh->neigh || !mesh->vertices || !mesh->global_id)
         return fail(PBSM3D_ERR_INVALID, "mesh arrays missing");
     int ndev = 0;
@@ -804,6 +1119,27 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
         }
 
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (auto& e : h->ev_in) CU(cudaEventCreate(&e));
+    CU(cudaEventCreate(&h->ev_asm));
+    CU(cudaEventCreate(&h->ev_flux));
+    CU(cudaEventCreate(&h->ev_out));
+    h->trace = getenv("PBSM3D_TRACE") != nullptr;
+    {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+        h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        // Off unless asked for: pinning x in a persisting carve-out makes a sweep ≈8 % faster on config c2 but takes the
+        // carve-out away from the deposition solve, whose whole working set otherwise lives in L2 (profiles/r1c).
+        const char* mb = getenv("PBSM3D_L2_PERSIST_MB");
+        h->l2_persist_max = mb ? std::min(h->l2_persist_max, (size_t)atol(mb) << 20) : 0;
+        if (getenv("PBSM3D_VERBOSE"))
+            fprintf(stderr, "[pbsm3d] L2 %d MB, persisting max %zu MB (using %zu MB), window max %zu MB\n", prop.l2CacheSize >> 20,
+                    (size_t)prop.persistingL2CacheMaxSize >> 20, h->l2_persist_max >> 20, h->l2_window_max >> 20);
+        if (h->l2_persist_max > 0) CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max));
+    }
     for (auto& e : h->ev) CU(cudaEventCreate(&e));
     for (auto& e : h->ev_sw) CU(cudaEventCreate(&e));
     CU(cudaMallocHost((void**)&h->h_sc, sizeof(Scalars)));
@@ -926,8 +1262,12 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     TRY(h->alloc_zero(&h->x, h->NS));
     TRY(h->alloc_zero(&h->Qsusp, h->S));
     TRY(h->alloc_zero(&h->cg_p, h->S));
+    TRY(h->alloc_zero(&h->qA, h->S));
+    TRY(h->alloc_zero(&h->qB, h->S));
+    TRY(h->alloc(&h->offS, (size_t)3 * Tp));
+    LAUNCH(h, deposition_scale_kernel, cdiv(Tp, 256), 256, Tp, h->doff, h->dinv, h->offS);
     double** perslot[] = {&h->Qsubl, &h->Qsubl_mass, &h->sum_subl, &h->drift_mass, &h->sum_drift, &h->more_avail,
-                          &h->drhs,  &h->q,          &h->cg_r,     &h->cg_Ap};
+                          &h->drhs,  &h->drhsS,      &h->cg_r,     &h->cg_Ap,      &h->cheb_d};
     for (double** p : perslot) TRY(h->alloc_zero(p, Tp));
     TRY(h->alloc(&h->out_stage, (size_t)8 * T));
     // drift_mass is a face variable that is -9999 until first written (variablestorage default)
@@ -959,6 +1299,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     dm.S = h->S;
     dm.nG = nG;
     dm.perm = h->perm;
+    dm.iperm = h->iperm;
     dm.nbs = h->nbs;
     dm.nx = h->nx;
     dm.ny = h->ny;
@@ -971,7 +1312,10 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     dm.stalk_dv = h->stalk_dv;
     dm.water = h->water;
 
+    LAUNCH(h, assemble_pads_kernel, cdiv(Tp, 256), 256, h->dm, h->ss, L);
     if (h->n_ranks > 1) TRY(setup_comm(h, mesh, comm, iperm));
+    CU(cudaStreamSynchronize(h->stream));
+    if (cfg->deposition_solver != PBSM3D_DEP_CG) TRY(estimate_spectrum(h));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     return 0;
@@ -1009,7 +1353,7 @@ int pbsm3d_step_device(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, con
     DevForcing df{f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch};
     OutTargets ot{};
     if (out) out_pointers(out, ot.dst);
-    return step_impl(h, dt, df, out ? &ot : nullptr, stats);
+    return step_impl(h, dt, df, nullptr, out ? &ot : nullptr, stats);
 }
 
 int pbsm3d_step(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm3d_outputs* out, pbsm3d_stats* stats) {
@@ -1019,8 +1363,6 @@ int pbsm3d_step(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm
     pbsm3d_stats local;
     if (!stats) stats = &local;
     const double* src[8] = {f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch};
-    for (int k = 0; k < 8; ++k)
-        if (src[k]) TRY(upload(h, h->forcing_buf[k], src[k], (size_t)h->T * sizeof(double)));
     DevForcing df{h->forcing_buf[0], h->forcing_buf[1], h->forcing_buf[2], h->forcing_buf[3], h->forcing_buf[4],
                   h->forcing_buf[5], h->forcing_buf[6], f->fetch ? h->forcing_buf[7] : nullptr};
     OutTargets ot{};
@@ -1028,7 +1370,7 @@ int pbsm3d_step(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm
         out_pointers(out, ot.host);
         for (int k = 0; k < 8; ++k) ot.dst[k] = ot.host[k] ? h->out_stage + (size_t)k * h->T : nullptr;
     }
-    return step_impl(h, dt, df, out ? &ot : nullptr, stats);
+    return step_impl(h, dt, df, src, out ? &ot : nullptr, stats);
 }
 
 int pbsm3d_get_state(pbsm3d_handle* h, double* sum_drift, double* sum_subl, double* drift_mass, double* more) {
@@ -1125,7 +1467,7 @@ int pbsm3d_get_deposition_system(pbsm3d_handle* h, double* diag, double* off, do
     TRY(fetch_chm(h, diag, h->ddiag, 1, Tp));
     TRY(fetch_chm(h, off, h->doff, 3, Tp));
     TRY(fetch_chm(h, rhs, h->drhs, 1, Tp));
-    TRY(fetch_chm(h, q, h->q, 1, Tp));
+    TRY(fetch_chm(h, q, h->h_sc->dep_buf ? h->qB : h->qA, 1, Tp));
     return 0;
 }
 
@@ -1142,14 +1484,21 @@ int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms) {
         if (pass == 1) CU(cudaEventRecord(h->ev[0], s));
         for (int k = 0; k < n; ++k) {
             switch (kernel) {
-                case 0: TRY(enqueue_sweeps(h, 1)); break;
-                case 1:
-                    LAUNCH(h, residual_kernel, red_grid(h->N), kRedThreads, h->ss, h->dm, h->L, h->x, h->partial, kRedBlocks, h->sc,
-                           h->red, 0, tol2, 0);
+                case 0:
+                    if (k == 0) TRY(l2_window(h, h->x, h->NS * sizeof(double)));
+                    TRY(enqueue_sweeps(h, 1));
                     break;
-                case 2: launch_assembly(h, h->last_forcing, h->last_dt); break;
+                case 1: launch_residual(h, 0, tol2, 0); break;
+                case 2: launch_assembly(h, h->last_forcing, h->last_dt, 0, h->T, 0); break;
                 case 3:
                     LAUNCH(h, cg_spmv_kernel, red_grid(h->Tp), kRedThreads, h->dm, h->ddiag, h->doff, h->cg_p, h->cg_Ap, h->partial,
+                           kRedBlocks, nullptr, h->red, tol2, 0);
+                    break;
+                case 4:
+                    if (!h->cheb_ready) return fail(PBSM3D_ERR_INVALID, "Chebyshev is not set up on this handle");
+                    // a_k = c_k = 0: the same traffic as a real iteration, and the converged iterate is only copied
+                    LAUNCH(h, cheb_iter_kernel<0>, red_grid(h->Tp), kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag,
+                           h->h_sc->dep_buf ? h->qB : h->qA, h->cheb_d, h->h_sc->dep_buf ? h->qA : h->qB, 0.0, 0.0, k, h->partial,
                            kRedBlocks, nullptr, h->red, tol2, 0);
                     break;
                 default: return fail(PBSM3D_ERR_INVALID, "unknown kernel id");
@@ -1157,6 +1506,7 @@ int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms) {
         }
         if (pass == 1) CU(cudaEventRecord(h->ev[1], s));
     }
+    TRY(l2_window(h, nullptr, 0));
     LAUNCH(h, flags_kernel, 1, 1, FLAGS_FORCE_SUSP_OK, h->sc, h->red, 0, tol2);
     CU(cudaStreamSynchronize(s));
     CU(cudaGetLastError());

@@ -33,6 +33,7 @@ struct DevConfig {
 struct DevMesh {
     int T, Tp, S, nG;
     const int* perm;       // [Tp] slot -> CHM local face, -1 = pad
+    const int* iperm;      // [T]  CHM local face -> slot
     const int* nbs;        // [3][Tp] neighbour slot (ghost g -> Tp+g); own slot when there is no neighbour
     const double* nx;      // [3][Tp]
     const double* ny;      // [3][Tp]
@@ -82,6 +83,9 @@ struct Scalars {
     int dep_ok;                       // deposition solve finished (converged)
     int tail_done;                    // flux/deposition-rhs ran on a finished suspension solve
     int drift_done;
+    int dep_buf;                      // Chebyshev: which of the two q buffers holds the converged iterate
+    int log_n, log_cap;               // setup only: CG recurrence log for the Lanczos spectrum estimate
+    double *log_alpha, *log_beta;
     unsigned ticket[4];
 };
 
@@ -290,21 +294,27 @@ __device__ __forceinline__ bool grid_fold(double v0, double v1, int op0, int op1
 // and ||b||^2 (the stopping rule of LinearAlgebra.cpp:168).
 // One thread per slot; for each layer the 32 lanes of a warp write 32 consecutive doubles of every output
 // stream.  Replaces ≈11 Tpetra sumIntoGlobalValues hash lookups per row by direct ELL stores.
-__device__ __forceinline__ double assemble_column(const DevConfig& c, const DevMesh& m, const DevForcing& f, const SuspSystem& s,
-                                                   double dt, int p) {
+// Padding slots are identity rows with a zero right-hand side; written once in pbsm3d_create.
+__global__ void assemble_pads_kernel(DevMesh m, SuspSystem s, int L) {
     const int Tp = m.Tp;
-    const int i = m.perm[p];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp || m.perm[p] >= 0) return;
+    s.Qsalt[p] = 0.0; s.c_salt[p] = 0.0; s.salt[p] = 0; s.rhs0[p] = 0.0; s.rhsS0[p] = 0.0;
+    for (int z = 0; z < L; ++z) {
+        const size_t r = (size_t)z * Tp + p;
+        s.diag[r] = 1.0; s.below[r] = 0.0; s.above[r] = 0.0; s.inv[r] = 1.0; s.cp[r] = 0.0; s.belowS[r] = 0.0;
+        s.u_z[r] = 0.0; s.csubl[r] = 0.0;
+        for (int j = 0; j < 3; ++j) { s.lat[((size_t)j * L + z) * Tp + p] = 0.0; s.latS[((size_t)j * L + z) * Tp + p] = 0.0; }
+    }
+}
+
+// One face column: CHM face i (forcing index), slot p (everything else).  Returns b of layer 0.
+__device__ __forceinline__ double assemble_column(const DevConfig& c, const DevMesh& m, const DevForcing& f, const SuspSystem& s,
+                                                   double dt, int p, int i) {
+    const int Tp = m.Tp;
     const int L = c.L;
     double b0 = 0.0;
-    if (i < 0) {  // padding slot: identity rows, zero right-hand side
-        s.Qsalt[p] = 0.0; s.c_salt[p] = 0.0; s.salt[p] = 0; s.rhs0[p] = 0.0; s.rhsS0[p] = 0.0;
-        for (int z = 0; z < L; ++z) {
-            const size_t r = (size_t)z * Tp + p;
-            s.diag[r] = 1.0; s.below[r] = 0.0; s.above[r] = 0.0; s.inv[r] = 1.0; s.cp[r] = 0.0; s.belowS[r] = 0.0;
-            s.u_z[r] = 0.0; s.csubl[r] = 0.0;
-            for (int j = 0; j < 3; ++j) { s.lat[((size_t)j * L + z) * Tp + p] = 0.0; s.latS[((size_t)j * L + z) * Tp + p] = 0.0; }
-        }
-    } else {
+    {
         double fetch = 1000.0;
         if ((c.use_exp_fetch || c.use_tanh_fetch) && f.fetch) fetch = f.fetch[i];
         const double uref = f.U_R[i];
@@ -408,17 +418,21 @@ __device__ __forceinline__ double assemble_column(const DevConfig& c, const DevM
             else u_z = fmax(0.01, uref);
             s.u_z[r] = u_z;
 
-            const double rm = 4.6e-5 * pow(cz, -0.258);
+            // x^y for x > 0 as exp(y log x): |y log x| < 40 on every use below, so the result is within ~1e-14
+            // relative of pow() (the parity bar on coefficients is 1e-12) at a fraction of pow()'s fp64 cost
+            const double lcz = log(cz);
+            const double rm = 4.6e-5 * exp(-0.258 * lcz);
             const double mm_alpha = 4.08 + 12.6 * cz;
             const double mm = 4.0 / 3.0 * kPi * kRhoIce * rm * rm * rm * (1.0 + 3.0 / mm_alpha + 2.0 / (mm_alpha * mm_alpha));
-            const double r_z = pow((3.0 * mm) / (4 * kPi * kRhoIce), 0.3333333);
-            const double xrz = 0.005 * pow(u_z, 1.36);
-            const double omega = c.do_fixed_settling ? c.settling_velocity : 1.1e7 * pow(r_z, 1.8);
+            const double lrz3 = log((3.0 * mm) / (4 * kPi * kRhoIce));
+            const double r_z = exp(0.3333333 * lrz3);
+            const double xrz = 0.005 * exp(1.36 * log(u_z));
+            const double omega = c.do_fixed_settling ? c.settling_velocity : 1.1e7 * exp(1.8 * log(r_z));
             const double Vr = omega + 3.0 * xrz * cos(kPi / 4.0);
             const double Re = 2.0 * r_z * Vr / 1.88e-5;
             const double Nu = 1.79 + 0.606 * sqrt(Re);
             const double Sh = Nu;
-            const double sigma = (rh - 1.0) * (1.019 + 0.027 * log(cz));
+            const double sigma = (rh - 1.0) * (1.019 + 0.027 * lcz);
             const double Qr = 0.9 * kPi * rm * rm * 120.0;
             const double dmdtz = Sh * rho_sat * D * (6.283185308 * Nu * Rg * r_z * sigma * t * t * lambda_t - Ls * Mw * Qr + Qr * Rg * t) /
                                  (D * Ls * Sh * (Ls * Mw - Rg * t) * rho_sat + lambda_t * t * t * Nu * Rg);
@@ -491,17 +505,20 @@ __device__ __forceinline__ double assemble_column(const DevConfig& c, const DevM
     return b0;
 }
 
-// Persistent-style grid (a multiple of the SM count, each block walks 128-slot tiles) so the fused reduction
-// folds a bounded number of partials.  red[0] = max|b|, red[1] = sum b^2 (this rank).
-__global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt,
+// Faces [i0, i1) of CHM's order (the order the forcing arrives in, so the step can assemble one chunk while the
+// next chunk's forcing is still crossing PCIe); each thread writes the column of its slot iperm[i].  Within a warp
+// the slots of one colour are consecutive, so every stream is still written in full 128-byte lines.
+// Persistent-style grid (a multiple of the SM count, each block walks 128-face tiles) so the fused reduction
+// folds a bounded number of partials.  red[0] = max|b|, red[1] = sum b^2 over the chunk (this rank).
+__global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt, int i0, int i1,
                                                        double* __restrict__ partial, int pstride, Scalars* sc,
                                                        double* __restrict__ red) {
     double mx = 0.0, ss = 0.0;
-    const int ntiles = (m.Tp + 127) / 128;
+    const int ntiles = (i1 - i0 + 127) / 128;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int p = tile * 128 + threadIdx.x;
-        if (p < m.Tp) {
-            const double b0 = assemble_column(c, m, f, s, dt, p);
+        const int i = i0 + tile * 128 + threadIdx.x;
+        if (i < i1) {
+            const double b0 = assemble_column(c, m, f, s, dt, m.iperm[i], i);
             mx = fmax(mx, fabs(b0));
             ss += b0 * b0;
         }
@@ -512,10 +529,18 @@ __global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, D
     }
 }
 
-
 // -------------------------------------------------------------------------------------- step control
 // One-thread bookkeeping between phases.  `red` holds the (already globally reduced) values of the kernel before.
-enum { FLAGS_SUSP = 0, FLAGS_SUSP_CHECK = 1, FLAGS_DEP = 2, FLAGS_FORCE_SUSP_OK = 3 };
+enum { FLAGS_SUSP = 0, FLAGS_SUSP_CHECK = 1, FLAGS_DEP = 2, FLAGS_FORCE_SUSP_OK = 3, FLAGS_CHEB_CHECK = 4, FLAGS_SETUP_CG = 5,
+       FLAGS_DEP_RESTART = 6, FLAGS_COMBINE = 7 };
+
+// Chebyshev stopping rule: iteration k measured ||b - A q_k||^2 of the iterate it READ (buffer k&1), which stays
+// intact in that buffer, so detection keeps exactly that iterate.
+__device__ __forceinline__ void cheb_check(Scalars* sc, double rr, int k, double tol2) {
+    sc->rr = rr;
+    if (rr <= tol2 * sc->bnorm2) { sc->done = 1; sc->dep_ok = 1; sc->iters = k; sc->dep_buf = k & 1; }
+    else if (!(rr == rr) || rr > 1e60 * sc->bnorm2) sc->done = 2;  // diverging: spectrum bounds were wrong
+}
 
 __device__ __forceinline__ void susp_check(Scalars* sc, double rr, int it_now, double tol2) {
     sc->susp_rr = rr;
@@ -528,9 +553,12 @@ __device__ __forceinline__ void susp_check(Scalars* sc, double rr, int it_now, d
 __global__ void flags_kernel(int stage, Scalars* sc, const double* __restrict__ red, int it_now, double tol2) {
     switch (stage) {
         case FLAGS_SUSP: {  // after assembly: suspension_present = ||b||_inf > 1e-12 (PBSM3D.cpp:1424-1427)
-            sc->susp_rhs_max = red[0];
-            sc->susp_bnorm2 = red[1];
-            const int present = red[0] > 1e-12;
+            // single rank: red holds it_now per-chunk pairs {max|b|, sum b^2}; multi rank: one reduced pair
+            double mx = 0.0, ss = 0.0;
+            for (int k = 0; k < it_now; ++k) { mx = fmax(mx, red[2 * k]); ss += red[2 * k + 1]; }
+            sc->susp_rhs_max = mx;
+            sc->susp_bnorm2 = ss;
+            const int present = mx > 1e-12;
             sc->susp_present = present;
             sc->susp_done = present ? 0 : 1;  // nothing to solve: the solution stays the zero vector (:1461-1465)
             sc->susp_ok = present ? 0 : 1;
@@ -543,11 +571,29 @@ __global__ void flags_kernel(int stage, Scalars* sc, const double* __restrict__ 
         case FLAGS_SUSP_CHECK:
             if (!sc->susp_done) susp_check(sc, red[0], it_now, tol2);
             break;
+        case FLAGS_COMBINE: {  // fold it_now per-chunk pairs {max, sum} into red[0..1] (ahead of the all-reduce)
+            double mx = 0.0, ss = 0.0;
+            for (int k = 0; k < it_now; ++k) { mx = fmax(mx, red[2 * k]); ss += red[2 * k + 1]; }
+            double* w = const_cast<double*>(red);
+            w[0] = mx; w[1] = ss;
+        } break;
         case FLAGS_DEP:  // deposition solve iff suspension_present && ||rhs||_inf > 1e-12 (PBSM3D.cpp:1661-1664)
             if (!sc->susp_ok || sc->tail_done) break;
             sc->dep_rhs_max = red[0];
             sc->dep_present = (sc->susp_present && red[0] > 1e-12) ? 1 : 0;
+            sc->bnorm2 = red[1];
+            sc->rr = red[1];
+            sc->done = 0; sc->iters = 0; sc->dep_buf = 0;
             sc->tail_done = 1;
+            break;
+        case FLAGS_CHEB_CHECK:
+            if (sc->tail_done && sc->dep_present && !sc->done) cheb_check(sc, red[0], it_now, tol2);
+            break;
+        case FLAGS_SETUP_CG:  // pbsm3d_create: open the CG kernels for the spectrum estimate
+            sc->tail_done = 1; sc->dep_present = 1; sc->done = 0; sc->dep_ok = 0; sc->iters = 0; sc->log_n = 0;
+            break;
+        case FLAGS_DEP_RESTART:  // Chebyshev gave up: hand the same right-hand side to CG
+            sc->done = 0; sc->dep_ok = 0; sc->iters = 0; sc->dep_buf = 0;
             break;
         case FLAGS_FORCE_SUSP_OK:  // the host-driven Krylov path converged
             sc->susp_ok = 1; sc->susp_done = 1;
@@ -639,6 +685,49 @@ __global__ void __launch_bounds__(kRedThreads) residual_kernel(SuspSystem s, Dev
         const int z = (int)(r / Tp), p = (int)(r - (size_t)z * Tp);
         const double v = ((z == 0) ? s.rhs0[p] : 0.0) - spmv_row(s, m, L, x, z, p);
         a += v * v;
+    }
+    double rr, unused;
+    if (grid_fold<1>(a, 0.0, 0, 0, partial, pstride, &sc->ticket[1], rr, unused)) {
+        if (threadIdx.x == 0) {
+            red[0] = rr;
+            if (fused) susp_check(sc, rr, it_now, tol2);
+        }
+    }
+}
+
+// Same quantity, column-structured like the sweep (one thread per face column, every load issued before the
+// arithmetic, compile-time layer count): the row-wise kernel above re-reads the neighbour slots per row and
+// divides per row, and reaches only about half the bandwidth.
+template <int LT>
+__global__ void __launch_bounds__(128) residual_col_kernel(SuspSystem s, DevMesh m, const double* __restrict__ x,
+                                                           double* __restrict__ partial, int pstride, Scalars* sc,
+                                                           double* __restrict__ red, int it_now, double tol2, int fused) {
+    if (sc->susp_done) return;
+    const int Tp = m.Tp, S = m.S;
+    double a = 0.0;
+    const int ntiles = (Tp + 127) / 128;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p = tile * 128 + threadIdx.x;
+        if (p >= Tp) continue;
+        const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
+        double xo[LT], g[LT];
+#pragma unroll
+        for (int z = 0; z < LT; ++z) xo[z] = x[(size_t)z * S + p];
+#pragma unroll
+        for (int z = 0; z < LT; ++z) {
+            const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
+            g[z] = __ldcs(s.lat + r) * x[xr + n0] + __ldcs(s.lat + (size_t)LT * Tp + r) * x[xr + n1] +
+                   __ldcs(s.lat + (size_t)2 * LT * Tp + r) * x[xr + n2];
+        }
+#pragma unroll
+        for (int z = 0; z < LT; ++z) {
+            const size_t r = (size_t)z * Tp + p;
+            double v = g[z] + __ldcs(s.diag + r) * xo[z];
+            if (z > 0) v += __ldcs(s.below + r) * xo[z - 1];
+            if (z < LT - 1) v += __ldcs(s.above + r) * xo[z + 1];
+            v = ((z == 0) ? s.rhs0[p] : 0.0) - v;
+            a += v * v;
+        }
     }
     double rr, unused;
     if (grid_fold<1>(a, 0.0, 0, 0, partial, pstride, &sc->ticket[1], rr, unused)) {
@@ -835,11 +924,12 @@ __global__ void __launch_bounds__(256) flux_kernel(int Tp, int S, int L, double 
 // Qsusp/Qsalt are ghost-extended [S] (tails filled by the halo exchange).  red[0] = max|rhs| of this rank.
 __global__ void __launch_bounds__(256) deposition_rhs_kernel(DevMesh m, const double* __restrict__ vw_dir,
                                                              const double* __restrict__ Qsusp, const double* __restrict__ Qsalt,
-                                                             double* __restrict__ rhs, double* __restrict__ partial, int pstride,
+                                                             const double* __restrict__ dinv, double* __restrict__ rhs,
+                                                             double* __restrict__ rhsS, double* __restrict__ partial, int pstride,
                                                              Scalars* sc, double* __restrict__ red) {
     if (!sc->susp_ok || sc->tail_done) return;
     const int Tp = m.Tp;
-    double val_abs = 0.0;
+    double val_abs = 0.0, sumsq = 0.0;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < Tp; p += gridDim.x * blockDim.x) {
         const int i = m.perm[p];
         double acc = 0.0;
@@ -862,11 +952,67 @@ __global__ void __launch_bounds__(256) deposition_rhs_kernel(DevMesh m, const do
             }
         }
         rhs[p] = acc;
+        rhsS[p] = acc * dinv[p];
         val_abs = fmax(val_abs, fabs(acc));
+        sumsq += acc * acc;
     }
-    double mx, unused;
-    if (grid_fold<1>(val_abs, 0.0, 1, 0, partial, pstride, &sc->ticket[2], mx, unused)) {
-        if (threadIdx.x == 0) red[0] = mx;
+    double mx, ss;
+    if (grid_fold<2>(val_abs, sumsq, 1, 0, partial, pstride, &sc->ticket[2], mx, ss)) {
+        if (threadIdx.x == 0) { red[0] = mx; red[1] = ss; }
+    }
+}
+
+// Jacobi-scaled off-diagonals of the (static) deposition matrix: offS_j = off_j / diag.
+__global__ void deposition_scale_kernel(int Tp, const double* __restrict__ doff, const double* __restrict__ dinv,
+                                        double* __restrict__ offS) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp) return;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) offS[(size_t)j * Tp + p] = doff[(size_t)j * Tp + p] * dinv[p];
+}
+// Deterministic pseudo-random right-hand side for the setup-time spectrum estimate (depends on the global face id
+// only, so every partitioning of a mesh probes the same vector).
+__global__ void probe_rhs_kernel(int Tp, const int* __restrict__ perm, long long gid0, double* __restrict__ b) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp) return;
+    const int i = perm[p];
+    if (i < 0) { b[p] = 0.0; return; }
+    unsigned long long h = (unsigned long long)(gid0 + i) * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+    b[p] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+// HOT LOOP 3: one iteration of the Jacobi-preconditioned Chebyshev iteration on the deposition system
+//     z = D^{-1}(b - A q_k),   d = a_k d + c_k z,   q_{k+1} = q_k + d
+// (a_k, c_k from the spectrum bounds of D^{-1}A estimated once in pbsm3d_create: the matrix is static).  One
+// launch per iteration, no dot products, no global reduction: per face 3 scaled off-diagonals + 3 neighbour slots
+// + scaled rhs + q_k (+ gathers) + d in, d and q_{k+1} out = 76 B.  q is ghost-extended and ping-pongs between two
+// buffers, so the iterate an iteration read is still intact when a CHECK iteration finds it converged.
+template <int CHECK>
+__global__ void __launch_bounds__(kRedThreads) cheb_iter_kernel(DevMesh m, const double* __restrict__ offS,
+                                                                const double* __restrict__ bS, const double* __restrict__ ddiag,
+                                                                const double* __restrict__ qin, double* __restrict__ d,
+                                                                double* __restrict__ qout, double ak, double ck, int k,
+                                                                double* __restrict__ partial, int pstride, Scalars* sc,
+                                                                double* __restrict__ red, double tol2, int fused) {
+    if (sc && (!sc->tail_done || !sc->dep_present || sc->done)) return;  // sc == null: stand-alone timing launch
+    const int Tp = m.Tp;
+    double rr = 0.0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < Tp; p += gridDim.x * blockDim.x) {
+        const double qp = qin[p];
+        double z = bS[p] - qp;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) z -= offS[(size_t)j * Tp + p] * qin[m.nbs[(size_t)j * Tp + p]];
+        if (CHECK) { const double r = z * ddiag[p]; rr += r * r; }
+        const double dn = ak * d[p] + ck * z;
+        d[p] = dn;
+        qout[p] = qp + dn;
+    }
+    if (CHECK && sc) {
+        double o0, unused;
+        if (grid_fold<1>(rr, 0.0, 0, 0, partial, pstride, &sc->ticket[3], o0, unused)) {
+            if (threadIdx.x == 0) { red[0] = o0; if (fused) cheb_check(sc, o0, k, tol2); }
+        }
     }
 }
 
@@ -883,8 +1029,10 @@ __device__ __forceinline__ void cg_scalars(int stage, Scalars* sc, double r0, do
         case 1:
             if (r0 == 0.0 || isnan(r0)) { sc->done = 2; break; }
             sc->alpha = sc->rho / r0;
+            if (sc->log_alpha && sc->log_n < sc->log_cap) sc->log_alpha[sc->log_n] = sc->alpha;
             break;
         case 2:
+            if (sc->log_beta && sc->log_n < sc->log_cap) { sc->log_beta[sc->log_n] = r0 / sc->rho; sc->log_n += 1; }
             sc->iters += 1;
             sc->rr = r1;
             if (r1 <= tol2 * sc->bnorm2) { sc->done = 1; sc->dep_ok = 1; break; }
@@ -970,8 +1118,9 @@ __global__ void __launch_bounds__(kRedThreads) cg_p_kernel(int Tp, const Scalars
 
 // Drift update (PBSM3D.cpp:1710-1740); runs only when the deposition solve happened and converged, otherwise
 // drift_mass keeps its previous value as in the reference.  swe is in CHM order.
-__global__ void __launch_bounds__(256) drift_kernel(int Tp, double dt, const int* __restrict__ perm, const double* __restrict__ q,
-                                                    const double* __restrict__ swe_in, const unsigned char* __restrict__ salt,
+__global__ void __launch_bounds__(256) drift_kernel(int Tp, double dt, const int* __restrict__ perm, const double* __restrict__ q0,
+                                                    const double* __restrict__ q1, const double* __restrict__ swe_in,
+                                                    const unsigned char* __restrict__ salt,
                                                     double* __restrict__ drift_mass, double* __restrict__ sum_drift,
                                                     double* __restrict__ more_than_avail, const Scalars* __restrict__ sc) {
     if (!sc->dep_ok || sc->drift_done) return;
@@ -979,7 +1128,7 @@ __global__ void __launch_bounds__(256) drift_kernel(int Tp, double dt, const int
     if (p >= Tp) return;
     const int i = perm[p];
     if (i < 0) return;
-    double qdep = q[p];
+    double qdep = sc->dep_buf ? q1[p] : q0[p];
     qdep = chm_is_nan(qdep) ? 0.0 : qdep;
     double mass = qdep * dt;
     double swe = swe_in[i];

@@ -74,7 +74,7 @@ class PBSM3D:
         "use_exp_fetch", "use_tanh_fetch", "use_PomLi_probability", "z0_ustar_coupling", "use_subgrid_topo",
         "use_subgrid_topo_V2", "use_R94_lambda", "debug_output",
         # solver controls (hard-coded in LinearAlgebra.cpp:164-168; exposed here)
-        "tolerance", "max_iterations", "solver",
+        "tolerance", "max_iterations", "solver", "deposition_solver",
         # keys CHM's config block carries that this path does not read
         "N", "dv",
     }

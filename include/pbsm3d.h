@@ -46,6 +46,12 @@ enum {
 };
 
 enum {
+    PBSM3D_DEP_AUTO = 0,       /* Chebyshev with setup-time spectrum bounds, falling back to CG if it does not converge */
+    PBSM3D_DEP_CG = 1,         /* Jacobi-preconditioned conjugate gradients */
+    PBSM3D_DEP_CHEBYSHEV = 2   /* Jacobi-preconditioned Chebyshev iteration (no global reductions) */
+};
+
+enum {
     PBSM3D_SOLVER_AUTO = 0,     /* line relaxation, falling back to BiCGStab if it stagnates */
     PBSM3D_SOLVER_LINE = 1,     /* multicolour line Gauss-Seidel sweeps (exact vertical tridiagonal solve per face column) */
     PBSM3D_SOLVER_BICGSTAB = 2  /* right-preconditioned BiCGStab, column-tridiagonal preconditioner */
@@ -77,7 +83,8 @@ typedef struct pbsm3d_config {
     /* Solver controls.  The reference hard-codes these (LinearAlgebra.cpp:164-168). */
     double tolerance;             /* 1e-8: ||b-Ax||2/||b||2, x0 = 0 */
     int max_iterations;           /* 1000 */
-    int solver;                   /* PBSM3D_SOLVER_AUTO */
+    int solver;                   /* PBSM3D_SOLVER_AUTO (suspension system) */
+    int deposition_solver;        /* PBSM3D_DEP_AUTO */
 } pbsm3d_config;
 
 /* One rank's share of the mesh, flattened from CHM's triangulation in CHM's own face order.
@@ -153,6 +160,8 @@ typedef struct pbsm3d_stats {
     float ms_line_sweeps;            /* CUDA-event time of the first `sweeps_timed` line sweeps of this step */
     int32_t sweeps_timed;            /* full sweeps (all colours) inside ms_line_sweeps */
     int32_t n_colours;               /* colour classes of the internal face order */
+    int32_t deposition_solver_used;  /* PBSM3D_DEP_CG / PBSM3D_DEP_CHEBYSHEV */
+    int32_t host_syncs;              /* stream synchronisations the step needed (1 when every prediction held) */
 } pbsm3d_stats;
 
 typedef struct pbsm3d_handle pbsm3d_handle;
@@ -200,7 +209,8 @@ int pbsm3d_get_deposition_system(pbsm3d_handle* h, double* diag, double* off, do
 
 /* Stand-alone kernels for measurement (bench.py roofline line, ncu): run `reps` launches of the named kernel on
  * the last assembled system and return the mean CUDA-event time per launch in milliseconds.
- * kernel: 0 = one full line sweep (all colour passes), 1 = residual (SpMV), 2 = assembly, 3 = deposition SpMV. */
+ * kernel: 0 = one full line sweep (all colour passes), 1 = residual (SpMV), 2 = assembly, 3 = deposition CG SpMV,
+ * 4 = deposition Chebyshev iteration. */
 int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms_per_launch);
 
 #ifdef __cplusplus

@@ -39,7 +39,7 @@ def test_config_defaults_are_the_reference_defaults(lib):
                   smooth_coeff=820.0, min_sd_trans=0.1, cutoff=0.3, snow_diffusion_const=0.3, rouault_diffusion_coef=0,
                   enable_veg=1, iterative_subl=0, use_exp_fetch=0, use_tanh_fetch=1, use_PomLi_probability=0,
                   z0_ustar_coupling=0, use_subgrid_topo=0, use_subgrid_topo_V2=0, use_R94_lambda=1, debug_output=0,
-                  tolerance=1e-8, max_iterations=1000, solver=0)
+                  tolerance=1e-8, max_iterations=1000, solver=0, deposition_solver=0)
     for k, v in expect.items():
         assert getattr(c, k) == v, k
     with pytest.raises(KeyError):
@@ -50,7 +50,7 @@ def test_struct_layouts_match_header(lib):
     # 20 ints/doubles + 3 solver fields; natural alignment, no packing pragmas in the header
     assert C.sizeof(capi.Forcing) == 8 * 8 and C.sizeof(capi.Outputs) == 8 * 8
     assert C.sizeof(capi.Comm) == 16
-    assert C.sizeof(capi.Stats) == 6 * 4 + 4 * 8 + 6 * 4 + 2 * 4
+    assert C.sizeof(capi.Stats) == 6 * 4 + 4 * 8 + 6 * 4 + 4 * 4
     assert C.sizeof(capi.Mesh) == 8 + 4 + 4 + 10 * 8
 
 
