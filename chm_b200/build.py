@@ -62,5 +62,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+DRIVER = os.path.join(HOST, "standalone_driver")
+
+
+def build_adaptor(force: bool = False) -> str:
+    """g++ build of the CHM adaptor (host/PBSM3D_gpu.cpp) over the stand-in CHM types (host/chm_shim.hpp) plus the
+    stand-alone driver, linked against libpbsm3d_b200.so.  Inside CHM the same PBSM3D_gpu.cpp is compiled against
+    CHM's own headers instead."""
+    srcs = [os.path.join(HOST, f) for f in ("PBSM3D_gpu.cpp", "standalone_driver.cpp")]
+    deps = srcs + [os.path.join(HOST, f) for f in ("PBSM3D_gpu.hpp", "chm_shim.hpp")] + [os.path.join(HERE, "..", "include", "pbsm3d.h"), LIB]
+    if not force and os.path.exists(DRIVER) and all(os.path.getmtime(d) <= os.path.getmtime(DRIVER) for d in deps):
+        return DRIVER
+    cmd = ["g++", "-std=c++17", "-O2", "-fopenmp", "-DPBSM3D_GPU_STANDALONE", "-I", os.path.join(HERE, "..", "include"), "-I", HOST,
+           *srcs, "-o", DRIVER, "-L", HERE, "-l:libpbsm3d_b200.so", "-Wl,-rpath," + HERE]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building the stand-alone adaptor driver")
+    return DRIVER
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_adaptor(force="--force" in sys.argv))

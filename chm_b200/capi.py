@@ -84,6 +84,8 @@ SYMBOLS = {
     "pbsm3d_last_error": (C.c_char_p, []),
     "pbsm3d_config_defaults": (None, [C.POINTER(Config)]),
     "pbsm3d_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "pbsm3d_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "pbsm3d_host_free": (None, [C.c_void_p]),
     "pbsm3d_create": (C.c_int, [C.POINTER(Config), C.POINTER(Mesh), C.c_int, C.POINTER(Comm), C.POINTER(C.c_void_p)]),
     "pbsm3d_destroy": (None, [C.c_void_p]),
     "pbsm3d_step": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(Forcing), C.POINTER(Outputs), C.POINTER(Stats)]),

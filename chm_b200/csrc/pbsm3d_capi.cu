@@ -1050,6 +1050,18 @@ int pbsm3d_nccl_unique_id(void* out) {
     return 0;
 }
 
+void* pbsm3d_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        g_last_error = "cudaMallocHost failed";
+        return nullptr;
+    }
+    return p;
+}
+void pbsm3d_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 void pbsm3d_destroy(pbsm3d_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);

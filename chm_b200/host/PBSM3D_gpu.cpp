@@ -2,6 +2,7 @@
 // run :400-1748, checkpoint :1753-1773) and src/math/LinearAlgebra.cpp (NearestNeighborProblem).
 #include "PBSM3D_gpu.hpp"
 
+#include <algorithm>
 #include <cstring>
 
 REGISTER_MODULE_CPP(PBSM3D_gpu);
@@ -219,9 +220,14 @@ void PBSM3D_gpu::init(mesh& domain)
         device = pcomm ? comm.rank % std::max(1, cfg.get("gpus_per_node", 8)) : 0;
     check(pbsm3d_create(&_c, &m, device, pcomm, &_h));
 
-    for (auto* v : {&_U_R, &_U2, &_sd, &_swe, &_t, &_rh, &_vw_dir, &_fetch, &_Qsalt, &_Qsusp, &_Qsubl, &_Qsubl_mass,
-                    &_sum_subl, &_drift_mass, &_sum_drift, &_more})
-        v->assign(ntri, 0.0);
+    _stage = (double*)pbsm3d_host_alloc(16 * ntri * sizeof(double));
+    if (!_stage)
+        CHM_THROW_EXCEPTION(module_error, std::string("PBSM3D_gpu: ") + pbsm3d_last_error());
+    std::memset(_stage, 0, 16 * ntri * sizeof(double));
+    double** slots[16] = {&_U_R,   &_U2,    &_sd,    &_swe,        &_t,        &_rh,         &_vw_dir,   &_fetch,
+                          &_Qsalt, &_Qsusp, &_Qsubl, &_Qsubl_mass, &_sum_subl, &_drift_mass, &_sum_drift, &_more};
+    for (int k = 0; k < 16; ++k)
+        *slots[k] = _stage + (size_t)k * ntri;
 }
 
 void PBSM3D_gpu::run(mesh& domain)
@@ -242,10 +248,8 @@ void PBSM3D_gpu::run(mesh& domain)
         if (_use_fetch)
             _fetch[i] = (*face)["fetch"_s];
     }
-    pbsm3d_forcing f{_U_R.data(), _U2.data(), _sd.data(), _swe.data(), _t.data(),
-                     _rh.data(),  _vw_dir.data(), _use_fetch ? _fetch.data() : nullptr};
-    pbsm3d_outputs o{_Qsalt.data(),    _Qsusp.data(),      _Qsubl.data(),     _Qsubl_mass.data(),
-                     _sum_subl.data(), _drift_mass.data(), _sum_drift.data(), _more.data()};
+    pbsm3d_forcing f{_U_R, _U2, _sd, _swe, _t, _rh, _vw_dir, _use_fetch ? _fetch : nullptr};
+    pbsm3d_outputs o{_Qsalt, _Qsusp, _Qsubl, _Qsubl_mass, _sum_subl, _drift_mass, _sum_drift, _more};
     check(pbsm3d_step(_h, global_param->dt(), &f, &o, &_stats));
     SPDLOG_DEBUG("  suspension iterations: {} residual: {}", _stats.suspension_iterations, _stats.suspension_residual);
     SPDLOG_DEBUG("  deposition iterations: {} residual: {}", _stats.deposition_iterations, _stats.deposition_residual);
@@ -271,7 +275,11 @@ void PBSM3D_gpu::run(mesh& domain)
     }
 }
 
-PBSM3D_gpu::~PBSM3D_gpu() { pbsm3d_destroy(_h); }
+PBSM3D_gpu::~PBSM3D_gpu()
+{
+    pbsm3d_destroy(_h);
+    pbsm3d_host_free(_stage);
+}
 
 void PBSM3D_gpu::checkpoint(mesh& domain, netcdf& chkpt)
 {

@@ -47,7 +47,11 @@ class PBSM3D_gpu : public module_base
     pbsm3d_stats _stats{};
     bool _use_fetch = true;
     size_t _ntri = 0;
-    // SoA staging buffers (host): forcing in, outputs out.  Allocated once in init().
-    std::vector<double> _U_R, _U2, _sd, _swe, _t, _rh, _vw_dir, _fetch;
-    std::vector<double> _Qsalt, _Qsusp, _Qsubl, _Qsubl_mass, _sum_subl, _drift_mass, _sum_drift, _more;
+    // SoA staging buffers (host, page-locked so the library can overlap PCIe with compute): forcing in, outputs out.
+    // One block of 16 arrays, allocated once in init() with pbsm3d_host_alloc.
+    double* _stage = nullptr;
+    double *_U_R = nullptr, *_U2 = nullptr, *_sd = nullptr, *_swe = nullptr, *_t = nullptr, *_rh = nullptr, *_vw_dir = nullptr,
+           *_fetch = nullptr;
+    double *_Qsalt = nullptr, *_Qsusp = nullptr, *_Qsubl = nullptr, *_Qsubl_mass = nullptr, *_sum_subl = nullptr,
+           *_drift_mass = nullptr, *_sum_drift = nullptr, *_more = nullptr;
 };

@@ -173,6 +173,11 @@ void pbsm3d_config_defaults(pbsm3d_config* cfg);
 /* rank 0 calls this, the host broadcasts the 128 bytes, every rank passes them in pbsm3d_comm. */
 int pbsm3d_nccl_unique_id(void* out_128_bytes);
 
+/* Page-locked host memory for the forcing/output staging arrays: with pinned buffers pbsm3d_step overlaps the PCIe
+ * transfers with the assembly and the solves (pageable buffers work too, without the overlap).  NULL on failure. */
+void* pbsm3d_host_alloc(size_t bytes);
+void pbsm3d_host_free(void* p);
+
 int pbsm3d_create(const pbsm3d_config* cfg, const pbsm3d_mesh* mesh, int device, const pbsm3d_comm* comm,
                   pbsm3d_handle** out);
 void pbsm3d_destroy(pbsm3d_handle* h);
