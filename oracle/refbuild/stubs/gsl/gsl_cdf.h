@@ -1,0 +1,3 @@
+// Stand-in: see gsl_math.h in this directory.
+#pragma once
+#include "gsl_math.h"
