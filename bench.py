@@ -11,7 +11,8 @@ deposition solve, drift update) on a synthetic mesh:
   N = 1  : config c2 of BASELINE.md — 708×708 squares of 30 m split into 1 002 528 triangles, nLayer 10, fp64,
            PBSM3D options = the functional-test block (functional_tests/mesh_versioning/json_mesh.json:82-99)
   N > 1  : weak scaling — the same generator at ≈1.0 M triangles per GPU, partitioned by CHM's contiguous
-           global-id rule, ghost-face halos and global reductions over NCCL.
+           global-id rule; ghost-face halos and global reductions go through peer memory over NVLink (cudaIpc
+           arenas; PBSM3D_HALO=nccl forces NCCL send/recv + all-reduce instead).
 `value` = (triangles × layers over all ranks) / (CUDA-event time of the step, max over ranks), forcing resident in HBM.
 `e2e`   = the same through pbsm3d_step() with pinned HOST buffers (H2D of 8 forcing arrays + D2H of 8 outputs inside
           the timed region).
@@ -314,6 +315,8 @@ def main():
                        "deposition_solver": "Jacobi-Chebyshev (auto)" if st["deposition_solver_used"] == 2 else "Jacobi-CG",
                        "suspension_residual": st["suspension_residual"], "deposition_residual": st["deposition_residual"],
                        "host_syncs_per_step": syncs / args.steps,
+                       "halo_transport": {0: "none (single rank)", 1: "nccl", 2: "peer memory (cudaIpc over NVLink)"}[st["halo_transport"]],
+                       "halo_exchanges_per_step": st["halo_exchanges"],
                        "l2_policy": "working set of one step (~1 GB of coefficient streams per rank) exceeds the 126 MB L2; no flush needed",
                        "phases_ms": {k: v / args.steps for k, v in phases.items()}, "wall_ms_per_step": wall_ms},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * 8 * T * world,

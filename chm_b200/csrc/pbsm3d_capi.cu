@@ -139,6 +139,16 @@ struct pbsm3d_handle {
     int n_send = 0;
     int *send_slot = nullptr, *send_boff = nullptr, *send_cnt = nullptr, *send_pos = nullptr;
     double *sendbuf = nullptr, *recvbuf = nullptr;
+    // peer-memory transport (cudaIpc arenas over NVLink); NCCL stays the fallback transport and the setup plumbing
+    bool peer = false;
+    unsigned char* arena = nullptr;                 // my exported arena: flags | all-reduce slots | 2 halo staging buffers
+    std::vector<void*> peer_base;                   // [n_ranks] mapped arenas of the other ranks (nullptr for me)
+    PeerTable* d_pt = nullptr;
+    double** stage_remote[2] = {nullptr, nullptr};  // [parity][n_send] where each send entry lands on its partner
+    double* stage_local[2] = {nullptr, nullptr};
+    unsigned* halo_ticket = nullptr;
+    unsigned long long halo_epoch = 0, ar_epoch = 0;
+    int halo_ops = 0;                               // halo exchanges enqueued by the step in flight
     // predictions carried from step to step (iteration counts only; every solve still starts from x0 = 0)
     int pred_sweeps = 0, pred_cg = 0;
     double sweep_rate2 = 0.0;  // observed per-sweep contraction of ||r||^2
@@ -181,12 +191,20 @@ inline int red_grid(size_t n) { return std::max(1, std::min(kRedBlocks, cdiv(n, 
 inline bool fused(const pbsm3d_handle* h) { return h->n_ranks == 1; }
 
 int allreduce(pbsm3d_handle* h, double* buf, int n, bool is_max) {
-    if (h->n_ranks > 1) NC(ncclAllReduce(buf, buf, n, ncclDouble, is_max ? ncclMax : ncclSum, h->comm, h->stream));
+    if (h->n_ranks == 1) return 0;
+    if (h->peer) {
+        ++h->ar_epoch;
+        LAUNCH(h, peer_allreduce_kernel, 1, 32, buf, n, is_max ? 1 : 0, h->d_pt, h->ar_epoch);
+        return 0;
+    }
+    NC(ncclAllReduce(buf, buf, n, ncclDouble, is_max ? ncclMax : ncclSum, h->comm, h->stream));
     return 0;
 }
 int sync_stream(pbsm3d_handle* h) {
     ++h->n_syncs;
     CU(cudaStreamSynchronize(h->stream));
+    if (h->peer && h->h_sc->peer_error)
+        return fail(PBSM3D_ERR_NCCL, "peer-memory halo: a partner rank did not arrive within the time-out");
     return 0;
 }
 int read_scalars(pbsm3d_handle* h) {
@@ -254,6 +272,17 @@ void colour_faces(int T, const int32_t* neigh, std::vector<int>& colour, int& n_
 // v is a ghost-extended [nl][S] vector on the device; the ghost tails v[z*S + Tp + g] are refreshed in place.
 int halo_exchange(pbsm3d_handle* h, double* v, int nl) {
     if (h->n_ranks == 1 || h->partners.empty()) return 0;
+    ++h->halo_ops;
+    if (h->peer) {
+        const unsigned long long epoch = ++h->halo_epoch;
+        const int par = (int)(epoch & 1ull);
+        const size_t ns = (size_t)h->n_send * nl, ng = (size_t)h->nG * nl;
+        LAUNCH(h, halo_push_kernel, std::max(1, std::min(cdiv(ns, 256), 148 * 4)), 256, h->n_send, nl, h->S, h->send_slot, h->send_cnt,
+               h->stage_remote[par], v, h->d_pt, epoch, h->halo_ticket);
+        LAUNCH(h, halo_wait_unpack_kernel, std::max(1, std::min(cdiv(ng, 256), 148 * 4)), 256, h->nG, nl, h->L, h->Tp, h->S, h->gstart,
+               h->gcnt, h->stage_local[par], v, h->d_pt, epoch);
+        return 0;
+    }
     if (h->n_send > 0) {
         size_t total = (size_t)h->n_send * nl;
         int blocks = std::min(cdiv(total, 256), 148 * 8);
@@ -273,6 +302,118 @@ int halo_exchange(pbsm3d_handle* h, double* v, int nl) {
         int blocks = std::min(cdiv(total, 256), 148 * 8);
         LAUNCH(h, halo_unpack_kernel, blocks, 256, h->nG, nl, h->Tp, h->S, h->gstart, h->gcnt, h->recvbuf, v);
     }
+    return 0;
+}
+
+// ---- peer-memory transport ----------------------------------------------------------------------------------
+// Arena layout (identical on every rank up to the staging size): halo flags | all-reduce flags | all-reduce slots |
+// staging[2][nGp * L].  M[r][q] = ghosts rank r needs from rank q, known to everyone, gives each rank the place of
+// its block in every partner's staging buffer without another exchange.
+constexpr size_t kArenaHaloFlag = 0, kArenaArFlag = kMaxRanks * 8, kArenaArSlots = 2 * kMaxRanks * 8,
+                 kArenaStage = kArenaArSlots + 2 * kMaxRanks * 4 * 8;
+struct PeerHello {
+    cudaIpcMemHandle_t mem;
+    int ok, pad;
+};
+void close_peer(pbsm3d_handle* h) {
+    for (void* b : h->peer_base)
+        if (b) cudaIpcCloseMemHandle(b);
+    h->peer_base.clear();
+    h->peer = false;
+}
+int setup_peer(pbsm3d_handle* h, const std::vector<int>& M) {
+    const int P = h->n_ranks, me = h->rank, L = h->L;
+    const char* want = getenv("PBSM3D_HALO");
+    const bool verbose = getenv("PBSM3D_VERBOSE") != nullptr;
+    if (want && std::string(want) == "nccl") return 0;
+    if (P > kMaxRanks) return 0;
+    auto ghosts_of = [&](int r) { int n = 0; for (int q = 0; q < P; ++q) n += M[(size_t)r * P + q]; return n; };
+    auto stage_elems = [&](int r) { return (size_t)align_up(std::max(ghosts_of(r), 1), 32) * L; };
+    const size_t arena_bytes = kArenaStage + 2 * stage_elems(me) * sizeof(double);
+    TRY(h->alloc(&h->arena, arena_bytes));
+    CU(cudaMemsetAsync(h->arena, 0, arena_bytes, h->stream));
+    PeerHello hello;
+    std::memset(&hello, 0, sizeof(hello));
+    hello.ok = cudaIpcGetMemHandle(&hello.mem, h->arena) == cudaSuccess ? 1 : 0;
+    if (!hello.ok) cudaGetLastError();
+    unsigned char *d_hello = nullptr, *d_all = nullptr;
+    TRY(h->alloc(&d_hello, sizeof(PeerHello)));
+    TRY(h->alloc(&d_all, sizeof(PeerHello) * P));
+    TRY(upload(h, d_hello, &hello, sizeof(hello)));
+    NC(ncclAllGather(d_hello, d_all, sizeof(PeerHello), ncclUint8, h->comm, h->stream));
+    std::vector<PeerHello> all(P);
+    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerHello) * P, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int ok = 1;
+    for (int q = 0; q < P; ++q) ok = ok && all[q].ok;
+    h->peer_base.assign(P, nullptr);
+    for (int q = 0; q < P && ok; ++q) {
+        if (q == me) continue;
+        void* b = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&b, all[q].mem, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            if (verbose) fprintf(stderr, "[pbsm3d] rank %d: cudaIpcOpenMemHandle(rank %d): %s\n", me, q, cudaGetErrorString(e));
+            cudaGetLastError();
+            ok = 0;
+        } else {
+            h->peer_base[q] = b;
+        }
+    }
+    // everyone or no one: a rank that cannot map a peer sends every rank back to NCCL
+    double* d_ok = nullptr;
+    TRY(h->alloc(&d_ok, 1));
+    double okd = ok;
+    TRY(upload(h, d_ok, &okd, sizeof(double)));
+    NC(ncclAllReduce(d_ok, d_ok, 1, ncclDouble, ncclMin, h->comm, h->stream));
+    CU(cudaMemcpyAsync(&okd, d_ok, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->release(d_hello);
+    h->release(d_all);
+    h->release(d_ok);
+    if (okd < 0.5) {
+        if (verbose && me == 0) fprintf(stderr, "[pbsm3d] peer-memory transport unavailable: halos and reductions go over NCCL\n");
+        close_peer(h);
+        return 0;
+    }
+    auto base_of = [&](int q) { return q == me ? h->arena : (unsigned char*)h->peer_base[q]; };
+    PeerTable pt;
+    std::memset(&pt, 0, sizeof(pt));
+    pt.n_ranks = P;
+    pt.me = me;
+    pt.n_partners = (int)h->partners.size();
+    for (int i = 0; i < pt.n_partners; ++i) {
+        const int r = h->partners[i].rank;
+        pt.partner_rank[i] = r;
+        pt.halo_flag_remote[i] = (unsigned long long*)(base_of(r) + kArenaHaloFlag) + me;
+    }
+    pt.halo_flag_local = (unsigned long long*)(h->arena + kArenaHaloFlag);
+    for (int q = 0; q < P; ++q) {
+        pt.ar_slots_remote[q] = (double*)(base_of(q) + kArenaArSlots);
+        pt.ar_flag_remote[q] = (unsigned long long*)(base_of(q) + kArenaArFlag) + me;
+    }
+    pt.ar_slots_local = (double*)(h->arena + kArenaArSlots);
+    pt.ar_flag_local = (unsigned long long*)(h->arena + kArenaArFlag);
+    pt.error = &h->sc->peer_error;
+    const char* to = getenv("PBSM3D_PEER_TIMEOUT_MS");
+    pt.timeout_ns = (unsigned long long)(to ? std::max(1L, atol(to)) : 20000L) * 1000000ull;
+    TRY(h->alloc(&h->d_pt, 1));
+    TRY(upload(h, h->d_pt, &pt, sizeof(pt)));
+    for (int par = 0; par < 2; ++par) {
+        h->stage_local[par] = (double*)(h->arena + kArenaStage) + (size_t)par * stage_elems(me);
+        std::vector<double*> dst((size_t)std::max(h->n_send, 1), nullptr);
+        for (const Partner& p : h->partners) {
+            size_t roff = 0;  // where the ghosts rank p.rank needs from me start in its ghost list
+            for (int q = 0; q < me; ++q) roff += M[(size_t)p.rank * P + q];
+            double* stage = (double*)(base_of(p.rank) + kArenaStage) + (size_t)par * stage_elems(p.rank);
+            for (int k = 0; k < p.send_cnt; ++k) dst[p.send_off + k] = stage + roff * L + k;
+        }
+        TRY(h->alloc(&h->stage_remote[par], dst.size()));
+        TRY(upload(h, h->stage_remote[par], dst.data(), dst.size() * sizeof(double*)));
+    }
+    TRY(h->alloc_zero(&h->halo_ticket, 1));
+    CU(cudaStreamSynchronize(h->stream));
+    h->peer = true;
+    if (verbose && me == 0) fprintf(stderr, "[pbsm3d] peer-memory transport: %d ranks, arena %zu KB per rank\n", P, arena_bytes >> 10);
     return 0;
 }
 
@@ -348,7 +489,7 @@ int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* com
     TRY(h->alloc(&h->sendbuf, (size_t)n_send * h->L));
     TRY(h->alloc(&h->recvbuf, (size_t)std::max(nG, 1) * h->L));
     CU(cudaStreamSynchronize(h->stream));
-    return 0;
+    return setup_peer(h, M);
 }
 
 // ---- suspension solve: multicolour line Gauss–Seidel ---------------------------------------------------------
@@ -784,6 +925,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const double* co
     const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
     const int maxit = h->cfg.max_iterations;
     h->n_syncs = 0;
+    h->halo_ops = 0;
     const auto t_host0 = std::chrono::steady_clock::now();
     h->last_forcing = f;
     h->last_dt = dt;
@@ -961,6 +1103,8 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const double* co
     st->sweeps_timed = h->sweeps_timed;
     st->n_colours = h->n_colours;
     st->kernel_launches = (int32_t)(h->n_launch - launch0);
+    st->halo_exchanges = h->halo_ops;
+    st->halo_transport = h->n_ranks == 1 ? PBSM3D_HALO_NONE : (h->peer ? PBSM3D_HALO_PEER : PBSM3D_HALO_NCCL);
     CU(cudaGetLastError());
     return 0;
 }
@@ -1073,6 +1217,8 @@ void pbsm3d_destroy(pbsm3d_handle* h) {
     if (h->ev_asm) cudaEventDestroy(h->ev_asm);
     if (h->ev_flux) cudaEventDestroy(h->ev_flux);
     if (h->ev_out) cudaEventDestroy(h->ev_out);
+    for (void* b : h->peer_base)
+        if (b) cudaIpcCloseMemHandle(b);
     if (h->comm) ncclCommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_sc) cudaFreeHost(h->h_sc);

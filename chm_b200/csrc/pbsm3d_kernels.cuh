@@ -87,6 +87,7 @@ struct Scalars {
     int log_n, log_cap;               // setup only: CG recurrence log for the Lanczos spectrum estimate
     double *log_alpha, *log_beta;
     unsigned ticket[4];
+    int peer_error;                   // sticky: a peer-memory wait timed out (see PeerTable)
 };
 
 // ---------------------------------------------------------------------------------------------- setup
@@ -1182,6 +1183,132 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(int nG, int nl, int Tp
         int z = (int)(e / nG), g = (int)(e - (size_t)z * nG);
         const int gs = gstart[g];
         v[(size_t)z * S + Tp + g] = buf[(size_t)gs * nl + (size_t)z * gcnt[g] + (g - gs)];
+    }
+}
+
+// ------------------------------------------------------------------------------ halo over peer memory
+// One process per GPU; every rank exports ONE arena (cudaIpc) holding its flags, all-reduce slots and two halo
+// staging buffers, and maps the arenas of the other ranks of the NVSwitch box.  A halo is then
+//     push : each rank stores the rows its partners need straight into THEIR staging buffer over NVLink, fences,
+//            and the last block raises the partner's flag to this exchange's epoch (st.release.sys)
+//     wait : the consumer spins on its own flags (ld.acquire.sys) until every partner's epoch arrived, then
+//            copies the staged rows into the ghost tails of the vector
+// with no host involvement, no NCCL proxy and no rendez-vous: two short launches, or none when the producer /
+// consumer kernels carry the push / wait themselves (cheb_iter_kernel).  Epochs count the halo operations of the
+// handle; every rank enqueues the same sequence (control flow depends only on globally reduced scalars), so
+// partners agree on them.  Staging is double-buffered on the epoch's parity: a rank can be at most one exchange
+// ahead of a partner (its next push needs the partner's previous one), so a buffer is never overwritten before
+// its owner has unpacked it.
+constexpr int kMaxRanks = 16;
+
+struct PeerTable {
+    int n_ranks, me;
+    int n_partners;                                   // halo partners (ranks that share a partition boundary with me)
+    int partner_rank[kMaxRanks];
+    unsigned long long* halo_flag_remote[kMaxRanks];  // [partner] -> that rank's halo_flag[me]
+    unsigned long long* halo_flag_local;              // [kMaxRanks] indexed by source rank (my arena)
+    double* ar_slots_remote[kMaxRanks];               // [rank] -> that rank's ar_slots
+    unsigned long long* ar_flag_remote[kMaxRanks];    // [rank] -> that rank's ar_flag[me]
+    double* ar_slots_local;                           // [2][kMaxRanks][4]
+    unsigned long long* ar_flag_local;                // [kMaxRanks]
+    int* error;                                       // sticky: 1 = a wait timed out (peer died / protocol bug)
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag >= epoch.  Bounded: a peer that never arrives sets the sticky error instead of hanging the GPU.
+__device__ __forceinline__ void peer_wait(const unsigned long long* flag, unsigned long long epoch, const PeerTable* pt) {
+    if (ld_acquire_sys(flag) >= epoch) return;
+    if (*(volatile int*)pt->error) return;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) < epoch) {
+        __nanosleep(40);
+        if (global_timer_ns() - t0 > pt->timeout_ns) { *(volatile int*)pt->error = 1; return; }
+    }
+}
+// every partner's halo of `epoch` has landed in my arena (call from all threads of a block; ends with a barrier)
+__device__ __forceinline__ void halo_wait_block(const PeerTable* pt, unsigned long long epoch) {
+    if ((int)threadIdx.x < pt->n_partners) peer_wait(pt->halo_flag_local + pt->partner_rank[threadIdx.x], epoch, pt);
+    __syncthreads();
+}
+// all remote stores of this grid are done (each thread fenced its own): the last block tells the partners
+__device__ __forceinline__ void halo_signal_grid(const PeerTable* pt, unsigned long long epoch, unsigned* ticket) {
+    __shared__ bool last_block;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicInc(ticket, gridDim.x - 1);
+        last_block = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last_block && (int)threadIdx.x < pt->n_partners) {
+        __threadfence_system();
+        st_release_sys(pt->halo_flag_remote[threadIdx.x], epoch);
+    }
+}
+
+// push: stage_remote[k] points at (partner's staging buffer of this parity) + (my block there) + send_pos[k]
+__global__ void __launch_bounds__(256) halo_push_kernel(int n_send, int nl, int S, const int* __restrict__ send_slot,
+                                                        const int* __restrict__ send_cnt, double* const* __restrict__ stage_remote,
+                                                        const double* __restrict__ v, const PeerTable* __restrict__ pt,
+                                                        unsigned long long epoch, unsigned* ticket) {
+    const size_t total = (size_t)n_send * nl;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int z = (int)(e / n_send), k = (int)(e - (size_t)z * n_send);
+        stage_remote[k][(size_t)z * send_cnt[k]] = __ldcg(v + (size_t)z * S + send_slot[k]);
+    }
+    halo_signal_grid(pt, epoch, ticket);
+}
+// wait + unpack: v[z*S + Tp + g] = stage[gstart*Lmax + z*gcnt + (g-gstart)]   (block of an owner: [nl][cnt] at gstart*Lmax)
+__global__ void __launch_bounds__(256) halo_wait_unpack_kernel(int nG, int nl, int Lmax, int Tp, int S, const int* __restrict__ gstart,
+                                                               const int* __restrict__ gcnt, const double* stage, double* __restrict__ v,
+                                                               const PeerTable* __restrict__ pt, unsigned long long epoch) {
+    halo_wait_block(pt, epoch);
+    const size_t total = (size_t)nG * nl;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int z = (int)(e / nG), g = (int)(e - (size_t)z * nG);
+        const int gs = gstart[g];
+        v[(size_t)z * S + Tp + g] = __ldcg(stage + (size_t)gs * Lmax + (size_t)z * gcnt[g] + (g - gs));
+    }
+}
+
+// All-reduce of n <= 4 doubles over all ranks through peer memory, in place in red[]: lane q stores my values into
+// rank q's slot [parity][me], raises rank q's flag, then waits for rank q's values; lane 0 folds the P slots in
+// RANK ORDER, so every rank gets the same bits and the result does not depend on arrival order.  One warp.
+__global__ void peer_allreduce_kernel(double* red, int n, int is_max, const PeerTable* __restrict__ pt, unsigned long long epoch) {
+    const int q = threadIdx.x, P = pt->n_ranks, me = pt->me;
+    const int parity = (int)(epoch & 1ull);
+    if (q < P) {
+        double* dst = pt->ar_slots_remote[q] + ((size_t)parity * kMaxRanks + me) * 4;
+        for (int i = 0; i < n; ++i) dst[i] = red[i];
+        __threadfence_system();
+        st_release_sys(pt->ar_flag_remote[q], epoch);
+        peer_wait(pt->ar_flag_local + q, epoch, pt);
+    }
+    __syncwarp();
+    if (q == 0) {
+        const double* base = pt->ar_slots_local + (size_t)parity * kMaxRanks * 4;
+        for (int i = 0; i < n; ++i) {
+            double acc = __ldcg(base + i);
+            for (int r = 1; r < P; ++r) {
+                const double w = __ldcg(base + (size_t)r * 4 + i);
+                acc = is_max ? fmax(acc, w) : acc + w;
+            }
+            red[i] = acc;
+        }
     }
 }
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PBSM3D_ABI_VERSION 1
+#define PBSM3D_ABI_VERSION 2
 
 enum {
     PBSM3D_OK = 0,
@@ -49,6 +49,16 @@ enum {
     PBSM3D_DEP_AUTO = 0,       /* Chebyshev with setup-time spectrum bounds, falling back to CG if it does not converge */
     PBSM3D_DEP_CG = 1,         /* Jacobi-preconditioned conjugate gradients */
     PBSM3D_DEP_CHEBYSHEV = 2   /* Jacobi-preconditioned Chebyshev iteration (no global reductions) */
+};
+
+/* How ghost-face halos and the solvers' global reductions travel between the ranks of one NVSwitch box
+ * (reference: MPI messages, triangulation.cpp:1976-2079).  PEER = direct stores into the partner's exported
+ * staging buffer over NVLink (cudaIpc), chosen whenever every rank can map every other rank's arena; NCCL
+ * send/recv + all-reduce otherwise, or when PBSM3D_HALO=nccl is set in the environment. */
+enum {
+    PBSM3D_HALO_NONE = 0,
+    PBSM3D_HALO_NCCL = 1,
+    PBSM3D_HALO_PEER = 2
 };
 
 enum {
@@ -162,6 +172,8 @@ typedef struct pbsm3d_stats {
     int32_t n_colours;               /* colour classes of the internal face order */
     int32_t deposition_solver_used;  /* PBSM3D_DEP_CG / PBSM3D_DEP_CHEBYSHEV */
     int32_t host_syncs;              /* stream synchronisations the step needed (1 when every prediction held) */
+    int32_t halo_exchanges;          /* ghost-face halo exchanges the step enqueued (0 on a single rank) */
+    int32_t halo_transport;          /* PBSM3D_HALO_NONE / _NCCL / _PEER */
 } pbsm3d_stats;
 
 typedef struct pbsm3d_handle pbsm3d_handle;

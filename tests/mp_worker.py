@@ -54,6 +54,7 @@ def main():
             gathered[f"{name}_{k}"] = torch.cat(parts).cpu().numpy()
         gathered[f"iters_{k}"] = np.array([st["suspension_iterations"], st["deposition_iterations"], st["suspension_present"],
                                            st["deposition_present"]])
+    gathered["halo_transport"] = np.array(st["halo_transport"])
     if rank == 0:
         np.savez(out_path, **gathered)
     h.close()

@@ -20,23 +20,30 @@ def ngpus():
     return torch.cuda.device_count()
 
 
-def run_ranks(tmp_path, world, meshname, L, solver, nsteps):
-    out = str(tmp_path / f"mp_{meshname}_{world}_{solver}.npz")
+def run_ranks(tmp_path, world, meshname, L, solver, nsteps, transport="peer"):
+    out = str(tmp_path / f"mp_{meshname}_{world}_{solver}_{transport}.npz")
+    env = dict(os.environ)
+    env.pop("PBSM3D_HALO", None)
+    if transport == "nccl":
+        env["PBSM3D_HALO"] = "nccl"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "mp_worker.py"), out, meshname, str(L), str(solver), str(nsteps)]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     return np.load(out)
 
 
-@pytest.mark.parametrize("solver", [capi.SOLVER_LINE, capi.SOLVER_BICGSTAB], ids=["line", "bicgstab"])
-def test_two_ranks_match_oracle_and_single_gpu(tmp_path, solver):
+@pytest.mark.parametrize("solver,transport", [(capi.SOLVER_LINE, "peer"), (capi.SOLVER_LINE, "nccl"), (capi.SOLVER_BICGSTAB, "peer")],
+                         ids=["line-peer", "line-nccl", "bicgstab-peer"])
+def test_two_ranks_match_oracle_and_single_gpu(tmp_path, solver, transport):
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")
     L = 6
     mesh = load_mesh("slope_metis")
     geo = mesh.geometry()
-    g = run_ranks(tmp_path, 2, "slope_metis", L, solver, 3)
+    g = run_ranks(tmp_path, 2, "slope_metis", L, solver, 3, transport)
+    # halos and reductions went the way that was asked for: peer memory (cudaIpc over NVLink) unless NCCL is forced
+    assert int(g["halo_transport"]) == (capi.HALO_NCCL if transport == "nccl" else capi.HALO_PEER)
     o = PBSM3DOracle(Config.functional_test(L), mesh.neigh, geo, mesh.global_id, mesh.n_global, mesh.params)
     h = capi.Handle(capi.default_config(solver=solver, tolerance=1e-10, **functest_kw(L)), mesh)
     for k in range(3):
@@ -59,6 +66,7 @@ def test_max_ranks_on_uniform_mesh(tmp_path):
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
     L = 10
     g = run_ranks(tmp_path, world, "uniform120", L, capi.SOLVER_AUTO, 1)
+    assert int(g["halo_transport"]) == capi.HALO_PEER
     mesh = synthetic.uniform_mesh(120, 120)
     geo = mesh.geometry()
     h = capi.Handle(capi.default_config(tolerance=1e-10, **functest_kw(L)), mesh)
