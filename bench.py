@@ -317,6 +317,7 @@ def main():
                        "host_syncs_per_step": syncs / args.steps,
                        "halo_transport": {0: "none (single rank)", 1: "nccl", 2: "peer memory (cudaIpc over NVLink)"}[st["halo_transport"]],
                        "halo_exchanges_per_step": st["halo_exchanges"],
+                       "halo_exchanges_inside_solver_kernels": st["halo_fused"],
                        "l2_policy": "working set of one step (~1 GB of coefficient streams per rank) exceeds the 126 MB L2; no flush needed",
                        "phases_ms": {k: v / args.steps for k, v in phases.items()}, "wall_ms_per_step": wall_ms},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * 8 * T * world,

@@ -24,7 +24,7 @@ c_uint8_p = C.POINTER(C.c_uint8)
 SOLVER_AUTO, SOLVER_LINE, SOLVER_BICGSTAB = 0, 1, 2
 DEP_AUTO, DEP_CG, DEP_CHEBYSHEV = 0, 1, 2
 HALO_NONE, HALO_NCCL, HALO_PEER = 0, 1, 2
-ABI_VERSION = 2  # include/pbsm3d.h PBSM3D_ABI_VERSION
+ABI_VERSION = 3  # include/pbsm3d.h PBSM3D_ABI_VERSION
 ERR_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "NOCONVERGE"}
 
 
@@ -71,7 +71,7 @@ class Stats(C.Structure):
         ("deposition_rhs_max", C.c_double), ("ms_assembly", C.c_float), ("ms_suspension_solve", C.c_float),
         ("ms_flux_and_halo", C.c_float), ("ms_deposition", C.c_float), ("ms_total", C.c_float), ("ms_line_sweeps", C.c_float),
         ("sweeps_timed", C.c_int32), ("n_colours", C.c_int32), ("deposition_solver_used", C.c_int32), ("host_syncs", C.c_int32),
-        ("halo_exchanges", C.c_int32), ("halo_transport", C.c_int32),
+        ("halo_exchanges", C.c_int32), ("halo_transport", C.c_int32), ("halo_fused", C.c_int32),
     ]
 
     def asdict(self):

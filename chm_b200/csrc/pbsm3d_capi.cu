@@ -149,6 +149,24 @@ struct pbsm3d_handle {
     unsigned* halo_ticket = nullptr;
     unsigned long long halo_epoch = 0, ar_epoch = 0;
     int halo_ops = 0;                               // halo exchanges enqueued by the step in flight
+    // halos carried by the solver kernels themselves (HaloLink): x of the line sweeps, q of the Chebyshev iteration
+    bool fused_halo = false;
+    int halo_fused_ops = 0;
+    std::vector<long long> give_ids;                // handshake: global ids of my faces the partners need, per partner block
+    std::vector<int> need_matrix;                   // M[r][q] = ghosts rank r needs from rank q
+    std::vector<unsigned char> is_boundary;         // [T] a partner needs this face
+    int nb[kMaxColours] = {0}, boff[kMaxColours] = {0}, nb_total = 0, n_entries = 0, nGp = 0;
+    int *bptr = nullptr, *rstride = nullptr;
+    double** x_remote[3] = {nullptr, nullptr, nullptr};
+    ulonglong2** q_remote[3] = {nullptr, nullptr, nullptr};  // tagged 16-byte entries (TaggedLink)
+    double* xg[3] = {nullptr, nullptr, nullptr};    // my ghost buffers (in the arena)
+    ulonglong2* qg[3] = {nullptr, nullptr, nullptr};
+    double* g_zero = nullptr;                       // [L][nGp] zeros: the ghosts of the first iteration of a solve
+    unsigned long long **xflag_remote = nullptr, **qflag_remote = nullptr;
+    unsigned long long *xflag_local = nullptr, *qflag_local = nullptr;
+    unsigned *xticket = nullptr, *qticket = nullptr;
+    unsigned long long xh_epoch = 0, qh_epoch = 0;  // iteration numbers of the two channels (monotonic)
+    bool x_first = true;                            // the next sweep is the first of a solve (x = 0: ghosts read as 0)
     // predictions carried from step to step (iteration counts only; every solve still starts from x0 = 0)
     int pred_sweeps = 0, pred_cg = 0;
     double sweep_rate2 = 0.0;  // observed per-sweep contraction of ||r||^2
@@ -310,7 +328,10 @@ int halo_exchange(pbsm3d_handle* h, double* v, int nl) {
 // staging[2][nGp * L].  M[r][q] = ghosts rank r needs from rank q, known to everyone, gives each rank the place of
 // its block in every partner's staging buffer without another exchange.
 constexpr size_t kArenaHaloFlag = 0, kArenaArFlag = kMaxRanks * 8, kArenaArSlots = 2 * kMaxRanks * 8,
-                 kArenaStage = kArenaArSlots + 2 * kMaxRanks * 4 * 8;
+                 kArenaXFlag = kArenaArSlots + 2 * kMaxRanks * 4 * 8, kArenaQFlag = kArenaXFlag + kMaxRanks * 8,
+                 kArenaStage = kArenaQFlag + kMaxRanks * 8;
+// after the two staging buffers: xg[3][L][gp] and qg[3][gp], the ghost buffers of the fused channels (gp = padded
+// ghost count of the arena's owner)
 struct PeerHello {
     cudaIpcMemHandle_t mem;
     int ok, pad;
@@ -321,15 +342,18 @@ void close_peer(pbsm3d_handle* h) {
     h->peer_base.clear();
     h->peer = false;
 }
-int setup_peer(pbsm3d_handle* h, const std::vector<int>& M) {
+int setup_peer(pbsm3d_handle* h, const std::vector<int>& M, const std::vector<int>& sslot) {
     const int P = h->n_ranks, me = h->rank, L = h->L;
     const char* want = getenv("PBSM3D_HALO");
     const bool verbose = getenv("PBSM3D_VERBOSE") != nullptr;
     if (want && std::string(want) == "nccl") return 0;
     if (P > kMaxRanks) return 0;
     auto ghosts_of = [&](int r) { int n = 0; for (int q = 0; q < P; ++q) n += M[(size_t)r * P + q]; return n; };
-    auto stage_elems = [&](int r) { return (size_t)align_up(std::max(ghosts_of(r), 1), 32) * L; };
-    const size_t arena_bytes = kArenaStage + 2 * stage_elems(me) * sizeof(double);
+    auto gp = [&](int r) { return (size_t)align_up(std::max(ghosts_of(r), 1), 32); };
+    auto stage_elems = [&](int r) { return gp(r) * L; };
+    auto off_xg = [&](int r) { return kArenaStage + 2 * stage_elems(r) * sizeof(double); };
+    auto off_qg = [&](int r) { return off_xg(r) + 3 * stage_elems(r) * sizeof(double); };
+    const size_t arena_bytes = off_qg(me) + 3 * gp(me) * sizeof(ulonglong2);
     TRY(h->alloc(&h->arena, arena_bytes));
     CU(cudaMemsetAsync(h->arena, 0, arena_bytes, h->stream));
     PeerHello hello;
@@ -381,10 +405,14 @@ int setup_peer(pbsm3d_handle* h, const std::vector<int>& M) {
     pt.n_ranks = P;
     pt.me = me;
     pt.n_partners = (int)h->partners.size();
+    const int np = std::max(pt.n_partners, 1);
+    std::vector<unsigned long long*> xfr(np, nullptr), qfr(np, nullptr);
     for (int i = 0; i < pt.n_partners; ++i) {
         const int r = h->partners[i].rank;
         pt.partner_rank[i] = r;
         pt.halo_flag_remote[i] = (unsigned long long*)(base_of(r) + kArenaHaloFlag) + me;
+        xfr[i] = (unsigned long long*)(base_of(r) + kArenaXFlag) + me;
+        qfr[i] = (unsigned long long*)(base_of(r) + kArenaQFlag) + me;
     }
     pt.halo_flag_local = (unsigned long long*)(h->arena + kArenaHaloFlag);
     for (int q = 0; q < P; ++q) {
@@ -398,12 +426,16 @@ int setup_peer(pbsm3d_handle* h, const std::vector<int>& M) {
     pt.timeout_ns = (unsigned long long)(to ? std::max(1L, atol(to)) : 20000L) * 1000000ull;
     TRY(h->alloc(&h->d_pt, 1));
     TRY(upload(h, h->d_pt, &pt, sizeof(pt)));
+    auto roff_at = [&](int r) {  // where the ghosts rank r needs from me start in its ghost list
+        size_t roff = 0;
+        for (int q = 0; q < me; ++q) roff += M[(size_t)r * P + q];
+        return roff;
+    };
     for (int par = 0; par < 2; ++par) {
         h->stage_local[par] = (double*)(h->arena + kArenaStage) + (size_t)par * stage_elems(me);
         std::vector<double*> dst((size_t)std::max(h->n_send, 1), nullptr);
         for (const Partner& p : h->partners) {
-            size_t roff = 0;  // where the ghosts rank p.rank needs from me start in its ghost list
-            for (int q = 0; q < me; ++q) roff += M[(size_t)p.rank * P + q];
+            const size_t roff = roff_at(p.rank);
             double* stage = (double*)(base_of(p.rank) + kArenaStage) + (size_t)par * stage_elems(p.rank);
             for (int k = 0; k < p.send_cnt; ++k) dst[p.send_off + k] = stage + roff * L + k;
         }
@@ -411,13 +443,77 @@ int setup_peer(pbsm3d_handle* h, const std::vector<int>& M) {
         TRY(upload(h, h->stage_remote[par], dst.data(), dst.size() * sizeof(double*)));
     }
     TRY(h->alloc_zero(&h->halo_ticket, 1));
+
+    // ---- fused channels: boundary CSR + where every send entry lands in the partner's ghost buffers
+    h->nGp = (int)gp(me);
+    for (int b = 0; b < 3; ++b) {
+        h->xg[b] = (double*)(h->arena + off_xg(me)) + (size_t)b * stage_elems(me);
+        h->qg[b] = (ulonglong2*)(h->arena + off_qg(me)) + (size_t)b * gp(me);
+    }
+    h->xflag_local = (unsigned long long*)(h->arena + kArenaXFlag);
+    h->qflag_local = (unsigned long long*)(h->arena + kArenaQFlag);
+    TRY(h->alloc(&h->xflag_remote, np));
+    TRY(h->alloc(&h->qflag_remote, np));
+    TRY(upload(h, h->xflag_remote, xfr.data(), np * sizeof(void*)));
+    TRY(upload(h, h->qflag_remote, qfr.data(), np * sizeof(void*)));
+    {
+        const int nbt = h->nb_total, ns = h->n_send;
+        std::vector<int> bidx(std::max(ns, 1), 0), bptr((size_t)nbt + 1, 0);
+        for (int k = 0; k < ns; ++k) {
+            int c = 0;
+            while (c + 1 < h->n_colours && sslot[k] >= h->cstart[c + 1]) ++c;
+            const int i = sslot[k] - h->cstart[c];
+            if (i < 0 || i >= h->nb[c]) return fail(PBSM3D_ERR_INVALID, "internal: a sent face is not in the boundary block of its colour");
+            bidx[k] = h->boff[c] + i;
+            bptr[(size_t)bidx[k] + 1]++;
+        }
+        for (int i = 0; i < nbt; ++i) bptr[(size_t)i + 1] += bptr[i];
+        std::vector<int> fillp(bptr.begin(), bptr.end() - 1), stride(std::max(ns, 1), 0);
+        std::vector<double*> xr[3];
+        std::vector<ulonglong2*> qr[3];
+        for (int b = 0; b < 3; ++b) { xr[b].assign(std::max(ns, 1), nullptr); qr[b].assign(std::max(ns, 1), nullptr); }
+        for (const Partner& p : h->partners) {
+            const int r = p.rank;
+            const size_t roff = roff_at(r);
+            for (int k = 0; k < p.send_cnt; ++k) {
+                const int pos = fillp[bidx[p.send_off + k]]++;
+                const size_t g = roff + k;
+                stride[pos] = (int)gp(r);
+                for (int b = 0; b < 3; ++b) {
+                    xr[b][pos] = (double*)(base_of(r) + off_xg(r)) + (size_t)b * stage_elems(r) + g;
+                    qr[b][pos] = (ulonglong2*)(base_of(r) + off_qg(r)) + (size_t)b * gp(r) + g;
+                }
+            }
+        }
+        h->n_entries = ns;
+        TRY(h->alloc(&h->bptr, bptr.size()));
+        TRY(upload(h, h->bptr, bptr.data(), bptr.size() * sizeof(int)));
+        TRY(h->alloc(&h->rstride, stride.size()));
+        TRY(upload(h, h->rstride, stride.data(), stride.size() * sizeof(int)));
+        for (int b = 0; b < 3; ++b) {
+            TRY(h->alloc(&h->x_remote[b], xr[b].size()));
+            TRY(upload(h, h->x_remote[b], xr[b].data(), xr[b].size() * sizeof(double*)));
+            TRY(h->alloc(&h->q_remote[b], qr[b].size()));
+            TRY(upload(h, h->q_remote[b], qr[b].data(), qr[b].size() * sizeof(ulonglong2*)));
+        }
+        TRY(h->alloc_zero(&h->g_zero, stage_elems(me)));
+        TRY(h->alloc_zero(&h->xticket, 1));
+        TRY(h->alloc_zero(&h->qticket, 1));
+        CU(cudaStreamSynchronize(h->stream));  // the host vectors above go out of scope
+    }
     CU(cudaStreamSynchronize(h->stream));
     h->peer = true;
-    if (verbose && me == 0) fprintf(stderr, "[pbsm3d] peer-memory transport: %d ranks, arena %zu KB per rank\n", P, arena_bytes >> 10);
+    h->fused_halo = !(want && std::string(want) == "staged");
+    if (verbose && me == 0)
+        fprintf(stderr, "[pbsm3d] peer-memory transport: %d ranks, arena %zu KB per rank, halos %s\n", P, arena_bytes >> 10,
+                h->fused_halo ? "inside the solver kernels" : "staged (push + wait/unpack launches)");
     return 0;
 }
 
-int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* comm, const std::vector<int>& iperm) {
+// Communicator + the negotiation of what each rank sends (setup_nearest_neighbor_communication,
+// triangulation.cpp:1845-1945).  Runs before the slot order is chosen: the faces a partner needs (h->is_boundary) go
+// first inside their colour class.
+int comm_handshake(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* comm) {
     const int P = h->n_ranks, me = h->rank, nG = h->nG;
     ncclUniqueId id;
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
@@ -441,17 +537,18 @@ int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* com
     TRY(h->alloc(&d_all, (size_t)P * P));
     TRY(upload(h, d_cnt, need_cnt.data(), P * sizeof(int)));
     NC(ncclAllGather(d_cnt, d_all, P, ncclInt32, h->comm, h->stream));
-    std::vector<int> M((size_t)P * P);
+    std::vector<int>& M = h->need_matrix;
+    M.assign((size_t)P * P, 0);
     CU(cudaMemcpyAsync(M.data(), d_all, M.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    // tell each owner which of its faces we need (setup_nearest_neighbor_communication, triangulation.cpp:1845-1945)
+    // tell each owner which of its faces we need
     int n_send = 0;
     for (int r = 0; r < P; ++r) n_send += M[(size_t)r * P + me];
     h->n_send = n_send;
     long long *d_need = nullptr, *d_give = nullptr;
     TRY(h->alloc(&d_need, (size_t)nG));
     TRY(h->alloc(&d_give, (size_t)n_send));
-    std::vector<long long> need_ids(nG);
+    std::vector<long long> need_ids(std::max(nG, 1));
     for (int g = 0; g < nG; ++g) need_ids[g] = mesh->global_id[h->T + g];
     TRY(upload(h, d_need, need_ids.data(), nG * sizeof(long long)));
     NC(ncclGroupStart());
@@ -465,14 +562,29 @@ int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* com
         soff += sc_;
     }
     NC(ncclGroupEnd());
-    std::vector<long long> give(n_send);
-    CU(cudaMemcpyAsync(give.data(), d_give, n_send * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    h->give_ids.assign(std::max(n_send, 1), 0);
+    CU(cudaMemcpyAsync(h->give_ids.data(), d_give, n_send * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    std::vector<int> sslot(n_send), sboff(n_send), scnt(n_send), spos(n_send);
+    h->release(d_cnt);
+    h->release(d_all);
+    h->release(d_need);
+    h->release(d_give);
+    h->is_boundary.assign(h->T, 0);
+    for (int k = 0; k < n_send; ++k) {
+        const long long loc = h->give_ids[k] - h->gstart_id;
+        if (loc < 0 || loc >= h->T) return fail(PBSM3D_ERR_INVALID, "a partner asked for a face this rank does not own");
+        h->is_boundary[(size_t)loc] = 1;
+    }
+    return 0;
+}
+
+// Send lists in slot numbering + the transport (after the slot order exists).
+int setup_comm(pbsm3d_handle* h, const std::vector<int>& iperm) {
+    const int n_send = h->n_send, nG = h->nG;
+    std::vector<int> sslot(std::max(n_send, 1)), sboff(std::max(n_send, 1)), scnt(std::max(n_send, 1)), spos(std::max(n_send, 1));
     for (const Partner& p : h->partners)
         for (int k = 0; k < p.send_cnt; ++k) {
-            long long loc = give[p.send_off + k] - h->gstart_id;
-            if (loc < 0 || loc >= h->T) return fail(PBSM3D_ERR_INVALID, "a partner asked for a face this rank does not own");
+            const long long loc = h->give_ids[p.send_off + k] - h->gstart_id;
             sslot[p.send_off + k] = iperm[(int)loc];
             sboff[p.send_off + k] = p.send_off;
             scnt[p.send_off + k] = p.send_cnt;
@@ -489,7 +601,7 @@ int setup_comm(pbsm3d_handle* h, const pbsm3d_mesh* mesh, const pbsm3d_comm* com
     TRY(h->alloc(&h->sendbuf, (size_t)n_send * h->L));
     TRY(h->alloc(&h->recvbuf, (size_t)std::max(nG, 1) * h->L));
     CU(cudaStreamSynchronize(h->stream));
-    return setup_peer(h, M);
+    return setup_peer(h, h->need_matrix, sslot);
 }
 
 // ---- suspension solve: multicolour line Gauss–Seidel ---------------------------------------------------------
@@ -498,10 +610,45 @@ void launch_colour(pbsm3d_handle* h, int c) {
     const int p0 = h->cstart[c], p1 = p0 + h->ccount[c];
     LAUNCH(h, gs_sweep_kernel<LT>, cdiv(h->ccount[c], 128), 128, h->ss, h->dm, h->L, p0, p1, h->x, h->sc);
 }
+// the x channel of iteration (sweep) number e: read my buffer e%3, write the partners' (e+1)%3
+HaloLink x_link(const pbsm3d_handle* h, unsigned long long e, bool ghosts_zero, bool signal) {
+    HaloLink hl;
+    hl.pt = h->d_pt;
+    hl.flag_remote = h->xflag_remote;
+    hl.flag_local = h->xflag_local;
+    hl.bptr = h->bptr;
+    hl.remote = h->x_remote[(e + 1) % 3];
+    hl.rstride = h->rstride;
+    hl.ghost = ghosts_zero ? h->g_zero : h->xg[e % 3];
+    hl.nGp = h->nGp;
+    hl.wait_epoch = e;
+    hl.signal_epoch = signal ? e + 1 : 0;
+    return hl;
+}
+template <int LT>
+void launch_colour_halo(pbsm3d_handle* h, int c, const HaloLink& hl) {
+    const int p0 = h->cstart[c], p1 = p0 + h->ccount[c];
+    LAUNCH(h, gs_sweep_halo_kernel<LT>, cdiv(h->ccount[c], 128), 128, h->ss, h->dm, h->L, p0, p1, h->x, h->sc, hl, h->nb[c], h->boff[c]);
+}
 int enqueue_sweeps(pbsm3d_handle* h, int n) {
+    const bool fh = h->fused_halo && h->n_ranks > 1;
+    int c_last = 0;
+    for (int c = 0; c < h->n_colours; ++c)
+        if (h->ccount[c] > 0) c_last = c;
     for (int k = 0; k < n; ++k) {
         for (int c = 0; c < h->n_colours; ++c) {
             if (h->ccount[c] == 0) continue;
+            if (fh) {
+                const HaloLink hl = x_link(h, h->xh_epoch, h->x_first, c == c_last);
+                switch (h->L) {
+                    case 5: launch_colour_halo<5>(h, c, hl); break;
+                    case 10: launch_colour_halo<10>(h, c, hl); break;
+                    case 15: launch_colour_halo<15>(h, c, hl); break;
+                    case 20: launch_colour_halo<20>(h, c, hl); break;
+                    default: launch_colour_halo<0>(h, c, hl); break;
+                }
+                continue;
+            }
             switch (h->L) {
                 case 5: launch_colour<5>(h, c); break;
                 case 10: launch_colour<10>(h, c); break;
@@ -510,12 +657,32 @@ int enqueue_sweeps(pbsm3d_handle* h, int n) {
                 default: launch_colour<0>(h, c); break;
             }
         }
-        TRY(halo_exchange(h, h->x, h->L));
+        if (fh) {
+            ++h->xh_epoch;
+            h->x_first = false;
+            ++h->halo_ops;
+            ++h->halo_fused_ops;
+        } else {
+            TRY(halo_exchange(h, h->x, h->L));
+        }
     }
     return 0;
 }
 void launch_residual(pbsm3d_handle* h, int it_now, double tol2, int fuse) {
     const int gcol = std::max(1, std::min(cdiv(h->Tp, 128), kRedBlocks));
+    if (h->fused_halo && h->n_ranks > 1) {  // ghosts come from the buffer the next sweep would read
+        const HaloLink hl = x_link(h, h->xh_epoch, h->x_first, false);
+#define RES_HALO(LT_) LAUNCH(h, residual_halo_kernel<LT_>, gcol, 128, h->ss, h->dm, h->L, h->x, h->partial, kRedBlocks, h->sc, h->red, hl)
+        switch (h->L) {
+            case 5: RES_HALO(5); break;
+            case 10: RES_HALO(10); break;
+            case 15: RES_HALO(15); break;
+            case 20: RES_HALO(20); break;
+            default: RES_HALO(0); break;
+        }
+#undef RES_HALO
+        return;
+    }
 #define RES_COL(LT_)                                                                                                         \
     LAUNCH(h, residual_col_kernel<LT_>, gcol, 128, h->ss, h->dm, h->x, h->partial, kRedBlocks, h->sc, h->red, it_now, tol2, fuse)
     switch (h->L) {
@@ -699,22 +866,56 @@ void cheb_coefficients(pbsm3d_handle* h, int upto) {
 int enqueue_cheb(pbsm3d_handle* h, int k0, int k1, int check_from) {
     const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
     const int g = red_grid(h->Tp), f = fused(h) ? 1 : 0;
+    const bool fh = h->fused_halo && h->n_ranks > 1;
     cheb_coefficients(h, k1);
+    BndRanges br;
+    std::memset(&br, 0, sizeof(br));
+    if (fh) {
+        br.n_colours = h->n_colours;
+        br.total = h->nb_total;
+        for (int c = 0; c < h->n_colours; ++c) {
+            br.start[c] = h->cstart[c];
+            br.count[c] = h->nb[c];
+            br.off[c] = h->boff[c];
+            br.end[c] = c + 1 < h->n_colours ? h->cstart[c + 1] : h->Tp;
+        }
+    }
     for (int k = k0; k < k1; ++k) {
         const double* qin = (k & 1) ? h->qB : h->qA;
         double* qout = (k & 1) ? h->qA : h->qB;
-        if (k >= check_from) {
+        const bool check = k >= check_from;
+        if (fh) {
+            const unsigned long long e = ++h->qh_epoch;  // tags start at 1: a zeroed arena never matches
+            TaggedLink hl;
+            hl.pt = h->d_pt;
+            hl.bptr = h->bptr;
+            hl.remote = h->q_remote[(e + 1) % 3];
+            hl.ghost = k == 0 ? nullptr : h->qg[e % 3];  // q_0 = 0
+            hl.read_tag = e;
+            hl.write_tag = e + 1;
+            // one wave: nbb boundary blocks + interior blocks, never more than the kRedBlocks partial-sum slots
+            const int nbb = std::max(1, std::min(cdiv(h->nb_total, kRedThreads), 64));
+            const int gh = std::max(1, std::min(g, kRedBlocks - nbb)) + nbb;
+            if (check)
+                LAUNCH(h, cheb_iter_halo_kernel<1>, gh, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
+                       h->cheb_c[k], h->partial, kRedBlocks, h->sc, h->red, hl, br, nbb);
+            else
+                LAUNCH(h, cheb_iter_halo_kernel<0>, gh, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
+                       h->cheb_c[k], h->partial, kRedBlocks, h->sc, h->red, hl, br, nbb);
+            ++h->halo_ops;
+            ++h->halo_fused_ops;
+        } else if (check) {
             LAUNCH(h, cheb_iter_kernel<1>, g, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
                    h->cheb_c[k], k, h->partial, kRedBlocks, h->sc, h->red, tol2, f);
-            if (!f) {
-                TRY(allreduce(h, h->red, 1, false));
-                LAUNCH(h, flags_kernel, 1, 1, FLAGS_CHEB_CHECK, h->sc, h->red, k, tol2);
-            }
         } else {
             LAUNCH(h, cheb_iter_kernel<0>, g, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
                    h->cheb_c[k], k, h->partial, kRedBlocks, h->sc, h->red, tol2, f);
         }
-        TRY(halo_exchange(h, qout, 1));
+        if (check && !f) {
+            TRY(allreduce(h, h->red, 1, false));
+            LAUNCH(h, flags_kernel, 1, 1, FLAGS_CHEB_CHECK, h->sc, h->red, k, tol2);
+        }
+        if (!fh) TRY(halo_exchange(h, qout, 1));
     }
     h->cheb_enqueued = k1;
     return 0;
@@ -926,6 +1127,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const double* co
     const int maxit = h->cfg.max_iterations;
     h->n_syncs = 0;
     h->halo_ops = 0;
+    h->halo_fused_ops = 0;
     const auto t_host0 = std::chrono::steady_clock::now();
     h->last_forcing = f;
     h->last_dt = dt;
@@ -933,6 +1135,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const double* co
     CU(cudaEventRecord(h->ev[0], s));
     // x0 = 0 (Belos starts from the zero vector); ghost tails included
     CU(cudaMemsetAsync(h->x, 0, h->NS * sizeof(double), s));
+    h->x_first = true;
     // A+B: zeroSystem is implicit (every coefficient is overwritten); saltation + suspension assembly,
     // C: suspension_present = ||rhs||_inf > 1e-12 and ||b||_2^2, reduced inside the assembly kernel
     // With host buffers the forcing crosses PCIe in chunks on its own stream and each chunk is assembled as it lands.
@@ -1104,6 +1307,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const double* co
     st->n_colours = h->n_colours;
     st->kernel_launches = (int32_t)(h->n_launch - launch0);
     st->halo_exchanges = h->halo_ops;
+    st->halo_fused = h->halo_fused_ops;
     st->halo_transport = h->n_ranks == 1 ? PBSM3D_HALO_NONE : (h->peer ? PBSM3D_HALO_PEER : PBSM3D_HALO_NCCL);
     CU(cudaGetLastError());
     return 0;
@@ -1303,26 +1507,40 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     CU(cudaMallocHost((void**)&h->h_sc, sizeof(Scalars)));
     std::memset(h->h_sc, 0, sizeof(Scalars));
 
-    // ---- colour-major slot order
+    // ---- who needs which of my faces (multi-rank): decides which faces go first inside their colour class
+    TRY(h->alloc_zero(&h->sc, 1));
+    if (h->n_ranks > 1) TRY(comm_handshake(h, mesh, comm));
+
+    // ---- colour-major slot order; inside a colour: the faces a partner rank needs first (so the blocks that own
+    // them run first and their halo is under way while the interior is computed), each group in CHM's order
     std::vector<int> colour;
     colour_faces(T, mesh->neigh, colour, h->n_colours);
     if (h->n_colours > kMaxColours) return fail(PBSM3D_ERR_INVALID, "face colouring needs too many colours");
-    std::vector<int> count(h->n_colours, 0);
-    for (int i = 0; i < T; ++i) count[colour[i]]++;
+    std::vector<int> count(h->n_colours, 0), bcount(h->n_colours, 0);
+    const bool have_bnd = !h->is_boundary.empty();
+    for (int i = 0; i < T; ++i) {
+        count[colour[i]]++;
+        if (have_bnd && h->is_boundary[i]) bcount[colour[i]]++;
+    }
     int Tp = 0;
+    h->nb_total = 0;
     for (int c = 0; c < h->n_colours; ++c) {
         h->cstart[c] = Tp;
         h->ccount[c] = count[c];
+        h->nb[c] = bcount[c];
+        h->boff[c] = h->nb_total;
+        h->nb_total += bcount[c];
         Tp = align_up(Tp + count[c], 32);
     }
     h->Tp = Tp;
     h->S = Tp + align_up(nG, 32);
     h->N = (size_t)L * Tp;
     h->NS = (size_t)L * h->S;
-    std::vector<int> perm(Tp, -1), iperm(T), fillpos(h->n_colours);
-    for (int c = 0; c < h->n_colours; ++c) fillpos[c] = h->cstart[c];
+    std::vector<int> perm(Tp, -1), iperm(T), fill_b(h->n_colours), fill_i(h->n_colours);
+    for (int c = 0; c < h->n_colours; ++c) { fill_b[c] = h->cstart[c]; fill_i[c] = h->cstart[c] + bcount[c]; }
     for (int i = 0; i < T; ++i) {
-        int p = fillpos[colour[i]]++;
+        const int c = colour[i];
+        int p = (have_bnd && h->is_boundary[i]) ? fill_b[c]++ : fill_i[c]++;
         perm[p] = i;
         iperm[i] = p;
     }
@@ -1432,7 +1650,6 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     LAUNCH(h, fill_slots_kernel, cdiv(Tp, 256), 256, Tp, h->perm, h->drift_mass, -9999.0);
     TRY(h->alloc_zero(&h->partial, (size_t)kRedBlocks * 4));
     TRY(h->alloc_zero(&h->red, 8));
-    TRY(h->alloc_zero(&h->sc, 1));
 
     DevConfig& dc = h->dc;
     dc.L = L;
@@ -1471,7 +1688,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     dm.water = h->water;
 
     LAUNCH(h, assemble_pads_kernel, cdiv(Tp, 256), 256, h->dm, h->ss, L);
-    if (h->n_ranks > 1) TRY(setup_comm(h, mesh, comm, iperm));
+    if (h->n_ranks > 1) TRY(setup_comm(h, iperm));
     CU(cudaStreamSynchronize(h->stream));
     if (cfg->deposition_solver != PBSM3D_DEP_CG) TRY(estimate_spectrum(h));
     CU(cudaStreamSynchronize(h->stream));

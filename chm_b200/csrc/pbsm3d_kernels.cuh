@@ -1312,6 +1312,303 @@ __global__ void peer_allreduce_kernel(double* red, int n, int is_max, const Peer
     }
 }
 
+// ------------------------------------------------------- halos carried by the solver kernels themselves
+// The two iterations that dominate a step exchange one halo per iteration (x of the line sweeps: L x n_shared
+// doubles; q of the Chebyshev iteration: n_shared doubles).  As separate push / wait-unpack launches each exchange
+// costs ~17 us on two B200s -- more than the Chebyshev iteration it serves.  Here the producer kernel itself stores
+// the values its partners need straight into THEIR ghost buffer over NVLink and the consumer kernel reads its
+// ghosts from that buffer: no pack, no unpack, no extra launch, and the transfer overlaps the interior work.
+//   * Slots are ordered boundary-first inside every colour class (boundary = a partner needs the face), so the
+//     boundary columns are the first blocks of a launch: they compute, store locally AND remotely, fence, and the
+//     last of them raises the partners' flags while the rest of the grid is still working on interior faces.
+//   * Ghost values live in THREE buffers per channel in the arena, indexed by the iteration number e (monotonic
+//     over the life of the handle): iteration e reads buffer e%3 (filled by the partners during their iteration
+//     e-1) and writes the partners' buffer (e+1)%3.  A rank starts iteration e only when every partner's flag is
+//     >= e, so it is never more than one iteration ahead, and the partner it is ahead of reads (e-1)%3: no buffer
+//     is written while it can still be read.  The first iteration of a solve reads ghosts as 0 (x0 = 0).
+//   * A launch that is a no-op because the solve has already converged still raises the flags (every rank takes
+//     the same decision from the same globally reduced scalars), so the epochs stay in step.
+struct HaloLink {
+    const PeerTable* pt;
+    unsigned long long* const* flag_remote;  // [n_partners] -> the partner's flag of this channel, slot [me]
+    const unsigned long long* flag_local;    // my flags of this channel, indexed by source rank
+    const int* bptr;                         // [n_boundary + 1] boundary face (in slot order) -> its send entries
+    double* const* remote;                   // [n_entries] where each entry lands in the partner's buffer written now
+    const int* rstride;                      // [n_entries] layer stride (the partner's padded ghost count)
+    const double* ghost;                     // [nl][nGp] my ghost buffer read by this launch (a zero buffer for x0 = 0)
+    int nGp;
+    unsigned long long wait_epoch, signal_epoch;  // signal_epoch == 0: push only, a later launch signals
+};
+struct BndRanges {  // boundary slots of colour c: [start[c], start[c] + count[c]), numbered off[c].. in bptr;
+    int n_colours, total;  // interior (and padding) slots of the class: [start[c] + count[c], end[c])
+    int start[8], count[8], off[8], end[8];
+};
+
+// Flags of the fused channels are COUNTERS: every launch that signals adds exactly kLinkUnits to each partner's flag,
+// spread over its boundary blocks (block 0 adds what the others do not), so no grid-wide ticket and no second
+// fence sit between a block's last remote store and the partner seeing it; iteration e is complete at the partner
+// when the counter reaches kLinkUnits * (e + 1).
+constexpr unsigned long long kLinkUnits = 1ull << 20;  // > the largest number of boundary blocks a launch may use
+
+__device__ __forceinline__ void link_wait(const HaloLink& hl) {
+    if ((int)threadIdx.x < hl.pt->n_partners)
+        peer_wait(hl.flag_local + hl.pt->partner_rank[threadIdx.x], hl.wait_epoch * kLinkUnits, hl.pt);
+    __syncthreads();
+}
+__device__ __forceinline__ void link_add(unsigned long long* flag, unsigned long long v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(flag), "l"(v) : "memory");
+}
+// the launch is a no-op on every rank: keep the partners' counters moving
+__device__ __forceinline__ void link_signal_idle(const HaloLink& hl) {
+    if (hl.signal_epoch && blockIdx.x == 0 && (int)threadIdx.x < hl.pt->n_partners) link_add(hl.flag_remote[threadIdx.x], kLinkUnits);
+}
+// Called by all threads of each of the first `nbb` blocks after their remote stores.  The barrier orders the
+// block's stores before the release (the PTX memory model's release is cumulative over barrier synchronisation).
+__device__ __forceinline__ void link_signal(const HaloLink& hl, int nbb) {
+    __syncthreads();
+    if ((int)threadIdx.x < hl.pt->n_partners) {
+        // push-only launch: fence, so its stores are ordered before the later launch's release; else the release itself
+        if (hl.signal_epoch) link_add(hl.flag_remote[threadIdx.x], blockIdx.x == 0 ? kLinkUnits - (unsigned long long)(nbb - 1) : 1ull);
+        else __threadfence_system();
+    }
+}
+// Branch-free gather: one address select, one load, so a column's loads can all be issued up front as in the
+// single-rank kernel.  Ghost lines are first touched after link_wait()'s acquire + barrier, and only by the
+// boundary blocks, so they cannot be stale in L1.
+__device__ __forceinline__ double link_gather(const HaloLink& hl, const double* v, size_t zS, size_t zG, int n, int Tp) {
+    const double* src = n < Tp ? v + zS + n : hl.ghost + zG + (n - Tp);
+    return *src;
+}
+
+// One colour pass of the line Gauss-Seidel sweep (see gs_sweep_kernel) with the halo inside.
+template <int LT>
+__global__ void __launch_bounds__(128, 4) gs_sweep_halo_kernel(SuspSystem s, DevMesh m, int Lrt, int p0, int p1, double* x,
+                                                               const Scalars* __restrict__ sc, HaloLink hl, int bnd_n, int bnd_off) {
+    if (sc->susp_done) { link_signal_idle(hl); return; }
+    const int Tp = m.Tp, S = m.S;
+    const int L = LT > 0 ? LT : Lrt;
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int nbb = max(1, (bnd_n + (int)blockDim.x - 1) / (int)blockDim.x);
+    // Only boundary faces have ghost neighbours (edge adjacency is symmetric: a face next to a ghost is a face the
+    // ghost's owner needs), and they sit in the first nbb blocks: nobody else waits or ever takes the ghost branch.
+    if ((int)blockIdx.x < nbb) link_wait(hl);
+    const bool act = p < p1;
+    double g[LT > 0 ? LT : 1];
+    if (act) {
+        const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
+        const double* __restrict__ l0 = s.latS;
+        const double* __restrict__ l1 = s.latS + (size_t)L * Tp;
+        const double* __restrict__ l2 = s.latS + (size_t)2 * L * Tp;
+        if (LT > 0) {
+#pragma unroll
+            for (int z = 0; z < LT; ++z) {
+                const size_t r = (size_t)z * Tp + p;
+                const size_t zS = (size_t)z * S, zG = (size_t)z * hl.nGp;
+                g[z] = -(__ldcs(l0 + r) * link_gather(hl, x, zS, zG, n0, Tp) + __ldcs(l1 + r) * link_gather(hl, x, zS, zG, n1, Tp) +
+                         __ldcs(l2 + r) * link_gather(hl, x, zS, zG, n2, Tp));
+            }
+            double bl[LT > 0 ? LT : 1], cu[LT > 0 ? LT : 1];
+#pragma unroll
+            for (int z = 0; z < LT; ++z) {
+                bl[z] = __ldcs(s.belowS + (size_t)z * Tp + p);
+                cu[z] = __ldcs(s.cp + (size_t)z * Tp + p);
+            }
+            double y = g[0] + s.rhsS0[p];
+            g[0] = y;
+#pragma unroll
+            for (int z = 1; z < LT; ++z) { y = g[z] - bl[z] * y; g[z] = y; }
+            x[(size_t)(LT - 1) * S + p] = y;
+#pragma unroll
+            for (int z = LT - 2; z >= 0; --z) { y = g[z] - cu[z] * y; g[z] = y; x[(size_t)z * S + p] = y; }
+        } else {
+            double y = 0.0;
+            for (int z = 0; z < L; ++z) {
+                const size_t r = (size_t)z * Tp + p;
+                const size_t zS = (size_t)z * S, zG = (size_t)z * hl.nGp;
+                double gg = -(__ldcs(l0 + r) * link_gather(hl, x, zS, zG, n0, Tp) + __ldcs(l1 + r) * link_gather(hl, x, zS, zG, n1, Tp) +
+                              __ldcs(l2 + r) * link_gather(hl, x, zS, zG, n2, Tp));
+                if (z == 0) gg += s.rhsS0[p];
+                y = gg - __ldcs(s.belowS + r) * y;
+                x[zS + p] = y;
+            }
+            for (int z = L - 2; z >= 0; --z) {
+                y = x[(size_t)z * S + p] - __ldcs(s.cp + (size_t)z * Tp + p) * y;
+                x[(size_t)z * S + p] = y;
+            }
+        }
+    }
+    if ((int)blockIdx.x < nbb) {
+        const int i = p - p0;
+        if (act && i < bnd_n) {
+            const int e0 = hl.bptr[bnd_off + i], e1 = hl.bptr[bnd_off + i + 1];
+            for (int e = e0; e < e1; ++e) {
+                double* dst = hl.remote[e];
+                const int st = hl.rstride[e];
+                if (LT > 0) {
+#pragma unroll
+                    for (int z = 0; z < LT; ++z) dst[(size_t)z * st] = g[z];
+                } else {
+                    for (int z = 0; z < L; ++z) dst[(size_t)z * st] = x[(size_t)z * S + p];
+                }
+            }
+        }
+        link_signal(hl, nbb);
+    }
+}
+
+// ||b - A x||^2 of this rank with the ghosts read from the halo buffer the NEXT sweep would read (residual_col_kernel).
+template <int LT>
+__global__ void __launch_bounds__(128) residual_halo_kernel(SuspSystem s, DevMesh m, int Lrt, const double* __restrict__ x,
+                                                            double* __restrict__ partial, int pstride, Scalars* sc,
+                                                            double* __restrict__ red, HaloLink hl) {
+    if (sc->susp_done) return;
+    link_wait(hl);
+    const int Tp = m.Tp, S = m.S;
+    const int L = LT > 0 ? LT : Lrt;
+    double a = 0.0;
+    const int ntiles = (Tp + 127) / 128;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p = tile * 128 + threadIdx.x;
+        if (p >= Tp) continue;
+        const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
+        double xm = 0.0, xc = x[p];
+        for (int z = 0; z < L; ++z) {
+            const size_t r = (size_t)z * Tp + p;
+            const size_t zS = (size_t)z * S, zG = (size_t)z * hl.nGp;
+            const double xp = z < L - 1 ? x[zS + S + p] : 0.0;
+            double v = __ldcs(s.lat + r) * link_gather(hl, x, zS, zG, n0, Tp) +
+                       __ldcs(s.lat + (size_t)L * Tp + r) * link_gather(hl, x, zS, zG, n1, Tp) +
+                       __ldcs(s.lat + (size_t)2 * L * Tp + r) * link_gather(hl, x, zS, zG, n2, Tp);
+            v += __ldcs(s.diag + r) * xc;
+            if (z > 0) v += __ldcs(s.below + r) * xm;
+            if (z < L - 1) v += __ldcs(s.above + r) * xp;
+            v = ((z == 0) ? s.rhs0[p] : 0.0) - v;
+            a += v * v;
+            xm = xc;
+            xc = xp;
+        }
+    }
+    double rr, unused;
+    if (grid_fold<1>(a, 0.0, 0, 0, partial, pstride, &sc->ticket[1], rr, unused)) {
+        if (threadIdx.x == 0) red[0] = rr;
+    }
+}
+
+// One Jacobi-Chebyshev iteration of the deposition solve (see cheb_iter_kernel) with the halo inside.
+// An iteration is ~8 us on 10^6 faces, so even one flag round trip per iteration shows.  The q channel therefore
+// carries its synchronisation IN the data (the LL idea of NCCL): a ghost entry is a 16-byte {value, tag} pair written
+// with one 16-byte store, tag = number of the iteration that will read it.  The consumer's boundary thread spins on
+// exactly the entries it gathers until their tag is its own iteration number: no flags, no fences, no signal, one
+// NVLink hop between a partner's store and its use.  Buffers rotate over three generations as for the x channel
+// (a writer reaches generation e+3 only after an iteration that consumed what the reader produced AFTER reading e).
+struct TaggedLink {
+    const PeerTable* pt;            // timeout + sticky error only
+    const int* bptr;                // [n_boundary + 1] boundary face -> its send entries
+    ulonglong2* const* remote;      // [n_entries] the partner's entry for this face in the generation written now
+    const ulonglong2* ghost;        // [nGp] my entries of the generation read now; null: q_0 = 0, ghosts read as 0
+    unsigned long long read_tag;    // = this iteration's number
+    unsigned long long write_tag;   // = read_tag + 1
+};
+__device__ __forceinline__ double tagged_read(const ulonglong2* e, unsigned long long tag, const PeerTable* pt) {
+    unsigned long long v, t;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(t) : "l"(e) : "memory");
+    if (t != tag && !*(volatile int*)pt->error) {
+        const unsigned long long t0 = global_timer_ns();
+        do {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(t) : "l"(e) : "memory");
+            if (t != tag && global_timer_ns() - t0 > pt->timeout_ns) { *(volatile int*)pt->error = 1; break; }
+        } while (t != tag);
+    }
+    return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ void tagged_write(ulonglong2* e, double v, unsigned long long tag) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(e), "l"((unsigned long long)__double_as_longlong(v)), "l"(tag) : "memory");
+}
+template <bool BND>
+__device__ __forceinline__ double cheb_face(const DevMesh& m, const double* __restrict__ offS, const double* __restrict__ bS,
+                                            const double* __restrict__ qin, double* __restrict__ d, double* __restrict__ qout,
+                                            double ak, double ck, int p, const TaggedLink& tl, double& z_out) {
+    const int Tp = m.Tp;
+    // everything that does not depend on the partners is loaded before the first ghost is waited for
+    const double qp = qin[p], bp = bS[p], dp = d[p];
+    int n[3];
+    double o[3], qn[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { n[j] = m.nbs[(size_t)j * Tp + p]; o[j] = offS[(size_t)j * Tp + p]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) qn[j] = (!BND || n[j] < Tp) ? qin[n[j]] : 0.0;
+    if (BND && tl.ghost) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (n[j] >= Tp) qn[j] = tagged_read(tl.ghost + (n[j] - Tp), tl.read_tag, tl.pt);
+    }
+    double z = bp - qp;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) z -= o[j] * qn[j];
+    const double dn = ak * dp + ck * z;
+    d[p] = dn;
+    const double qnew = qp + dn;
+    qout[p] = qnew;
+    z_out = z;
+    return qnew;
+}
+// The boundary faces of one iteration (a function of its own so that the spin loop's registers are not the interior
+// loop's): update, then one tagged 16-byte store per partner that needs the face.
+template <int CHECK>
+__device__ __noinline__ double cheb_boundary(const DevMesh& m, const double* __restrict__ offS, const double* __restrict__ bS,
+                                             const double* __restrict__ ddiag, const double* __restrict__ qin, double* __restrict__ d,
+                                             double* __restrict__ qout, double ak, double ck, const TaggedLink& tl, const BndRanges& br,
+                                             int nbb) {
+    double rr = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < br.total; i += nbb * blockDim.x) {
+        int p = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < br.n_colours && i >= br.off[c] && i < br.off[c] + br.count[c]) p = br.start[c] + (i - br.off[c]);
+        const int e0 = tl.bptr[i], e1 = tl.bptr[i + 1];
+        ulonglong2* dst0 = e1 > e0 ? tl.remote[e0] : nullptr;
+        double z;
+        const double qn = cheb_face<true>(m, offS, bS, qin, d, qout, ak, ck, p, tl, z);
+        if (dst0) tagged_write(dst0, qn, tl.write_tag);
+        for (int e = e0 + 1; e < e1; ++e) tagged_write(tl.remote[e], qn, tl.write_tag);
+        if (CHECK) { const double r = z * ddiag[p]; rr += r * r; }
+    }
+    return rr;
+}
+// Grid = nbb boundary blocks + the interior blocks, all co-resident (the host sizes the grid to one wave).  The
+// boundary blocks only do the boundary faces and leave; the interior blocks never read a ghost.
+template <int CHECK>
+__global__ void __launch_bounds__(kRedThreads, 8) cheb_iter_halo_kernel(const __grid_constant__ DevMesh m, const double* __restrict__ offS,
+                                                                        const double* __restrict__ bS, const double* __restrict__ ddiag,
+                                                                        const double* __restrict__ qin, double* __restrict__ d,
+                                                                        double* __restrict__ qout, double ak, double ck,
+                                                                        double* __restrict__ partial, int pstride, Scalars* sc,
+                                                                        double* __restrict__ red, const __grid_constant__ TaggedLink tl,
+                                                                        const __grid_constant__ BndRanges br, int nbb) {
+    if (!sc->tail_done || !sc->dep_present || sc->done) return;
+    double rr = 0.0;
+    if ((int)blockIdx.x < nbb) {
+        rr = cheb_boundary<CHECK>(m, offS, bS, ddiag, qin, d, qout, ak, ck, tl, br, nbb);
+    } else {
+        const int nmain = gridDim.x - nbb;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // the interior slots of each colour class (static indices into br)
+            if (c >= br.n_colours) break;
+            for (int p = br.start[c] + br.count[c] + (blockIdx.x - nbb) * blockDim.x + threadIdx.x; p < br.end[c]; p += nmain * blockDim.x) {
+                double z;
+                cheb_face<false>(m, offS, bS, qin, d, qout, ak, ck, p, tl, z);
+                if (CHECK) { const double r = z * ddiag[p]; rr += r * r; }
+            }
+        }
+    }
+    if (CHECK) {
+        double o0, unused;
+        if (grid_fold<1>(rr, 0.0, 0, 0, partial, pstride, &sc->ticket[3], o0, unused)) {
+            if (threadIdx.x == 0) red[0] = o0;
+        }
+    }
+}
+
 __global__ void fill_slots_kernel(int Tp, const int* __restrict__ perm, double* __restrict__ a, double v) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < Tp) a[p] = perm[p] >= 0 ? v : 0.0;

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PBSM3D_ABI_VERSION 2
+#define PBSM3D_ABI_VERSION 3
 
 enum {
     PBSM3D_OK = 0,
@@ -54,7 +54,9 @@ enum {
 /* How ghost-face halos and the solvers' global reductions travel between the ranks of one NVSwitch box
  * (reference: MPI messages, triangulation.cpp:1976-2079).  PEER = direct stores into the partner's exported
  * staging buffer over NVLink (cudaIpc), chosen whenever every rank can map every other rank's arena; NCCL
- * send/recv + all-reduce otherwise, or when PBSM3D_HALO=nccl is set in the environment. */
+ * send/recv + all-reduce otherwise, or when PBSM3D_HALO=nccl is set in the environment.  With PEER the halos of the
+ * two dominant iterations (line sweeps, Chebyshev) are carried by the solver kernels themselves (stats.halo_fused);
+ * PBSM3D_HALO=staged keeps them as separate push / wait-unpack launches (the path every other vector uses). */
 enum {
     PBSM3D_HALO_NONE = 0,
     PBSM3D_HALO_NCCL = 1,
@@ -174,6 +176,8 @@ typedef struct pbsm3d_stats {
     int32_t host_syncs;              /* stream synchronisations the step needed (1 when every prediction held) */
     int32_t halo_exchanges;          /* ghost-face halo exchanges the step enqueued (0 on a single rank) */
     int32_t halo_transport;          /* PBSM3D_HALO_NONE / _NCCL / _PEER */
+    int32_t halo_fused;              /* of halo_exchanges: carried by the solver kernels themselves (direct stores into the
+                                        partner's ghost buffer from the producing kernel; no pack/unpack launch) */
 } pbsm3d_stats;
 
 typedef struct pbsm3d_handle pbsm3d_handle;

@@ -55,6 +55,8 @@ def main():
         gathered[f"iters_{k}"] = np.array([st["suspension_iterations"], st["deposition_iterations"], st["suspension_present"],
                                            st["deposition_present"]])
     gathered["halo_transport"] = np.array(st["halo_transport"])
+    gathered["halo_fused"] = np.array(st["halo_fused"])
+    gathered["halo_exchanges"] = np.array(st["halo_exchanges"])
     if rank == 0:
         np.savez(out_path, **gathered)
     h.close()

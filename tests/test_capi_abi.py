@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pbsm3d.h but not exported"
     assert set(syms) == set(capi.SYMBOLS), "ctypes table and header disagree"
-    assert lib.pbsm3d_abi_version() == capi.ABI_VERSION == 2
+    assert lib.pbsm3d_abi_version() == capi.ABI_VERSION == 3
 
 
 def test_config_defaults_are_the_reference_defaults(lib):
@@ -50,7 +50,7 @@ def test_struct_layouts_match_header(lib):
     # 20 ints/doubles + 3 solver fields; natural alignment, no packing pragmas in the header
     assert C.sizeof(capi.Forcing) == 8 * 8 and C.sizeof(capi.Outputs) == 8 * 8
     assert C.sizeof(capi.Comm) == 16
-    assert C.sizeof(capi.Stats) == 6 * 4 + 4 * 8 + 6 * 4 + 6 * 4
+    assert C.sizeof(capi.Stats) == 6 * 4 + 4 * 8 + 6 * 4 + 7 * 4 + 4  # 7 trailing int32 + tail padding to 8
     assert C.sizeof(capi.Mesh) == 8 + 4 + 4 + 10 * 8
 
 

@@ -24,8 +24,8 @@ def run_ranks(tmp_path, world, meshname, L, solver, nsteps, transport="peer"):
     out = str(tmp_path / f"mp_{meshname}_{world}_{solver}_{transport}.npz")
     env = dict(os.environ)
     env.pop("PBSM3D_HALO", None)
-    if transport == "nccl":
-        env["PBSM3D_HALO"] = "nccl"
+    if transport in ("nccl", "staged"):
+        env["PBSM3D_HALO"] = transport
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "mp_worker.py"), out, meshname, str(L), str(solver), str(nsteps)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
@@ -33,8 +33,9 @@ def run_ranks(tmp_path, world, meshname, L, solver, nsteps, transport="peer"):
     return np.load(out)
 
 
-@pytest.mark.parametrize("solver,transport", [(capi.SOLVER_LINE, "peer"), (capi.SOLVER_LINE, "nccl"), (capi.SOLVER_BICGSTAB, "peer")],
-                         ids=["line-peer", "line-nccl", "bicgstab-peer"])
+@pytest.mark.parametrize("solver,transport", [(capi.SOLVER_LINE, "peer"), (capi.SOLVER_LINE, "staged"), (capi.SOLVER_LINE, "nccl"),
+                                              (capi.SOLVER_BICGSTAB, "peer")],
+                         ids=["line-peer-fused", "line-peer-staged", "line-nccl", "bicgstab-peer"])
 def test_two_ranks_match_oracle_and_single_gpu(tmp_path, solver, transport):
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")
@@ -44,6 +45,12 @@ def test_two_ranks_match_oracle_and_single_gpu(tmp_path, solver, transport):
     g = run_ranks(tmp_path, 2, "slope_metis", L, solver, 3, transport)
     # halos and reductions went the way that was asked for: peer memory (cudaIpc over NVLink) unless NCCL is forced
     assert int(g["halo_transport"]) == (capi.HALO_NCCL if transport == "nccl" else capi.HALO_PEER)
+    # default peer transport: the halos of the line sweeps and of the Chebyshev iteration ride inside the solver kernels
+    fused, total = int(g["halo_fused"]), int(g["halo_exchanges"])
+    if transport == "peer" and solver == capi.SOLVER_LINE:
+        assert fused > 0 and total - fused <= 4, (fused, total)
+    elif transport != "peer":
+        assert fused == 0
     o = PBSM3DOracle(Config.functional_test(L), mesh.neigh, geo, mesh.global_id, mesh.n_global, mesh.params)
     h = capi.Handle(capi.default_config(solver=solver, tolerance=1e-10, **functest_kw(L)), mesh)
     for k in range(3):
@@ -66,7 +73,7 @@ def test_max_ranks_on_uniform_mesh(tmp_path):
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
     L = 10
     g = run_ranks(tmp_path, world, "uniform120", L, capi.SOLVER_AUTO, 1)
-    assert int(g["halo_transport"]) == capi.HALO_PEER
+    assert int(g["halo_transport"]) == capi.HALO_PEER and int(g["halo_fused"]) > 0
     mesh = synthetic.uniform_mesh(120, 120)
     geo = mesh.geometry()
     h = capi.Handle(capi.default_config(tolerance=1e-10, **functest_kw(L)), mesh)
