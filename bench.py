@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--side", type=int, default=0, help="override squares per side (debug)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 (default, the driver's line): uniform 1 M triangles per GPU; c3 / c4: BASELINE's variable-resolution "
+                         "5 M / 10 M-triangle Delaunay meshes (strong scaling over the GPUs given), recorded in profiles/")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -218,7 +221,13 @@ def main():
         uid = bytes(buf.cpu().numpy().tobytes())
 
     side = args.side or mesh_side(world)
-    gmesh = synthetic.uniform_mesh(side, side)
+    if args.workload == "c2":
+        gmesh = synthetic.uniform_mesh(side, side)
+        wl = f"BASELINE c2 generator: {side}x{side} squares of 30 m"
+    else:
+        target = {"c3": 5_000_000, "c4": 10_000_000}[args.workload]
+        gmesh = synthetic.variable_mesh(target)
+        wl = f"BASELINE {args.workload} generator: variable-resolution Delaunay mesh (10:1 area range, seed 20250101), target {target}"
     G = gmesh.n_local
     mesh = partition_mesh(gmesh, rank, world) if world > 1 else gmesh
     del gmesh
@@ -304,9 +313,10 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong",
+            "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"BASELINE c2 generator: {side}x{side} squares of 30 m -> {G} triangles x nLayer {NLAYER} "
+            "config": {"workload": f"{wl} -> {G} triangles x nLayer {NLAYER} "
                                    f"({total_rows} unknowns), Morton order, functional-test PBSM3D block, tol 1e-8"
                                    + ("" if world == 1 else f", {world} ranks by CHM contiguous global-id partition"),
                        "triangles": G, "nLayer": NLAYER, "solver": "multicolour line Gauss-Seidel (auto)", "colours": st["n_colours"],
@@ -329,7 +339,7 @@ def main():
                          "launches_timed": int(sweeps), "share_of_step": sweep_ms / max(ev_ms, 1e-9)},
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)
     h.close()
