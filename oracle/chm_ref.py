@@ -85,6 +85,10 @@ def lib():
         L.chmref_bearing_to_cartesian.argtypes = [C.c_double, C.c_void_p]
         L.chmref_distance_UTM.restype = C.c_double
         L.chmref_distance_UTM.argtypes = [C.c_void_p, C.c_void_p]
+        L.chmref_run_scale_wind_vert.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.chmref_run_fetchr.argtypes = [C.c_void_p, C.c_char_p]
+        L.chmref_tpspline.restype = C.c_double
+        L.chmref_tpspline.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.chmref_set_solver(_direct_solve)
         _lib = L
     return _lib
@@ -188,6 +192,23 @@ class ReferencePBSM3D:
         out["q_dep"] = q
         return out
 
+    def scale_wind_vert(self, U_R, snowdepthavg=None, cfg: Optional[Dict] = None, point_only: bool = False):
+        """The reference's scale_wind_vert (scale_wind_vert.cpp, compiled unmodified) on this mesh: domain mode
+        (point_scale + neighbour thin plate spline) or, with point_only, run(face) per face.  Returns U_2m_above_srf."""
+        self.set_var("U_R", U_R)
+        if snowdepthavg is not None:
+            self.set_var("snowdepthavg", snowdepthavg)
+        if lib().chmref_run_scale_wind_vert(self.h, _cfg_text(cfg or {}), int(snowdepthavg is not None), int(point_only)) != 0:
+            raise RuntimeError("reference scale_wind_vert threw: " + lib().chmref_last_error().decode())
+        return self.get_var("U_2m_above_srf")
+
+    def fetchr(self, vw_dir, cfg: Optional[Dict] = None):
+        """The reference's fetchr (fetchr.cpp, compiled unmodified), run(face) for every face.  Returns fetch."""
+        self.set_var("vw_dir", vw_dir)
+        if lib().chmref_run_fetchr(self.h, _cfg_text(cfg or {})) != 0:
+            raise RuntimeError("reference fetchr threw: " + lib().chmref_last_error().decode())
+        return self.get_var("fetch")
+
     def checkpoint(self):
         out = np.empty(self.T)
         lib().chmref_checkpoint(self.h, out.ctypes.data)
@@ -196,6 +217,13 @@ class ReferencePBSM3D:
     def load_checkpoint(self, sum_drift):
         a = np.ascontiguousarray(np.asarray(sum_drift, dtype=np.float64))
         lib().chmref_load_checkpoint(self.h, a.ctypes.data)
+
+
+def tpspline(sample_xyv, query_xy):
+    """stubs/interpolation.hpp (the C++ restatement of TPSpline.cpp the compiled scale_wind_vert.cpp calls)."""
+    a = np.ascontiguousarray(np.asarray(sample_xyv, dtype=np.float64))
+    q = np.ascontiguousarray(np.asarray(query_xy, dtype=np.float64))
+    return lib().chmref_tpspline(a.shape[0], a.ctypes.data, q.ctypes.data)
 
 
 def log_scale_wind(u, Z_in, Z_out, sd, z0=0.01):

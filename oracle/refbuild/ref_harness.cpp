@@ -1,10 +1,13 @@
 // Harness around the UNMODIFIED reference sources (compiled where they lie under /root/reference by oracle/refbuild/Makefile):
 //     src/modules/PBSM3D.cpp   src/math/coordinates.cpp   src/physics/Atmosphere.cpp
+//     src/modules/scale_wind_vert.cpp   src/modules/fetchr.cpp        (the two per-face providers of PBSM3D inputs)
 // against the stand-in headers in stubs/.  This file holds (1) the stand-in NearestNeighborProblem implementation
 // (pattern + numbering of LinearAlgebra.cpp:31-152; Solve() = a registered sparse direct solve) and (2) a small C API
 // that builds a CHM-like mesh from flat arrays, runs PBSM3D::init/run and reads variables / assembled systems back.
 // Test infrastructure only: used by tests/ and tests/golden/make_ref_golden.py to pin oracle/pbsm3d_oracle.py.
 #include "PBSM3D.hpp"
+#include "fetchr.hpp"
+#include "scale_wind_vert.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -147,6 +150,7 @@ void* chmref_create(int T, const double* vx, const double* vy, const double* vz,
 {
     try {
         math::gis::distance = math::gis::distance_UTM;  // what core.cpp installs for a projected (UTM) mesh
+        math::gis::point_from_bearing = math::gis::point_from_bearing_UTM;
         auto h = new Harness;
         h->glob = std::make_shared<global>();
         parse_kv(global_kv, h->glob->parameters);
@@ -260,6 +264,59 @@ int chmref_load_checkpoint(void* hv, const double* sum_drift)
     for (std::size_t i = 0; i < h->domain->size_faces(); ++i) h->chk.put_var1D("PBSM3D:sum_drift", i, sum_drift[i]);
     h->mod->load_checkpoint(h->domain, h->chk);
     return 0;
+}
+
+// scale_wind_vert in domain mode (ctor -> init(mesh) -> run(mesh), scale_wind_vert.cpp:27-229) on the harness mesh; reads U_R
+// (+ snowdepthavg when has_snowdepth, i.e. when another module provides the optional input), writes U_2m_above_srf.
+// point_only: run(face) per face instead, i.e. point_scale without the neighbour spline (data-parallel mode).
+int chmref_run_scale_wind_vert(void* hv, const char* cfg_kv, int has_snowdepth, int point_only)
+{
+    auto h = static_cast<Harness*>(hv);
+    try {
+        config_file cfg;
+        parse_kv(cfg_kv, cfg);
+        scale_wind_vert m(cfg);
+        m.global_param = h->glob;
+        m.ID = 7;  // module-data slot distinct from PBSM3D's
+        if (has_snowdepth) m._optional_found["snowdepthavg"] = true;
+        m.init(h->domain);
+        if (point_only) {
+            for (std::size_t i = 0; i < h->domain->size_faces(); ++i) { auto f = h->domain->face(i); m.run(f); }
+        } else {
+            m.run(h->domain);
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return 1;
+    }
+}
+
+// fetchr (parallel::data: core calls run(face) for every face, fetchr.cpp:54-119); reads vw_dir, writes fetch.
+int chmref_run_fetchr(void* hv, const char* cfg_kv)
+{
+    auto h = static_cast<Harness*>(hv);
+    try {
+        config_file cfg;
+        parse_kv(cfg_kv, cfg);
+        fetchr m(cfg);
+        m.global_param = h->glob;
+        for (std::size_t i = 0; i < h->domain->size_faces(); ++i) { auto f = h->domain->face(i); m.run(f); }
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return 1;
+    }
+}
+
+// The interpolant scale_wind_vert uses (stubs/interpolation.hpp, a restatement of TPSpline.cpp): n samples (x,y,v), one query.
+double chmref_tpspline(int n, const double* xyv, const double* query)
+{
+    std::vector<boost::tuple<double, double, double>> s;
+    for (int i = 0; i < n; ++i) s.push_back(boost::make_tuple(xyv[3 * i], xyv[3 * i + 1], xyv[3 * i + 2]));
+    auto q = boost::make_tuple(query[0], query[1], 0.0);
+    interpolation it(interp_alg::tpspline, n);
+    return it(s, q);
 }
 
 // The reference's scalar helpers, straight from the compiled reference objects (Atmosphere.cpp, coordinates.cpp).

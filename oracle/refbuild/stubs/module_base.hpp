@@ -2,6 +2,7 @@
 // following module_base.hpp:471-491.  Test infrastructure (oracle/), never linked into the product.
 #pragma once
 #include "triangulation.hpp"
+#include "interpolation.hpp"
 #include <cmath>
 #include <memory>
 #include <string>
@@ -37,6 +38,11 @@ public:
     void depends(const std::string& n) { _depends.push_back(n); }
     void provides(const std::string& n) { _provides.push_back(n); }
     void provides_vector(const std::string& n) { _vectors.push_back(n); }
+    // module_base.hpp:416-435: an optional input counts as found when another module provides it; the harness says which
+    std::map<std::string, bool> _optional_found;
+    void optional(const std::string& n) { _optional_found.emplace(n, false); }
+    bool has_optional(const std::string& n) { auto it = _optional_found.find(n); return it != _optional_found.end() && it->second; }
+    virtual void run(mesh_elem&) {}
 
     bool is_nan(const double& variable)
     {

@@ -8,6 +8,7 @@
 // Test infrastructure (oracle/), never linked into the product.
 #pragma once
 #include <CGAL/Exact_predicates_inexact_constructions_kernel.h>
+#include <boost/function.hpp>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -69,7 +70,9 @@ class global {
 public:
     ptree_stub parameters;
     double _dt = 3600;
+    bool _is_point_mode = false;
     double dt() const { return _dt; }
+    bool is_point_mode() const { return _is_point_mode; }  // global.hpp:65-71
 };
 
 class face_info { public: virtual ~face_info() {} };
@@ -121,6 +124,10 @@ public:
     double edge_length(int i) const { return CGAL::sqrt(edge(i).squared_length()); }
     Point_3 center() const { return Point_3((vx[0] + vx[1] + vx[2]) / 3, (vy[0] + vy[1] + vy[2]) / 3, (vz[0] + vz[1] + vz[2]) / 3); }
     double get_z() const { return center().z(); }
+    double get_x() const { return center().x(); }  // triangulation.hpp:1755-1771
+    double get_y() const { return center().y(); }
+    // triangulation.hpp:1543-1546 -> triangulation.cpp:170-186: nearest face CENTRE to the point `distance` along `azimuth`
+    face_stub* find_closest_face(double azimuth, double distance);
     double get_area() const
     {
         if (has_parameter("area")) return parameter("area");
@@ -150,6 +157,21 @@ public:
     void print_ghost_neighbor_info() {}
 };
 typedef std::shared_ptr<triangulation> mesh;
+
+// CGAL's kd-tree k=1 query over the centres of _faces (triangulation.cpp:1037-1058), restated as an exhaustive search.
+namespace math { namespace gis { extern boost::function<Point_2(Point_3 src, double bearing, double distance)> point_from_bearing; } }
+inline face_stub* face_stub::find_closest_face(double azimuth, double distance)
+{
+    const Point_2 q = math::gis::point_from_bearing(center(), azimuth, distance);
+    face_stub* best = nullptr;
+    double bd = 0;
+    for (auto& f : _domain->_faces) {
+        const Point_3 c = f->center();
+        const double d = (c.x() - q.x()) * (c.x() - q.x()) + (c.y() - q.y()) * (c.y() - q.y());
+        if (!best || d < bd) { best = f.get(); bd = d; }
+    }
+    return best;
+}
 
 inline double face_stub::veg_attribute(const std::string& variable)
 {
