@@ -78,6 +78,12 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class WindConfig(C.Structure):
+    """pbsm3d_wind_config: scale_wind_vert / fetchr config keys (scale_wind_vert.cpp:161, fetchr.cpp:34-43)."""
+    _fields_ = [("ignore_canopy", C.c_int32), ("point_mode", C.c_int32), ("fetch_steps", C.c_int32), ("fetch_incl_veg", C.c_int32),
+                ("fetch_max_distance", C.c_double), ("fetch_I", C.c_double)]
+
+
 FORCING_NAMES = [n for n, _ in Forcing._fields_]
 OUTPUT_NAMES = [n for n, _ in Outputs._fields_]
 
@@ -101,6 +107,10 @@ SYMBOLS = {
     "pbsm3d_get_suspension_system": (C.c_int, [C.c_void_p] + [c_double_p] * 8 + [c_uint8_p]),
     "pbsm3d_get_deposition_system": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
     "pbsm3d_time_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "pbsm3d_wind_config_defaults": (None, [C.POINTER(WindConfig)]),
+    "pbsm3d_scale_wind_vert": (C.c_int, [C.c_void_p, C.POINTER(WindConfig), c_double_p, c_double_p, c_double_p, C.c_int]),
+    "pbsm3d_fetchr": (C.c_int, [C.c_void_p, C.POINTER(WindConfig), c_double_p, c_double_p, C.c_int]),
+    "pbsm3d_set_providers": (C.c_int, [C.c_void_p, C.POINTER(WindConfig)]),
 }
 
 _lib = None
@@ -150,6 +160,17 @@ def default_config(**overrides) -> Config:
     for k, v in overrides.items():
         if not hasattr(cfg, k):
             raise KeyError(f"unknown PBSM3D config key {k}")
+        setattr(cfg, k, type(getattr(cfg, k))(v))
+    return cfg
+
+
+def default_wind_config(**overrides) -> WindConfig:
+    lib = load_library()
+    cfg = WindConfig()
+    lib.pbsm3d_wind_config_defaults(C.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise KeyError(f"unknown wind config key {k}")
         setattr(cfg, k, type(getattr(cfg, k))(v))
     return cfg
 
@@ -242,6 +263,26 @@ class Handle:
         fn = self.lib.pbsm3d_step_device if device else self.lib.pbsm3d_step
         _check(self.lib, fn(self.h, dt, C.byref(f), C.byref(o), C.byref(st)))
         return st.asdict()
+
+    # ------------------------------------------------------------------ providers of PBSM3D inputs
+    def scale_wind_vert(self, U_R, snowdepthavg=None, cfg: Optional[WindConfig] = None) -> np.ndarray:
+        """scale_wind_vert::run on the device: U_R [+ snowdepthavg] -> U_2m_above_srf (host arrays)."""
+        u = np.ascontiguousarray(U_R, dtype=np.float64)
+        sd = None if snowdepthavg is None else np.ascontiguousarray(snowdepthavg, dtype=np.float64)
+        out = np.empty(self.T)
+        _check(self.lib, self.lib.pbsm3d_scale_wind_vert(self.h, C.byref(cfg) if cfg is not None else None, _dp(u), _dp(sd), _dp(out), 0))
+        return out
+
+    def fetchr(self, vw_dir, cfg: Optional[WindConfig] = None) -> np.ndarray:
+        """fetchr::run for every face on the device: vw_dir -> fetch (host arrays)."""
+        v = np.ascontiguousarray(vw_dir, dtype=np.float64)
+        out = np.empty(self.T)
+        _check(self.lib, self.lib.pbsm3d_fetchr(self.h, C.byref(cfg) if cfg is not None else None, _dp(v), _dp(out), 0))
+        return out
+
+    def set_providers(self, cfg: Optional[WindConfig]):
+        """Fuse the providers into step(): U_2m_above_srf / fetch left out of the forcing are derived on the device."""
+        _check(self.lib, self.lib.pbsm3d_set_providers(self.h, C.byref(cfg) if cfg is not None else None))
 
     # ------------------------------------------------------------------ inspection
     def geometry(self):

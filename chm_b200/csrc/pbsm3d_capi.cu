@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "pbsm3d_kernels.cuh"
+#include "pbsm3d_wind.cuh"
 
 using namespace pbsm3d;
 
@@ -167,6 +168,15 @@ struct pbsm3d_handle {
     unsigned *xticket = nullptr, *qticket = nullptr;
     unsigned long long xh_epoch = 0, qh_epoch = 0;  // iteration numbers of the two channels (monotonic)
     bool x_first = true;                            // the next sweep is the first of a solve (x = 0: ghosts read as 0)
+    // providers of U_2m_above_srf / fetch (scale_wind_vert, fetchr): vegetation in slot order, work vector, centre grid
+    double *wv_canopy = nullptr, *wv_lai = nullptr;  // [Tp] or null (the mesh carries no such parameter)
+    double* wv_u = nullptr;                           // [S] point-scaled wind, ghost-extended
+    bool grid_ready = false;
+    CellGrid grid{};
+    int *grid_start = nullptr, *grid_face = nullptr;
+    bool providers_on = false;                        // pbsm3d_set_providers: the step derives missing inputs itself
+    pbsm3d_wind_config wind_cfg{};
+    float ms_providers = 0.f;
     // predictions carried from step to step (iteration counts only; every solve still starts from x0 = 0)
     int pred_sweeps = 0, pred_cg = 0;
     double sweep_rate2 = 0.0;  // observed per-sweep contraction of ||r||^2
@@ -1117,9 +1127,106 @@ void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt, int i0, i
 }
 
 // One PBSM3D::run with device-resident forcing (reference PBSM3D.cpp:400-1748, phases A–I of SURVEY §3.2).
-int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const double* const* host_in, const OutTargets* out,
+// ---- providers of two PBSM3D inputs: host side
+// U_R, sd: device, CHM order (sd may be null: no module provides snowdepthavg); out: device, CHM order
+int enqueue_scale_wind_vert(pbsm3d_handle* h, const pbsm3d_wind_config* wc, const double* U_R, const double* sd, double* out) {
+    const int T = h->T;
+    const bool canopy_on = !wc->ignore_canopy && h->wv_canopy;
+    if (canopy_on && !h->wv_lai) return fail(PBSM3D_ERR_INVALID, "Parameter LAI does not exist.");  // triangulation.hpp:1685-1688
+    LAUNCH(h, wind_point_kernel, cdiv(T, 256), 256, T, h->iperm, U_R, sd, h->wv_canopy, h->wv_lai, wc->ignore_canopy, h->wv_u,
+           wc->point_mode ? out : nullptr);
+    if (wc->point_mode) return 0;
+    TRY(halo_exchange(h, h->wv_u, 1));  // domain->ghost_neighbors_communicate_variable("U_2m_above_srf"), scale_wind_vert.cpp:178
+    LAUNCH(h, wind_spline_kernel, cdiv(T, 128), 128, T, h->dm, h->cx, h->cy, h->wv_u, out);
+    return 0;
+}
+
+// Uniform cell grid over the centres of the owned faces (≈4 faces per cell), built once on the host from the
+// device-computed centres.  Stands in for the reference's kd-tree of face centres (triangulation.cpp:1037-1058).
+int ensure_grid(pbsm3d_handle* h) {
+    if (h->grid_ready) return 0;
+    const int Tp = h->Tp;
+    std::vector<double> cx(Tp), cy(Tp);
+    std::vector<int> perm(Tp);
+    CU(cudaMemcpyAsync(cx.data(), h->cx, (size_t)Tp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(cy.data(), h->cy, (size_t)Tp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(perm.data(), h->perm, (size_t)Tp * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int p = 0; p < Tp; ++p)
+        if (perm[p] >= 0) { x0 = std::min(x0, cx[p]); x1 = std::max(x1, cx[p]); y0 = std::min(y0, cy[p]); y1 = std::max(y1, cy[p]); }
+    const double w = std::max(x1 - x0, 1e-9), hh = std::max(y1 - y0, 1e-9);
+    double cell = std::sqrt(4.0 * w * hh / std::max(h->T, 1));
+    if (!(cell > 0)) cell = 1.0;
+    CellGrid g;
+    g.x0 = x0; g.y0 = y0; g.h = cell; g.inv_h = 1.0 / cell;
+    g.ncx = std::max(1, std::min(1 << 14, (int)(w / cell) + 1));
+    g.ncy = std::max(1, std::min(1 << 14, (int)(hh / cell) + 1));
+    const size_t nc = (size_t)g.ncx * g.ncy;
+    auto cell_of = [&](int p) {
+        int ix = (int)std::floor((cx[p] - g.x0) * g.inv_h), iy = (int)std::floor((cy[p] - g.y0) * g.inv_h);
+        ix = std::min(std::max(ix, 0), g.ncx - 1);
+        iy = std::min(std::max(iy, 0), g.ncy - 1);
+        return (size_t)iy * g.ncx + ix;
+    };
+    std::vector<int> start(nc + 1, 0), faces(std::max(h->T, 1));
+    for (int p = 0; p < Tp; ++p)
+        if (perm[p] >= 0) start[cell_of(p) + 1]++;
+    for (size_t c = 0; c < nc; ++c) start[c + 1] += start[c];
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (int p = 0; p < Tp; ++p)
+        if (perm[p] >= 0) faces[fill[cell_of(p)]++] = p;
+    TRY(h->alloc(&h->grid_start, nc + 1));
+    TRY(h->alloc(&h->grid_face, faces.size()));
+    TRY(upload(h, h->grid_start, start.data(), (nc + 1) * sizeof(int)));
+    TRY(upload(h, h->grid_face, faces.data(), faces.size() * sizeof(int)));
+    CU(cudaStreamSynchronize(h->stream));
+    g.cell_start = h->grid_start;
+    g.cell_face = h->grid_face;
+    h->grid = g;
+    h->grid_ready = true;
+    return 0;
+}
+int enqueue_fetchr(pbsm3d_handle* h, const pbsm3d_wind_config* wc, const double* vw_dir, double* out) {
+    if (wc->fetch_steps < 1 || !(wc->fetch_max_distance > 0)) return fail(PBSM3D_ERR_INVALID, "fetchr: steps and max_distance must be positive");
+    TRY(ensure_grid(h));
+    LAUNCH(h, fetchr_kernel, cdiv(h->T, 128), 128, h->T, h->iperm, h->grid, h->cx, h->cy, h->cz, h->wv_canopy, vw_dir, wc->fetch_steps,
+           wc->fetch_max_distance, wc->fetch_I, wc->fetch_incl_veg, out);
+    return 0;
+}
+// host or device pointers in, host or device pointer out, through the handle's staging buffers
+int provider_call(pbsm3d_handle* h, const pbsm3d_wind_config* wc, int which, const double* in0, const double* in1, double* out,
+                  int device_ptrs) {
+    if (!h || !in0 || !out) return fail(PBSM3D_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    pbsm3d_wind_config local;
+    if (!wc) { pbsm3d_wind_config_defaults(&local); wc = &local; }
+    const size_t bytes = (size_t)h->T * sizeof(double);
+    const double *d0 = in0, *d1 = in1;
+    double* dout = out;
+    if (!device_ptrs) {
+        TRY(upload(h, h->forcing_buf[0], in0, bytes));
+        d0 = h->forcing_buf[0];
+        if (in1) { TRY(upload(h, h->forcing_buf[2], in1, bytes)); d1 = h->forcing_buf[2]; }
+        dout = h->out_stage;
+    }
+    if (which == 0) TRY(enqueue_scale_wind_vert(h, wc, d0, d1, dout));
+    else TRY(enqueue_fetchr(h, wc, d0, dout));
+    if (!device_ptrs) CU(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, h->stream));
+    TRY(sync_stream(h));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double* const* host_in, const OutTargets* out,
               pbsm3d_stats* st) {
     cudaStream_t s = h->stream;
+    DevForcing f = f_in;
+    // pbsm3d_set_providers: inputs the caller left out are derived on the device (scale_wind_vert, fetchr) before assembly
+    const bool derive_u2 = h->providers_on && f.u2 == nullptr;
+    const bool derive_fetch = h->providers_on && f.fetch == nullptr && (h->cfg.use_exp_fetch || h->cfg.use_tanh_fetch);
+    if (derive_u2) f.u2 = h->forcing_buf[1];
+    if (derive_fetch) f.fetch = h->forcing_buf[7];
     const int T = h->T;
     std::memset(st, 0, sizeof(*st));
     const long long launch0 = h->n_launch;
@@ -1139,7 +1246,8 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const double* co
     // A+B: zeroSystem is implicit (every coefficient is overwritten); saltation + suspension assembly,
     // C: suspension_present = ||rhs||_inf > 1e-12 and ||b||_2^2, reduced inside the assembly kernel
     // With host buffers the forcing crosses PCIe in chunks on its own stream and each chunk is assembled as it lands.
-    const int nch = host_in ? std::max(1, std::min(kChunks, T / 32768)) : 1;
+    // (the providers need whole fields: no chunking when they run)
+    const int nch = (host_in && !derive_u2 && !derive_fetch) ? std::max(1, std::min(kChunks, T / 32768)) : 1;
     if (host_in)
         for (int c = 0; c < nch; ++c) {
             const size_t i0 = (size_t)T * c / nch, i1 = (size_t)T * (c + 1) / nch;
@@ -1151,6 +1259,8 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f, const double* co
         }
     for (int c = 0; c < nch; ++c) {
         if (host_in) CU(cudaStreamWaitEvent(s, h->ev_in[c], 0));
+        if (derive_u2) TRY(enqueue_scale_wind_vert(h, &h->wind_cfg, f.U_R, f.sd, h->forcing_buf[1]));
+        if (derive_fetch) TRY(enqueue_fetchr(h, &h->wind_cfg, f.vw_dir, h->forcing_buf[7]));
         launch_assembly(h, f, dt, (int)((size_t)T * c / nch), (int)((size_t)T * (c + 1) / nch), c);
     }
     h->have_system = true;
@@ -1615,6 +1725,13 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
         }
     }
     if (mesh->is_water) TRY(slots_from_host<unsigned char>(h, &h->water, mesh->is_water, (unsigned char)0));
+    // the providers read vegetation whatever PBSM3D's own enable_veg / use_R94_lambda say
+    if (mesh->canopy_height) {
+        if (h->canopy) h->wv_canopy = h->canopy; else TRY(slots_from_host(h, &h->wv_canopy, mesh->canopy_height, 0.0));
+        if (mesh->lai) { if (h->lai) h->wv_lai = h->lai; else TRY(slots_from_host(h, &h->wv_lai, mesh->lai, 0.0)); }
+    }
+    TRY(h->alloc_zero(&h->wv_u, h->S));
+    pbsm3d_wind_config_defaults(&h->wind_cfg);
 
     // ---- per-step arrays
     for (auto& b : h->forcing_buf) TRY(h->alloc(&b, T));
@@ -1711,8 +1828,8 @@ int pbsm3d_create(const pbsm3d_config* cfg, const pbsm3d_mesh* mesh, int device,
     return 0;
 }
 
-static bool forcing_complete(const pbsm3d_forcing* f) {
-    return f->U_R && f->U_2m_above_srf && f->snowdepthavg && f->swe && f->t && f->rh && f->vw_dir;
+static bool forcing_complete(const pbsm3d_handle* h, const pbsm3d_forcing* f) {
+    return f->U_R && (f->U_2m_above_srf || h->providers_on) && f->snowdepthavg && f->swe && f->t && f->rh && f->vw_dir;
 }
 static void out_pointers(const pbsm3d_outputs* o, double* p[8]) {
     p[0] = o->Qsalt; p[1] = o->Qsusp; p[2] = o->Qsubl; p[3] = o->Qsubl_mass; p[4] = o->sum_subl; p[5] = o->drift_mass;
@@ -1721,7 +1838,7 @@ static void out_pointers(const pbsm3d_outputs* o, double* p[8]) {
 
 int pbsm3d_step_device(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm3d_outputs* out, pbsm3d_stats* stats) {
     if (!h || !f) return fail(PBSM3D_ERR_INVALID, "null argument");
-    if (!forcing_complete(f)) return fail(PBSM3D_ERR_INVALID, "forcing array missing");
+    if (!forcing_complete(h, f)) return fail(PBSM3D_ERR_INVALID, "forcing array missing");
     CU(cudaSetDevice(h->device));
     pbsm3d_stats local;
     if (!stats) stats = &local;
@@ -1733,13 +1850,13 @@ int pbsm3d_step_device(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, con
 
 int pbsm3d_step(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm3d_outputs* out, pbsm3d_stats* stats) {
     if (!h || !f) return fail(PBSM3D_ERR_INVALID, "null argument");
-    if (!forcing_complete(f)) return fail(PBSM3D_ERR_INVALID, "forcing array missing");
+    if (!forcing_complete(h, f)) return fail(PBSM3D_ERR_INVALID, "forcing array missing");
     CU(cudaSetDevice(h->device));
     pbsm3d_stats local;
     if (!stats) stats = &local;
     const double* src[8] = {f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch};
-    DevForcing df{h->forcing_buf[0], h->forcing_buf[1], h->forcing_buf[2], h->forcing_buf[3], h->forcing_buf[4],
-                  h->forcing_buf[5], h->forcing_buf[6], f->fetch ? h->forcing_buf[7] : nullptr};
+    DevForcing df{h->forcing_buf[0], f->U_2m_above_srf ? h->forcing_buf[1] : nullptr, h->forcing_buf[2], h->forcing_buf[3],
+                  h->forcing_buf[4], h->forcing_buf[5], h->forcing_buf[6], f->fetch ? h->forcing_buf[7] : nullptr};
     OutTargets ot{};
     if (out) {
         out_pointers(out, ot.host);
@@ -1843,6 +1960,32 @@ int pbsm3d_get_deposition_system(pbsm3d_handle* h, double* diag, double* off, do
     TRY(fetch_chm(h, off, h->doff, 3, Tp));
     TRY(fetch_chm(h, rhs, h->drhs, 1, Tp));
     TRY(fetch_chm(h, q, h->h_sc->dep_buf ? h->qB : h->qA, 1, Tp));
+    return 0;
+}
+
+// ---- providers of two PBSM3D inputs ------------------------------------------------------
+void pbsm3d_wind_config_defaults(pbsm3d_wind_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->ignore_canopy = 0;          // scale_wind_vert.cpp:161
+    c->point_mode = 0;             // domain mode unless CHM runs in point mode (scale_wind_vert.cpp:140-142)
+    c->fetch_steps = 10;           // fetchr.cpp:34
+    c->fetch_max_distance = 1000;  // :36
+    c->fetch_I = 0.06;             // :41
+    c->fetch_incl_veg = 1;         // :43
+}
+
+int pbsm3d_scale_wind_vert(pbsm3d_handle* h, const pbsm3d_wind_config* wc, const double* U_R, const double* snowdepthavg,
+                           double* U_2m_above_srf, int device_ptrs) {
+    return provider_call(h, wc, 0, U_R, snowdepthavg, U_2m_above_srf, device_ptrs);
+}
+int pbsm3d_fetchr(pbsm3d_handle* h, const pbsm3d_wind_config* wc, const double* vw_dir, double* fetch, int device_ptrs) {
+    return provider_call(h, wc, 1, vw_dir, nullptr, fetch, device_ptrs);
+}
+int pbsm3d_set_providers(pbsm3d_handle* h, const pbsm3d_wind_config* wc) {
+    if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
+    h->providers_on = wc != nullptr;
+    if (wc) h->wind_cfg = *wc;
     return 0;
 }
 

@@ -181,3 +181,78 @@ class PBSM3D:
         if self.handle is not None:
             self.handle.close()
             self.handle = None
+
+
+class scale_wind_vert:
+    """Mirror of the reference module (src/modules/scale_wind_vert.cpp:27-229) on the device kernels of a PBSM3D handle.
+
+    depends U_R, optional snowdepthavg, provides U_2m_above_srf; config key ``ignore_canopy`` (default false).  In CHM
+    the module is data-parallel in point mode and domain-parallel otherwise (:140-142); ``point_mode`` selects which.
+    The mesh substrate (geometry, neighbours, vegetation, halo plan) is the PBSM3D handle's, so it takes the module."""
+
+    name = "scale_wind_vert"
+
+    def __init__(self, cfg: Optional[dict] = None, point_mode: bool = False):
+        cfg = dict(cfg or {})
+        unknown = set(cfg) - {"ignore_canopy"}
+        if unknown:
+            raise module_error(f"scale_wind_vert: unknown config key(s) {sorted(unknown)}")
+        self.wind_cfg_kw = dict(ignore_canopy=int(bool(PBSM3D._coerce(cfg.get("ignore_canopy", False)))), point_mode=int(point_mode))
+        self._depends, self._optional, self._provides = ["U_R"], ["snowdepthavg"], ["U_2m_above_srf"]
+        self.parallel = "data" if point_mode else "domain"
+
+    def get_depends(self):
+        return list(self._depends)
+
+    def get_optionals(self):
+        return list(self._optional)
+
+    def get_provides(self):
+        return list(self._provides)
+
+    def init(self, domain: Domain):
+        domain.init_face_data(self._provides)
+
+    def run(self, domain: Domain, pbsm: PBSM3D):
+        if pbsm.handle is None:
+            raise module_error("scale_wind_vert::run needs an initialised PBSM3D handle (it owns the device mesh)")
+        sd = domain["snowdepthavg"] if domain.has("snowdepthavg") else None  # has_optional("snowdepthavg")
+        try:
+            domain["U_2m_above_srf"] = pbsm.handle.scale_wind_vert(domain["U_R"], sd, capi.default_wind_config(**self.wind_cfg_kw))
+        except capi.Pbsm3dError as e:
+            raise module_error(str(e)) from e
+
+
+class fetchr:
+    """Mirror of the reference module (src/modules/fetchr.cpp:27-119): depends vw_dir, provides fetch; config keys
+    ``steps`` (10), ``max_distance`` (1000), ``I`` (0.06), ``incl_veg`` (true)."""
+
+    name = "fetchr"
+    parallel = "data"
+
+    def __init__(self, cfg: Optional[dict] = None):
+        cfg = dict(cfg or {})
+        unknown = set(cfg) - {"steps", "max_distance", "I", "incl_veg"}
+        if unknown:
+            raise module_error(f"fetchr: unknown config key(s) {sorted(unknown)}")
+        c = {k: PBSM3D._coerce(v) for k, v in cfg.items()}
+        self.wind_cfg_kw = dict(fetch_steps=int(c.get("steps", 10)), fetch_max_distance=float(c.get("max_distance", 1000.0)),
+                                fetch_I=float(c.get("I", 0.06)), fetch_incl_veg=int(bool(c.get("incl_veg", True))))
+        self._depends, self._provides = ["vw_dir"], ["fetch"]
+
+    def get_depends(self):
+        return list(self._depends)
+
+    def get_provides(self):
+        return list(self._provides)
+
+    def init(self, domain: Domain):
+        domain.init_face_data(self._provides)
+
+    def run(self, domain: Domain, pbsm: PBSM3D):
+        if pbsm.handle is None:
+            raise module_error("fetchr::run needs an initialised PBSM3D handle (it owns the device mesh)")
+        try:
+            domain["fetch"] = pbsm.handle.fetchr(domain["vw_dir"], capi.default_wind_config(**self.wind_cfg_kw))
+        except capi.Pbsm3dError as e:
+            raise module_error(str(e)) from e

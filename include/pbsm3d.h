@@ -228,6 +228,31 @@ int pbsm3d_get_suspension_system(pbsm3d_handle* h, double* diag, double* lat, do
 /* Last deposition system: diag [n_local], off [3][n_local], rhs [n_local], solution q [n_local]. */
 int pbsm3d_get_deposition_system(pbsm3d_handle* h, double* diag, double* off, double* rhs, double* q);
 
+/* ---- providers of two PBSM3D inputs, on the device ----
+ * scale_wind_vert (src/modules/scale_wind_vert.cpp:27-229): U_R [+ snowdepthavg] -> U_2m_above_srf; in domain mode every
+ * face then takes the thin plate spline (src/interpolation/TPSpline.cpp:40-173) of its edge neighbours' values.
+ * fetchr (src/modules/fetchr.cpp:27-119): vw_dir -> fetch, `steps` nearest-face-centre queries up-wind per face; the
+ * search covers this rank's owned faces.  Vegetation comes from pbsm3d_mesh.canopy_height / .lai (NULL = the mesh has
+ * no vegetation parameters, face->has_vegetation() false). */
+typedef struct pbsm3d_wind_config {
+    int32_t ignore_canopy;       /* scale_wind_vert "ignore_canopy", default false (scale_wind_vert.cpp:161) */
+    int32_t point_mode;          /* 1: point_scale only (CHM's point mode / run(face)); 0: domain mode with the neighbour spline */
+    int32_t fetch_steps;         /* fetchr "steps", default 10 (fetchr.cpp:34) */
+    int32_t fetch_incl_veg;      /* "incl_veg", default true (:43) */
+    double fetch_max_distance;   /* "max_distance", default 1000 m (:36) */
+    double fetch_I;              /* "I", default 0.06 m/m (:41) */
+} pbsm3d_wind_config;
+void pbsm3d_wind_config_defaults(pbsm3d_wind_config* cfg);
+/* Each array [n_local] in CHM face order; device_ptrs: 0 = host buffers, 1 = device buffers.  snowdepthavg may be NULL
+ * (no module provides the optional input).  cfg NULL = defaults. */
+int pbsm3d_scale_wind_vert(pbsm3d_handle* h, const pbsm3d_wind_config* cfg, const double* U_R, const double* snowdepthavg,
+                           double* U_2m_above_srf, int device_ptrs);
+int pbsm3d_fetchr(pbsm3d_handle* h, const pbsm3d_wind_config* cfg, const double* vw_dir, double* fetch, int device_ptrs);
+/* Fuse the providers into the step: after this call pbsm3d_step / pbsm3d_step_device accept forcing->U_2m_above_srf == NULL
+ * and (with exp/tanh fetch on) forcing->fetch == NULL and derive them on the device before the assembly, so the two arrays
+ * never cross PCIe.  cfg NULL switches the fusion off again. */
+int pbsm3d_set_providers(pbsm3d_handle* h, const pbsm3d_wind_config* cfg);
+
 /* Stand-alone kernels for measurement (bench.py roofline line, ncu): run `reps` launches of the named kernel on
  * the last assembled system and return the mean CUDA-event time per launch in milliseconds.
  * kernel: 0 = one full line sweep (all colour passes), 1 = residual (SpMV), 2 = assembly, 3 = deposition CG SpMV,
