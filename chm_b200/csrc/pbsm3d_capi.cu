@@ -173,7 +173,8 @@ struct pbsm3d_handle {
     double* wv_u = nullptr;                           // [S] point-scaled wind, ghost-extended
     bool grid_ready = false;
     CellGrid grid{};
-    int *grid_start = nullptr, *grid_face = nullptr;
+    int* grid_start = nullptr;
+    double2 *grid_xy = nullptr, *grid_zc = nullptr;
     bool providers_on = false;                        // pbsm3d_set_providers: the step derives missing inputs itself
     pbsm3d_wind_config wind_cfg{};
     float ms_providers = 0.f;
@@ -1146,17 +1147,19 @@ int enqueue_scale_wind_vert(pbsm3d_handle* h, const pbsm3d_wind_config* wc, cons
 int ensure_grid(pbsm3d_handle* h) {
     if (h->grid_ready) return 0;
     const int Tp = h->Tp;
-    std::vector<double> cx(Tp), cy(Tp);
+    std::vector<double> cx(Tp), cy(Tp), cz(Tp), can(Tp, 0.0);
     std::vector<int> perm(Tp);
     CU(cudaMemcpyAsync(cx.data(), h->cx, (size_t)Tp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(cy.data(), h->cy, (size_t)Tp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(cz.data(), h->cz, (size_t)Tp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->wv_canopy) CU(cudaMemcpyAsync(can.data(), h->wv_canopy, (size_t)Tp * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(perm.data(), h->perm, (size_t)Tp * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
     for (int p = 0; p < Tp; ++p)
         if (perm[p] >= 0) { x0 = std::min(x0, cx[p]); x1 = std::max(x1, cx[p]); y0 = std::min(y0, cy[p]); y1 = std::max(y1, cy[p]); }
     const double w = std::max(x1 - x0, 1e-9), hh = std::max(y1 - y0, 1e-9);
-    double cell = std::sqrt(4.0 * w * hh / std::max(h->T, 1));
+    double cell = std::sqrt(2.0 * w * hh / std::max(h->T, 1));  // ≈ 2 faces per cell
     if (!(cell > 0)) cell = 1.0;
     CellGrid g;
     g.x0 = x0; g.y0 = y0; g.h = cell; g.inv_h = 1.0 / cell;
@@ -1169,20 +1172,29 @@ int ensure_grid(pbsm3d_handle* h) {
         iy = std::min(std::max(iy, 0), g.ncy - 1);
         return (size_t)iy * g.ncx + ix;
     };
-    std::vector<int> start(nc + 1, 0), faces(std::max(h->T, 1));
+    const size_t nf = (size_t)std::max(h->T, 1);
+    std::vector<int> start(nc + 1, 0);
+    std::vector<double2> xy(nf), zc(nf);
     for (int p = 0; p < Tp; ++p)
         if (perm[p] >= 0) start[cell_of(p) + 1]++;
     for (size_t c = 0; c < nc; ++c) start[c + 1] += start[c];
     std::vector<int> fill(start.begin(), start.end() - 1);
     for (int p = 0; p < Tp; ++p)
-        if (perm[p] >= 0) faces[fill[cell_of(p)]++] = p;
+        if (perm[p] >= 0) {
+            const int k = fill[cell_of(p)]++;
+            xy[k] = make_double2(cx[p], cy[p]);
+            zc[k] = make_double2(cz[p], can[p]);
+        }
     TRY(h->alloc(&h->grid_start, nc + 1));
-    TRY(h->alloc(&h->grid_face, faces.size()));
+    TRY(h->alloc(&h->grid_xy, nf));
+    TRY(h->alloc(&h->grid_zc, nf));
     TRY(upload(h, h->grid_start, start.data(), (nc + 1) * sizeof(int)));
-    TRY(upload(h, h->grid_face, faces.data(), faces.size() * sizeof(int)));
+    TRY(upload(h, h->grid_xy, xy.data(), nf * sizeof(double2)));
+    TRY(upload(h, h->grid_zc, zc.data(), nf * sizeof(double2)));
     CU(cudaStreamSynchronize(h->stream));
     g.cell_start = h->grid_start;
-    g.cell_face = h->grid_face;
+    g.xy = h->grid_xy;
+    g.zc = h->grid_zc;
     h->grid = g;
     h->grid_ready = true;
     return 0;

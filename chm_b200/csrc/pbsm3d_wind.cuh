@@ -171,39 +171,45 @@ __global__ void __launch_bounds__(128) wind_spline_kernel(int T, DevMesh m, cons
 }
 
 // ---------------------------------------------------------------------------------------------- fetchr
+// Uniform cell grid over the face centres.  Faces are stored SORTED BY CELL (row-major), so the faces of a run of
+// x-adjacent cells are one contiguous range: a (2r+1)^2 block is 2r+1 contiguous reads of {x, y} pairs, and what a
+// query needs from the face it finds (centre elevation, canopy height) sits at the same index in `zc`.
 struct CellGrid {
     double x0, y0, h, inv_h;
     int ncx, ncy;
     const int* cell_start;  // [ncx*ncy + 1]
-    const int* cell_face;   // [n faces] slot ids sorted by cell
+    const double2* xy;      // [n faces] centre (x, y), cell order
+    const double2* zc;      // [n faces] (centre z, CanopyHeight or 0), cell order
 };
 
-// Nearest face centre to (qx, qy) among the faces in the grid (exact; ties broken by scan order).
-__device__ __forceinline__ int nearest_centre(const CellGrid& g, const double* __restrict__ cx, const double* __restrict__ cy,
-                                              double qx, double qy) {
+// Index (cell order) of the nearest face centre to (qx, qy); exact, ties broken by scan order.
+__device__ __forceinline__ int nearest_centre(const CellGrid& g, double qx, double qy) {
     int qcx = (int)floor((qx - g.x0) * g.inv_h), qcy = (int)floor((qy - g.y0) * g.inv_h);
     qcx = min(max(qcx, 0), g.ncx - 1);
     qcy = min(max(qcy, 0), g.ncy - 1);
     double best = 1e300;
     int bi = -1;
-    const int rmax = max(g.ncx, g.ncy);
-    auto scan = [&](int xx, int yy) {
-        if (xx < 0 || xx >= g.ncx || yy < 0 || yy >= g.ncy) return;
-        const int c = yy * g.ncx + xx;
-        for (int k = g.cell_start[c]; k < g.cell_start[c + 1]; ++k) {
-            const int f = g.cell_face[k];
-            const double dx = cx[f] - qx, dy = cy[f] - qy;
+    auto scan_run = [&](int yy, int xa, int xb) {  // cells [xa, xb] of row yy, clipped to the grid
+        if (yy < 0 || yy >= g.ncy) return;
+        xa = max(xa, 0);
+        xb = min(xb, g.ncx - 1);
+        if (xa > xb) return;
+        const int k1 = g.cell_start[yy * g.ncx + xb + 1];
+        for (int k = g.cell_start[yy * g.ncx + xa]; k < k1; ++k) {
+            const double2 c = g.xy[k];
+            const double dx = c.x - qx, dy = c.y - qy;
             const double d2 = dx * dx + dy * dy;
-            if (d2 < best) { best = d2; bi = f; }
+            if (d2 < best) { best = d2; bi = k; }
         }
     };
-    for (int r = 0; r <= rmax; ++r) {
+    const int rmax = max(g.ncx, g.ncy);
+    for (int r = 1; r <= rmax; ++r) {
         const int y0 = qcy - r, y1 = qcy + r, x0 = qcx - r, x1 = qcx + r;
-        if (r == 0) {
-            scan(qcx, qcy);
-        } else {  // the border of the (2r+1)^2 block
-            for (int xx = x0; xx <= x1; ++xx) { scan(xx, y0); scan(xx, y1); }
-            for (int yy = y0 + 1; yy < y1; ++yy) { scan(x0, yy); scan(x1, yy); }
+        if (r == 1) {  // the 3x3 block around the query's cell: three contiguous runs
+            scan_run(y0, x0, x1); scan_run(qcy, x0, x1); scan_run(y1, x0, x1);
+        } else {       // the border of the (2r+1)^2 block
+            scan_run(y0, x0, x1); scan_run(y1, x0, x1);
+            for (int yy = y0 + 1; yy < y1; ++yy) { scan_run(yy, x0, x0); scan_run(yy, x1, x1); }
         }
         // every face not yet examined lies beyond one of the sides of the examined block that is inside the grid
         double lb = 1e300;
@@ -237,12 +243,14 @@ __global__ void __launch_bounds__(128) fetchr_kernel(int T, const int* __restric
     for (int j = 1; j <= steps; ++j) {
         const double distance = j * size_of_step;
         // no FMA contraction: the query point and Z_core are the reference's two-rounding expressions
-        const int f = nearest_centre(g, cx, cy, __dadd_rn(mx, __dmul_rn(distance, sb)), __dadd_rn(my, __dmul_rn(distance, cb)));
-        const double Z_CanTop = veg ? canopy[f] : 0.0;
-        const double Z_test = __dadd_rn(cz[f], Z_CanTop);
+        const int k = nearest_centre(g, __dadd_rn(mx, __dmul_rn(distance, sb)), __dadd_rn(my, __dmul_rn(distance, cb)));
+        const double2 zc = g.zc[k];
+        const double Z_CanTop = veg ? zc.y : 0.0;
+        const double Z_test = __dadd_rn(zc.x, Z_CanTop);
         const double Z_core = __dadd_rn(mz, __dmul_rn(distance, I));
         const double z0_1 = 0.12 * Z_CanTop, z0_2 = 0.001, n = 1.0 / 0.8, h = 5.0;
-        const double x_sss = pow(((33.33333333 * h - 25. * z0_2) / (log(z0_1 / z0_2) * z0_2)), n) * z0_2;
+        // x_sss = 0 without a canopy on the face found (log(0) = -inf, pow(-0, n) = 0): skip the transcendental there
+        const double x_sss = Z_CanTop == 0.0 ? 0.0 : pow(((33.33333333 * h - 25. * z0_2) / (log(z0_1 / z0_2) * z0_2)), n) * z0_2;
         if (Z_test >= Z_core || (incl_veg && distance < x_sss)) { out = distance; break; }
     }
     fetch[i] = out;

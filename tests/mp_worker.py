@@ -54,6 +54,14 @@ def main():
             gathered[f"{name}_{k}"] = torch.cat(parts).cpu().numpy()
         gathered[f"iters_{k}"] = np.array([st["suspension_iterations"], st["deposition_iterations"], st["suspension_present"],
                                            st["deposition_present"]])
+    # scale_wind_vert in domain mode on the partition: its neighbour spline needs the partners' point-scaled values (halo)
+    Fg = synthetic.forcing(ggeo.cx, ggeo.cy, seed=7, step=0)
+    u2 = h.scale_wind_vert(Fg["U_R"][s:s + T], Fg["snowdepthavg"][s:s + T])
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([T], dtype=torch.int64, device="cuda"))
+    parts = [torch.zeros(int(n_.item()), dtype=torch.float64, device="cuda") for n_ in sizes]
+    dist.all_gather(parts, torch.from_numpy(u2).cuda())
+    gathered["u2_domain"] = torch.cat(parts).cpu().numpy()
     gathered["halo_transport"] = np.array(st["halo_transport"])
     gathered["halo_fused"] = np.array(st["halo_fused"])
     gathered["halo_exchanges"] = np.array(st["halo_exchanges"])

@@ -82,4 +82,8 @@ def test_max_ranks_on_uniform_mesh(tmp_path):
     assert rel_l2(c, h.solution()) <= 1e-7
     for v in ("Qsusp", "Qsalt", "drift_mass"):
         assert rel_l2(g[f"{v}_0"], outs[v]) <= 1e-7, v
+    # scale_wind_vert's neighbour spline across partition boundaries (halo of the point-scaled wind) = the global run
+    F0 = synthetic.forcing(geo.cx, geo.cy, seed=7, step=0)
+    u2 = h.scale_wind_vert(F0["U_R"], F0["snowdepthavg"])
+    assert np.max(np.abs(g["u2_domain"] - u2) / u2) <= 1e-12
     h.close()
