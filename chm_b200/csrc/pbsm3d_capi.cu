@@ -95,7 +95,7 @@ struct pbsm3d_handle {
     int cstart[kMaxColours] = {0}, ccount[kMaxColours] = {0};
     cudaStream_t stream = nullptr;                  // compute
     cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D of the forcing / export + D2H of the outputs
-    cudaEvent_t ev_in[kChunks] = {nullptr}, ev_asm = nullptr, ev_flux = nullptr, ev_out = nullptr;
+    cudaEvent_t ev_in[kChunks] = {nullptr}, ev_asm = nullptr, ev_flux = nullptr, ev_out = nullptr, ev_prov = nullptr;
     std::vector<void*> allocs;
 
     // mesh / static (slot order)
@@ -116,7 +116,7 @@ struct pbsm3d_handle {
            *sum_drift = nullptr, *more_avail = nullptr;
     double *drhs = nullptr, *drhsS = nullptr, *cg_r = nullptr, *cg_p = nullptr /*[S]*/, *cg_Ap = nullptr;
     double *qA = nullptr, *qB = nullptr;  // [S] deposition iterate (Chebyshev ping-pong; CG uses qA)
-    double *cheb_d = nullptr, *offS = nullptr;
+    double* offS = nullptr;
     // Chebyshev: spectrum bounds of D^-1 A (static matrix, estimated once) and the coefficient sequence
     bool cheb_ready = false;
     double cheb_lmin = 0.0, cheb_lmax = 0.0;
@@ -908,18 +908,18 @@ int enqueue_cheb(pbsm3d_handle* h, int k0, int k1, int check_from) {
             const int nbb = std::max(1, std::min(cdiv(h->nb_total, kRedThreads), 64));
             const int gh = std::max(1, std::min(g, kRedBlocks - nbb)) + nbb;
             if (check)
-                LAUNCH(h, cheb_iter_halo_kernel<1>, gh, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
+                LAUNCH(h, cheb_iter_halo_kernel<1>, gh, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, qout, h->cheb_a[k],
                        h->cheb_c[k], h->partial, kRedBlocks, h->sc, h->red, hl, br, nbb);
             else
-                LAUNCH(h, cheb_iter_halo_kernel<0>, gh, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
+                LAUNCH(h, cheb_iter_halo_kernel<0>, gh, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, qout, h->cheb_a[k],
                        h->cheb_c[k], h->partial, kRedBlocks, h->sc, h->red, hl, br, nbb);
             ++h->halo_ops;
             ++h->halo_fused_ops;
         } else if (check) {
-            LAUNCH(h, cheb_iter_kernel<1>, g, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
+            LAUNCH(h, cheb_iter_kernel<1>, g, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, qout, h->cheb_a[k],
                    h->cheb_c[k], k, h->partial, kRedBlocks, h->sc, h->red, tol2, f);
         } else {
-            LAUNCH(h, cheb_iter_kernel<0>, g, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, h->cheb_d, qout, h->cheb_a[k],
+            LAUNCH(h, cheb_iter_kernel<0>, g, kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, qin, qout, h->cheb_a[k],
                    h->cheb_c[k], k, h->partial, kRedBlocks, h->sc, h->red, tol2, f);
         }
         if (check && !f) {
@@ -1094,7 +1094,7 @@ int enqueue_tail(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTarg
     // deposition solve (x0 = 0)
     CU(cudaMemsetAsync(h->qA, 0, (size_t)h->S * sizeof(double), s));
     if (use_chebyshev(h)) {
-        CU(cudaMemsetAsync(h->cheb_d, 0, (size_t)Tp * sizeof(double), s));
+        CU(cudaMemsetAsync(h->qB, 0, (size_t)h->S * sizeof(double), s));  // q_{-1}: multiplied by a_0 = 0, must be finite
         const int maxit = h->cfg.max_iterations;
         const bool known = h->pred_dep > 0;
         const int n = known ? h->pred_dep : h->cheb_kest;
@@ -1258,21 +1258,34 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
     // A+B: zeroSystem is implicit (every coefficient is overwritten); saltation + suspension assembly,
     // C: suspension_present = ||rhs||_inf > 1e-12 and ||b||_2^2, reduced inside the assembly kernel
     // With host buffers the forcing crosses PCIe in chunks on its own stream and each chunk is assembled as it lands.
-    // (the providers need whole fields: no chunking when they run)
-    const int nch = (host_in && !derive_u2 && !derive_fetch) ? std::max(1, std::min(kChunks, T / 32768)) : 1;
-    if (host_in)
+    // With the providers fused in, their inputs (U_R, snowdepthavg, vw_dir) cross first as whole fields and the
+    // provider kernels run while the chunks of the other arrays are still on their way.
+    const bool derive = derive_u2 || derive_fetch;
+    const int nch = host_in ? std::max(1, std::min(kChunks, T / 32768)) : 1;
+    auto provider_input = [&](int k) { return derive && (k == 0 || k == 2 || k == 6); };
+    if (host_in) {
+        if (derive) {
+            for (int k = 0; k < 8; ++k)
+                if (host_in[k] && provider_input(k))
+                    CU(cudaMemcpyAsync(h->forcing_buf[k], host_in[k], (size_t)T * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+            CU(cudaEventRecord(h->ev_prov, h->s_in));
+        }
         for (int c = 0; c < nch; ++c) {
             const size_t i0 = (size_t)T * c / nch, i1 = (size_t)T * (c + 1) / nch;
             for (int k = 0; k < 8; ++k)
-                if (host_in[k])
+                if (host_in[k] && !provider_input(k))
                     CU(cudaMemcpyAsync(h->forcing_buf[k] + i0, host_in[k] + i0, (i1 - i0) * sizeof(double), cudaMemcpyHostToDevice,
                                        h->s_in));
             CU(cudaEventRecord(h->ev_in[c], h->s_in));
         }
-    for (int c = 0; c < nch; ++c) {
-        if (host_in) CU(cudaStreamWaitEvent(s, h->ev_in[c], 0));
+    }
+    if (derive) {
+        if (host_in) CU(cudaStreamWaitEvent(s, h->ev_prov, 0));
         if (derive_u2) TRY(enqueue_scale_wind_vert(h, &h->wind_cfg, f.U_R, f.sd, h->forcing_buf[1]));
         if (derive_fetch) TRY(enqueue_fetchr(h, &h->wind_cfg, f.vw_dir, h->forcing_buf[7]));
+    }
+    for (int c = 0; c < nch; ++c) {
+        if (host_in) CU(cudaStreamWaitEvent(s, h->ev_in[c], 0));
         launch_assembly(h, f, dt, (int)((size_t)T * c / nch), (int)((size_t)T * (c + 1) / nch), c);
     }
     h->have_system = true;
@@ -1543,6 +1556,7 @@ void pbsm3d_destroy(pbsm3d_handle* h) {
     if (h->ev_asm) cudaEventDestroy(h->ev_asm);
     if (h->ev_flux) cudaEventDestroy(h->ev_flux);
     if (h->ev_out) cudaEventDestroy(h->ev_out);
+    if (h->ev_prov) cudaEventDestroy(h->ev_prov);
     for (void* b : h->peer_base)
         if (b) cudaIpcCloseMemHandle(b);
     if (h->comm) ncclCommDestroy(h->comm);
@@ -1609,6 +1623,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     CU(cudaEventCreate(&h->ev_asm));
     CU(cudaEventCreate(&h->ev_flux));
     CU(cudaEventCreate(&h->ev_out));
+    CU(cudaEventCreate(&h->ev_prov));
     h->trace = getenv("PBSM3D_TRACE") != nullptr;
     {
         cudaDeviceProp prop;
@@ -1772,7 +1787,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     TRY(h->alloc(&h->offS, (size_t)3 * Tp));
     LAUNCH(h, deposition_scale_kernel, cdiv(Tp, 256), 256, Tp, h->doff, h->dinv, h->offS);
     double** perslot[] = {&h->Qsubl, &h->Qsubl_mass, &h->sum_subl, &h->drift_mass, &h->sum_drift, &h->more_avail,
-                          &h->drhs,  &h->drhsS,      &h->cg_r,     &h->cg_Ap,      &h->cheb_d};
+                          &h->drhs,  &h->drhsS,      &h->cg_r,     &h->cg_Ap};
     for (double** p : perslot) TRY(h->alloc_zero(p, Tp));
     TRY(h->alloc(&h->out_stage, (size_t)8 * T));
     // drift_mass is a face variable that is -9999 until first written (variablestorage default)
@@ -2028,7 +2043,7 @@ int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms) {
                     if (!h->cheb_ready) return fail(PBSM3D_ERR_INVALID, "Chebyshev is not set up on this handle");
                     // a_k = c_k = 0: the same traffic as a real iteration, and the converged iterate is only copied
                     LAUNCH(h, cheb_iter_kernel<0>, red_grid(h->Tp), kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag,
-                           h->h_sc->dep_buf ? h->qB : h->qA, h->cheb_d, h->h_sc->dep_buf ? h->qA : h->qB, 0.0, 0.0, k, h->partial,
+                           h->h_sc->dep_buf ? h->qB : h->qA, h->h_sc->dep_buf ? h->qA : h->qB, 0.0, 0.0, k, h->partial,
                            kRedBlocks, nullptr, h->red, tol2, 0);
                     break;
                 default: return fail(PBSM3D_ERR_INVALID, "unknown kernel id");

@@ -983,19 +983,21 @@ __global__ void probe_rhs_kernel(int Tp, const int* __restrict__ perm, long long
     b[p] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
 }
 
-// HOT LOOP 3: one iteration of the Jacobi-preconditioned Chebyshev iteration on the deposition system
-//     z = D^{-1}(b - A q_k),   d = a_k d + c_k z,   q_{k+1} = q_k + d
-// (a_k, c_k from the spectrum bounds of D^{-1}A estimated once in pbsm3d_create: the matrix is static).  One
-// launch per iteration, no dot products, no global reduction: per face 3 scaled off-diagonals + 3 neighbour slots
-// + scaled rhs + q_k (+ gathers) + d in, d and q_{k+1} out = 76 B.  q is ghost-extended and ping-pongs between two
-// buffers, so the iterate an iteration read is still intact when a CHECK iteration finds it converged.
+// HOT LOOP 3: one iteration of the Jacobi-preconditioned Chebyshev iteration on the deposition system, in its
+// three-term form
+//     z = D^{-1}(b - A q_k),   q_{k+1} = q_k + a_k (q_k - q_{k-1}) + c_k z
+// (a_k, c_k from the spectrum bounds of D^{-1}A estimated once in pbsm3d_create: the matrix is static; a_0 = 0).  One
+// launch per iteration, no dot products, no global reduction.  q ping-pongs between two ghost-extended buffers:
+// iteration k reads q_k from one, and OVERWRITES q_{k-1} with q_{k+1} in the other (each thread touches only its own
+// element of it), so no separate direction vector is streamed: per face 3 scaled off-diagonals + 3 neighbour slots +
+// scaled rhs + q_k (+ gathers) + q_{k-1} in, q_{k+1} out = 68 B.  The iterate an iteration read is still intact when
+// a CHECK iteration finds it converged.
 template <int CHECK>
 __global__ void __launch_bounds__(kRedThreads) cheb_iter_kernel(DevMesh m, const double* __restrict__ offS,
                                                                 const double* __restrict__ bS, const double* __restrict__ ddiag,
-                                                                const double* __restrict__ qin, double* __restrict__ d,
-                                                                double* __restrict__ qout, double ak, double ck, int k,
-                                                                double* __restrict__ partial, int pstride, Scalars* sc,
-                                                                double* __restrict__ red, double tol2, int fused) {
+                                                                const double* __restrict__ qin, double* __restrict__ qout, double ak,
+                                                                double ck, int k, double* __restrict__ partial, int pstride,
+                                                                Scalars* sc, double* __restrict__ red, double tol2, int fused) {
     if (sc && (!sc->tail_done || !sc->dep_present || sc->done)) return;  // sc == null: stand-alone timing launch
     const int Tp = m.Tp;
     double rr = 0.0;
@@ -1005,9 +1007,7 @@ __global__ void __launch_bounds__(kRedThreads) cheb_iter_kernel(DevMesh m, const
 #pragma unroll
         for (int j = 0; j < 3; ++j) z -= offS[(size_t)j * Tp + p] * qin[m.nbs[(size_t)j * Tp + p]];
         if (CHECK) { const double r = z * ddiag[p]; rr += r * r; }
-        const double dn = ak * d[p] + ck * z;
-        d[p] = dn;
-        qout[p] = qp + dn;
+        qout[p] = qp + (ak * (qp - qout[p]) + ck * z);
     }
     if (CHECK && sc) {
         double o0, unused;
@@ -1526,11 +1526,11 @@ __device__ __forceinline__ void tagged_write(ulonglong2* e, double v, unsigned l
 }
 template <bool BND>
 __device__ __forceinline__ double cheb_face(const DevMesh& m, const double* __restrict__ offS, const double* __restrict__ bS,
-                                            const double* __restrict__ qin, double* __restrict__ d, double* __restrict__ qout,
+                                            const double* __restrict__ qin, double* __restrict__ qout,
                                             double ak, double ck, int p, const TaggedLink& tl, double& z_out) {
     const int Tp = m.Tp;
     // everything that does not depend on the partners is loaded before the first ghost is waited for
-    const double qp = qin[p], bp = bS[p], dp = d[p];
+    const double qp = qin[p], bp = bS[p], qm = qout[p];  // qout still holds q_{k-1}
     int n[3];
     double o[3], qn[3];
 #pragma unroll
@@ -1545,9 +1545,7 @@ __device__ __forceinline__ double cheb_face(const DevMesh& m, const double* __re
     double z = bp - qp;
 #pragma unroll
     for (int j = 0; j < 3; ++j) z -= o[j] * qn[j];
-    const double dn = ak * dp + ck * z;
-    d[p] = dn;
-    const double qnew = qp + dn;
+    const double qnew = qp + (ak * (qp - qm) + ck * z);
     qout[p] = qnew;
     z_out = z;
     return qnew;
@@ -1556,7 +1554,7 @@ __device__ __forceinline__ double cheb_face(const DevMesh& m, const double* __re
 // loop's): update, then one tagged 16-byte store per partner that needs the face.
 template <int CHECK>
 __device__ __noinline__ double cheb_boundary(const DevMesh& m, const double* __restrict__ offS, const double* __restrict__ bS,
-                                             const double* __restrict__ ddiag, const double* __restrict__ qin, double* __restrict__ d,
+                                             const double* __restrict__ ddiag, const double* __restrict__ qin,
                                              double* __restrict__ qout, double ak, double ck, const TaggedLink& tl, const BndRanges& br,
                                              int nbb) {
     double rr = 0.0;
@@ -1568,7 +1566,7 @@ __device__ __noinline__ double cheb_boundary(const DevMesh& m, const double* __r
         const int e0 = tl.bptr[i], e1 = tl.bptr[i + 1];
         ulonglong2* dst0 = e1 > e0 ? tl.remote[e0] : nullptr;
         double z;
-        const double qn = cheb_face<true>(m, offS, bS, qin, d, qout, ak, ck, p, tl, z);
+        const double qn = cheb_face<true>(m, offS, bS, qin, qout, ak, ck, p, tl, z);
         if (dst0) tagged_write(dst0, qn, tl.write_tag);
         for (int e = e0 + 1; e < e1; ++e) tagged_write(tl.remote[e], qn, tl.write_tag);
         if (CHECK) { const double r = z * ddiag[p]; rr += r * r; }
@@ -1580,7 +1578,7 @@ __device__ __noinline__ double cheb_boundary(const DevMesh& m, const double* __r
 template <int CHECK>
 __global__ void __launch_bounds__(kRedThreads, 8) cheb_iter_halo_kernel(const __grid_constant__ DevMesh m, const double* __restrict__ offS,
                                                                         const double* __restrict__ bS, const double* __restrict__ ddiag,
-                                                                        const double* __restrict__ qin, double* __restrict__ d,
+                                                                        const double* __restrict__ qin,
                                                                         double* __restrict__ qout, double ak, double ck,
                                                                         double* __restrict__ partial, int pstride, Scalars* sc,
                                                                         double* __restrict__ red, const __grid_constant__ TaggedLink tl,
@@ -1588,7 +1586,7 @@ __global__ void __launch_bounds__(kRedThreads, 8) cheb_iter_halo_kernel(const __
     if (!sc->tail_done || !sc->dep_present || sc->done) return;
     double rr = 0.0;
     if ((int)blockIdx.x < nbb) {
-        rr = cheb_boundary<CHECK>(m, offS, bS, ddiag, qin, d, qout, ak, ck, tl, br, nbb);
+        rr = cheb_boundary<CHECK>(m, offS, bS, ddiag, qin, qout, ak, ck, tl, br, nbb);
     } else {
         const int nmain = gridDim.x - nbb;
 #pragma unroll
@@ -1596,7 +1594,7 @@ __global__ void __launch_bounds__(kRedThreads, 8) cheb_iter_halo_kernel(const __
             if (c >= br.n_colours) break;
             for (int p = br.start[c] + br.count[c] + (blockIdx.x - nbb) * blockDim.x + threadIdx.x; p < br.end[c]; p += nmain * blockDim.x) {
                 double z;
-                cheb_face<false>(m, offS, bS, qin, d, qout, ak, ck, p, tl, z);
+                cheb_face<false>(m, offS, bS, qin, qout, ak, ck, p, tl, z);
                 if (CHECK) { const double r = z * ddiag[p]; rr += r * r; }
             }
         }

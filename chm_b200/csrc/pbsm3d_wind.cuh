@@ -183,8 +183,13 @@ struct CellGrid {
 };
 
 // Index (cell order) of the nearest face centre to (qx, qy); exact, ties broken by scan order.
+// A query outside the grid (up-wind of the domain edge) is searched from its projection q' onto the grid's box:
+// for every centre p in the box |q-p|^2 >= |q-q'|^2 + |q'-p|^2, so rings around q' bound what is left, and the
+// search still ends after a ring or two instead of growing to the distance between q and the domain.
 __device__ __forceinline__ int nearest_centre(const CellGrid& g, double qx, double qy) {
-    int qcx = (int)floor((qx - g.x0) * g.inv_h), qcy = (int)floor((qy - g.y0) * g.inv_h);
+    const double bx = fmin(fmax(qx, g.x0), g.x0 + g.ncx * g.h), by = fmin(fmax(qy, g.y0), g.y0 + g.ncy * g.h);
+    const double out2 = (qx - bx) * (qx - bx) + (qy - by) * (qy - by);  // 0 for a query inside the box
+    int qcx = (int)floor((bx - g.x0) * g.inv_h), qcy = (int)floor((by - g.y0) * g.inv_h);
     qcx = min(max(qcx, 0), g.ncx - 1);
     qcy = min(max(qcy, 0), g.ncy - 1);
     double best = 1e300;
@@ -205,20 +210,20 @@ __device__ __forceinline__ int nearest_centre(const CellGrid& g, double qx, doub
     const int rmax = max(g.ncx, g.ncy);
     for (int r = 1; r <= rmax; ++r) {
         const int y0 = qcy - r, y1 = qcy + r, x0 = qcx - r, x1 = qcx + r;
-        if (r == 1) {  // the 3x3 block around the query's cell: three contiguous runs
+        if (r == 1) {  // the 3x3 block around the cell: three contiguous runs
             scan_run(y0, x0, x1); scan_run(qcy, x0, x1); scan_run(y1, x0, x1);
         } else {       // the border of the (2r+1)^2 block
             scan_run(y0, x0, x1); scan_run(y1, x0, x1);
             for (int yy = y0 + 1; yy < y1; ++yy) { scan_run(yy, x0, x0); scan_run(yy, x1, x1); }
         }
-        // every face not yet examined lies beyond one of the sides of the examined block that is inside the grid
+        // every centre not yet examined lies beyond one of the sides of the examined block that is inside the grid
         double lb = 1e300;
-        if (x0 > 0) lb = fmin(lb, fmax(0.0, qx - (g.x0 + x0 * g.h)));
-        if (x1 < g.ncx - 1) lb = fmin(lb, fmax(0.0, (g.x0 + (x1 + 1) * g.h) - qx));
-        if (y0 > 0) lb = fmin(lb, fmax(0.0, qy - (g.y0 + y0 * g.h)));
-        if (y1 < g.ncy - 1) lb = fmin(lb, fmax(0.0, (g.y0 + (y1 + 1) * g.h) - qy));
-        if (lb >= 1e300) break;                 // the whole grid has been examined
-        if (bi >= 0 && best <= lb * lb) break;  // nothing closer can be left
+        if (x0 > 0) lb = fmin(lb, fmax(0.0, bx - (g.x0 + x0 * g.h)));
+        if (x1 < g.ncx - 1) lb = fmin(lb, fmax(0.0, (g.x0 + (x1 + 1) * g.h) - bx));
+        if (y0 > 0) lb = fmin(lb, fmax(0.0, by - (g.y0 + y0 * g.h)));
+        if (y1 < g.ncy - 1) lb = fmin(lb, fmax(0.0, (g.y0 + (y1 + 1) * g.h) - by));
+        if (lb >= 1e300) break;                        // the whole grid has been examined
+        if (bi >= 0 && best <= out2 + lb * lb) break;  // nothing closer can be left
     }
     return bi;
 }

@@ -20,8 +20,12 @@ void check(int rc)
 
 PBSM3D_gpu::PBSM3D_gpu(config_file cfg) : module_base("PBSM3D_gpu", parallel::domain, cfg)
 {
-    // identical dependency declarations to PBSM3D::PBSM3D (PBSM3D.cpp:105-202)
-    depends("U_2m_above_srf");
+    // identical dependency declarations to PBSM3D::PBSM3D (PBSM3D.cpp:105-202), except that with "fuse_providers"
+    // U_2m_above_srf and fetch are derived on the device from U_R / snowdepthavg / vw_dir (scale_wind_vert.cpp, fetchr.cpp)
+    // and no longer come from other modules
+    _fuse = cfg.get("fuse_providers", false);
+    if (!_fuse)
+        depends("U_2m_above_srf");
     depends("vw_dir");
     depends("swe");
     depends("t");
@@ -45,7 +49,10 @@ PBSM3D_gpu::PBSM3D_gpu(config_file cfg) : module_base("PBSM3D_gpu", parallel::do
     }
     _use_fetch = _c.use_exp_fetch || _c.use_tanh_fetch;
     if (_use_fetch)
-        depends("fetch");
+    {
+        if (!_fuse)
+            depends("fetch");
+    }
     else
         depends("p_snow_hours");
     _c.use_R94_lambda = cfg.get("use_R94_lambda", true);
@@ -134,8 +141,9 @@ void PBSM3D_gpu::init(mesh& domain)
         return (int32_t)(ntri + (it - ghosts.begin()));
     };
 
-    bool has_area = true, has_veg = true;
+    bool has_area = true, has_veg = true, any_wveg = false, has_wlai = true;
     std::vector<double> area(ntri), canopy(ntri), lai(ntri), sn(ntri, 1.0), sdv(ntri, 0.8);
+    std::vector<double> wcanopy(_fuse ? ntri : 0, 0.0), wlai(_fuse ? ntri : 0, 0.0);
     std::vector<uint8_t> water(ntri, 0);
     for (size_t i = 0; i < ntri; i++)
     {
@@ -157,6 +165,19 @@ void PBSM3D_gpu::init(mesh& domain)
         else
             has_area = false;
         water[i] = is_water(face) ? 1 : 0;
+        if (_fuse && face->has_vegetation())
+        { // the providers look at vegetation face by face (scale_wind_vert.cpp:60-63, fetchr.cpp:63-72,86-90)
+            any_wveg = true;
+            wcanopy[i] = face->veg_attribute("CanopyHeight");
+            try
+            {
+                wlai[i] = face->veg_attribute("LAI");
+            }
+            catch (module_error& e)
+            {
+                has_wlai = false;
+            }
+        }
         if (!face->has_vegetation())
             has_veg = false; // one face without vegetation data turns veg off globally (PBSM3D.cpp:317-324)
         else if (_c.enable_veg && has_veg)
@@ -197,6 +218,14 @@ void PBSM3D_gpu::init(mesh& domain)
     m.stalk_number = (veg && !_c.use_R94_lambda) ? sn.data() : nullptr;
     m.stalk_diameter = (veg && !_c.use_R94_lambda) ? sdv.data() : nullptr;
     m.is_water = water.data();
+    if (_fuse && any_wveg && !veg)
+    { // PBSM3D's own vegetation is off (disabled, or a face lacks the data) but the providers still see the canopy where it exists
+        _c.enable_veg = 0;
+        m.canopy_height = wcanopy.data();
+        m.lai = has_wlai ? wlai.data() : nullptr;
+    }
+    else if (_fuse && veg && !m.lai && has_wlai)
+        m.lai = wlai.data(); // stalk-based lambda for PBSM3D, LAI for scale_wind_vert's canopy profile
 
     pbsm3d_comm comm;
     std::memset(&comm, 0, sizeof(comm));
@@ -219,6 +248,17 @@ void PBSM3D_gpu::init(mesh& domain)
     if (device < 0)
         device = pcomm ? comm.rank % std::max(1, cfg.get("gpus_per_node", 8)) : 0;
     check(pbsm3d_create(&_c, &m, device, pcomm, &_h));
+    if (_fuse)
+    { // the provider modules' own config keys (scale_wind_vert.cpp:161, fetchr.cpp:34-43)
+        pbsm3d_wind_config w;
+        pbsm3d_wind_config_defaults(&w);
+        w.ignore_canopy = cfg.get("ignore_canopy", false);
+        w.fetch_steps = cfg.get("steps", 10);
+        w.fetch_max_distance = cfg.get("max_distance", 1000.0);
+        w.fetch_I = cfg.get("I", 0.06);
+        w.fetch_incl_veg = cfg.get("incl_veg", true);
+        check(pbsm3d_set_providers(_h, &w));
+    }
 
     _stage = (double*)pbsm3d_host_alloc(16 * ntri * sizeof(double));
     if (!_stage)
@@ -239,16 +279,17 @@ void PBSM3D_gpu::run(mesh& domain)
     {
         auto face = domain->face(i);
         _U_R[i] = (*face)["U_R"_s];
-        _U2[i] = (*face)["U_2m_above_srf"_s];
+        if (!_fuse)
+            _U2[i] = (*face)["U_2m_above_srf"_s];
         _sd[i] = (*face)["snowdepthavg"_s];
         _swe[i] = (*face)["swe"_s];
         _t[i] = (*face)["t"_s];
         _rh[i] = (*face)["rh"_s];
         _vw_dir[i] = (*face)["vw_dir"_s];
-        if (_use_fetch)
+        if (_use_fetch && !_fuse)
             _fetch[i] = (*face)["fetch"_s];
     }
-    pbsm3d_forcing f{_U_R, _U2, _sd, _swe, _t, _rh, _vw_dir, _use_fetch ? _fetch : nullptr};
+    pbsm3d_forcing f{_U_R, _fuse ? nullptr : _U2, _sd, _swe, _t, _rh, _vw_dir, (_use_fetch && !_fuse) ? _fetch : nullptr};
     pbsm3d_outputs o{_Qsalt, _Qsusp, _Qsubl, _Qsubl_mass, _sum_subl, _drift_mass, _sum_drift, _more};
     check(pbsm3d_step(_h, global_param->dt(), &f, &o, &_stats));
     SPDLOG_DEBUG("  suspension iterations: {} residual: {}", _stats.suspension_iterations, _stats.suspension_residual);

@@ -46,6 +46,7 @@ class PBSM3D_gpu : public module_base
     pbsm3d_handle* _h = nullptr;
     pbsm3d_stats _stats{};
     bool _use_fetch = true;
+    bool _fuse = false; // "fuse_providers": scale_wind_vert and fetchr run inside the library (pbsm3d_set_providers)
     size_t _ntri = 0;
     // SoA staging buffers (host, page-locked so the library can overlap PCIe with compute): forcing in, outputs out.
     // One block of 16 arrays, allocated once in init() with pbsm3d_host_alloc.

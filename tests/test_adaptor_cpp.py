@@ -19,7 +19,7 @@ def test_adaptor_compiles_against_the_c_abi():
     assert os.path.exists(exe)
     # it registers the same dependency lists as PBSM3D::PBSM3D (PBSM3D.cpp:105-202)
     src = open(os.path.join(build.HOST, "PBSM3D_gpu.cpp")).read()
-    for v in ("U_2m_above_srf", "vw_dir", "swe", "t", "rh", "U_R"):
+    for v in ("U_2m_above_srf", "vw_dir", "swe", "t", "rh", "U_R", "fetch"):
         assert f'depends("{v}")' in src
     for v in OUT + ["global_cell_id", "blowingsnow_probability"]:
         assert f'provides("{v}")' in src
@@ -66,3 +66,27 @@ def test_adaptor_turns_library_errors_into_module_error(tmp_path):
     write_case(tmp_path, mesh, ["nLayer 5", "iterative_subl true"], [synthetic.forcing(geo.cx, geo.cy)])
     res = subprocess.run([build.build_adaptor(), str(tmp_path), "1"], capture_output=True, text=True, timeout=300)
     assert res.returncode == 1 and "module_error" in res.stderr and "iterative_subl" in res.stderr
+
+
+@pytest.mark.gpu
+def test_adaptor_with_fused_providers(tmp_path):
+    """"fuse_providers": the adaptor stops depending on U_2m_above_srf / fetch; the library derives them on the device
+    (scale_wind_vert + fetchr kernels).  Same outputs as the plain adaptor fed the oracle's provider outputs."""
+    from oracle import wind_oracle as wo
+    mesh = load_mesh("granger1m")
+    geo = mesh.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy, seed=7, step=0)
+    u2, _ = wo.scale_wind_vert(F["U_R"], mesh.neigh, geo.cx, geo.cy, F["snowdepthavg"])
+    fetch = wo.fetchr(F["vw_dir"], geo.cx, geo.cy, geo.cz, None)
+    exe = build.build_adaptor()
+    plain, fused = tmp_path / "plain", tmp_path / "fused"
+    plain.mkdir(); fused.mkdir()
+    write_case(plain, mesh, ["nLayer 5"], [dict(F, U_2m_above_srf=u2, fetch=fetch)])
+    garbage = dict(F, U_2m_above_srf=np.full(mesh.n_local, -9999.0), fetch=np.full(mesh.n_local, -9999.0))  # must not be read
+    write_case(fused, mesh, ["nLayer 5", "fuse_providers true"], [garbage])
+    for d in (plain, fused):
+        res = subprocess.run([exe, str(d), "1"], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+    for v in ("Qsalt", "Qsusp", "Qsubl", "drift_mass"):
+        a, b = np.fromfile(plain / f"out_0_{v}.bin"), np.fromfile(fused / f"out_0_{v}.bin")
+        assert np.abs(b).max() > 0 and rel_l2(b, a) <= 1e-9, v
