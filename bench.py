@@ -356,7 +356,7 @@ def main():
                        "triangles": G, "nLayer": NLAYER, "solver": "multicolour line Gauss-Seidel (auto)", "colours": st["n_colours"],
                        "forcing": f"{N_FORCING} distinct seeded fields cycled over the steps; every solve starts from x0 = 0",
                        "suspension_iterations": susp_its, "deposition_iterations": dep_its,
-                       "deposition_solver": "Jacobi-Chebyshev (auto)" if st["deposition_solver_used"] == 2 else "Jacobi-CG",
+                       "deposition_solver": {1: "Jacobi-CG", 2: "Jacobi-Chebyshev (auto)", 3: "multicolour SOR, Young's omega (auto)"}.get(st["deposition_solver_used"], "?"),
                        "suspension_residual": st["suspension_residual"], "deposition_residual": st["deposition_residual"],
                        "host_syncs_per_step": syncs / args.steps,
                        "halo_transport": {0: "none (single rank)", 1: "nccl", 2: "peer memory (cudaIpc over NVLink)"}[st["halo_transport"]],

@@ -22,7 +22,7 @@ c_int64_p = C.POINTER(C.c_int64)
 c_uint8_p = C.POINTER(C.c_uint8)
 
 SOLVER_AUTO, SOLVER_LINE, SOLVER_BICGSTAB = 0, 1, 2
-DEP_AUTO, DEP_CG, DEP_CHEBYSHEV = 0, 1, 2
+DEP_AUTO, DEP_CG, DEP_CHEBYSHEV, DEP_SOR = 0, 1, 2, 3
 HALO_NONE, HALO_NCCL, HALO_PEER = 0, 1, 2
 ABI_VERSION = 3  # include/pbsm3d.h PBSM3D_ABI_VERSION
 ERR_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "NOCONVERGE"}

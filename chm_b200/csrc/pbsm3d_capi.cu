@@ -122,6 +122,9 @@ struct pbsm3d_handle {
     double cheb_lmin = 0.0, cheb_lmax = 0.0;
     std::vector<double> cheb_a, cheb_c;
     int cheb_kest = 0, cheb_enqueued = 0, pred_dep = 0;
+    // multicolour SOR on the deposition system: Young's omega from the same spectrum estimate
+    double sor_omega = 0.0;
+    int sor_kest = 0, sor_enqueued = 0, pred_sor = 0;
     int lanczos_steps = 0;
     int n_syncs = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;
@@ -932,6 +935,47 @@ int enqueue_cheb(pbsm3d_handle* h, int k0, int k1, int check_from) {
     return 0;
 }
 bool use_chebyshev(const pbsm3d_handle* h) { return h->cheb_ready && h->cfg.deposition_solver != PBSM3D_DEP_CG; }
+// SOR: asked for, or AUTO on a single rank (across ranks it needs a globally consistent colouring and a halo per colour
+// pass: with rank-local colours and ghosts one sweep old, over-relaxation diverges)
+bool use_sor(const pbsm3d_handle* h) {
+    if (!h->cheb_ready || !(h->sor_omega > 0) || h->n_ranks > 1) return false;
+    return h->cfg.deposition_solver == PBSM3D_DEP_SOR || h->cfg.deposition_solver == PBSM3D_DEP_AUTO;
+}
+int enqueue_sor_sweeps(pbsm3d_handle* h, int n) {
+    for (int k = 0; k < n; ++k)
+        for (int c = 0; c < h->n_colours; ++c) {
+            if (h->ccount[c] == 0) continue;
+            const int p0 = h->cstart[c], p1 = p0 + h->ccount[c];
+            LAUNCH(h, sor_pass_kernel, cdiv(h->ccount[c], 256), 256, h->dm, h->offS, h->drhsS, h->qA, h->sor_omega, p0, p1, h->sc);
+        }
+    h->sor_enqueued += n;
+    return 0;
+}
+int enqueue_sor_check(pbsm3d_handle* h) {
+    const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    const int f = fused(h) ? 1 : 0;
+    LAUNCH(h, dep_residual_kernel, red_grid(h->Tp), kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, h->qA, h->sor_enqueued, h->partial,
+           kRedBlocks, h->sc, h->red, tol2, f);
+    if (!f) {
+        TRY(allreduce(h, h->red, 1, false));
+        LAUNCH(h, flags_kernel, 1, 1, FLAGS_SOR_CHECK, h->sc, h->red, h->sor_enqueued, tol2);
+    }
+    return 0;
+}
+// predicted number of sweeps, a check, three short speculative rounds (no-ops once converged)
+int enqueue_sor_initial(pbsm3d_handle* h) {
+    const int maxit = h->cfg.max_iterations;
+    const bool known = h->pred_sor > 0;
+    h->sor_enqueued = 0;
+    TRY(enqueue_sor_sweeps(h, std::min(maxit, known ? h->pred_sor : h->sor_kest)));
+    TRY(enqueue_sor_check(h));
+    const int spec_known[3] = {1, 1, 2}, spec_unknown[3] = {4, 8, 8};
+    for (int k = 0; k < 3 && h->sor_enqueued < maxit; ++k) {
+        TRY(enqueue_sor_sweeps(h, std::min(known ? spec_known[k] : spec_unknown[k], maxit - h->sor_enqueued)));
+        TRY(enqueue_sor_check(h));
+    }
+    return 0;
+}
 
 int enqueue_cg_start(pbsm3d_handle* h, int n_cg) {
     const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
@@ -1036,6 +1080,13 @@ int estimate_spectrum(pbsm3d_handle* h) {
     const double qf = (std::sqrt(kappa) - 1.0) / (std::sqrt(kappa) + 1.0);
     h->cheb_kest = qf > 0 ? (int)std::ceil(std::log(h->cfg.tolerance / 2.0) / std::log(qf)) + 2 : 4;
     h->cheb_ready = true;
+    {   // Young's optimal relaxation factor for the Jacobi matrix J = I - D^-1 A, rho(J) = 1 - lambda_min.  The bound is the
+        // widened (smaller) lambda_min: erring towards a larger omega costs a few sweeps, a smaller one many.
+        const double rho = std::min(1.0 - h->cheb_lmin, 1.0 - 1e-12);
+        h->sor_omega = 2.0 / (1.0 + std::sqrt(std::max(1.0 - rho * rho, 1e-24)));
+        const double fac = h->sor_omega - 1.0;  // asymptotic error reduction per sweep
+        h->sor_kest = fac > 0 && fac < 1 ? (int)std::ceil(std::log(h->cfg.tolerance) / std::log(fac)) + 8 : 64;
+    }
     return 0;
 }
 
@@ -1093,7 +1144,9 @@ int enqueue_tail(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTarg
     CU(cudaEventRecord(h->ev[3], s));
     // deposition solve (x0 = 0)
     CU(cudaMemsetAsync(h->qA, 0, (size_t)h->S * sizeof(double), s));
-    if (use_chebyshev(h)) {
+    if (use_sor(h)) {
+        TRY(enqueue_sor_initial(h));
+    } else if (use_chebyshev(h)) {
         CU(cudaMemsetAsync(h->qB, 0, (size_t)h->S * sizeof(double), s));  // q_{-1}: multiplied by a_0 = 0, must be finite
         const int maxit = h->cfg.max_iterations;
         const bool known = h->pred_dep > 0;
@@ -1393,10 +1446,26 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
         TRY(sync_stream(h));
     }
     // deposition solve still open?
-    bool cheb = use_chebyshev(h);
-    int dep_used = cheb ? PBSM3D_DEP_CHEBYSHEV : PBSM3D_DEP_CG;
+    bool sor = use_sor(h);
+    bool cheb = !sor && use_chebyshev(h);
+    int dep_used = sor ? PBSM3D_DEP_SOR : (cheb ? PBSM3D_DEP_CHEBYSHEV : PBSM3D_DEP_CG);
     while (h->h_sc->tail_done && h->h_sc->dep_present && !h->h_sc->dep_ok) {
-        if (cheb) {
+        if (sor) {
+            const bool gave_up = h->h_sc->done == 2 || h->sor_enqueued >= std::min(maxit, 6 * h->sor_kest + 64);
+            if (gave_up && h->cfg.deposition_solver == PBSM3D_DEP_SOR)
+                return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver (SOR) failed to converge");
+            if (gave_up) {  // the relaxation factor does not suit this mesh: CG needs no parameter
+                sor = false;
+                dep_used = PBSM3D_DEP_CG;
+                h->sor_omega = 0.0;
+                LAUNCH(h, flags_kernel, 1, 1, FLAGS_DEP_RESTART, h->sc, h->red, 0, tol2);
+                CU(cudaMemsetAsync(h->qA, 0, (size_t)h->S * sizeof(double), s));
+                TRY(enqueue_cg_start(h, n_cg));
+            } else {
+                TRY(enqueue_sor_sweeps(h, std::min(8, maxit - h->sor_enqueued)));
+                TRY(enqueue_sor_check(h));
+            }
+        } else if (cheb) {
             const bool gave_up = h->h_sc->done == 2 || h->cheb_enqueued >= std::min(maxit, 4 * h->cheb_kest + 32);
             if (gave_up && h->cfg.deposition_solver == PBSM3D_DEP_CHEBYSHEV)
                 return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver (Chebyshev) failed to converge");
@@ -1429,7 +1498,16 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
         st->deposition_residual = c.bnorm2 > 0 ? std::sqrt(c.rr / c.bnorm2) : 0.0;
         st->deposition_solver_used = dep_used;
         if (dep_used == PBSM3D_DEP_CHEBYSHEV) h->pred_dep = c.iters;
-        else h->pred_cg = c.iters;
+        else if (dep_used == PBSM3D_DEP_SOR) {
+            // sweeps the detection overshot the tolerance by, from the asymptotic rate (omega - 1 per sweep on the error)
+            int pred = c.iters;
+            const double fac2 = (h->sor_omega - 1.0) * (h->sor_omega - 1.0);
+            if (c.rr > 0 && c.bnorm2 > 0 && fac2 > 0 && fac2 < 1) {
+                const double over = std::log(tol2 * c.bnorm2 / c.rr) / std::log(fac2);
+                if (over <= -2.0) pred = std::max(1, pred + (int)std::ceil(over + 1.0));
+            }
+            h->pred_sor = pred;
+        } else h->pred_cg = c.iters;
     }
     st->host_syncs = h->n_syncs;
     CU(cudaEventElapsedTime(&st->ms_assembly, h->ev[0], h->ev[1]));
@@ -1582,7 +1660,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     if (cfg->use_subgrid_topo || cfg->use_subgrid_topo_V2) return fail(PBSM3D_ERR_UNSUPPORTED, "use_subgrid_topo* is not implemented");
     if (cfg->debug_output) return fail(PBSM3D_ERR_UNSUPPORTED, "debug_output is not implemented");
     if (!(cfg->tolerance > 0) || cfg->max_iterations < 1) return fail(PBSM3D_ERR_INVALID, "bad solver controls");
-    if (cfg->solver < 0 || cfg->solver > 2 || cfg->deposition_solver < 0 || cfg->deposition_solver > 2)
+    if (cfg->solver < 0 || cfg->solver > 2 || cfg->deposition_solver < 0 || cfg->deposition_solver > 3)
         return fail(PBSM3D_ERR_INVALID, "unknown solver id");
     if (mesh->n_local < 1 || mesh->n_ghost < 0 || !mesh->neigh || !mesh->vertices || !mesh->global_id)
         return fail(PBSM3D_ERR_INVALID, "mesh arrays missing");

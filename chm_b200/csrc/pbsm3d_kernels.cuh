@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, D
 // -------------------------------------------------------------------------------------- step control
 // One-thread bookkeeping between phases.  `red` holds the (already globally reduced) values of the kernel before.
 enum { FLAGS_SUSP = 0, FLAGS_SUSP_CHECK = 1, FLAGS_DEP = 2, FLAGS_FORCE_SUSP_OK = 3, FLAGS_CHEB_CHECK = 4, FLAGS_SETUP_CG = 5,
-       FLAGS_DEP_RESTART = 6, FLAGS_COMBINE = 7 };
+       FLAGS_DEP_RESTART = 6, FLAGS_COMBINE = 7, FLAGS_SOR_CHECK = 8 };
 
 // Chebyshev stopping rule: iteration k measured ||b - A q_k||^2 of the iterate it READ (buffer k&1), which stays
 // intact in that buffer, so detection keeps exactly that iterate.
@@ -541,6 +541,13 @@ __device__ __forceinline__ void cheb_check(Scalars* sc, double rr, int k, double
     sc->rr = rr;
     if (rr <= tol2 * sc->bnorm2) { sc->done = 1; sc->dep_ok = 1; sc->iters = k; sc->dep_buf = k & 1; }
     else if (!(rr == rr) || rr > 1e60 * sc->bnorm2) sc->done = 2;  // diverging: spectrum bounds were wrong
+}
+
+// SOR keeps its iterate in one buffer (qA)
+__device__ __forceinline__ void sor_check(Scalars* sc, double rr, int k, double tol2) {
+    sc->rr = rr;
+    if (rr <= tol2 * sc->bnorm2) { sc->done = 1; sc->dep_ok = 1; sc->iters = k; sc->dep_buf = 0; }
+    else if (!(rr == rr) || rr > 1e60 * sc->bnorm2) sc->done = 2;
 }
 
 __device__ __forceinline__ void susp_check(Scalars* sc, double rr, int it_now, double tol2) {
@@ -589,6 +596,9 @@ __global__ void flags_kernel(int stage, Scalars* sc, const double* __restrict__ 
             break;
         case FLAGS_CHEB_CHECK:
             if (sc->tail_done && sc->dep_present && !sc->done) cheb_check(sc, red[0], it_now, tol2);
+            break;
+        case FLAGS_SOR_CHECK:
+            if (sc->tail_done && sc->dep_present && !sc->done) sor_check(sc, red[0], it_now, tol2);
             break;
         case FLAGS_SETUP_CG:  // pbsm3d_create: open the CG kernels for the spectrum estimate
             sc->tail_done = 1; sc->dep_present = 1; sc->done = 0; sc->dep_ok = 0; sc->iters = 0; sc->log_n = 0;
@@ -1014,6 +1024,45 @@ __global__ void __launch_bounds__(kRedThreads) cheb_iter_kernel(DevMesh m, const
         if (grid_fold<1>(rr, 0.0, 0, 0, partial, pstride, &sc->ticket[3], o0, unused)) {
             if (threadIdx.x == 0) { red[0] = o0; if (fused) cheb_check(sc, o0, k, tol2); }
         }
+    }
+}
+
+// HOT LOOP 3b: multicolour SOR on the Jacobi-scaled deposition system,  q_c <- q_c + w (D^-1 b - q - D^-1 A_off q)_c
+// for one colour class c, IN PLACE (faces of one colour are never neighbours).  With Young's w = 2 / (1 + sqrt(1 - rho^2)),
+// rho = 1 - lambda_min(D^-1 A) from the setup-time spectrum estimate, a sweep over all colours converges about twice as
+// fast as a Chebyshev-accelerated Jacobi iteration (measured 74 vs 125 sweeps on the uniform mesh, 124 vs 198 on the
+// variable-resolution one) and streams less: 3 scaled off-diagonals + 3 slots + scaled rhs + q in/out = 60 B per face.
+__global__ void __launch_bounds__(256) sor_pass_kernel(DevMesh m, const double* __restrict__ offS, const double* __restrict__ bS,
+                                                       double* q, double omega, int p0, int p1, const Scalars* __restrict__ sc) {
+    if (sc && (!sc->tail_done || !sc->dep_present || sc->done)) return;
+    const int Tp = m.Tp;
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    const double qp = q[p];
+    double z = bS[p] - qp;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) z -= __ldcs(offS + (size_t)j * Tp + p) * q[m.nbs[(size_t)j * Tp + p]];
+    q[p] = qp + omega * z;
+}
+// ||b - A q||^2 of this rank (the stopping rule of the deposition solve) for an iterate that lives in one buffer.
+__global__ void __launch_bounds__(kRedThreads) dep_residual_kernel(DevMesh m, const double* __restrict__ offS,
+                                                                   const double* __restrict__ bS, const double* __restrict__ ddiag,
+                                                                   const double* __restrict__ q, int k, double* __restrict__ partial,
+                                                                   int pstride, Scalars* sc, double* __restrict__ red, double tol2,
+                                                                   int fused) {
+    if (!sc->tail_done || !sc->dep_present || sc->done) return;
+    const int Tp = m.Tp;
+    double rr = 0.0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < Tp; p += gridDim.x * blockDim.x) {
+        double z = bS[p] - q[p];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) z -= offS[(size_t)j * Tp + p] * q[m.nbs[(size_t)j * Tp + p]];
+        const double r = z * ddiag[p];
+        rr += r * r;
+    }
+    double o0, unused;
+    if (grid_fold<1>(rr, 0.0, 0, 0, partial, pstride, &sc->ticket[3], o0, unused)) {
+        if (threadIdx.x == 0) { red[0] = o0; if (fused) sor_check(sc, o0, k, tol2); }
     }
 }
 

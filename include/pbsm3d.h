@@ -46,9 +46,10 @@ enum {
 };
 
 enum {
-    PBSM3D_DEP_AUTO = 0,       /* Chebyshev with setup-time spectrum bounds, falling back to CG if it does not converge */
+    PBSM3D_DEP_AUTO = 0,       /* one rank: multicolour SOR; several ranks: Chebyshev; either falls back to CG if it does not converge */
     PBSM3D_DEP_CG = 1,         /* Jacobi-preconditioned conjugate gradients */
-    PBSM3D_DEP_CHEBYSHEV = 2   /* Jacobi-preconditioned Chebyshev iteration (no global reductions) */
+    PBSM3D_DEP_CHEBYSHEV = 2,  /* Jacobi-preconditioned Chebyshev iteration (no global reductions) */
+    PBSM3D_DEP_SOR = 3         /* multicolour SOR, Young's relaxation factor from the setup-time spectrum estimate (one rank) */
 };
 
 /* How ghost-face halos and the solvers' global reductions travel between the ranks of one NVSwitch box
@@ -172,7 +173,7 @@ typedef struct pbsm3d_stats {
     float ms_line_sweeps;            /* CUDA-event time of the first `sweeps_timed` line sweeps of this step */
     int32_t sweeps_timed;            /* full sweeps (all colours) inside ms_line_sweeps */
     int32_t n_colours;               /* colour classes of the internal face order */
-    int32_t deposition_solver_used;  /* PBSM3D_DEP_CG / PBSM3D_DEP_CHEBYSHEV */
+    int32_t deposition_solver_used;  /* PBSM3D_DEP_CG / _CHEBYSHEV / _SOR */
     int32_t host_syncs;              /* stream synchronisations the step needed (1 when every prediction held) */
     int32_t halo_exchanges;          /* ghost-face halo exchanges the step enqueued (0 on a single rank) */
     int32_t halo_transport;          /* PBSM3D_HALO_NONE / _NCCL / _PEER */

@@ -274,10 +274,10 @@ def test_iteration_prediction_never_changes_results(slope):
 
 
 @pytest.mark.parametrize("meshname", ["slope", "variable"])
-@pytest.mark.parametrize("dep", [capi.DEP_CG, capi.DEP_CHEBYSHEV, capi.DEP_AUTO], ids=["cg", "chebyshev", "auto"])
+@pytest.mark.parametrize("dep", [capi.DEP_CG, capi.DEP_CHEBYSHEV, capi.DEP_SOR, capi.DEP_AUTO], ids=["cg", "chebyshev", "sor", "auto"])
 def test_deposition_solvers_match_direct_solve(meshname, dep):
-    """Both device solvers of the (SPD) deposition system against the oracle's sparse direct solve; the Chebyshev
-    iteration uses spectrum bounds estimated once per mesh and must report the true residual."""
+    """The device solvers of the (SPD) deposition system against the oracle's sparse direct solve; the Chebyshev iteration
+    and the multicolour SOR use a spectrum estimate made once per mesh and must report the true residual."""
     mesh = load_mesh("slope") if meshname == "slope" else synthetic.variable_mesh(8000)
     geo = mesh.geometry()
     F = synthetic.forcing(geo.cx, geo.cy, seed=9)
@@ -286,7 +286,8 @@ def test_deposition_solvers_match_direct_solve(meshname, dep):
     for rep in range(3):  # first step: unknown iteration count; later steps: predicted schedule
         outs, st = h.step(3600.0, F)
         assert st["deposition_present"] == 1 and st["deposition_residual"] <= 1e-11
-        assert st["deposition_solver_used"] == (capi.DEP_CG if dep == capi.DEP_CG else capi.DEP_CHEBYSHEV)
+        assert st["deposition_solver_used"] == {capi.DEP_CG: capi.DEP_CG, capi.DEP_CHEBYSHEV: capi.DEP_CHEBYSHEV,
+                                                capi.DEP_SOR: capi.DEP_SOR, capi.DEP_AUTO: capi.DEP_SOR}[dep]  # AUTO on one rank: SOR
         d = h.deposition_system()
         A = oracle_for(mesh, Config.functional_test(6)).deposition_csr(d["diag"], d["off"])
         res = np.linalg.norm(d["rhs"] - A @ d["q"]) / np.linalg.norm(d["rhs"])
@@ -294,4 +295,9 @@ def test_deposition_solvers_match_direct_solve(meshname, dep):
         assert rel_l2(d["q"], r["q_dep"]) <= 1e-8
         assert rel_l2(outs["drift_mass"], r["drift_mass"]) <= 1e-8
     assert st["host_syncs"] == 1  # steady state: every prediction held, one synchronisation per step
+    if dep == capi.DEP_SOR:  # about twice as fast as Chebyshev-accelerated Jacobi, sweep for iteration
+        hc = capi.Handle(capi.default_config(deposition_solver=capi.DEP_CHEBYSHEV, tolerance=1e-11, **functest_kw(6)), mesh)
+        _, sc = hc.step(3600.0, F)
+        assert st["deposition_iterations"] <= 0.75 * sc["deposition_iterations"], (st["deposition_iterations"], sc["deposition_iterations"])
+        hc.close()
     h.close()
