@@ -125,6 +125,8 @@ struct pbsm3d_handle {
     // multicolour SOR on the deposition system: Young's omega from the same spectrum estimate
     double sor_omega = 0.0;
     int sor_kest = 0, sor_enqueued = 0, pred_sor = 0;
+    int* ghost_key = nullptr;                       // [nG] (colour, rank) key of every ghost face: the global SOR order
+    unsigned long long sor_epoch = 1ull << 40;      // sweep numbers = tags of the SOR ghost entries (disjoint from the Chebyshev tags)
     int lanczos_steps = 0;
     int n_syncs = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;
@@ -615,7 +617,26 @@ int setup_comm(pbsm3d_handle* h, const std::vector<int>& iperm) {
     TRY(h->alloc(&h->sendbuf, (size_t)n_send * h->L));
     TRY(h->alloc(&h->recvbuf, (size_t)std::max(nG, 1) * h->L));
     CU(cudaStreamSynchronize(h->stream));
-    return setup_peer(h, h->need_matrix, sslot);
+    TRY(setup_peer(h, h->need_matrix, sslot));
+    if (h->peer && h->fused_halo && nG > 0) {
+        // (colour, rank) keys of the ghost faces: one halo of the owners' keys, through the staged path
+        std::vector<double> key((size_t)h->S, 0.0);
+        for (int c = 0; c < h->n_colours; ++c)
+            for (int p = h->cstart[c]; p < h->cstart[c] + h->ccount[c]; ++p) key[p] = (double)(c * h->n_ranks + h->rank);
+        double* d_key = nullptr;
+        TRY(h->alloc(&d_key, (size_t)h->S));
+        TRY(upload(h, d_key, key.data(), key.size() * sizeof(double)));
+        TRY(halo_exchange(h, d_key, 1));
+        CU(cudaMemcpyAsync(key.data(), d_key, key.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        TRY(sync_stream(h));
+        std::vector<int> gk((size_t)nG);
+        for (int g = 0; g < nG; ++g) gk[g] = (int)key[(size_t)h->Tp + g];
+        TRY(h->alloc(&h->ghost_key, (size_t)nG));
+        TRY(upload(h, h->ghost_key, gk.data(), gk.size() * sizeof(int)));
+        CU(cudaStreamSynchronize(h->stream));
+        h->release(d_key);
+    }
+    return 0;
 }
 
 // ---- suspension solve: multicolour line Gauss–Seidel ---------------------------------------------------------
@@ -935,27 +956,52 @@ int enqueue_cheb(pbsm3d_handle* h, int k0, int k1, int check_from) {
     return 0;
 }
 bool use_chebyshev(const pbsm3d_handle* h) { return h->cheb_ready && h->cfg.deposition_solver != PBSM3D_DEP_CG; }
-// SOR: asked for, or AUTO on a single rank (across ranks it needs a globally consistent colouring and a halo per colour
-// pass: with rank-local colours and ghosts one sweep old, over-relaxation diverges)
+// SOR: asked for or AUTO.  Across ranks the sweep order is (colour, rank) and every colour pass carries its own halo
+// (sor_pass_halo_kernel); with rank-local colours and ghosts one sweep old, over-relaxation would diverge.
 bool use_sor(const pbsm3d_handle* h) {
-    if (!h->cheb_ready || !(h->sor_omega > 0) || h->n_ranks > 1) return false;
+    if (!h->cheb_ready || !(h->sor_omega > 0)) return false;
+    if (h->n_ranks > 1 && !(h->peer && h->fused_halo)) return false;  // across ranks it lives on the tagged in-kernel halo
     return h->cfg.deposition_solver == PBSM3D_DEP_SOR || h->cfg.deposition_solver == PBSM3D_DEP_AUTO;
 }
+SorLink sor_link(const pbsm3d_handle* h) {
+    SorLink sl;
+    std::memset(&sl, 0, sizeof(sl));
+    sl.tl.pt = h->d_pt;
+    sl.tl.bptr = h->bptr;
+    sl.tl.remote = h->q_remote[0];
+    sl.tl.ghost = h->qg[0];
+    sl.ghost_key = h->ghost_key;
+    return sl;
+}
 int enqueue_sor_sweeps(pbsm3d_handle* h, int n) {
-    for (int k = 0; k < n; ++k)
+    const bool multi = h->n_ranks > 1;
+    const SorLink sl = multi ? sor_link(h) : SorLink{};
+    for (int k = 0; k < n; ++k) {
+        const unsigned long long e = ++h->sor_epoch;
+        const int first = (h->sor_enqueued + k) == 0 ? 1 : 0;
         for (int c = 0; c < h->n_colours; ++c) {
             if (h->ccount[c] == 0) continue;
             const int p0 = h->cstart[c], p1 = p0 + h->ccount[c];
-            LAUNCH(h, sor_pass_kernel, cdiv(h->ccount[c], 256), 256, h->dm, h->offS, h->drhsS, h->qA, h->sor_omega, p0, p1, h->sc);
+            if (multi)
+                LAUNCH(h, sor_pass_halo_kernel, cdiv(h->ccount[c], 256), 256, h->dm, h->offS, h->drhsS, h->qA, h->sor_omega, p0, p1,
+                       h->nb[c], h->boff[c], h->sc, sl, c * h->n_ranks + h->rank, e, first);
+            else
+                LAUNCH(h, sor_pass_kernel, cdiv(h->ccount[c], 256), 256, h->dm, h->offS, h->drhsS, h->qA, h->sor_omega, p0, p1, h->sc);
         }
+        if (multi) { ++h->halo_ops; ++h->halo_fused_ops; }
+    }
     h->sor_enqueued += n;
     return 0;
 }
 int enqueue_sor_check(pbsm3d_handle* h) {
     const double tol2 = h->cfg.tolerance * h->cfg.tolerance;
     const int f = fused(h) ? 1 : 0;
-    LAUNCH(h, dep_residual_kernel, red_grid(h->Tp), kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, h->qA, h->sor_enqueued, h->partial,
-           kRedBlocks, h->sc, h->red, tol2, f);
+    if (h->n_ranks > 1)
+        LAUNCH(h, dep_residual_halo_kernel, red_grid(h->Tp), kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, h->qA, h->partial, kRedBlocks,
+               h->sc, h->red, sor_link(h), h->sor_epoch);
+    else
+        LAUNCH(h, dep_residual_kernel, red_grid(h->Tp), kRedThreads, h->dm, h->offS, h->drhsS, h->ddiag, h->qA, h->sor_enqueued,
+               h->partial, kRedBlocks, h->sc, h->red, tol2, f);
     if (!f) {
         TRY(allreduce(h, h->red, 1, false));
         LAUNCH(h, flags_kernel, 1, 1, FLAGS_SOR_CHECK, h->sc, h->red, h->sor_enqueued, tol2);

@@ -1656,6 +1656,77 @@ __global__ void __launch_bounds__(kRedThreads, 8) cheb_iter_halo_kernel(const __
     }
 }
 
+// Multicolour SOR across ranks.  Colours are rank-local, so the sweep order is made global by the key
+// (colour, rank): a face is updated after every neighbour with a smaller key and before every neighbour with a larger one
+// -- a proper sequential ordering (two faces with the same key are on the same rank and have the same colour, hence are not
+// neighbours), i.e. true SOR on the global system, not a block-hybrid.  Ghost values travel as tagged 16-byte entries
+// written by the owner's boundary thread the moment it has updated the face (tag = sweep number): a boundary thread of
+// sweep e reads a ghost with a smaller key at tag e (spinning until it lands) and one with a larger key at tag e-1 (0 in
+// the first sweep of a solve: q0 = 0).  One buffer suffices: every reader of an entry is a neighbour of the face behind it,
+// and that face's next update needs that neighbour's next value, which is produced after the read.
+struct SorLink {
+    TaggedLink tl;          // ghost = my tagged ghost entries, remote/bptr = where my boundary faces go
+    const int* ghost_key;   // [nG] colour * n_ranks + rank of each ghost face
+    int my_key_base;        // this rank's key for colour c is c * n_ranks + rank: passed per launch as my_key
+};
+__device__ __forceinline__ double sor_ghost(const SorLink& sl, int g, int my_key, unsigned long long e, int first) {
+    if (sl.ghost_key[g] < my_key) return tagged_read(sl.tl.ghost + g, e, sl.tl.pt);
+    return first ? 0.0 : tagged_read(sl.tl.ghost + g, e - 1, sl.tl.pt);
+}
+__global__ void __launch_bounds__(256) sor_pass_halo_kernel(const __grid_constant__ DevMesh m, const double* __restrict__ offS,
+                                                            const double* __restrict__ bS, double* q, double omega, int p0, int p1,
+                                                            int bnd_n, int bnd_off, const Scalars* __restrict__ sc,
+                                                            const __grid_constant__ SorLink sl, int my_key, unsigned long long e,
+                                                            int first) {
+    if (!sc->tail_done || !sc->dep_present || sc->done) return;
+    const int Tp = m.Tp;
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    const double qp = q[p];
+    double z = bS[p] - qp;
+    const int i = p - p0;
+    if (i < bnd_n) {  // boundary faces (first in their colour class): the only ones with ghost neighbours
+        int n[3];
+        double o[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { n[j] = m.nbs[(size_t)j * Tp + p]; o[j] = offS[(size_t)j * Tp + p]; }
+        const int e0 = sl.tl.bptr[bnd_off + i], e1 = sl.tl.bptr[bnd_off + i + 1];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) z -= o[j] * (n[j] < Tp ? q[n[j]] : sor_ghost(sl, n[j] - Tp, my_key, e, first));
+        const double qn = qp + omega * z;
+        q[p] = qn;
+        for (int k = e0; k < e1; ++k) tagged_write(sl.tl.remote[k], qn, e);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) z -= __ldcs(offS + (size_t)j * Tp + p) * q[m.nbs[(size_t)j * Tp + p]];
+        q[p] = qp + omega * z;
+    }
+}
+// ||b - A q||^2 of this rank after sweep e (every ghost entry then carries tag e)
+__global__ void __launch_bounds__(kRedThreads) dep_residual_halo_kernel(const __grid_constant__ DevMesh m, const double* __restrict__ offS,
+                                                                        const double* __restrict__ bS, const double* __restrict__ ddiag,
+                                                                        const double* __restrict__ q, double* __restrict__ partial,
+                                                                        int pstride, Scalars* sc, double* __restrict__ red,
+                                                                        const __grid_constant__ SorLink sl, unsigned long long e) {
+    if (!sc->tail_done || !sc->dep_present || sc->done) return;
+    const int Tp = m.Tp;
+    double rr = 0.0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < Tp; p += gridDim.x * blockDim.x) {
+        double z = bS[p] - q[p];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int n = m.nbs[(size_t)j * Tp + p];
+            z -= offS[(size_t)j * Tp + p] * (n < Tp ? q[n] : tagged_read(sl.tl.ghost + (n - Tp), e, sl.tl.pt));
+        }
+        const double r = z * ddiag[p];
+        rr += r * r;
+    }
+    double o0, unused;
+    if (grid_fold<1>(rr, 0.0, 0, 0, partial, pstride, &sc->ticket[3], o0, unused)) {
+        if (threadIdx.x == 0) red[0] = o0;
+    }
+}
+
 __global__ void fill_slots_kernel(int Tp, const int* __restrict__ perm, double* __restrict__ a, double v) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < Tp) a[p] = perm[p] >= 0 ? v : 0.0;

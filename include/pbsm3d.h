@@ -46,10 +46,11 @@ enum {
 };
 
 enum {
-    PBSM3D_DEP_AUTO = 0,       /* one rank: multicolour SOR; several ranks: Chebyshev; either falls back to CG if it does not converge */
+    PBSM3D_DEP_AUTO = 0,       /* multicolour SOR (Chebyshev across ranks without peer memory); falls back to CG if it does not converge */
     PBSM3D_DEP_CG = 1,         /* Jacobi-preconditioned conjugate gradients */
     PBSM3D_DEP_CHEBYSHEV = 2,  /* Jacobi-preconditioned Chebyshev iteration (no global reductions) */
-    PBSM3D_DEP_SOR = 3         /* multicolour SOR, Young's relaxation factor from the setup-time spectrum estimate (one rank) */
+    PBSM3D_DEP_SOR = 3         /* multicolour SOR, Young's relaxation factor from the setup-time spectrum estimate; across ranks the
+                                  sweep order is (colour, rank) and ghosts travel inside the colour passes (peer memory only) */
 };
 
 /* How ghost-face halos and the solvers' global reductions travel between the ranks of one NVSwitch box
