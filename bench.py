@@ -98,11 +98,12 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def sweep_bytes_per_row(L: int) -> float:
+def sweep_bytes_per_row(L: int, fp32_streams: bool = False) -> float:
     """Algorithmic HBM bytes of one full line Gauss-Seidel sweep per unknown row:
-    3 row-scaled lateral coefficients + scaled sub-diagonal + cp (5×8) + x read once + x written once (2×8)
-    = 56 B/row, plus per face 3 int32 neighbour slots + the scaled rhs (20 B) amortised over L layers."""
-    return 56.0 + 20.0 / L
+    3 row-scaled lateral coefficients + scaled sub-diagonal + cp (5×8, or 5×4 for the fp32-rounded copies the sweeps far from
+    convergence stream) + x read once + x written once (2×8) = 56 (36) B/row, plus per face 3 int32 neighbour slots + the
+    scaled rhs (20 B) amortised over L layers."""
+    return (36.0 if fp32_streams else 56.0) + 20.0 / L
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
@@ -264,7 +265,7 @@ def main():
     barrier()
     if rank == 0:
         sampler.start()
-    ev_ms, launches, sweep_ms, sweeps = 0.0, 0, 0.0, 0
+    ev_ms, launches, sweep_ms, sweeps, sweep32_ms, sweeps32 = 0.0, 0, 0.0, 0, 0.0, 0
     phases = {"ms_assembly": 0.0, "ms_suspension_solve": 0.0, "ms_flux_and_halo": 0.0, "ms_deposition": 0.0}
     t0 = time.perf_counter()
     syncs, susp_its, dep_its = 0, [], []
@@ -277,6 +278,8 @@ def main():
         launches += st["kernel_launches"]
         sweep_ms += st["ms_line_sweeps"]
         sweeps += st["sweeps_timed"]
+        sweep32_ms += st["ms_line_sweeps_fp32"]
+        sweeps32 += st["sweeps_timed_fp32"]
         for k in phases:
             phases[k] += st[k]
     barrier()
@@ -335,15 +338,22 @@ def main():
     e2e = total_rows / (e2e_ms * 1e-3)
     # ---- roofline of the dominant kernel (line sweep), timed live inside the timed steps with CUDA events
     peak, peak_src = measured_peak_gbs()
-    avg_sweep_ms = sweep_ms / max(sweeps, 1)
-    ach = sweep_bytes_per_row(NLAYER) * T * NLAYER / (avg_sweep_ms * 1e-3) / 1e9 if sweeps else 0.0
-    traffic = None
+    # the dominant kernel is the sweep on fp32-rounded coefficient streams when the step used it (most sweeps do), else the fp64 one
+    use32 = sweeps32 > 0
+    n_dom = sweeps32 if use32 else sweeps
+    avg_sweep_ms = (sweep32_ms if use32 else sweep_ms) / max(n_dom, 1)
+    row_bytes = sweep_bytes_per_row(NLAYER, use32)
+    ach = row_bytes * T * NLAYER / (avg_sweep_ms * 1e-3) / 1e9 if n_dom else 0.0
+    avg64_ms = (sweep_ms - sweep32_ms) / max(sweeps - sweeps32, 1)
+    ach64 = sweep_bytes_per_row(NLAYER) * T * NLAYER / (avg64_ms * 1e-3) / 1e9 if sweeps > sweeps32 else None
+    traffic = traffic32 = None
     tp = os.path.join(ROOT, "profiles", "sweep_dram_bytes_per_launch.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic, traffic32 = tj.get("dram_bytes_per_launch"), tj.get("dram_bytes_per_launch_fp32_streams")
         except Exception:
-            traffic = None
+            traffic = traffic32 = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -368,10 +378,17 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * 8 * T * world,
                     "d2h_bytes_per_step": 8 * 8 * T * world},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "gs_sweep_kernel<10> (one full sweep = all colour passes)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_launch": sweep_bytes_per_row(NLAYER) * T * NLAYER, "avg_launch_ms": avg_sweep_ms,
-                         "launches_timed": int(sweeps), "share_of_step": sweep_ms / max(ev_ms, 1e-9)},
+            "roofline": {"bound": "hbm",
+                         "kernel": ("gs_sweep_kernel<10, float> (fp32-rounded coefficient streams, fp64 x and arithmetic; " if use32
+                                    else "gs_sweep_kernel<10, double> (") + "one full sweep = all colour passes)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": traffic if not use32 else traffic32, "peak_source": peak_src,
+                         "bytes_per_launch": row_bytes * T * NLAYER, "avg_launch_ms": avg_sweep_ms,
+                         "launches_timed": int(n_dom), "share_of_step": (sweep32_ms if use32 else sweep_ms) / max(ev_ms, 1e-9),
+                         "fp64_stream_sweeps": {"launches_timed": int(sweeps - sweeps32), "avg_launch_ms": avg64_ms, "achieved": ach64,
+                                                "frac": (ach64 / peak) if ach64 else None,
+                                                "bytes_per_launch": sweep_bytes_per_row(NLAYER) * T * NLAYER,
+                                                "share_of_step": (sweep_ms - sweep32_ms) / max(ev_ms, 1e-9)}},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == "c2":

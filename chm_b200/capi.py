@@ -38,6 +38,7 @@ class Config(C.Structure):
         ("z0_ustar_coupling", C.c_int), ("use_subgrid_topo", C.c_int), ("use_subgrid_topo_V2", C.c_int),
         ("use_R94_lambda", C.c_int), ("debug_output", C.c_int),
         ("tolerance", C.c_double), ("max_iterations", C.c_int), ("solver", C.c_int), ("deposition_solver", C.c_int),
+        ("fp32_sweep_streams", C.c_int),
     ]
 
 
@@ -70,7 +71,7 @@ class Stats(C.Structure):
         ("suspension_residual", C.c_double), ("deposition_residual", C.c_double), ("suspension_rhs_max", C.c_double),
         ("deposition_rhs_max", C.c_double), ("ms_assembly", C.c_float), ("ms_suspension_solve", C.c_float),
         ("ms_flux_and_halo", C.c_float), ("ms_deposition", C.c_float), ("ms_total", C.c_float), ("ms_line_sweeps", C.c_float),
-        ("sweeps_timed", C.c_int32), ("n_colours", C.c_int32), ("deposition_solver_used", C.c_int32), ("host_syncs", C.c_int32),
+        ("sweeps_timed", C.c_int32), ("sweeps_timed_fp32", C.c_int32), ("ms_line_sweeps_fp32", C.c_float), ("n_colours", C.c_int32), ("deposition_solver_used", C.c_int32), ("host_syncs", C.c_int32),
         ("halo_exchanges", C.c_int32), ("halo_transport", C.c_int32), ("halo_fused", C.c_int32),
     ]
 

@@ -188,8 +188,9 @@ struct pbsm3d_handle {
     double sweep_rate2 = 0.0;  // observed per-sweep contraction of ||r||^2
     // timing
     cudaEvent_t ev[6] = {nullptr};
-    cudaEvent_t ev_sw[2] = {nullptr};
-    int sweeps_timed = 0;
+    cudaEvent_t ev_sw[3] = {nullptr};
+    int sweeps_timed = 0, sweeps_timed32 = 0;
+    int pred_n32 = 0;  // leading sweeps of the next solve that may stream fp32 coefficient copies
     bool have_system = false;
     long long n_launch = 0;
 
@@ -640,10 +641,10 @@ int setup_comm(pbsm3d_handle* h, const std::vector<int>& iperm) {
 }
 
 // ---- suspension solve: multicolour line Gauss–Seidel ---------------------------------------------------------
-template <int LT>
+template <int LT, typename CT>
 void launch_colour(pbsm3d_handle* h, int c) {
     const int p0 = h->cstart[c], p1 = p0 + h->ccount[c];
-    LAUNCH(h, gs_sweep_kernel<LT>, cdiv(h->ccount[c], 128), 128, h->ss, h->dm, h->L, p0, p1, h->x, h->sc);
+    LAUNCH(h, (gs_sweep_kernel<LT, CT>), cdiv(h->ccount[c], 128), 128, h->ss, h->dm, h->L, p0, p1, h->x, h->sc);
 }
 // the x channel of iteration (sweep) number e: read my buffer e%3, write the partners' (e+1)%3
 HaloLink x_link(const pbsm3d_handle* h, unsigned long long e, bool ghosts_zero, bool signal) {
@@ -660,12 +661,20 @@ HaloLink x_link(const pbsm3d_handle* h, unsigned long long e, bool ghosts_zero, 
     hl.signal_epoch = signal ? e + 1 : 0;
     return hl;
 }
-template <int LT>
+template <int LT, typename CT>
 void launch_colour_halo(pbsm3d_handle* h, int c, const HaloLink& hl) {
     const int p0 = h->cstart[c], p1 = p0 + h->ccount[c];
-    LAUNCH(h, gs_sweep_halo_kernel<LT>, cdiv(h->ccount[c], 128), 128, h->ss, h->dm, h->L, p0, p1, h->x, h->sc, hl, h->nb[c], h->boff[c]);
+    LAUNCH(h, (gs_sweep_halo_kernel<LT, CT>), cdiv(h->ccount[c], 128), 128, h->ss, h->dm, h->L, p0, p1, h->x, h->sc, hl, h->nb[c],
+           h->boff[c]);
 }
-int enqueue_sweeps(pbsm3d_handle* h, int n) {
+template <typename CT>
+int enqueue_sweeps_t(pbsm3d_handle* h, int n);
+// n full sweeps; fp32 = stream the fp32-rounded coefficient copies (sweeps far from convergence only)
+int enqueue_sweeps(pbsm3d_handle* h, int n, bool fp32 = false) {
+    return fp32 ? enqueue_sweeps_t<float>(h, n) : enqueue_sweeps_t<double>(h, n);
+}
+template <typename CT>
+int enqueue_sweeps_t(pbsm3d_handle* h, int n) {
     const bool fh = h->fused_halo && h->n_ranks > 1;
     int c_last = 0;
     for (int c = 0; c < h->n_colours; ++c)
@@ -676,20 +685,20 @@ int enqueue_sweeps(pbsm3d_handle* h, int n) {
             if (fh) {
                 const HaloLink hl = x_link(h, h->xh_epoch, h->x_first, c == c_last);
                 switch (h->L) {
-                    case 5: launch_colour_halo<5>(h, c, hl); break;
-                    case 10: launch_colour_halo<10>(h, c, hl); break;
-                    case 15: launch_colour_halo<15>(h, c, hl); break;
-                    case 20: launch_colour_halo<20>(h, c, hl); break;
-                    default: launch_colour_halo<0>(h, c, hl); break;
+                    case 5: launch_colour_halo<5, CT>(h, c, hl); break;
+                    case 10: launch_colour_halo<10, CT>(h, c, hl); break;
+                    case 15: launch_colour_halo<15, CT>(h, c, hl); break;
+                    case 20: launch_colour_halo<20, CT>(h, c, hl); break;
+                    default: launch_colour_halo<0, CT>(h, c, hl); break;
                 }
                 continue;
             }
             switch (h->L) {
-                case 5: launch_colour<5>(h, c); break;
-                case 10: launch_colour<10>(h, c); break;
-                case 15: launch_colour<15>(h, c); break;
-                case 20: launch_colour<20>(h, c); break;
-                default: launch_colour<0>(h, c); break;
+                case 5: launch_colour<5, CT>(h, c); break;
+                case 10: launch_colour<10, CT>(h, c); break;
+                case 15: launch_colour<15, CT>(h, c); break;
+                case 20: launch_colour<20, CT>(h, c); break;
+                default: launch_colour<0, CT>(h, c); break;
             }
         }
         if (fh) {
@@ -748,10 +757,15 @@ int line_enqueue_initial(pbsm3d_handle* h, int* total_out) {
     int total = 0;
     const bool known = h->pred_sweeps > 0;
     int first = std::min(known ? h->pred_sweeps : 8, maxit);
+    // the leading sweeps, while the residual is still above ~1e-6 ||b||, may stream the fp32 coefficient copies
+    const int n32 = (known && h->cfg.fp32_sweep_streams) ? std::max(0, std::min(h->pred_n32, first - 3)) : 0;
     CU(cudaEventRecord(h->ev_sw[0], h->stream));
-    TRY(enqueue_sweeps(h, first));
+    if (n32 > 0) TRY(enqueue_sweeps(h, n32, true));
+    CU(cudaEventRecord(h->ev_sw[2], h->stream));
+    TRY(enqueue_sweeps(h, first - n32));
     CU(cudaEventRecord(h->ev_sw[1], h->stream));
     h->sweeps_timed = first;
+    h->sweeps_timed32 = n32;
     total = first;
     TRY(enqueue_check(h, total));
     const int spec_known[3] = {1, 1, 2}, spec_unknown[3] = {8, 8, 8};
@@ -1409,6 +1423,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
     int total = 0;
     bool line = (solver == PBSM3D_SOLVER_AUTO || solver == PBSM3D_SOLVER_LINE);
     h->sweeps_timed = 0;
+    h->sweeps_timed32 = 0;
     if (line) {
         TRY(l2_window(h, h->x, h->NS * sizeof(double)));
         TRY(line_enqueue_initial(h, &total));
@@ -1485,6 +1500,8 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
             if (over <= -1.0) pred = std::max(1, pred + (int)std::ceil(over + 1e-9));
         }
         h->pred_sweeps = pred;
+        // sweeps until the residual is down to 1e-6 ||b|| (||r||^2 contracts by sweep_rate2 per sweep), one in hand
+        h->pred_n32 = (h->sweep_rate2 > 0 && h->sweep_rate2 < 1) ? std::max(0, (int)std::floor(std::log(1e-12) / std::log(h->sweep_rate2)) - 1) : 0;
     }
     if (redo_tail) {
         TRY(enqueue_tail(h, f, dt, nullptr, n_cg));
@@ -1561,8 +1578,12 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
     CU(cudaEventElapsedTime(&st->ms_flux_and_halo, h->ev[2], h->ev[3]));
     CU(cudaEventElapsedTime(&st->ms_deposition, h->ev[3], h->ev[4]));
     CU(cudaEventElapsedTime(&st->ms_total, h->ev[0], h->ev[4]));
-    if (h->sweeps_timed > 0) CU(cudaEventElapsedTime(&st->ms_line_sweeps, h->ev_sw[0], h->ev_sw[1]));
+    if (h->sweeps_timed > 0) {
+        CU(cudaEventElapsedTime(&st->ms_line_sweeps, h->ev_sw[0], h->ev_sw[1]));
+        CU(cudaEventElapsedTime(&st->ms_line_sweeps_fp32, h->ev_sw[0], h->ev_sw[2]));
+    }
     st->sweeps_timed = h->sweeps_timed;
+    st->sweeps_timed_fp32 = h->sweeps_timed32;
     st->n_colours = h->n_colours;
     st->kernel_launches = (int32_t)(h->n_launch - launch0);
     st->halo_exchanges = h->halo_ops;
@@ -1647,6 +1668,7 @@ void pbsm3d_config_defaults(pbsm3d_config* c) {
     c->max_iterations = 1000;   // LinearAlgebra.cpp:167
     c->solver = PBSM3D_SOLVER_AUTO;
     c->deposition_solver = PBSM3D_DEP_AUTO;
+    c->fp32_sweep_streams = 1;
 }
 
 int pbsm3d_nccl_unique_id(void* out) {
@@ -1896,6 +1918,9 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     TRY(h->alloc(&ss.inv, N));
     TRY(h->alloc(&ss.latS, 3 * N));
     TRY(h->alloc(&ss.belowS, N));
+    TRY(h->alloc(&ss.latS32, 3 * N));
+    TRY(h->alloc(&ss.belowS32, N));
+    TRY(h->alloc(&ss.cp32, N));
     TRY(h->alloc(&ss.u_z, N));
     TRY(h->alloc(&ss.csubl, N));
     TRY(h->alloc(&ss.rhs0, Tp));

@@ -57,6 +57,7 @@ struct SuspSystem {
     double *cp, *inv;              // [L][Tp]   Thomas factors of the vertical (column) blocks
     double* latS;                  // [3][L][Tp] lat * inv   } the row-scaled copies the line sweep streams
     double* belowS;                // [L][Tp]   below * inv  }
+    float *latS32, *belowS32, *cp32;  // the same three sweep streams rounded to fp32: what the sweeps far from convergence stream
     double* rhs0;                  // [Tp]      b of layer 0 (all other layers are 0)
     double* rhsS0;                 // [Tp]      rhs0 * inv[0]
     double *u_z, *csubl;           // [L][Tp]
@@ -304,8 +305,11 @@ __global__ void assemble_pads_kernel(DevMesh m, SuspSystem s, int L) {
     for (int z = 0; z < L; ++z) {
         const size_t r = (size_t)z * Tp + p;
         s.diag[r] = 1.0; s.below[r] = 0.0; s.above[r] = 0.0; s.inv[r] = 1.0; s.cp[r] = 0.0; s.belowS[r] = 0.0;
+        s.cp32[r] = 0.f; s.belowS32[r] = 0.f;
         s.u_z[r] = 0.0; s.csubl[r] = 0.0;
-        for (int j = 0; j < 3; ++j) { s.lat[((size_t)j * L + z) * Tp + p] = 0.0; s.latS[((size_t)j * L + z) * Tp + p] = 0.0; }
+        for (int j = 0; j < 3; ++j) {
+            s.lat[((size_t)j * L + z) * Tp + p] = 0.0; s.latS[((size_t)j * L + z) * Tp + p] = 0.0; s.latS32[((size_t)j * L + z) * Tp + p] = 0.f;
+        }
     }
 }
 
@@ -498,8 +502,14 @@ __device__ __forceinline__ double assemble_column(const DevConfig& c, const DevM
             s.inv[r] = inv;
             s.cp[r] = cp_prev;
             s.belowS[r] = lo * inv;
+            s.cp32[r] = (float)cp_prev;
+            s.belowS32[r] = (float)(lo * inv);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) s.latS[((size_t)j * L + z) * Tp + p] = offj[j] * inv;
+            for (int j = 0; j < 3; ++j) {
+                const double v = offj[j] * inv;
+                s.latS[((size_t)j * L + z) * Tp + p] = v;
+                s.latS32[((size_t)j * L + z) * Tp + p] = (float)v;
+            }
             if (z == 0) s.rhsS0[p] = rhs * inv;
         }
     }
@@ -622,7 +632,23 @@ __global__ void flags_kernel(int stage, Scalars* sc, const double* __restrict__ 
 // 3·L gathers x[z*S + nbs] are branch-free and hit L1/L2.  All loads of a column are independent of the
 // Thomas recurrence, so they are issued up front and the dependent chain runs on registers.
 // LT > 0: compile-time layer count; LT == 0: any L (the own column of x is the scratch for the forward pass).
-template <int LT>
+// The sweep streams in fp64 or rounded to fp32 (CT).  x, the right-hand side and all arithmetic stay fp64: the fp32 streams
+// only perturb the operator by <= 6e-8 relative per coefficient, so the iteration they drive has its fixed point within a
+// few 1e-7 of the true solution -- good for every sweep until the residual is down to ~1e-6; the last sweeps, and every
+// residual check, use the fp64 coefficients.  40 -> 20 B of the 58 B a sweep moves per row.
+template <typename CT> struct SweepStreams;
+template <> struct SweepStreams<double> {
+    static __device__ __forceinline__ const double* lat(const SuspSystem& s) { return s.latS; }
+    static __device__ __forceinline__ const double* below(const SuspSystem& s) { return s.belowS; }
+    static __device__ __forceinline__ const double* cp(const SuspSystem& s) { return s.cp; }
+};
+template <> struct SweepStreams<float> {
+    static __device__ __forceinline__ const float* lat(const SuspSystem& s) { return s.latS32; }
+    static __device__ __forceinline__ const float* below(const SuspSystem& s) { return s.belowS32; }
+    static __device__ __forceinline__ const float* cp(const SuspSystem& s) { return s.cp32; }
+};
+
+template <int LT, typename CT>
 __global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh m, int Lrt, int p0, int p1, double* x,
                                                           const Scalars* __restrict__ sc) {
     if (sc->susp_done) return;
@@ -631,21 +657,23 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh 
     const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p1) return;
     const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
-    const double* __restrict__ l0 = s.latS;
-    const double* __restrict__ l1 = s.latS + (size_t)L * Tp;
-    const double* __restrict__ l2 = s.latS + (size_t)2 * L * Tp;
+    const CT* __restrict__ l0 = SweepStreams<CT>::lat(s);
+    const CT* __restrict__ l1 = l0 + (size_t)L * Tp;
+    const CT* __restrict__ l2 = l0 + (size_t)2 * L * Tp;
+    const CT* __restrict__ sb = SweepStreams<CT>::below(s);
+    const CT* __restrict__ sc_ = SweepStreams<CT>::cp(s);
     if (LT > 0) {
         double g[LT > 0 ? LT : 1];
 #pragma unroll
         for (int z = 0; z < LT; ++z) {
             const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
-            g[z] = -(__ldcs(l0 + r) * x[xr + n0] + __ldcs(l1 + r) * x[xr + n1] + __ldcs(l2 + r) * x[xr + n2]);
+            g[z] = -((double)__ldcs(l0 + r) * x[xr + n0] + (double)__ldcs(l1 + r) * x[xr + n1] + (double)__ldcs(l2 + r) * x[xr + n2]);
         }
         double bl[LT > 0 ? LT : 1], cu[LT > 0 ? LT : 1];
 #pragma unroll
         for (int z = 0; z < LT; ++z) {
-            bl[z] = __ldcs(s.belowS + (size_t)z * Tp + p);
-            cu[z] = __ldcs(s.cp + (size_t)z * Tp + p);
+            bl[z] = (double)__ldcs(sb + (size_t)z * Tp + p);
+            cu[z] = (double)__ldcs(sc_ + (size_t)z * Tp + p);
         }
         double y = g[0] + s.rhsS0[p];
         g[0] = y;
@@ -658,13 +686,13 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh 
         double y = 0.0;
         for (int z = 0; z < L; ++z) {
             const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
-            double g = -(__ldcs(l0 + r) * x[xr + n0] + __ldcs(l1 + r) * x[xr + n1] + __ldcs(l2 + r) * x[xr + n2]);
+            double g = -((double)__ldcs(l0 + r) * x[xr + n0] + (double)__ldcs(l1 + r) * x[xr + n1] + (double)__ldcs(l2 + r) * x[xr + n2]);
             if (z == 0) g += s.rhsS0[p];
-            y = g - __ldcs(s.belowS + r) * y;
+            y = g - (double)__ldcs(sb + r) * y;
             x[xr + p] = y;
         }
         for (int z = L - 2; z >= 0; --z) {
-            y = x[(size_t)z * S + p] - __ldcs(s.cp + (size_t)z * Tp + p) * y;
+            y = x[(size_t)z * S + p] - (double)__ldcs(sc_ + (size_t)z * Tp + p) * y;
             x[(size_t)z * S + p] = y;
         }
     }
@@ -1430,7 +1458,7 @@ __device__ __forceinline__ double link_gather(const HaloLink& hl, const double* 
 }
 
 // One colour pass of the line Gauss-Seidel sweep (see gs_sweep_kernel) with the halo inside.
-template <int LT>
+template <int LT, typename CT>
 __global__ void __launch_bounds__(128, 4) gs_sweep_halo_kernel(SuspSystem s, DevMesh m, int Lrt, int p0, int p1, double* x,
                                                                const Scalars* __restrict__ sc, HaloLink hl, int bnd_n, int bnd_off) {
     if (sc->susp_done) { link_signal_idle(hl); return; }
@@ -1445,22 +1473,24 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_halo_kernel(SuspSystem s, Dev
     double g[LT > 0 ? LT : 1];
     if (act) {
         const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
-        const double* __restrict__ l0 = s.latS;
-        const double* __restrict__ l1 = s.latS + (size_t)L * Tp;
-        const double* __restrict__ l2 = s.latS + (size_t)2 * L * Tp;
+        const CT* __restrict__ l0 = SweepStreams<CT>::lat(s);
+        const CT* __restrict__ l1 = l0 + (size_t)L * Tp;
+        const CT* __restrict__ l2 = l0 + (size_t)2 * L * Tp;
+        const CT* __restrict__ sb = SweepStreams<CT>::below(s);
+        const CT* __restrict__ sc_ = SweepStreams<CT>::cp(s);
         if (LT > 0) {
 #pragma unroll
             for (int z = 0; z < LT; ++z) {
                 const size_t r = (size_t)z * Tp + p;
                 const size_t zS = (size_t)z * S, zG = (size_t)z * hl.nGp;
-                g[z] = -(__ldcs(l0 + r) * link_gather(hl, x, zS, zG, n0, Tp) + __ldcs(l1 + r) * link_gather(hl, x, zS, zG, n1, Tp) +
-                         __ldcs(l2 + r) * link_gather(hl, x, zS, zG, n2, Tp));
+                g[z] = -((double)__ldcs(l0 + r) * link_gather(hl, x, zS, zG, n0, Tp) + (double)__ldcs(l1 + r) * link_gather(hl, x, zS, zG, n1, Tp) +
+                         (double)__ldcs(l2 + r) * link_gather(hl, x, zS, zG, n2, Tp));
             }
             double bl[LT > 0 ? LT : 1], cu[LT > 0 ? LT : 1];
 #pragma unroll
             for (int z = 0; z < LT; ++z) {
-                bl[z] = __ldcs(s.belowS + (size_t)z * Tp + p);
-                cu[z] = __ldcs(s.cp + (size_t)z * Tp + p);
+                bl[z] = (double)__ldcs(sb + (size_t)z * Tp + p);
+                cu[z] = (double)__ldcs(sc_ + (size_t)z * Tp + p);
             }
             double y = g[0] + s.rhsS0[p];
             g[0] = y;
@@ -1474,14 +1504,14 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_halo_kernel(SuspSystem s, Dev
             for (int z = 0; z < L; ++z) {
                 const size_t r = (size_t)z * Tp + p;
                 const size_t zS = (size_t)z * S, zG = (size_t)z * hl.nGp;
-                double gg = -(__ldcs(l0 + r) * link_gather(hl, x, zS, zG, n0, Tp) + __ldcs(l1 + r) * link_gather(hl, x, zS, zG, n1, Tp) +
-                              __ldcs(l2 + r) * link_gather(hl, x, zS, zG, n2, Tp));
+                double gg = -((double)__ldcs(l0 + r) * link_gather(hl, x, zS, zG, n0, Tp) + (double)__ldcs(l1 + r) * link_gather(hl, x, zS, zG, n1, Tp) +
+                              (double)__ldcs(l2 + r) * link_gather(hl, x, zS, zG, n2, Tp));
                 if (z == 0) gg += s.rhsS0[p];
-                y = gg - __ldcs(s.belowS + r) * y;
+                y = gg - (double)__ldcs(sb + r) * y;
                 x[zS + p] = y;
             }
             for (int z = L - 2; z >= 0; --z) {
-                y = x[(size_t)z * S + p] - __ldcs(s.cp + (size_t)z * Tp + p) * y;
+                y = x[(size_t)z * S + p] - (double)__ldcs(sc_ + (size_t)z * Tp + p) * y;
                 x[(size_t)z * S + p] = y;
             }
         }

@@ -89,6 +89,7 @@ void PBSM3D_gpu::init(mesh& domain)
     _c.max_iterations = cfg.get("max_iterations", 1000);
     _c.solver = cfg.get("solver", (int)PBSM3D_SOLVER_AUTO);
     _c.deposition_solver = cfg.get("deposition_solver", (int)PBSM3D_DEP_AUTO);
+    _c.fp32_sweep_streams = cfg.get("fp32_sweep_streams", true);
 
     const size_t ntri = _ntri = domain->size_faces();
 

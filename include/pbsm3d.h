@@ -99,6 +99,9 @@ typedef struct pbsm3d_config {
     int max_iterations;           /* 1000 */
     int solver;                   /* PBSM3D_SOLVER_AUTO (suspension system) */
     int deposition_solver;        /* PBSM3D_DEP_AUTO */
+    int fp32_sweep_streams;       /* 1: line sweeps far from convergence stream fp32-rounded copies of their coefficients (fp64 x,
+                                     fp64 arithmetic); the last sweeps and every residual check use the fp64 coefficients, so the
+                                     stopping rule is unchanged.  0: fp64 streams throughout. */
 } pbsm3d_config;
 
 /* One rank's share of the mesh, flattened from CHM's triangulation in CHM's own face order.
@@ -173,6 +176,8 @@ typedef struct pbsm3d_stats {
     float ms_total;
     float ms_line_sweeps;            /* CUDA-event time of the first `sweeps_timed` line sweeps of this step */
     int32_t sweeps_timed;            /* full sweeps (all colours) inside ms_line_sweeps */
+    int32_t sweeps_timed_fp32;       /* of those, the leading ones that streamed fp32 coefficient copies ... */
+    float ms_line_sweeps_fp32;       /* ... and their CUDA-event time (ms_line_sweeps - this = the fp64-stream sweeps) */
     int32_t n_colours;               /* colour classes of the internal face order */
     int32_t deposition_solver_used;  /* PBSM3D_DEP_CG / _CHEBYSHEV / _SOR */
     int32_t host_syncs;              /* stream synchronisations the step needed (1 when every prediction held) */

@@ -39,20 +39,36 @@ def test_config_defaults_are_the_reference_defaults(lib):
                   smooth_coeff=820.0, min_sd_trans=0.1, cutoff=0.3, snow_diffusion_const=0.3, rouault_diffusion_coef=0,
                   enable_veg=1, iterative_subl=0, use_exp_fetch=0, use_tanh_fetch=1, use_PomLi_probability=0,
                   z0_ustar_coupling=0, use_subgrid_topo=0, use_subgrid_topo_V2=0, use_R94_lambda=1, debug_output=0,
-                  tolerance=1e-8, max_iterations=1000, solver=0, deposition_solver=0)
+                  tolerance=1e-8, max_iterations=1000, solver=0, deposition_solver=0, fp32_sweep_streams=1)
     for k, v in expect.items():
         assert getattr(c, k) == v, k
     with pytest.raises(KeyError):
         capi.default_config(not_a_key=1)
 
 
-def test_struct_layouts_match_header(lib):
-    # 20 ints/doubles + 3 solver fields; natural alignment, no packing pragmas in the header
-    assert C.sizeof(capi.Forcing) == 8 * 8 and C.sizeof(capi.Outputs) == 8 * 8
-    assert C.sizeof(capi.Comm) == 16
-    assert C.sizeof(capi.Stats) == 6 * 4 + 4 * 8 + 6 * 4 + 7 * 4 + 4  # 7 trailing int32 + tail padding to 8
-    assert C.sizeof(capi.Mesh) == 8 + 4 + 4 + 10 * 8
-
+def test_struct_layouts_match_header(lib, tmp_path):
+    """The ctypes mirrors against the C compiler's view of include/pbsm3d.h: sizes and the offset of every struct's last field."""
+    import subprocess
+    probes = {"pbsm3d_forcing": (capi.Forcing, "fetch"), "pbsm3d_outputs": (capi.Outputs, "pbsm_more_than_avail"),
+              "pbsm3d_comm": (capi.Comm, None), "pbsm3d_stats": (capi.Stats, "halo_fused"), "pbsm3d_mesh": (capi.Mesh, None),
+              "pbsm3d_config": (capi.Config, "fp32_sweep_streams"), "pbsm3d_wind_config": (capi.WindConfig, "fetch_I")}
+    lines = []
+    for cname, (_, last) in probes.items():
+        lines.append(f'printf("{cname} %zu %zu\\n", sizeof({cname}), {"offsetof(" + cname + ", " + last + ")" if last else "(size_t)0"});')
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pbsm3d.h"\nint main(void){' + "".join(lines) + "return 0;}\n")
+    exe = tmp_path / "probe"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.splitlines():
+        cname, size, off = line.split()
+        ct, last = probes[cname]
+        assert C.sizeof(ct) == int(size), cname
+        if last:
+            assert getattr(ct, last).offset == int(off), (cname, last)
+    for name, _ in capi.Stats._fields_ + capi.Config._fields_:  # every mirrored field is a member of the C struct
+        assert name in open(os.path.join(inc, "pbsm3d.h")).read(), name
 
 def test_create_fails_loudly_without_cuda(lib, granger):
     import torch

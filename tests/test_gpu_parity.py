@@ -301,3 +301,26 @@ def test_deposition_solvers_match_direct_solve(meshname, dep):
         assert st["deposition_iterations"] <= 0.75 * sc["deposition_iterations"], (st["deposition_iterations"], sc["deposition_iterations"])
         hc.close()
     h.close()
+
+
+def test_fp32_sweep_streams_do_not_move_the_answer(slope):
+    """Sweeps far from convergence may stream fp32-rounded copies of their coefficients (fp64 x, fp64 arithmetic); the last
+    sweeps and every residual check use the fp64 coefficients, so the result meets the same stopping rule and agrees with the
+    all-fp64 schedule and the direct solve to the solver tolerance."""
+    geo = slope.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy, seed=4)
+    r = oracle_for(slope, Config.functional_test(10)).step(F, 3600.0)
+    res = {}
+    for flag in (1, 0):
+        h = capi.Handle(capi.default_config(tolerance=1e-10, fp32_sweep_streams=flag, **functest_kw(10)), slope)
+        for rep in range(3):  # the fp32 phase needs a sweep-count prediction: it starts with the second step
+            outs, st = h.step(3600.0, F)
+        res[flag] = (h.solution(), outs, st)
+        assert st["suspension_residual"] <= 1e-10 and st["host_syncs"] == 1
+        assert rel_l2(h.solution(), r["c"]) <= 1e-8
+        h.close()
+    assert res[1][2]["sweeps_timed_fp32"] > 0 and res[0][2]["sweeps_timed_fp32"] == 0
+    assert abs(res[1][2]["suspension_iterations"] - res[0][2]["suspension_iterations"]) <= 2
+    assert rel_l2(res[1][0], res[0][0]) <= 1e-9
+    for v in ("Qsusp", "drift_mass"):
+        assert rel_l2(res[1][1][v], res[0][1][v]) <= 1e-8
