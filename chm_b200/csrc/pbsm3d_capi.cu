@@ -1918,8 +1918,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     TRY(h->alloc(&ss.inv, N));
     TRY(h->alloc(&ss.latS, 3 * N));
     TRY(h->alloc(&ss.belowS, N));
-    TRY(h->alloc(&ss.latS32, 3 * N));
-    TRY(h->alloc(&ss.belowS32, N));
+    TRY(h->alloc(&ss.pack32, N));
     TRY(h->alloc(&ss.cp32, N));
     TRY(h->alloc(&ss.u_z, N));
     TRY(h->alloc(&ss.csubl, N));

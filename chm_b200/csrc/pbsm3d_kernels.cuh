@@ -57,7 +57,8 @@ struct SuspSystem {
     double *cp, *inv;              // [L][Tp]   Thomas factors of the vertical (column) blocks
     double* latS;                  // [3][L][Tp] lat * inv   } the row-scaled copies the line sweep streams
     double* belowS;                // [L][Tp]   below * inv  }
-    float *latS32, *belowS32, *cp32;  // the same three sweep streams rounded to fp32: what the sweeps far from convergence stream
+    float4* pack32;                // [L][Tp] {latS_0, latS_1, latS_2, belowS} rounded to fp32, one 16-byte load per row: what the
+    float* cp32;                   // [L][Tp] sweeps far from convergence stream instead of the five fp64 arrays above
     double* rhs0;                  // [Tp]      b of layer 0 (all other layers are 0)
     double* rhsS0;                 // [Tp]      rhs0 * inv[0]
     double *u_z, *csubl;           // [L][Tp]
@@ -305,11 +306,9 @@ __global__ void assemble_pads_kernel(DevMesh m, SuspSystem s, int L) {
     for (int z = 0; z < L; ++z) {
         const size_t r = (size_t)z * Tp + p;
         s.diag[r] = 1.0; s.below[r] = 0.0; s.above[r] = 0.0; s.inv[r] = 1.0; s.cp[r] = 0.0; s.belowS[r] = 0.0;
-        s.cp32[r] = 0.f; s.belowS32[r] = 0.f;
+        s.cp32[r] = 0.f; s.pack32[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         s.u_z[r] = 0.0; s.csubl[r] = 0.0;
-        for (int j = 0; j < 3; ++j) {
-            s.lat[((size_t)j * L + z) * Tp + p] = 0.0; s.latS[((size_t)j * L + z) * Tp + p] = 0.0; s.latS32[((size_t)j * L + z) * Tp + p] = 0.f;
-        }
+        for (int j = 0; j < 3; ++j) { s.lat[((size_t)j * L + z) * Tp + p] = 0.0; s.latS[((size_t)j * L + z) * Tp + p] = 0.0; }
     }
 }
 
@@ -503,13 +502,9 @@ __device__ __forceinline__ double assemble_column(const DevConfig& c, const DevM
             s.cp[r] = cp_prev;
             s.belowS[r] = lo * inv;
             s.cp32[r] = (float)cp_prev;
-            s.belowS32[r] = (float)(lo * inv);
+            s.pack32[r] = make_float4((float)(offj[0] * inv), (float)(offj[1] * inv), (float)(offj[2] * inv), (float)(lo * inv));
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const double v = offj[j] * inv;
-                s.latS[((size_t)j * L + z) * Tp + p] = v;
-                s.latS32[((size_t)j * L + z) * Tp + p] = (float)v;
-            }
+            for (int j = 0; j < 3; ++j) s.latS[((size_t)j * L + z) * Tp + p] = offj[j] * inv;
             if (z == 0) s.rhsS0[p] = rhs * inv;
         }
     }
@@ -636,17 +631,18 @@ __global__ void flags_kernel(int stage, Scalars* sc, const double* __restrict__ 
 // only perturb the operator by <= 6e-8 relative per coefficient, so the iteration they drive has its fixed point within a
 // few 1e-7 of the true solution -- good for every sweep until the residual is down to ~1e-6; the last sweeps, and every
 // residual check, use the fp64 coefficients.  40 -> 20 B of the 58 B a sweep moves per row.
-template <typename CT> struct SweepStreams;
-template <> struct SweepStreams<double> {
-    static __device__ __forceinline__ const double* lat(const SuspSystem& s) { return s.latS; }
-    static __device__ __forceinline__ const double* below(const SuspSystem& s) { return s.belowS; }
-    static __device__ __forceinline__ const double* cp(const SuspSystem& s) { return s.cp; }
-};
-template <> struct SweepStreams<float> {
-    static __device__ __forceinline__ const float* lat(const SuspSystem& s) { return s.latS32; }
-    static __device__ __forceinline__ const float* below(const SuspSystem& s) { return s.belowS32; }
-    static __device__ __forceinline__ const float* cp(const SuspSystem& s) { return s.cp32; }
-};
+template <typename CT> struct RowCoef { CT l0, l1, l2, bl; };
+template <typename CT> __device__ __forceinline__ RowCoef<CT> load_row(const SuspSystem& s, size_t r, size_t LTp);
+template <> __device__ __forceinline__ RowCoef<double> load_row<double>(const SuspSystem& s, size_t r, size_t LTp) {
+    return {__ldcs(s.latS + r), __ldcs(s.latS + LTp + r), __ldcs(s.latS + 2 * LTp + r), __ldcs(s.belowS + r)};
+}
+template <> __device__ __forceinline__ RowCoef<float> load_row<float>(const SuspSystem& s, size_t r, size_t) {
+    const float4 v = __ldcs(s.pack32 + r);  // one 16-byte load (512 B per warp) instead of four 4-byte ones
+    return {v.x, v.y, v.z, v.w};
+}
+template <typename CT> __device__ __forceinline__ CT load_cp(const SuspSystem& s, size_t r);
+template <> __device__ __forceinline__ double load_cp<double>(const SuspSystem& s, size_t r) { return __ldcs(s.cp + r); }
+template <> __device__ __forceinline__ float load_cp<float>(const SuspSystem& s, size_t r) { return __ldcs(s.cp32 + r); }
 
 template <int LT, typename CT>
 __global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh m, int Lrt, int p0, int p1, double* x,
@@ -657,42 +653,38 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh 
     const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p1) return;
     const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
-    const CT* __restrict__ l0 = SweepStreams<CT>::lat(s);
-    const CT* __restrict__ l1 = l0 + (size_t)L * Tp;
-    const CT* __restrict__ l2 = l0 + (size_t)2 * L * Tp;
-    const CT* __restrict__ sb = SweepStreams<CT>::below(s);
-    const CT* __restrict__ sc_ = SweepStreams<CT>::cp(s);
+    const size_t LTp = (size_t)L * Tp;
     if (LT > 0) {
         double g[LT > 0 ? LT : 1];
+        CT bl[LT > 0 ? LT : 1], cu[LT > 0 ? LT : 1];
 #pragma unroll
         for (int z = 0; z < LT; ++z) {
             const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
-            g[z] = -((double)__ldcs(l0 + r) * x[xr + n0] + (double)__ldcs(l1 + r) * x[xr + n1] + (double)__ldcs(l2 + r) * x[xr + n2]);
+            const RowCoef<CT> c = load_row<CT>(s, r, LTp);
+            g[z] = -((double)c.l0 * x[xr + n0] + (double)c.l1 * x[xr + n1] + (double)c.l2 * x[xr + n2]);
+            bl[z] = c.bl;
         }
-        double bl[LT > 0 ? LT : 1], cu[LT > 0 ? LT : 1];
 #pragma unroll
-        for (int z = 0; z < LT; ++z) {
-            bl[z] = (double)__ldcs(sb + (size_t)z * Tp + p);
-            cu[z] = (double)__ldcs(sc_ + (size_t)z * Tp + p);
-        }
+        for (int z = 0; z < LT; ++z) cu[z] = load_cp<CT>(s, (size_t)z * Tp + p);
         double y = g[0] + s.rhsS0[p];
         g[0] = y;
 #pragma unroll
-        for (int z = 1; z < LT; ++z) { y = g[z] - bl[z] * y; g[z] = y; }
+        for (int z = 1; z < LT; ++z) { y = g[z] - (double)bl[z] * y; g[z] = y; }
         x[(size_t)(LT - 1) * S + p] = y;
 #pragma unroll
-        for (int z = LT - 2; z >= 0; --z) { y = g[z] - cu[z] * y; x[(size_t)z * S + p] = y; }
+        for (int z = LT - 2; z >= 0; --z) { y = g[z] - (double)cu[z] * y; x[(size_t)z * S + p] = y; }
     } else {
         double y = 0.0;
         for (int z = 0; z < L; ++z) {
             const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
-            double g = -((double)__ldcs(l0 + r) * x[xr + n0] + (double)__ldcs(l1 + r) * x[xr + n1] + (double)__ldcs(l2 + r) * x[xr + n2]);
+            const RowCoef<CT> c = load_row<CT>(s, r, LTp);
+            double g = -((double)c.l0 * x[xr + n0] + (double)c.l1 * x[xr + n1] + (double)c.l2 * x[xr + n2]);
             if (z == 0) g += s.rhsS0[p];
-            y = g - (double)__ldcs(sb + r) * y;
+            y = g - (double)c.bl * y;
             x[xr + p] = y;
         }
         for (int z = L - 2; z >= 0; --z) {
-            y = x[(size_t)z * S + p] - (double)__ldcs(sc_ + (size_t)z * Tp + p) * y;
+            y = x[(size_t)z * S + p] - (double)load_cp<CT>(s, (size_t)z * Tp + p) * y;
             x[(size_t)z * S + p] = y;
         }
     }
@@ -1473,45 +1465,41 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_halo_kernel(SuspSystem s, Dev
     double g[LT > 0 ? LT : 1];
     if (act) {
         const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
-        const CT* __restrict__ l0 = SweepStreams<CT>::lat(s);
-        const CT* __restrict__ l1 = l0 + (size_t)L * Tp;
-        const CT* __restrict__ l2 = l0 + (size_t)2 * L * Tp;
-        const CT* __restrict__ sb = SweepStreams<CT>::below(s);
-        const CT* __restrict__ sc_ = SweepStreams<CT>::cp(s);
+        const size_t LTp = (size_t)L * Tp;
         if (LT > 0) {
+            CT bl[LT > 0 ? LT : 1], cu[LT > 0 ? LT : 1];
 #pragma unroll
             for (int z = 0; z < LT; ++z) {
                 const size_t r = (size_t)z * Tp + p;
                 const size_t zS = (size_t)z * S, zG = (size_t)z * hl.nGp;
-                g[z] = -((double)__ldcs(l0 + r) * link_gather(hl, x, zS, zG, n0, Tp) + (double)__ldcs(l1 + r) * link_gather(hl, x, zS, zG, n1, Tp) +
-                         (double)__ldcs(l2 + r) * link_gather(hl, x, zS, zG, n2, Tp));
+                const RowCoef<CT> c = load_row<CT>(s, r, LTp);
+                g[z] = -((double)c.l0 * link_gather(hl, x, zS, zG, n0, Tp) + (double)c.l1 * link_gather(hl, x, zS, zG, n1, Tp) +
+                         (double)c.l2 * link_gather(hl, x, zS, zG, n2, Tp));
+                bl[z] = c.bl;
             }
-            double bl[LT > 0 ? LT : 1], cu[LT > 0 ? LT : 1];
 #pragma unroll
-            for (int z = 0; z < LT; ++z) {
-                bl[z] = (double)__ldcs(sb + (size_t)z * Tp + p);
-                cu[z] = (double)__ldcs(sc_ + (size_t)z * Tp + p);
-            }
+            for (int z = 0; z < LT; ++z) cu[z] = load_cp<CT>(s, (size_t)z * Tp + p);
             double y = g[0] + s.rhsS0[p];
             g[0] = y;
 #pragma unroll
-            for (int z = 1; z < LT; ++z) { y = g[z] - bl[z] * y; g[z] = y; }
+            for (int z = 1; z < LT; ++z) { y = g[z] - (double)bl[z] * y; g[z] = y; }
             x[(size_t)(LT - 1) * S + p] = y;
 #pragma unroll
-            for (int z = LT - 2; z >= 0; --z) { y = g[z] - cu[z] * y; g[z] = y; x[(size_t)z * S + p] = y; }
+            for (int z = LT - 2; z >= 0; --z) { y = g[z] - (double)cu[z] * y; g[z] = y; x[(size_t)z * S + p] = y; }
         } else {
             double y = 0.0;
             for (int z = 0; z < L; ++z) {
                 const size_t r = (size_t)z * Tp + p;
                 const size_t zS = (size_t)z * S, zG = (size_t)z * hl.nGp;
-                double gg = -((double)__ldcs(l0 + r) * link_gather(hl, x, zS, zG, n0, Tp) + (double)__ldcs(l1 + r) * link_gather(hl, x, zS, zG, n1, Tp) +
-                              (double)__ldcs(l2 + r) * link_gather(hl, x, zS, zG, n2, Tp));
+                const RowCoef<CT> c = load_row<CT>(s, r, LTp);
+                double gg = -((double)c.l0 * link_gather(hl, x, zS, zG, n0, Tp) + (double)c.l1 * link_gather(hl, x, zS, zG, n1, Tp) +
+                              (double)c.l2 * link_gather(hl, x, zS, zG, n2, Tp));
                 if (z == 0) gg += s.rhsS0[p];
-                y = gg - (double)__ldcs(sb + r) * y;
+                y = gg - (double)c.bl * y;
                 x[zS + p] = y;
             }
             for (int z = L - 2; z >= 0; --z) {
-                y = x[(size_t)z * S + p] - (double)__ldcs(sc_ + (size_t)z * Tp + p) * y;
+                y = x[(size_t)z * S + p] - (double)load_cp<CT>(s, (size_t)z * Tp + p) * y;
                 x[(size_t)z * S + p] = y;
             }
         }
