@@ -1,11 +1,13 @@
 // libpbsm3d_b200.so — C-ABI (include/pbsm3d.h) and host orchestration of one PBSM3D timestep on one B200.
-// One process per GPU; NCCL carries the ghost-face halos and the global reductions.  No CPU fallback.
+// One process per GPU.  Ghost-face halos and global reductions travel through peer memory over NVLink (cudaIpc arenas;
+// the halos of the two solves are written by the solver kernels themselves); NCCL bootstraps and is the fallback
+// transport.  No CPU fallback.
 //
-// A step is enqueued optimistically: assembly, a predicted number of line-relaxation sweeps with residual
-// checks, flux integration, the deposition right-hand side, a predicted number of CG iterations, the drift
-// update and the export to CHM order all go onto one stream, each kernel guarded by device-resident flags
-// (suspension converged? deposition present? CG converged?), and the host synchronises ONCE at the end.  Only
-// when a prediction was too short does the host add more sweeps / iterations and re-enqueue the tail.
+// A step is enqueued optimistically: assembly, a predicted number of line Gauss-Seidel sweeps with residual
+// checks, flux integration, the deposition right-hand side, a predicted number of SOR sweeps (or Chebyshev / CG
+// iterations), the drift update and the export to CHM order all go onto one stream, each kernel guarded by
+// device-resident flags (suspension converged? deposition present? deposition converged?), and the host synchronises
+// ONCE at the end.  Only when a prediction was too short does the host add more sweeps / iterations and re-enqueue the tail.
 #include "../../include/pbsm3d.h"
 
 #include <cuda_runtime.h>
@@ -170,7 +172,6 @@ struct pbsm3d_handle {
     double* g_zero = nullptr;                       // [L][nGp] zeros: the ghosts of the first iteration of a solve
     unsigned long long **xflag_remote = nullptr, **qflag_remote = nullptr;
     unsigned long long *xflag_local = nullptr, *qflag_local = nullptr;
-    unsigned *xticket = nullptr, *qticket = nullptr;
     unsigned long long xh_epoch = 0, qh_epoch = 0;  // iteration numbers of the two channels (monotonic)
     bool x_first = true;                            // the next sweep is the first of a solve (x = 0: ghosts read as 0)
     // providers of U_2m_above_srf / fetch (scale_wind_vert, fetchr): vegetation in slot order, work vector, centre grid
@@ -514,8 +515,6 @@ int setup_peer(pbsm3d_handle* h, const std::vector<int>& M, const std::vector<in
             TRY(upload(h, h->q_remote[b], qr[b].data(), qr[b].size() * sizeof(ulonglong2*)));
         }
         TRY(h->alloc_zero(&h->g_zero, stage_elems(me)));
-        TRY(h->alloc_zero(&h->xticket, 1));
-        TRY(h->alloc_zero(&h->qticket, 1));
         CU(cudaStreamSynchronize(h->stream));  // the host vectors above go out of scope
     }
     CU(cudaStreamSynchronize(h->stream));

@@ -1685,7 +1685,6 @@ __global__ void __launch_bounds__(kRedThreads, 8) cheb_iter_halo_kernel(const __
 struct SorLink {
     TaggedLink tl;          // ghost = my tagged ghost entries, remote/bptr = where my boundary faces go
     const int* ghost_key;   // [nG] colour * n_ranks + rank of each ghost face
-    int my_key_base;        // this rank's key for colour c is c * n_ranks + rank: passed per launch as my_key
 };
 __device__ __forceinline__ double sor_ghost(const SorLink& sl, int g, int my_key, unsigned long long e, int first) {
     if (sl.ghost_key[g] < my_key) return tagged_read(sl.tl.ghost + g, e, sl.tl.pt);
