@@ -238,11 +238,11 @@ def main():
     cfg = capi.default_config(**FUNCTEST)
     h = capi.Handle(cfg, mesh, device=local_rank, rank=rank, n_ranks=world, unique_id=uid)
 
-    names = capi.FORCING_NAMES
+    names = capi.DEFAULT_FORCING_NAMES
     dev_in = [{n: torch.from_numpy(F[n]).cuda() for n in names} for F in Fs]
-    dev_out = {n: torch.empty(T, dtype=torch.float64, device="cuda") for n in capi.OUTPUT_NAMES}
+    dev_out = {n: torch.empty(T, dtype=torch.float64, device="cuda") for n in capi.DEFAULT_OUTPUT_NAMES}
     pin_in = [{n: torch.from_numpy(F[n]).pin_memory() for n in names} for F in Fs]
-    pin_out = {n: torch.empty(T, dtype=torch.float64).pin_memory() for n in capi.OUTPUT_NAMES}
+    pin_out = {n: torch.empty(T, dtype=torch.float64).pin_memory() for n in capi.DEFAULT_OUTPUT_NAMES}
     dptr = lambda d: {n: t.data_ptr() for n, t in d.items()}
 
     def barrier():

@@ -56,12 +56,12 @@ class Comm(C.Structure):
 
 
 class Forcing(C.Structure):
-    _fields_ = [(n, c_double_p) for n in ("U_R", "U_2m_above_srf", "snowdepthavg", "swe", "t", "rh", "vw_dir", "fetch")]
+    _fields_ = [(n, c_double_p) for n in ("U_R", "U_2m_above_srf", "snowdepthavg", "swe", "t", "rh", "vw_dir", "fetch", "p_snow_hours")]
 
 
 class Outputs(C.Structure):
     _fields_ = [(n, c_double_p) for n in ("Qsalt", "Qsusp", "Qsubl", "Qsubl_mass", "sum_subl", "drift_mass", "sum_drift",
-                                          "pbsm_more_than_avail")]
+                                          "pbsm_more_than_avail", "blowingsnow_probability")]
 
 
 class Stats(C.Structure):
@@ -87,6 +87,9 @@ class WindConfig(C.Structure):
 
 FORCING_NAMES = [n for n, _ in Forcing._fields_]
 OUTPUT_NAMES = [n for n, _ in Outputs._fields_]
+# what the default path reads / writes (p_snow_hours and blowingsnow_probability belong to use_PomLi_probability)
+DEFAULT_FORCING_NAMES = [n for n in FORCING_NAMES if n != "p_snow_hours"]
+DEFAULT_OUTPUT_NAMES = [n for n in OUTPUT_NAMES if n != "blowingsnow_probability"]
 
 # every symbol include/pbsm3d.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -191,6 +194,7 @@ class Handle:
         self.lib = load_library()
         self.T = mesh.n_local
         self.L = int(cfg.nLayer)
+        self.pomli = bool(cfg.use_PomLi_probability)
         self._keep = []
 
         def arr(a, dt):
@@ -233,8 +237,10 @@ class Handle:
             pass
 
     # ------------------------------------------------------------------ stepping
-    def step(self, dt: float, forcing: Dict[str, np.ndarray], want=OUTPUT_NAMES):
+    def step(self, dt: float, forcing: Dict[str, np.ndarray], want=None):
         """Host-buffer entry point (what the CHM adaptor calls).  Returns (outputs dict, stats dict)."""
+        if want is None:
+            want = OUTPUT_NAMES if self.pomli else DEFAULT_OUTPUT_NAMES
         f = Forcing()
         keep = []
         for n in FORCING_NAMES:

@@ -79,6 +79,7 @@ struct Partner {
 };
 
 constexpr int kMaxColours = 8;
+constexpr int kIn = 9, kOut = 9;  // forcing arrays / output arrays that cross the C-ABI (pbsm3d_forcing, pbsm3d_outputs)
 constexpr int kChunks = 4;  // forcing chunks of the host-buffer entry point (H2D of chunk c+1 overlaps assembly of chunk c)
 
 }  // namespace
@@ -107,7 +108,7 @@ struct pbsm3d_handle {
     unsigned char* water = nullptr;
     double *ddiag = nullptr, *doff = nullptr, *dinv = nullptr;
     // forcing (own device copies for the host-pointer entry point), CHM order
-    double* forcing_buf[8] = {nullptr};
+    double* forcing_buf[kIn] = {nullptr};
     DevForcing last_forcing{};
     double last_dt = 0.0;
     // solution / work
@@ -133,7 +134,7 @@ struct pbsm3d_handle {
     int n_syncs = 0;
     size_t l2_persist_max = 0, l2_window_max = 0;
     bool trace = false;
-    double* out_stage = nullptr;  // [8][T] CHM-ordered outputs on their way to host buffers
+    double* out_stage = nullptr;  // [kOut][T] CHM-ordered outputs on their way to host buffers
     double* scratch = nullptr;    // inspection getters
     size_t scratch_n = 0;
     // reductions
@@ -1150,8 +1151,8 @@ int estimate_spectrum(pbsm3d_handle* h) {
 }
 
 struct OutTargets {
-    double* dst[8];       // where export_kernel writes (device pointers: caller's buffers or out_stage)
-    double* host[8];      // optional host destinations for a following D2H
+    double* dst[kOut];    // where export_kernel writes (device pointers: caller's buffers or out_stage)
+    double* host[kOut];   // optional host destinations for a following D2H
 };
 
 // Export of the outputs in `mask` to CHM order on `stream` (+ D2H when the caller's buffers are on the host).
@@ -1159,21 +1160,22 @@ int enqueue_export(pbsm3d_handle* h, cudaStream_t stream, const OutTargets* out,
     if (!out) return 0;
     const int T = h->T;
     ExportPtrs e;
-    const double* src[8] = {h->ss.Qsalt, h->Qsusp, h->Qsubl, h->Qsubl_mass, h->sum_subl, h->drift_mass, h->sum_drift, h->more_avail};
+    const double* src[kOut] = {h->ss.Qsalt, h->Qsusp, h->Qsubl, h->Qsubl_mass, h->sum_subl, h->drift_mass, h->sum_drift, h->more_avail,
+                               h->ss.prob};
     bool any = false;
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < kOut; ++k) {
         e.src[k] = src[k];
         e.dst[k] = (mask >> k & 1u) ? out->dst[k] : nullptr;
         any = any || e.dst[k];
     }
     if (!any) return 0;
     LAUNCH_ON(h, stream, export_kernel, cdiv(T, 256), 256, T, h->iperm, e);
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < kOut; ++k)
         if (e.dst[k] && out->host[k])
             CU(cudaMemcpyAsync(out->host[k], out->dst[k], (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, stream));
     return 0;
 }
-constexpr unsigned kOutQsalt = 1u << 0, kOutFlux = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4), kOutDrift = (1u << 5) | (1u << 6) | (1u << 7);
+constexpr unsigned kOutQsalt = (1u << 0) | (1u << 8) /* Qsalt and blowingsnow_probability: final after the assembly */, kOutFlux = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4), kOutDrift = (1u << 5) | (1u << 6) | (1u << 7);
 
 // E..I of SURVEY §3.2 plus the export: everything after the suspension solve.  Safe to enqueue before the host
 // knows whether the solve converged (device guards), and safe to enqueue again if it had not.
@@ -1377,14 +1379,14 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
     auto provider_input = [&](int k) { return derive && (k == 0 || k == 2 || k == 6); };
     if (host_in) {
         if (derive) {
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < kIn; ++k)
                 if (host_in[k] && provider_input(k))
                     CU(cudaMemcpyAsync(h->forcing_buf[k], host_in[k], (size_t)T * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
             CU(cudaEventRecord(h->ev_prov, h->s_in));
         }
         for (int c = 0; c < nch; ++c) {
             const size_t i0 = (size_t)T * c / nch, i1 = (size_t)T * (c + 1) / nch;
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < kIn; ++k)
                 if (host_in[k] && !provider_input(k))
                     CU(cudaMemcpyAsync(h->forcing_buf[k] + i0, host_in[k] + i0, (i1 - i0) * sizeof(double), cudaMemcpyHostToDevice,
                                        h->s_in));
@@ -1443,7 +1445,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
     // E..I, optimistic
     int n_cg = std::min(maxit, h->pred_cg > 0 ? h->pred_cg + std::max(4, h->pred_cg / 16) : 64);
     TRY(enqueue_tail(h, f, dt, early ? out : nullptr, n_cg));
-    TRY(enqueue_finish(h, f, dt, out, early ? kOutDrift : 0xffu));
+    TRY(enqueue_finish(h, f, dt, out, early ? kOutDrift : 0x1ffu));
     if (early) {
         CU(cudaEventRecord(h->ev_out, h->s_out));
         CU(cudaStreamWaitEvent(s, h->ev_out, 0));
@@ -1504,7 +1506,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
     }
     if (redo_tail) {
         TRY(enqueue_tail(h, f, dt, nullptr, n_cg));
-        TRY(enqueue_finish(h, f, dt, out, 0xffu));
+        TRY(enqueue_finish(h, f, dt, out, 0x1ffu));
         TRY(sync_stream(h));
     }
     // deposition solve still open?
@@ -1547,7 +1549,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
                 return fail(PBSM3D_ERR_NOCONVERGE, "deposition solver failed to converge");
             TRY(enqueue_cg_iterations(h, std::min(64, maxit - h->h_sc->iters)));
         }
-        TRY(enqueue_finish(h, f, dt, out, 0xffu));
+        TRY(enqueue_finish(h, f, dt, out, 0x1ffu));
         TRY(sync_stream(h));
     }
     const Scalars& c = *h->h_sc;
@@ -1722,7 +1724,6 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     if (cfg->settling_velocity < 0) return fail(PBSM3D_ERR_INVALID, "PBSM3D settling velocity must be positive");  // :239-242
     if (cfg->nLayer < 2) return fail(PBSM3D_ERR_INVALID, "nLayer must be >= 2 (top and bottom layers are distinct rows)");
     if (cfg->iterative_subl) return fail(PBSM3D_ERR_UNSUPPORTED, "iterative_subl is not implemented");
-    if (cfg->use_PomLi_probability) return fail(PBSM3D_ERR_UNSUPPORTED, "use_PomLi_probability is not implemented");
     if (cfg->z0_ustar_coupling) return fail(PBSM3D_ERR_UNSUPPORTED, "z0_ustar_coupling is not implemented");
     if (cfg->use_subgrid_topo || cfg->use_subgrid_topo_V2) return fail(PBSM3D_ERR_UNSUPPORTED, "use_subgrid_topo* is not implemented");
     if (cfg->debug_output) return fail(PBSM3D_ERR_UNSUPPORTED, "debug_output is not implemented");
@@ -1926,6 +1927,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     TRY(h->alloc_zero(&ss.Qsalt, h->S));
     TRY(h->alloc(&ss.c_salt, Tp));
     TRY(h->alloc(&ss.salt, Tp));
+    TRY(h->alloc(&ss.prob, Tp));
     TRY(h->alloc_zero(&h->x, h->NS));
     TRY(h->alloc_zero(&h->Qsusp, h->S));
     TRY(h->alloc_zero(&h->cg_p, h->S));
@@ -1936,9 +1938,10 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     double** perslot[] = {&h->Qsubl, &h->Qsubl_mass, &h->sum_subl, &h->drift_mass, &h->sum_drift, &h->more_avail,
                           &h->drhs,  &h->drhsS,      &h->cg_r,     &h->cg_Ap};
     for (double** p : perslot) TRY(h->alloc_zero(p, Tp));
-    TRY(h->alloc(&h->out_stage, (size_t)8 * T));
+    TRY(h->alloc(&h->out_stage, (size_t)kOut * T));
     // drift_mass is a face variable that is -9999 until first written (variablestorage default)
     LAUNCH(h, fill_slots_kernel, cdiv(Tp, 256), 256, Tp, h->perm, h->drift_mass, -9999.0);
+    LAUNCH(h, fill_slots_kernel, cdiv(Tp, 256), 256, Tp, h->perm, h->ss.prob, -9999.0);  // blowingsnow_probability: unset face variable
     TRY(h->alloc_zero(&h->partial, (size_t)kRedBlocks * 4));
     TRY(h->alloc_zero(&h->red, 8));
 
@@ -1952,6 +1955,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     dc.use_exp_fetch = cfg->use_exp_fetch;
     dc.use_tanh_fetch = cfg->use_tanh_fetch;
     dc.use_R94_lambda = cfg->use_R94_lambda;
+    dc.use_PomLi = cfg->use_PomLi_probability;
     dc.settling_velocity = cfg->settling_velocity;
     dc.eps = cfg->smooth_coeff;
     dc.min_sd_trans = cfg->min_sd_trans;
@@ -2003,11 +2007,12 @@ int pbsm3d_create(const pbsm3d_config* cfg, const pbsm3d_mesh* mesh, int device,
 }
 
 static bool forcing_complete(const pbsm3d_handle* h, const pbsm3d_forcing* f) {
-    return f->U_R && (f->U_2m_above_srf || h->providers_on) && f->snowdepthavg && f->swe && f->t && f->rh && f->vw_dir;
+    return f->U_R && (f->U_2m_above_srf || h->providers_on) && f->snowdepthavg && f->swe && f->t && f->rh && f->vw_dir &&
+           (f->p_snow_hours || !h->cfg.use_PomLi_probability);
 }
-static void out_pointers(const pbsm3d_outputs* o, double* p[8]) {
+static void out_pointers(const pbsm3d_outputs* o, double* p[kOut]) {
     p[0] = o->Qsalt; p[1] = o->Qsusp; p[2] = o->Qsubl; p[3] = o->Qsubl_mass; p[4] = o->sum_subl; p[5] = o->drift_mass;
-    p[6] = o->sum_drift; p[7] = o->pbsm_more_than_avail;
+    p[6] = o->sum_drift; p[7] = o->pbsm_more_than_avail; p[8] = o->blowingsnow_probability;
 }
 
 int pbsm3d_step_device(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm3d_outputs* out, pbsm3d_stats* stats) {
@@ -2016,7 +2021,7 @@ int pbsm3d_step_device(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, con
     CU(cudaSetDevice(h->device));
     pbsm3d_stats local;
     if (!stats) stats = &local;
-    DevForcing df{f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch};
+    DevForcing df{f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch, f->p_snow_hours};
     OutTargets ot{};
     if (out) out_pointers(out, ot.dst);
     return step_impl(h, dt, df, nullptr, out ? &ot : nullptr, stats);
@@ -2028,13 +2033,14 @@ int pbsm3d_step(pbsm3d_handle* h, double dt, const pbsm3d_forcing* f, const pbsm
     CU(cudaSetDevice(h->device));
     pbsm3d_stats local;
     if (!stats) stats = &local;
-    const double* src[8] = {f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch};
+    const double* src[kIn] = {f->U_R, f->U_2m_above_srf, f->snowdepthavg, f->swe, f->t, f->rh, f->vw_dir, f->fetch, f->p_snow_hours};
     DevForcing df{h->forcing_buf[0], f->U_2m_above_srf ? h->forcing_buf[1] : nullptr, h->forcing_buf[2], h->forcing_buf[3],
-                  h->forcing_buf[4], h->forcing_buf[5], h->forcing_buf[6], f->fetch ? h->forcing_buf[7] : nullptr};
+                  h->forcing_buf[4], h->forcing_buf[5], h->forcing_buf[6], f->fetch ? h->forcing_buf[7] : nullptr,
+                  f->p_snow_hours ? h->forcing_buf[8] : nullptr};
     OutTargets ot{};
     if (out) {
         out_pointers(out, ot.host);
-        for (int k = 0; k < 8; ++k) ot.dst[k] = ot.host[k] ? h->out_stage + (size_t)k * h->T : nullptr;
+        for (int k = 0; k < kOut; ++k) ot.dst[k] = ot.host[k] ? h->out_stage + (size_t)k * h->T : nullptr;
     }
     return step_impl(h, dt, df, src, out ? &ot : nullptr, stats);
 }

@@ -24,7 +24,7 @@ namespace pbsm3d {
 struct DevConfig {
     int L;
     int do_fixed_settling, do_sublimation, do_lateral_diff, rouault, enable_veg;
-    int use_exp_fetch, use_tanh_fetch, use_R94_lambda;
+    int use_exp_fetch, use_tanh_fetch, use_R94_lambda, use_PomLi;
     double settling_velocity, eps, min_sd_trans, cutoff, snow_diffusion_const;
     double dz;     // v_edge_height = susp_depth / nLayer (PBSM3D.cpp:225-226)
     double l_max;  // 40 (PBSM3D.cpp:227)
@@ -48,7 +48,7 @@ struct DevMesh {
 };
 
 struct DevForcing {  // CHM order, [T]
-    const double *U_R, *u2, *sd, *swe, *t, *rh, *vw_dir, *fetch;
+    const double *U_R, *u2, *sd, *swe, *t, *rh, *vw_dir, *fetch, *psh /* p_snow_hours: use_PomLi_probability only */;
 };
 
 struct SuspSystem {
@@ -64,6 +64,7 @@ struct SuspSystem {
     double *u_z, *csubl;           // [L][Tp]
     double *Qsalt, *c_salt;        // [Tp]
     unsigned char* salt;           // [Tp]
+    double* prob;                  // [Tp] blowingsnow_probability (face variable; written on saltating faces with use_PomLi_probability)
 };
 
 // Device-resident control block: recurrence scalars, convergence flags and the tickets of the fused
@@ -377,6 +378,18 @@ __device__ __forceinline__ double assemble_column(const DevConfig& c, const DevM
             } else if (c.use_tanh_fetch && fetch <= 300.0) {
                 const double Lc = 0.5 * tanh(0.1333333333e-1 * 300.0 - 2.0) + 0.5;  // fetch_ref inside tanh, as the reference
                 c_salt *= Lc;
+            }
+            if (c.use_PomLi) {  // Pomeroy & Li 2000 upscaled probability of blowing snow (PBSM3D.cpp:848-866)
+                const double A = f.psh[i];  // hours since the last snowfall
+                const double z10 = 10.0 + sd;
+                const double u10 = z10 < kZUR ? log_scale_wind(uref, kZUR, z10, sd, kZ0Snow) : uref;  // :451-463
+                const double u_mean = 11.2 + 0.365 * Tc + 0.00706 * Tc * Tc + 0.9 * log(A);
+                const double delta = 0.145 * Tc + 0.00196 * Tc * Tc + 4.3;
+                const double z0v = (Nst * dv * height_diff) / 2.0;
+                const double us = u10 / sqrt((1 + 340.0 * z0v));
+                const double Pu10 = 1.0 / (1.0 + exp((sqrt(kPi) * (u_mean - us)) / delta));
+                s.prob[p] = Pu10;
+                c_salt *= Pu10;
             }
             const double uhs = 2.8 * ust_th;
             Qsalt = c_salt * uhs * hs;
@@ -1214,15 +1227,15 @@ __global__ void drift_done_kernel(Scalars* sc) {
 
 // Outputs back to CHM face order (the order of every array that crosses the C-ABI).
 struct ExportPtrs {
-    const double* src[8];
-    double* dst[8];
+    const double* src[9];
+    double* dst[9];
 };
 __global__ void __launch_bounds__(256) export_kernel(int T, const int* __restrict__ iperm, ExportPtrs e) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     const int p = iperm[i];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < 9; ++k)
         if (e.dst[k]) e.dst[k][i] = e.src[k][p];
 }
 // dst[iperm[i]] = src[i] (state restore)

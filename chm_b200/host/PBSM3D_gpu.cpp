@@ -261,13 +261,13 @@ void PBSM3D_gpu::init(mesh& domain)
         check(pbsm3d_set_providers(_h, &w));
     }
 
-    _stage = (double*)pbsm3d_host_alloc(16 * ntri * sizeof(double));
+    _stage = (double*)pbsm3d_host_alloc(18 * ntri * sizeof(double));
     if (!_stage)
         CHM_THROW_EXCEPTION(module_error, std::string("PBSM3D_gpu: ") + pbsm3d_last_error());
-    std::memset(_stage, 0, 16 * ntri * sizeof(double));
-    double** slots[16] = {&_U_R,   &_U2,    &_sd,    &_swe,        &_t,        &_rh,         &_vw_dir,   &_fetch,
-                          &_Qsalt, &_Qsusp, &_Qsubl, &_Qsubl_mass, &_sum_subl, &_drift_mass, &_sum_drift, &_more};
-    for (int k = 0; k < 16; ++k)
+    std::memset(_stage, 0, 18 * ntri * sizeof(double));
+    double** slots[18] = {&_U_R,   &_U2,    &_sd,    &_swe,        &_t,        &_rh,         &_vw_dir,   &_fetch,     &_psh,
+                          &_Qsalt, &_Qsusp, &_Qsubl, &_Qsubl_mass, &_sum_subl, &_drift_mass, &_sum_drift, &_more,     &_prob};
+    for (int k = 0; k < 18; ++k)
         *slots[k] = _stage + (size_t)k * ntri;
 }
 
@@ -289,9 +289,13 @@ void PBSM3D_gpu::run(mesh& domain)
         _vw_dir[i] = (*face)["vw_dir"_s];
         if (_use_fetch && !_fuse)
             _fetch[i] = (*face)["fetch"_s];
+        if (_c.use_PomLi_probability)
+            _psh[i] = (*face)["p_snow_hours"_s]; // read even when only "fetch" was declared (PBSM3D.cpp:137-141 vs :853)
     }
-    pbsm3d_forcing f{_U_R, _fuse ? nullptr : _U2, _sd, _swe, _t, _rh, _vw_dir, (_use_fetch && !_fuse) ? _fetch : nullptr};
-    pbsm3d_outputs o{_Qsalt, _Qsusp, _Qsubl, _Qsubl_mass, _sum_subl, _drift_mass, _sum_drift, _more};
+    pbsm3d_forcing f{_U_R, _fuse ? nullptr : _U2, _sd, _swe, _t, _rh, _vw_dir, (_use_fetch && !_fuse) ? _fetch : nullptr,
+                     _c.use_PomLi_probability ? _psh : nullptr};
+    pbsm3d_outputs o{_Qsalt, _Qsusp, _Qsubl, _Qsubl_mass, _sum_subl, _drift_mass, _sum_drift, _more,
+                     _c.use_PomLi_probability ? _prob : nullptr};
     check(pbsm3d_step(_h, global_param->dt(), &f, &o, &_stats));
     SPDLOG_DEBUG("  suspension iterations: {} residual: {}", _stats.suspension_iterations, _stats.suspension_residual);
     SPDLOG_DEBUG("  deposition iterations: {} residual: {}", _stats.deposition_iterations, _stats.deposition_residual);
@@ -307,6 +311,8 @@ void PBSM3D_gpu::run(mesh& domain)
         (*face)["Qsubl"_s] = _Qsubl[i];
         (*face)["Qsubl_mass"_s] = _Qsubl_mass[i];
         (*face)["sum_subl"_s] = _sum_subl[i];
+        if (_c.use_PomLi_probability && _prob[i] != -9999.0)
+            (*face)["blowingsnow_probability"_s] = _prob[i]; // only faces that have saltated carry a value (PBSM3D.cpp:861)
         if (dep)
         { // untouched on steps without a deposition solve (PBSM3D.cpp:1675,1742-1745)
             if (_more[i] > 0)

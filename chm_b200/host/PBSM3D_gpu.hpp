@@ -52,7 +52,7 @@ class PBSM3D_gpu : public module_base
     // One block of 16 arrays, allocated once in init() with pbsm3d_host_alloc.
     double* _stage = nullptr;
     double *_U_R = nullptr, *_U2 = nullptr, *_sd = nullptr, *_swe = nullptr, *_t = nullptr, *_rh = nullptr, *_vw_dir = nullptr,
-           *_fetch = nullptr;
+           *_fetch = nullptr, *_psh = nullptr;
     double *_Qsalt = nullptr, *_Qsusp = nullptr, *_Qsubl = nullptr, *_Qsubl_mass = nullptr, *_sum_subl = nullptr,
-           *_drift_mass = nullptr, *_sum_drift = nullptr, *_more = nullptr;
+           *_drift_mass = nullptr, *_sum_drift = nullptr, *_more = nullptr, *_prob = nullptr;
 };

@@ -153,6 +153,8 @@ class PBSM3D:
         F["snowdepthavg"] = domain["snowdepthavg"] if domain.has("snowdepthavg") else np.full(domain.size_faces(), MISSING)
         if "fetch" in self._depends:
             F["fetch"] = domain["fetch"]
+        if self.cfg.get("use_PomLi_probability", False):
+            F["p_snow_hours"] = domain["p_snow_hours"]  # read whether or not it was declared (PBSM3D.cpp:137-141 vs :853)
         try:
             outs, stats = self.handle.step(domain.dt, F)
         except capi.Pbsm3dError as e:

@@ -88,7 +88,7 @@ typedef struct pbsm3d_config {
     int iterative_subl;           /* false — unsupported if true */
     int use_exp_fetch;            /* false */
     int use_tanh_fetch;           /* true */
-    int use_PomLi_probability;    /* false — unsupported if true */
+    int use_PomLi_probability;    /* false; needs forcing.p_snow_hours */
     int z0_ustar_coupling;        /* false — unsupported if true */
     int use_subgrid_topo;         /* false — unsupported if true */
     int use_subgrid_topo_V2;      /* false — unsupported if true */
@@ -143,6 +143,7 @@ typedef struct pbsm3d_forcing {
     const double* rh;
     const double* vw_dir;
     const double* fetch;          /* may be NULL when neither fetch option is on (1000 m is used) */
+    const double* p_snow_hours;   /* hours since the last snowfall: read iff use_PomLi_probability (PBSM3D.cpp:853), else may be NULL */
 } pbsm3d_forcing;
 
 /* Per-face outputs PBSM3D::run writes back (provides(), PBSM3D.cpp:194-202).  Each [n_local];
@@ -156,6 +157,8 @@ typedef struct pbsm3d_outputs {
     double* drift_mass;           /* unchanged from the previous step when no deposition solve ran */
     double* sum_drift;
     double* pbsm_more_than_avail; /* sticky 0/1 flag */
+    double* blowingsnow_probability; /* use_PomLi_probability: written on the faces that saltate this step (PBSM3D.cpp:861), all
+                                        others keep their previous value (-9999 until first written) */
 } pbsm3d_outputs;
 
 typedef struct pbsm3d_stats {

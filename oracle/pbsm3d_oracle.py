@@ -110,6 +110,7 @@ class State:
     sum_subl: np.ndarray
     drift_mass: np.ndarray  # stale on no-deposition steps (SURVEY a-note 8)
     pbsm_more_than_avail: np.ndarray  # never reset
+    blowingsnow_probability: Optional[np.ndarray] = None  # face variable, written only on saltating faces with use_PomLi_probability
 
 
 @dataclass
@@ -128,6 +129,7 @@ class Assembled:
     hs: np.ndarray
     ustar: np.ndarray
     z0: np.ndarray
+    prob: Optional[np.ndarray] = None  # [T] Pomeroy-Li probability where it was written this step, NaN elsewhere
 
 
 class PBSM3DOracle:
@@ -139,8 +141,7 @@ class PBSM3DOracle:
     def __init__(self, cfg: Config, neigh, geo, global_id, n_global, params: Optional[Dict[str, np.ndarray]] = None,
                  is_water=None):
         # ---- PBSM3D::init (PBSM3D.cpp:221-398)
-        for k in ("iterative_subl", "use_subgrid_topo", "use_subgrid_topo_V2", "use_PomLi_probability",
-                  "z0_ustar_coupling", "debug_output"):
+        for k in ("iterative_subl", "use_subgrid_topo", "use_subgrid_topo_V2", "z0_ustar_coupling", "debug_output"):
             if getattr(cfg, k):
                 raise NotImplementedError(f"optional path {k} is not restated (SURVEY.md §8a-notes)")
         if cfg.use_exp_fetch and cfg.use_tanh_fetch:
@@ -178,7 +179,7 @@ class PBSM3DOracle:
             self.dv = np.zeros(T)
         self.is_water = np.zeros(T, dtype=bool) if is_water is None else np.asarray(is_water, dtype=bool)
         self.face_neigh = self.neigh >= 0  # [T,3]
-        self.state = State(np.zeros(T), np.zeros(T), np.full(T, -9999.0), np.zeros(T))
+        self.state = State(np.zeros(T), np.zeros(T), np.full(T, -9999.0), np.zeros(T), np.full(T, -9999.0))
 
     # ------------------------------------------------------------------ hot loop 1
     def assemble(self, F: Dict[str, np.ndarray], dt: float) -> Assembled:
@@ -228,6 +229,19 @@ class PBSM3DOracle:
         elif cfg.use_tanh_fetch:
             Lc = 0.5 * np.tanh(0.1333333333e-1 * 300.0 - 2.0) + 0.5  # fetch_ref, not fetch: :839-845
             c_salt = np.where(fetch <= 300.0, c_salt * Lc, c_salt)
+        prob = None
+        if cfg.use_PomLi_probability:  # Pomeroy & Li 2000 upscaled probability of blowing snow, :848-866
+            A = np.asarray(F["p_snow_hours"], dtype=np.float64)  # hours since the last snowfall
+            z10 = 10.0 + sd
+            with np.errstate(all="ignore"):
+                u10 = np.where(z10 < Z_U_R, uref * np.log((z10 - (sd + Z0_SNOW)) / Z0_SNOW) / np.log((Z_U_R - (sd + Z0_SNOW)) / Z0_SNOW), uref)  # :451-463
+                u_mean = 11.2 + 0.365 * Tc + 0.00706 * Tc * Tc + 0.9 * np.log(A)  # eqn 10
+                delta = 0.145 * Tc + 0.00196 * Tc * Tc + 4.3  # eqn 11
+                z0v = (self.N * self.dv * height_diff) / 2.0  # eqn 14
+                us = u10 / np.sqrt(1.0 + 340.0 * z0v)  # eqn 13
+                Pu10 = 1.0 / (1.0 + np.exp((np.sqrt(np.pi) * (u_mean - us)) / delta))  # eqn 12
+            prob = np.where(salt, Pu10, np.nan)  # written on every face that entered the saltation block
+            c_salt = c_salt * Pu10
         uhs = 2.8 * ust_th  # :874
         Qsalt = c_salt * uhs * hs  # :877
         mass = np.zeros(T)
@@ -362,7 +376,7 @@ class PBSM3DOracle:
                 d = d + db_
                 below[z] = lo
             diag[z] = d
-        return Assembled(diag, lat, below, above, rhs, u_z_all, csubl_all, Qsalt, c_salt, saltation, hs, ustar, z0)
+        return Assembled(diag, lat, below, above, rhs, u_z_all, csubl_all, Qsalt, c_salt, saltation, hs, ustar, z0, prob)
 
     # ------------------------------------------------------------------ matrices in the reference ordering
     def suspension_csr(self, asm: Assembled, n_cols_ghost: int = 0):
@@ -466,6 +480,8 @@ class PBSM3DOracle:
             x, info["susp_iters"] = solve(A, asm.rhs.reshape(-1), solver, tol)
         Qsusp, Qsubl = self.flux_integrate(x, asm, dt)
         st = self.state
+        if asm.prob is not None:
+            st.blowingsnow_probability = np.where(np.isnan(asm.prob), st.blowingsnow_probability, asm.prob)
         Qsubl_mass = Qsubl * dt
         st.sum_subl = st.sum_subl + Qsubl_mass
         diag, off, drhs = self.deposition_system(F, Qsusp, asm.Qsalt)
@@ -477,7 +493,8 @@ class PBSM3DOracle:
             self.drift_update(q, F, asm.saltation, dt)
         return {"c": x.reshape(L, T), "Qsusp": Qsusp, "Qsalt": asm.Qsalt, "Qsubl": Qsubl, "Qsubl_mass": Qsubl_mass,
                 "sum_subl": st.sum_subl.copy(), "drift_mass": st.drift_mass.copy(), "sum_drift": st.sum_drift.copy(),
-                "pbsm_more_than_avail": st.pbsm_more_than_avail.copy(), "q_dep": q, "asm": asm,
+                "pbsm_more_than_avail": st.pbsm_more_than_avail.copy(), "blowingsnow_probability": st.blowingsnow_probability.copy(),
+                "q_dep": q, "asm": asm,
                 "dep": (diag, off, drhs), "suspension_present": suspension_present,
                 "deposition_present": deposition_present, **info}
 

@@ -13,6 +13,7 @@
      golden_granger1m_L5_default.npz   24 hourly steps, nLayer 5, code defaults (config c1's shape), calm hours at k%8==5
      golden_slope_L10_functest.npz     3 steps, nLayer 10, functional-test PBSM3D block
      golden_variants.npz               every supported config key / vegetation / water / missing-value variant, 2 steps
+     golden_pomli.npz                  use_PomLi_probability with stalk and R94 vegetation, 3 steps (blowingsnow_probability too)
      golden_helpers.npz                the reference's scalar helpers on a sample grid
 
     python tests/golden/make_golden.py
@@ -162,6 +163,27 @@ def run_variants(mesh):
     np.savez_compressed(os.path.join(OUT, "golden_variants.npz"), **out)
 
 
+def run_pomli(mesh):
+    """use_PomLi_probability (PBSM3D.cpp:848-866): stalk vegetation (z0v > 0 on part-buried shrubs) and R94 (N = dv = 0),
+    p_snow_hours from a seeded field; 3 steps so that blowingsnow_probability shows its keep-previous-value behaviour."""
+    geo = mesh.geometry()
+    n = mesh.n_local
+    shrub = synthetic.shrub_params(n, canopy=0.45)  # 0.2-1.5 m of snow: buried, and exposed by less than `cutoff`
+    out = {}
+    for name, r94 in (("pomli_stalks", False), ("pomli_R94", True)):
+        cfg = Config(nLayer=5, use_PomLi_probability=True, use_R94_lambda=r94)
+        ref = chm_ref.ReferencePBSM3D(mesh.vertex, mesh.elem, mesh.neigh, dict(mesh.params, **shrub), cfg_dict(cfg))
+        for k in range(3):
+            F = synthetic.forcing(geo.cx, geo.cy, seed=3, step=k, calm=(k == 1))
+            F["p_snow_hours"] = np.random.default_rng(40 + k).uniform(0.5, 240.0, n)
+            r = ref.step(F, 3600.0)
+            record(out, name + "/", k, r, mesh, 5, k == 0, compact=True)
+            out[f"{name}/blowingsnow_probability_{k}"] = ref.get_var("blowingsnow_probability")
+            out[f"{name}/p_snow_hours_{k}"] = F["p_snow_hours"]
+        ref.close()
+    np.savez_compressed(os.path.join(OUT, "golden_pomli.npz"), **out)
+
+
 def run_helpers():
     rng = np.random.default_rng(5)
     u = rng.uniform(0.5, 25, 200); zout = rng.uniform(0.3, 49, 200); sd = rng.uniform(0, 0.2, 200)
@@ -176,6 +198,11 @@ def run_helpers():
 
 if __name__ == "__main__":
     chm_ref.build()
+    if "--pomli-only" in sys.argv:  # added after the other vectors were committed; those are not regenerated
+        d = np.load(os.path.join(OUT, "granger1m.npz"))
+        run_pomli(TriMesh(d["vertex"], d["elem"], d["neigh"], {k[6:]: d[k] for k in d.files if k.startswith("param_")}))
+        print("ok")
+        sys.exit(0)
     g = read_chm_mesh(f"{REF}/test_data/meshes/granger1m.mesh", [f"{REF}/test_data/meshes/granger1m.param"])
     save_mesh("granger1m", g)
     s = read_chm_mesh(f"{REF}/functional_tests/mesh_versioning/slope.mesh", [f"{REF}/functional_tests/mesh_versioning/slope.param"])
@@ -185,5 +212,6 @@ if __name__ == "__main__":
     run_golden("golden_granger1m_L5_default", g, Config(nLayer=5), 24)
     run_golden("golden_slope_L10_functest", s, Config.functional_test(10), 3)
     run_variants(g)
+    run_pomli(g)
     run_helpers()
     print("ok")

@@ -85,7 +85,7 @@ def test_argument_errors_do_not_need_a_gpu(lib, granger):
         capi.Handle(capi.default_config(use_exp_fetch=1, use_tanh_fetch=1), granger)
     with pytest.raises(capi.Pbsm3dError, match="settling velocity must be positive"):
         capi.Handle(capi.default_config(settling_velocity=-1.0), granger)
-    for k in ("iterative_subl", "use_PomLi_probability", "z0_ustar_coupling", "use_subgrid_topo", "debug_output"):
+    for k in ("iterative_subl", "z0_ustar_coupling", "use_subgrid_topo", "debug_output"):
         with pytest.raises(capi.Pbsm3dError) as e:
             capi.Handle(capi.default_config(**{k: 1}), granger)
         assert e.value.code == 2

@@ -143,7 +143,7 @@ def test_veg_switches_off_without_parameters(granger):
 
 
 def test_unsupported_options_raise(granger):
-    for k in ("iterative_subl", "use_subgrid_topo", "use_PomLi_probability", "z0_ustar_coupling", "debug_output"):
+    for k in ("iterative_subl", "use_subgrid_topo", "z0_ustar_coupling", "debug_output"):
         with pytest.raises(NotImplementedError):
             make(granger, Config(**{k: True}))
     with pytest.raises(ValueError):
