@@ -12,16 +12,20 @@
  *   NearestNeighborProblem ctor        LinearAlgebra.cpp:31-197 pbsm3d_create (static sparsity = mesh adjacency)
  *   PBSM3D::run(mesh&)                 PBSM3D.cpp:400-1748      pbsm3d_step / pbsm3d_step_device
  *   NearestNeighborProblem::Solve      LinearAlgebra.cpp:228-252  (inside pbsm3d_step)
- *   ghost_neighbors_communicate_variable  triangulation.cpp:1976-2079  (inside pbsm3d_step, NCCL)
+ *   ghost_neighbors_communicate_variable  triangulation.cpp:1976-2079  (inside pbsm3d_step: peer memory over NVLink, NCCL fallback)
  *   getSolutionView                    LinearAlgebra.cpp:272-275  pbsm3d_get_solution
  *   writeSystemMatrixMarket (debug)    LinearAlgebra.cpp:277-287  pbsm3d_get_suspension_system / _deposition_system
  *   PBSM3D::checkpoint/load_checkpoint PBSM3D.cpp:1753-1773     pbsm3d_get_state / pbsm3d_set_state
  *   ~PBSM3D                                                     pbsm3d_destroy
+ *   scale_wind_vert::run(mesh&)        scale_wind_vert.cpp:167-229  pbsm3d_scale_wind_vert   } the providers of two PBSM3D inputs,
+ *   fetchr::run(face), every face      fetchr.cpp:54-119            pbsm3d_fetchr            } optionally fused into the step
+ *                                                                   (pbsm3d_set_providers)
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
  * code on failure with a message available from pbsm3d_last_error() (the adaptor turns it into
  * CHM's module_error).  The caller owns all host buffers; the library owns all device memory.
- * A handle is bound to one CUDA device and is not re-entrant.  All floating point is fp64.
+ * A handle is bound to one CUDA device and is not re-entrant.  All floating point is fp64 (pbsm3d_config.fp32_sweep_streams
+ * concerns the storage of coefficient copies the early sweeps read, not the arithmetic or the stopping rule).
  * There is no CPU fallback: without a CUDA device pbsm3d_create fails.
  */
 #ifndef PBSM3D_B200_H
@@ -136,13 +140,13 @@ typedef struct pbsm3d_comm {
  * (PBSM3D.cpp:436-449,468,670,880,927).  Each is [n_local]; -9999 / NaN mean "missing" as in CHM. */
 typedef struct pbsm3d_forcing {
     const double* U_R;
-    const double* U_2m_above_srf;
+    const double* U_2m_above_srf; /* may be NULL after pbsm3d_set_providers (derived on the device from U_R, snowdepthavg) */
     const double* snowdepthavg;
     const double* swe;
     const double* t;
     const double* rh;
     const double* vw_dir;
-    const double* fetch;          /* may be NULL when neither fetch option is on (1000 m is used) */
+    const double* fetch;          /* may be NULL when neither fetch option is on (1000 m is used), or after pbsm3d_set_providers */
     const double* p_snow_hours;   /* hours since the last snowfall: read iff use_PomLi_probability (PBSM3D.cpp:853), else may be NULL */
 } pbsm3d_forcing;
 
