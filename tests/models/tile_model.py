@@ -1,5 +1,5 @@
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla, sys, time
-sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 from chm_b200 import synthetic
 from oracle.pbsm3d_oracle import Config, PBSM3DOracle
 
