@@ -17,7 +17,7 @@ def greedy(neigh):
     return col
 
 
-def run(ntri, tile, ks, L=10):
+def run(ntri, tile, ks, L=10, strips=False):
     mesh = synthetic.variable_mesh(ntri); T = mesh.n_local
     geo = mesh.geometry()
     o = PBSM3DOracle(Config.functional_test(L), mesh.neigh, geo, mesh.global_id, mesh.n_global, mesh.params)
@@ -51,12 +51,13 @@ def run(ntri, tile, ks, L=10):
     for k in range(300):
         sweep(allf, x)
         if resid(x) <= 1e-8: kg = k + 1; break
-    tid = np.arange(T) // tile
+    # tiles: runs of consecutive faces in Morton order, or (strips) bins of the centroid's projection on the mean wind
+    tid = (np.argsort(np.argsort(geo.cx[:T])) // tile) if strips else (np.arange(T) // tile)
     ntile = tid.max() + 1
     # mean wind blows towards (-cos, -sin)(450 - 270) = +x: order tiles by mean centroid x
     order = np.argsort([geo.cx[:T][tid == t].mean() for t in range(ntile)])
     members = [np.where(tid == t)[0] for t in range(ntile)]
-    print(f"variable mesh T={T} colours {nc}: global multicolour GS sweeps {kg}; {ntile} tiles of {tile} faces")
+    print(f"variable mesh T={T} colours {nc}: global multicolour GS sweeps {kg}; {ntile} {'wind-perpendicular strips' if strips else 'Morton-run tiles'} of {tile} faces")
     for kin in ks:
         x = np.zeros((L, T)); kout = None
         for it in range(80):
@@ -68,3 +69,4 @@ def run(ntri, tile, ks, L=10):
 
 if __name__ == "__main__":
     run(30000, 400, (2, 4, 8, 12))
+    run(30000, 400, (4, 8), strips=True)
