@@ -324,3 +324,21 @@ def test_fp32_sweep_streams_do_not_move_the_answer(slope):
     assert rel_l2(res[1][0], res[0][0]) <= 1e-9
     for v in ("Qsusp", "drift_mass"):
         assert rel_l2(res[1][1][v], res[0][1][v]) <= 1e-8
+
+
+@pytest.mark.parametrize("L", [15, 20, 12])
+def test_all_layer_count_specialisations(slope, L):
+    """nLayer 15 and 20 have compile-time sweep/residual kernels of their own (config c5 uses 20), 12 takes the generic path; each on
+    fp64 and fp32-rounded sweep streams (the latter start with the second step of a handle)."""
+    geo = slope.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy, seed=11)
+    r = oracle_for(slope, Config.functional_test(L)).step(F, 3600.0)
+    h = capi.Handle(capi.default_config(tolerance=1e-10, **functest_kw(L)), slope)
+    for rep in range(3):
+        outs, st = h.step(3600.0, F)
+        assert st["suspension_residual"] <= 1e-10
+        assert rel_l2(h.solution(), r["c"]) <= 1e-8, (L, rep)
+        for v in ("Qsusp", "Qsalt", "Qsubl", "drift_mass"):
+            assert rel_l2(outs[v], r[v]) <= 1e-7, (L, rep, v)
+    assert st["sweeps_timed_fp32"] > 0
+    h.close()
