@@ -342,3 +342,23 @@ def test_all_layer_count_specialisations(slope, L):
             assert rel_l2(outs[v], r[v]) <= 1e-7, (L, rep, v)
     assert st["sweeps_timed_fp32"] > 0
     h.close()
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (2, 3), (5, 4)])
+def test_tiny_meshes(nx, ny):
+    """2, 12 and 40 faces: fewer faces than a warp, every face on the hull, a spectrum estimate with next to no Krylov space."""
+    mesh = synthetic.uniform_mesh(nx, ny)
+    geo = mesh.geometry()
+    F = synthetic.forcing(geo.cx, geo.cy, seed=2)
+    F["U_R"] = np.full(mesh.n_local, 14.0)
+    F["U_2m_above_srf"] = np.full(mesh.n_local, 9.0)
+    r = oracle_for(mesh, Config.functional_test(5)).step(F, 3600.0)
+    h = capi.Handle(capi.default_config(tolerance=1e-10, **functest_kw(5)), mesh)
+    for rep in range(2):
+        outs, st = h.step(3600.0, F)
+        assert st["suspension_present"] == int(r["suspension_present"]) and st["deposition_present"] == int(r["deposition_present"])
+        assert rel_l2(h.solution(), r["c"]) <= 1e-8
+        for v in ("Qsusp", "Qsalt", "drift_mass"):
+            assert rel_l2(outs[v], r[v]) <= 1e-7, v
+    assert np.array_equal(h.fetchr(F["vw_dir"]), __import__("oracle.wind_oracle", fromlist=["fetchr"]).fetchr(F["vw_dir"], geo.cx, geo.cy, geo.cz, None))
+    h.close()
