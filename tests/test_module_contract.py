@@ -36,3 +36,22 @@ def test_domain_store_defaults_to_missing(granger):
         d["nope"]
     with pytest.raises(module_error, match="before init"):
         PBSM3D({}).run(d)
+
+
+def test_provider_mirrors_declare_the_reference_contract():
+    """scale_wind_vert.cpp:27-45 and fetchr.cpp:27-49: depends / optional / provides and config keys (no GPU needed)."""
+    from chm_b200 import module
+    sw = module.scale_wind_vert()
+    assert sw.get_depends() == ["U_R"] and sw.get_optionals() == ["snowdepthavg"] and sw.get_provides() == ["U_2m_above_srf"]
+    assert sw.parallel == "domain" and module.scale_wind_vert(point_mode=True).parallel == "data"
+    assert module.scale_wind_vert({"ignore_canopy": "true"}).wind_cfg_kw["ignore_canopy"] == 1
+    fe = module.fetchr()
+    assert fe.get_depends() == ["vw_dir"] and fe.get_provides() == ["fetch"] and fe.parallel == "data"
+    assert fe.wind_cfg_kw == dict(fetch_steps=10, fetch_max_distance=1000.0, fetch_I=0.06, fetch_incl_veg=1)
+    assert module.fetchr({"steps": "7", "max_distance": "650", "I": "0.03", "incl_veg": "false"}).wind_cfg_kw == \
+        dict(fetch_steps=7, fetch_max_distance=650.0, fetch_I=0.03, fetch_incl_veg=0)
+    import pytest
+    with pytest.raises(module.module_error):
+        module.scale_wind_vert({"ignore_canopi": True})
+    with pytest.raises(module.module_error):  # run before the PBSM3D handle exists
+        module.fetchr().run(module.Domain.__new__(module.Domain), module.PBSM3D({"nLayer": 5}))
