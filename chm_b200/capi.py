@@ -24,7 +24,7 @@ c_uint8_p = C.POINTER(C.c_uint8)
 SOLVER_AUTO, SOLVER_LINE, SOLVER_BICGSTAB = 0, 1, 2
 DEP_AUTO, DEP_CG, DEP_CHEBYSHEV, DEP_SOR = 0, 1, 2, 3
 HALO_NONE, HALO_NCCL, HALO_PEER = 0, 1, 2
-ABI_VERSION = 3  # include/pbsm3d.h PBSM3D_ABI_VERSION
+ABI_VERSION = 4  # include/pbsm3d.h PBSM3D_ABI_VERSION
 ERR_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "NOCONVERGE"}
 
 
@@ -47,7 +47,7 @@ class Mesh(C.Structure):
         ("n_global", C.c_int64), ("n_local", C.c_int32), ("n_ghost", C.c_int32),
         ("global_id", c_int64_p), ("ghost_owner", c_int32_p), ("neigh", c_int32_p), ("vertices", c_double_p),
         ("area", c_double_p), ("canopy_height", c_double_p), ("lai", c_double_p), ("stalk_number", c_double_p),
-        ("stalk_diameter", c_double_p), ("is_water", c_uint8_p),
+        ("stalk_diameter", c_double_p), ("is_water", c_uint8_p), ("is_geographic", C.c_int32),
     ]
 
 
@@ -217,6 +217,7 @@ class Handle:
         m.stalk_number = _dp(arr(p["stalk_number"], np.float64)) if "stalk_number" in p else None
         m.stalk_diameter = _dp(arr(p["stalk_diameter"], np.float64)) if "stalk_diameter" in p else None
         m.is_water = arr(is_water, np.uint8).ctypes.data_as(c_uint8_p) if is_water is not None else None
+        m.is_geographic = 1 if getattr(mesh, "is_geographic", False) else 0
         comm = None
         if n_ranks > 1:
             self._uid = C.create_string_buffer(unique_id, 128)

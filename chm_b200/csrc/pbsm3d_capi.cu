@@ -182,6 +182,7 @@ struct pbsm3d_handle {
     CellGrid grid{};
     int* grid_start = nullptr;
     double2 *grid_xy = nullptr, *grid_zc = nullptr;
+    bool geographic = false;                          // pbsm3d_mesh.is_geographic: dx of the deposition matrix is a haversine distance
     bool providers_on = false;                        // pbsm3d_set_providers: the step derives missing inputs itself
     pbsm3d_wind_config wind_cfg{};
     float ms_providers = 0.f;
@@ -192,6 +193,9 @@ struct pbsm3d_handle {
     cudaEvent_t ev[6] = {nullptr};
     cudaEvent_t ev_sw[3] = {nullptr};
     int sweeps_timed = 0, sweeps_timed32 = 0;
+    int asm_nw = 0, asm_grid = 1;  // assembly: warps per block of the tile kernel (0 = column kernel), persistent grid size
+    size_t asm_smem = 0;
+    void* asm_fn = nullptr;
     int pred_n32 = 0;  // leading sweeps of the next solve that may stream fp32 coefficient copies
     bool have_system = false;
     long long n_launch = 0;
@@ -1235,10 +1239,50 @@ int enqueue_finish(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTa
 }
 
 // Assembly of CHM faces [i0, i1); its {max|b|, sum b^2} go to red[2*chunk ..].
+// The layer-parallel tile kernel runs with one warp per layer (nLayer <= 32; block sizes 4/5/8/10/16/20/32 warps, surplus warps
+// only keep the barriers); deeper columns, or PBSM3D_ASSEMBLY=column, take the column-walking kernel.
+using AsmKernel = void (*)(DevConfig, DevMesh, DevForcing, SuspSystem, double, int, int, double*, int, Scalars*, double*);
+template <int NW, int MINB>
+int setup_assembly_nw(pbsm3d_handle* h) {
+    h->asm_nw = NW;
+    h->asm_fn = (void*)(AsmKernel)assemble_tile_kernel<NW, MINB>;
+    h->asm_smem = (size_t)(kRecD * 32 + 32 + 3 * h->L * 32) * sizeof(double);
+    CU(cudaFuncSetAttribute(assemble_tile_kernel<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->asm_smem));
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, assemble_tile_kernel<NW, MINB>, NW * 32, h->asm_smem));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    h->asm_grid = std::max(1, std::min(kRedBlocks, std::max(nb, 1) * prop.multiProcessorCount));
+    if (getenv("PBSM3D_VERBOSE"))
+        fprintf(stderr, "[pbsm3d] assembly: tile kernel, %d warps per block, %d blocks per SM, grid %d\n", NW, nb, h->asm_grid);
+    return 0;
+}
+int setup_assembly(pbsm3d_handle* h) {
+    const char* want = getenv("PBSM3D_ASSEMBLY");
+    const char* mb = getenv("PBSM3D_ASM_MINB");  // tuning knob: resident blocks per SM the tile kernel is compiled for
+    const int minb = mb ? atoi(mb) : 0;
+    h->asm_nw = 0;
+    if ((want && std::string(want) == "column") || h->L > 32) return 0;
+    const int L = h->L;
+    if (L <= 4) return setup_assembly_nw<4, 4>(h);
+    if (L <= 5) return setup_assembly_nw<5, 4>(h);
+    if (L <= 8) return setup_assembly_nw<8, 3>(h);
+    if (L <= 10) return minb == 2 ? setup_assembly_nw<10, 2>(h) : (minb == 4 ? setup_assembly_nw<10, 4>(h) : setup_assembly_nw<10, 3>(h));
+    if (L <= 16) return setup_assembly_nw<16, 2>(h);
+    if (L <= 20) return setup_assembly_nw<20, 1>(h);
+    return setup_assembly_nw<32, 1>(h);
+}
 void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt, int i0, int i1, int chunk) {
-    const int ntiles = cdiv((size_t)(i1 - i0), 128);
-    LAUNCH(h, assemble_kernel, std::max(1, std::min(ntiles, kRedBlocks)), 128, h->dc, h->dm, f, h->ss, dt, i0, i1, h->partial,
-           kRedBlocks, h->sc, h->red + 2 * chunk);
+    if (h->asm_nw == 0) {
+        const int ntiles = cdiv((size_t)(i1 - i0), 128);
+        LAUNCH(h, assemble_kernel, std::max(1, std::min(ntiles, kRedBlocks)), 128, h->dc, h->dm, f, h->ss, dt, i0, i1, h->partial,
+               kRedBlocks, h->sc, h->red + 2 * chunk);
+        return;
+    }
+    const int grid = std::max(1, std::min(cdiv((size_t)(i1 - i0), 32), h->asm_grid));
+    ++h->n_launch;
+    ((AsmKernel)h->asm_fn)<<<grid, h->asm_nw * 32, h->asm_smem, h->stream>>>(h->dc, h->dm, f, h->ss, dt, i0, i1, h->partial, kRedBlocks,
+                                                                            h->sc, h->red + 2 * chunk);
 }
 
 // One PBSM3D::run with device-resident forcing (reference PBSM3D.cpp:400-1748, phases A–I of SURVEY §3.2).
@@ -1314,6 +1358,9 @@ int ensure_grid(pbsm3d_handle* h) {
     return 0;
 }
 int enqueue_fetchr(pbsm3d_handle* h, const pbsm3d_wind_config* wc, const double* vw_dir, double* out) {
+    // On a geographic mesh the reference walks up-wind with point_from_bearing_latlong, which returns (lat, lon) where the
+    // kd-tree expects (x = lon, y = lat) (coordinates.cpp:33-61): not a behaviour worth reproducing -- refuse, never guess.
+    if (h->geographic) return fail(PBSM3D_ERR_UNSUPPORTED, "fetchr on a geographic (lat/long) mesh is not implemented");
     if (wc->fetch_steps < 1 || !(wc->fetch_max_distance > 0)) return fail(PBSM3D_ERR_INVALID, "fetchr: steps and max_distance must be positive");
     TRY(ensure_grid(h));
     LAUNCH(h, fetchr_kernel, cdiv(h->T, 128), 128, h->T, h->iperm, h->grid, h->cx, h->cy, h->cz, h->wv_canopy, vw_dir, wc->fetch_steps,
@@ -1722,7 +1769,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     if (cfg->use_exp_fetch && cfg->use_tanh_fetch)
         return fail(PBSM3D_ERR_INVALID, "PBSM3d: Cannot specify both exp_fetch and tanh_fetch");  // PBSM3D.cpp:132-135
     if (cfg->settling_velocity < 0) return fail(PBSM3D_ERR_INVALID, "PBSM3D settling velocity must be positive");  // :239-242
-    if (cfg->nLayer < 2) return fail(PBSM3D_ERR_INVALID, "nLayer must be >= 2 (top and bottom layers are distinct rows)");
+    if (cfg->nLayer < 1) return fail(PBSM3D_ERR_INVALID, "nLayer must be >= 1");  // nLayer == 1: only the z == 0 branch runs (PBSM3D.cpp:1285-1321)
     if (cfg->iterative_subl) return fail(PBSM3D_ERR_UNSUPPORTED, "iterative_subl is not implemented");
     if (cfg->z0_ustar_coupling) return fail(PBSM3D_ERR_UNSUPPORTED, "z0_ustar_coupling is not implemented");
     if (cfg->use_subgrid_topo || cfg->use_subgrid_topo_V2) return fail(PBSM3D_ERR_UNSUPPORTED, "use_subgrid_topo* is not implemented");
@@ -1741,6 +1788,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     h->cfg = *cfg;
     const int T = h->T = mesh->n_local, nG = h->nG = mesh->n_ghost, L = h->L = cfg->nLayer;
     h->G = mesh->n_global;
+    h->geographic = mesh->is_geographic != 0;
     h->rank = comm ? comm->rank : 0;
     h->n_ranks = comm ? comm->n_ranks : 1;
     if (h->n_ranks > 1 && !comm->nccl_unique_id) return fail(PBSM3D_ERR_INVALID, "nccl_unique_id missing");
@@ -1877,7 +1925,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
         TRY(h->alloc(&h->ddiag, Tp));
         TRY(h->alloc(&h->doff, (size_t)3 * Tp));
         TRY(h->alloc(&h->dinv, Tp));
-        LAUNCH(h, deposition_matrix_kernel, cdiv(Tp, 256), 256, Tp, cfg->smooth_coeff, h->perm, h->nbs, h->elen, h->area, h->cx, h->cy,
+        LAUNCH(h, deposition_matrix_kernel, cdiv(Tp, 256), 256, Tp, cfg->smooth_coeff, h->geographic ? 1 : 0, h->perm, h->nbs, h->elen, h->area, h->cx, h->cy,
                h->dx, h->ddiag, h->doff, h->dinv);
         CU(cudaStreamSynchronize(h->stream));
         CU(cudaGetLastError());
@@ -1910,12 +1958,8 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     for (auto& b : h->forcing_buf) TRY(h->alloc(&b, T));
     SuspSystem& ss = h->ss;
     const size_t N = h->N;
-    TRY(h->alloc(&ss.diag, N));
-    TRY(h->alloc(&ss.below, N));
-    TRY(h->alloc(&ss.above, N));
-    TRY(h->alloc(&ss.lat, 3 * N));
+    TRY(h->alloc(&ss.den, N));
     TRY(h->alloc(&ss.cp, N));
-    TRY(h->alloc(&ss.inv, N));
     TRY(h->alloc(&ss.latS, 3 * N));
     TRY(h->alloc(&ss.belowS, N));
     TRY(h->alloc(&ss.pack32, N));
@@ -1982,6 +2026,13 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     dm.stalk_dv = h->stalk_dv;
     dm.water = h->water;
 
+    {   // per-layer constants of a column with hs = 0 (every non-saltating face)
+        double* tab = nullptr;
+        TRY(h->alloc(&tab, (size_t)kTabN * L));
+        LAUNCH(h, layer_table_kernel, 1, std::max(32, align_up(L, 32)), h->dc, tab);
+        h->ss.ltab = tab;
+    }
+    TRY(setup_assembly(h));
     LAUNCH(h, assemble_pads_kernel, cdiv(Tp, 256), 256, h->dm, h->ss, L);
     if (h->n_ranks > 1) TRY(setup_comm(h, iperm));
     CU(cudaStreamSynchronize(h->stream));
@@ -2007,8 +2058,9 @@ int pbsm3d_create(const pbsm3d_config* cfg, const pbsm3d_mesh* mesh, int device,
 }
 
 static bool forcing_complete(const pbsm3d_handle* h, const pbsm3d_forcing* f) {
+    const bool fetch_on = h->cfg.use_exp_fetch || h->cfg.use_tanh_fetch;  // depends("fetch"), PBSM3D.cpp:181-184
     return f->U_R && (f->U_2m_above_srf || h->providers_on) && f->snowdepthavg && f->swe && f->t && f->rh && f->vw_dir &&
-           (f->p_snow_hours || !h->cfg.use_PomLi_probability);
+           (f->fetch || !fetch_on || h->providers_on) && (f->p_snow_hours || !h->cfg.use_PomLi_probability);
 }
 static void out_pointers(const pbsm3d_outputs* o, double* p[kOut]) {
     p[0] = o->Qsalt; p[1] = o->Qsusp; p[2] = o->Qsubl; p[3] = o->Qsubl_mass; p[4] = o->sum_subl; p[5] = o->drift_mass;
@@ -2114,10 +2166,18 @@ int pbsm3d_get_suspension_system(pbsm3d_handle* h, double* diag, double* lat, do
     CU(cudaSetDevice(h->device));
     const size_t Tp = h->Tp;
     const int L = h->L;
-    TRY(fetch_chm(h, diag, h->ss.diag, L, Tp));
-    TRY(fetch_chm(h, lat, h->ss.lat, 3 * L, Tp));
-    TRY(fetch_chm(h, below, h->ss.below, L, Tp));
-    TRY(fetch_chm(h, above, h->ss.above, L, Tp));
+    if (diag || lat || below || above) {  // the reference's own coefficients from the stored pivots and scaled rows
+        double* tmp = nullptr;
+        const size_t N = h->N;
+        TRY(h->alloc(&tmp, 6 * N));
+        LAUNCH(h, reconstruct_rows_kernel, cdiv(Tp, 128), 128, h->ss, (int)Tp, L, tmp, tmp + N, tmp + 4 * N, tmp + 5 * N);
+        int rc = fetch_chm(h, diag, tmp, L, Tp);
+        if (!rc) rc = fetch_chm(h, lat, tmp + N, 3 * L, Tp);
+        if (!rc) rc = fetch_chm(h, below, tmp + 4 * N, L, Tp);
+        if (!rc) rc = fetch_chm(h, above, tmp + 5 * N, L, Tp);
+        h->release(tmp);
+        if (rc) return rc;
+    }
     TRY(fetch_chm(h, rhs0, h->ss.rhs0, 1, Tp));
     TRY(fetch_chm(h, u_z, h->ss.u_z, L, Tp));
     TRY(fetch_chm(h, csubl, h->ss.csubl, L, Tp));

@@ -52,19 +52,21 @@ struct DevForcing {  // CHM order, [T]
 };
 
 struct SuspSystem {
-    double *diag, *below, *above;  // [L][Tp]   the assembled rows (reference values)
-    double* lat;                   // [3][L][Tp]
-    double *cp, *inv;              // [L][Tp]   Thomas factors of the vertical (column) blocks
-    double* latS;                  // [3][L][Tp] lat * inv   } the row-scaled copies the line sweep streams
-    double* belowS;                // [L][Tp]   below * inv  }
+    // The assembled suspension system in the form the line solver uses (see "assembly" below): Thomas pivots and row-scaled
+    // coefficients; the reference's diag/lat/below/above follow from them (reconstruct_rows_kernel).
+    double* den;                   // [L][Tp]   den_z = d_z - lo_z cp_{z-1}
+    double* cp;                    // [L][Tp]   up_z / den_z
+    double* latS;                  // [3][L][Tp] lat_j / den
+    double* belowS;                // [L][Tp]   lo / den
     float4* pack32;                // [L][Tp] {latS_0, latS_1, latS_2, belowS} rounded to fp32, one 16-byte load per row: what the
     float* cp32;                   // [L][Tp] sweeps far from convergence stream instead of the five fp64 arrays above
     double* rhs0;                  // [Tp]      b of layer 0 (all other layers are 0)
-    double* rhsS0;                 // [Tp]      rhs0 * inv[0]
+    double* rhsS0;                 // [Tp]      rhs0 / den[0]
     double *u_z, *csubl;           // [L][Tp]
     double *Qsalt, *c_salt;        // [Tp]
     unsigned char* salt;           // [Tp]
     double* prob;                  // [Tp] blowingsnow_probability (face variable; written on saltating faces with use_PomLi_probability)
+    const double* ltab;            // [kTabN][L] per-layer constants of a column with hs = 0 (layer_table_kernel)
 };
 
 // Device-resident control block: recurrence scalars, convergence flags and the tickets of the fused
@@ -191,9 +193,20 @@ __global__ void geometry_kernel(int T, int Tp, int nG, const int* __restrict__ p
 }
 
 // Static part of the deposition system (reference re-derives it every step, PBSM3D.cpp:1546,1609-1628):
-// diag = area + sum eps*E_j/dx_j, off_j = -eps*E_j/dx_j, dx_j = 2-D centroid distance (coordinates.cpp:100-106).
+// diag = area + sum eps*E_j/dx_j, off_j = -eps*E_j/dx_j, dx_j = math::gis::distance of the two centroids: 2-D Euclidean on a
+// projected mesh (distance_UTM, coordinates.cpp:94-100), haversine on a geographic one (distance_latlong, :68-92).
 // cx/cy are [Tp + nG], so a neighbour that is a ghost face resolves like any other.
-__global__ void deposition_matrix_kernel(int Tp, double eps, const int* __restrict__ perm, const int* __restrict__ nbs,
+// math::gis::distance_latlong (coordinates.cpp:68-92): haversine on a sphere of radius 6378137 m, x = longitude, y = latitude
+// in degrees.  What core.cpp:809-821 installs as math::gis::distance on a geographic mesh.
+__device__ __forceinline__ double distance_latlong(double x1, double y1, double x2, double y2) {
+    const double d2r = kPi / 180.0;
+    const double lat1 = y1 * d2r, lon1 = x1 * d2r, lat2 = y2 * d2r, lon2 = x2 * d2r;
+    const double dphi = lat2 - lat1, dlon = lon2 - lon1;
+    const double sp = sin(dphi / 2.), sl = sin(dlon / 2.);
+    const double a = sp * sp + cos(lat1) * cos(lat2) * sl * sl;
+    return 6378137.0 * (2. * atan2(sqrt(a), sqrt(1. - a)));
+}
+__global__ void deposition_matrix_kernel(int Tp, double eps, int geographic, const int* __restrict__ perm, const int* __restrict__ nbs,
                                          const double* __restrict__ elen, const double* __restrict__ area,
                                          const double* __restrict__ cx, const double* __restrict__ cy, double* __restrict__ dx,
                                          double* __restrict__ ddiag, double* __restrict__ doff, double* __restrict__ dinv) {
@@ -206,8 +219,12 @@ __global__ void deposition_matrix_kernel(int Tp, double eps, const int* __restri
         int n = nbs[(size_t)j * Tp + p];
         double dist = 2.0, c = 0.0;  // dx[] default 2.0, PBSM3D.cpp:1534
         if (n != p && !pad) {
-            double ddx = __dsub_rn(cx[p], cx[n]), ddy = __dsub_rn(cy[p], cy[n]);
-            dist = __dsqrt_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+            if (geographic) {
+                dist = distance_latlong(cx[p], cy[p], cx[n], cy[n]);
+            } else {
+                double ddx = __dsub_rn(cx[p], cx[n]), ddy = __dsub_rn(cy[p], cy[n]);
+                dist = __dsqrt_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+            }
             c = __ddiv_rn(__dmul_rn(eps, elen[(size_t)j * Tp + p]), dist);
         }
         dx[(size_t)j * Tp + p] = dist;
@@ -292,12 +309,17 @@ __device__ __forceinline__ bool grid_fold(double v0, double v1, int op0, int op1
 }
 
 // ------------------------------------------------------------------------------------------- assembly
-// HOT LOOP 1: saltation + every layer of one face column (reference PBSM3D.cpp:436-1406), fused with the
-// forward elimination of that column's tridiagonal block (the line-solver factor), the row scaling the sweep
-// streams, and the two global facts the step needs next: max|b| (suspension_present, PBSM3D.cpp:1424-1427)
-// and ||b||^2 (the stopping rule of LinearAlgebra.cpp:168).
-// One thread per slot; for each layer the 32 lanes of a warp write 32 consecutive doubles of every output
-// stream.  Replaces ≈11 Tpetra sumIntoGlobalValues hash lookups per row by direct ELL stores.
+// HOT LOOP 1: saltation + suspension assembly (reference PBSM3D.cpp:436-1406) fused with the forward elimination of every
+// column's tridiagonal block (the line-solver factor), the row scaling the sweep streams, and the two global facts the step
+// needs next: max|b| (suspension_present, PBSM3D.cpp:1424-1427) and ||b||^2 (the stopping rule of LinearAlgebra.cpp:168).
+//
+// What is stored per row (84 B; the reference's own values are recovered on demand, see row_of_A below):
+//     den  = d - lo*cp_{z-1}   (Thomas pivot)          cp     = up / den
+//     latS = lat_j / den  (3)                          belowS = lo / den
+//     pack32 = {latS_0..2, belowS} and cp32 rounded to fp32 (what the sweeps far from convergence stream)
+//     u_z, csubl (flux integration)
+// with  diag = den (1 + belowS cp_{z-1}),  below = belowS den,  above = cp den,  lat_j = latS_j den.
+//
 // Padding slots are identity rows with a zero right-hand side; written once in pbsm3d_create.
 __global__ void assemble_pads_kernel(DevMesh m, SuspSystem s, int L) {
     const int Tp = m.Tp;
@@ -306,245 +328,452 @@ __global__ void assemble_pads_kernel(DevMesh m, SuspSystem s, int L) {
     s.Qsalt[p] = 0.0; s.c_salt[p] = 0.0; s.salt[p] = 0; s.rhs0[p] = 0.0; s.rhsS0[p] = 0.0;
     for (int z = 0; z < L; ++z) {
         const size_t r = (size_t)z * Tp + p;
-        s.diag[r] = 1.0; s.below[r] = 0.0; s.above[r] = 0.0; s.inv[r] = 1.0; s.cp[r] = 0.0; s.belowS[r] = 0.0;
+        s.den[r] = 1.0; s.cp[r] = 0.0; s.belowS[r] = 0.0;
         s.cp32[r] = 0.f; s.pack32[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         s.u_z[r] = 0.0; s.csubl[r] = 0.0;
-        for (int j = 0; j < 3; ++j) { s.lat[((size_t)j * L + z) * Tp + p] = 0.0; s.latS[((size_t)j * L + z) * Tp + p] = 0.0; }
+        for (int j = 0; j < 3; ++j) s.latS[((size_t)j * L + z) * Tp + p] = 0.0;
     }
 }
 
-// One face column: CHM face i (forcing index), slot p (everything else).  Returns b of layer 0.
-__device__ __forceinline__ double assemble_column(const DevConfig& c, const DevMesh& m, const DevForcing& f, const SuspSystem& s,
+// ---- what depends on the height above the saltation layer only (PBSM3D.cpp:1003-1039, 1156-1158)
+struct LayerConsts {
+    double cz;       // z*dz + hs + dz/2
+    double inv_mm;   // 1 / mean particle mass
+    double r_z;      // mean particle radius
+    double omega;    // settling velocity
+    double Qr;       // radiative term of the sublimation model
+    double sig;      // 1.019 + 0.027 ln cz
+    double lmix;     // mixing length
+    double ulog;     // ln((cz - z0)/z0): the log-profile factor of u_z
+};
+constexpr int kTabN = 8;  // doubles per layer in SuspSystem::ltab (LayerConsts, field order)
+
+// x^y for x > 0 as exp(y log x): |y log x| < 40 on every use below, so the result is within ~1e-14 relative of pow() (the
+// parity bar on coefficients is 1e-12) at a fraction of pow()'s fp64 cost.
+__device__ __forceinline__ LayerConsts layer_consts(const DevConfig& c, double cz, double sd) {
+    LayerConsts o;
+    o.cz = cz;
+    const double lcz = log(cz);
+    const double lrm = -0.258 * lcz;                        // rm = 4.6e-5 cz^-0.258 (:1009)
+    const double rm = 4.6e-5 * exp(lrm);
+    const double mm_alpha = 4.08 + 12.6 * cz;               // :1012
+    const double P = 1.0 + 3.0 / mm_alpha + 2.0 / (mm_alpha * mm_alpha);
+    const double mm = 4.0 / 3.0 * kPi * kRhoIce * rm * rm * rm * P;  // :1013-1014
+    o.inv_mm = 1.0 / mm;
+    // r_z = (3 mm / (4 pi rho_p))^0.3333333 (:1017, the literal exponent) = (rm^3 P)^(1/3 - e), e = 1/3 - 0.3333333:
+    //     = rm cbrt(P) exp(-e ln(rm^3 P)); the last factor is 1 + O(1e-6), so ln(rm^3 P) is needed to ~1e-9 only.
+    {
+        const double e = 1.0 / 3.0 - 0.3333333;
+        const double l3 = 3.0 * (log(4.6e-5) + lrm) + (double)__logf((float)P);
+        const double t = -e * l3;  // |t| < 2e-6: three terms of exp() are exact to 1e-19
+        o.r_z = rm * cbrt(P) * (1.0 + t * (1.0 + t * (0.5 + t * (1.0 / 6.0))));
+    }
+    o.omega = c.do_fixed_settling ? c.settling_velocity : 1.1e7 * exp(1.8 * log(o.r_z));  // :1024-1033
+    o.Qr = 0.9 * kPi * rm * rm * 120.0;                     // :1097
+    o.sig = 1.019 + 0.027 * lcz;                            // :1095
+    o.lmix = kKappa * (cz + kZ0Snow) * c.l_max / (kKappa * (cz + kZ0Snow) + c.l_max);  // :1156
+    o.ulog = log(((cz + sd) - (sd + kZ0Snow)) / kZ0Snow);   // :970-976 with hz = cz + sd
+    return o;
+}
+// Table of LayerConsts for hs = 0 (every non-saltating face: hs = 0, z0 = Z0_SNOW), built once in pbsm3d_create by
+// the same device code the saltating faces run per row.
+__global__ void layer_table_kernel(DevConfig c, double* __restrict__ tab) {
+    const int z = threadIdx.x;
+    if (z >= c.L) return;
+    const LayerConsts o = layer_consts(c, z * c.dz + 0.0 + c.dz / 2.0, 0.0);
+    const double v[kTabN] = {o.cz, o.inv_mm, o.r_z, o.omega, o.Qr, o.sig, o.lmix, o.ulog};
+    for (int k = 0; k < kTabN; ++k) tab[k * c.L + z] = v[k];
+}
+
+// ---- per-face part: saltation (PBSM3D.cpp:436-925) and the factors of the layer loop that do not depend on z
+struct FaceConsts {
+    double hs, height_diff, u28 /* 2.8 u*_t */, UQ /* U_R / ln((Z_UR - (sd+z0))/z0) */, uref, sd;
+    double C1p, C2;       // dm/dt = C1p sig Nu r_z + C2 Qr   (the reference's expression :1105-1123 with Sh = Nu cancelled)
+    double ustar, area, c_salt;
+    double Aj[3], g[3];   // lateral face areas E_j dz; unit wind . edge normal
+    int flags;            // bit 0 saltation, bits 1-3 neighbour j present, bit 4 active (a real face)
+    int p;                // slot
+};
+__device__ __forceinline__ FaceConsts face_prelude(const DevConfig& c, const DevMesh& m, const DevForcing& f, const SuspSystem& s,
                                                    double dt, int p, int i) {
     const int Tp = m.Tp;
-    const int L = c.L;
-    double b0 = 0.0;
-    {
-        double fetch = 1000.0;
-        if ((c.use_exp_fetch || c.use_tanh_fetch) && f.fetch) fetch = f.fetch[i];
-        const double uref = f.U_R[i];
-        double sd = f.sd[i];
-        sd = chm_is_nan(sd) ? 0.0 : sd;
-        const double u2 = f.u2[i];
-        double swe = f.swe[i];
-        swe = chm_is_nan(swe) ? 0.0 : swe;
-        const double Tc = f.t[i];
-        const double phi = f.vw_dir[i];
-        const double area = m.area[p];
-        double nxj[3], nyj[3], Ej[3];
-        bool has[3];
+    FaceConsts o;
+    o.p = p;
+    double fetch = 1000.0;
+    if (c.use_exp_fetch || c.use_tanh_fetch) fetch = f.fetch[i];  // depends("fetch"), PBSM3D.cpp:181-184: the host insists on it
+    const double uref = f.U_R[i];
+    double sd = f.sd[i];
+    sd = chm_is_nan(sd) ? 0.0 : sd;
+    const double u2 = f.u2[i];
+    double swe = f.swe[i];
+    swe = chm_is_nan(swe) ? 0.0 : swe;
+    const double Tc = f.t[i];
+    const double phi = f.vw_dir[i];
+    const double area = m.area[p];
+    double nxj[3], nyj[3], Ej[3];
+    int flags = 16;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        nxj[j] = m.nx[(size_t)j * Tp + p];
+        nyj[j] = m.ny[(size_t)j * Tp + p];
+        Ej[j] = m.elen[(size_t)j * Tp + p];
+        if (m.nbs[(size_t)j * Tp + p] != p) flags |= 2 << j;
+    }
+    double height_diff = 0.0, LAI = 0.0, Nst = 0.0, dv = 0.0;
+    if (c.enable_veg) {
+        height_diff = fmax(0.0, m.canopy[p] - sd);
+        if (c.use_R94_lambda) LAI = m.lai[p];
+        else { Nst = m.stalk_n ? m.stalk_n[p] : 1.0; dv = m.stalk_dv ? m.stalk_dv[p] : 0.8; }
+    }
+    const bool water = m.water ? (m.water[p] != 0) : false;
+    const double ust_th = 0.35 + (1.0 / 150.0) * Tc + (1.0 / 8200.0) * Tc * Tc;
+
+    bool salt = false;
+    double lambda = 0.0, ustar = 1.3;
+    if (height_diff <= c.cutoff && sd >= c.min_sd_trans && !water) {
+        lambda = c.use_R94_lambda ? 0.5 * LAI * height_diff : Nst * dv * height_diff;
+        ustar = u2 * kKappa / log(2.0 / 0.0002);
+        if (ustar >= ust_th) salt = true;
+    }
+    const double z0 = kZ0Snow;
+    if (!salt) ustar = fmax(0.01, kKappa * uref / log(kZUR / z0));
+    ustar = fmax(0.01, ustar);
+    const double hs = salt ? 0.08436 * pow(ustar, 1.27) : 0.0;
+
+    const double t = Tc + 273.15;
+    double vx, vy;
+    wind_unit_vector(phi, vx, vy);
+    double Qsalt = 0.0, c_salt = 0.0;
+    if (salt) {
+        const double rho_f = std_dry_air_density(m.zc[p], t);
+        const double mB = 0.16 * 202.0;
+        const double tau_n_ratio = (mB * lambda) / (1.0 + mB * lambda);
+        c_salt = rho_f / (3.29 * ustar) * (1.0 - tau_n_ratio - (ust_th * ust_th) / (ustar * ustar));
+        if (c_salt < 0 || isnan(c_salt)) { c_salt = 0.0; salt = false; }
+        if (c.use_exp_fetch && fetch < 500.0) {
+            c_salt *= 1.0 - exp(-3.0 * fetch / 500.0);
+        } else if (c.use_tanh_fetch && fetch <= 300.0) {
+            const double Lc = 0.5 * tanh(0.1333333333e-1 * 300.0 - 2.0) + 0.5;  // fetch_ref inside tanh, as the reference
+            c_salt *= Lc;
+        }
+        if (c.use_PomLi) {  // Pomeroy & Li 2000 upscaled probability of blowing snow (PBSM3D.cpp:848-866)
+            const double A = f.psh[i];  // hours since the last snowfall
+            const double z10 = 10.0 + sd;
+            const double u10 = z10 < kZUR ? log_scale_wind(uref, kZUR, z10, sd, kZ0Snow) : uref;  // :451-463
+            const double u_mean = 11.2 + 0.365 * Tc + 0.00706 * Tc * Tc + 0.9 * log(A);
+            const double delta = 0.145 * Tc + 0.00196 * Tc * Tc + 4.3;
+            const double z0v = (Nst * dv * height_diff) / 2.0;
+            const double us = u10 / sqrt((1 + 340.0 * z0v));
+            const double Pu10 = 1.0 / (1.0 + exp((sqrt(kPi) * (u_mean - us)) / delta));
+            s.prob[p] = Pu10;
+            c_salt *= Pu10;
+        }
+        const double uhs = 2.8 * ust_th;
+        Qsalt = c_salt * uhs * hs;
+        double mass = 0.0;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            nxj[j] = m.nx[(size_t)j * Tp + p];
-            nyj[j] = m.ny[(size_t)j * Tp + p];
-            Ej[j] = m.elen[(size_t)j * Tp + p];
-            has[j] = m.nbs[(size_t)j * Tp + p] != p;
+            double udotm = vx * nxj[j] + vy * nyj[j];
+            mass += -Ej[j] * Qsalt * udotm;
         }
+        mass = mass / area * dt;
+        if (mass < 0 && fabs(mass) > swe) { c_salt = 0.0; Qsalt = c_salt * uhs * hs; }  // saltation flag survives
+    }
+    s.Qsalt[p] = Qsalt;
+    s.c_salt[p] = c_salt;
+    s.salt[p] = salt ? 1 : 0;
+    if (salt) flags |= 1;
 
-        double height_diff = 0.0, LAI = 0.0, Nst = 0.0, dv = 0.0;
-        if (c.enable_veg) {
-            height_diff = fmax(0.0, m.canopy[p] - sd);
-            if (c.use_R94_lambda) LAI = m.lai[p];
-            else { Nst = m.stalk_n ? m.stalk_n[p] : 1.0; dv = m.stalk_dv ? m.stalk_dv[p] : 0.8; }
-        }
-        const bool water = m.water ? (m.water[p] != 0) : false;
-        const double ust_th = 0.35 + (1.0 / 150.0) * Tc + (1.0 / 8200.0) * Tc * Tc;
-
-        bool salt = false;
-        double lambda = 0.0, ustar = 1.3;
-        if (height_diff <= c.cutoff && sd >= c.min_sd_trans && !water) {
-            lambda = c.use_R94_lambda ? 0.5 * LAI * height_diff : Nst * dv * height_diff;
-            ustar = u2 * kKappa / log(2.0 / 0.0002);
-            if (ustar >= ust_th) salt = true;
-        }
-        double z0 = kZ0Snow;
-        if (!salt) ustar = fmax(0.01, kKappa * uref / log(kZUR / z0));
-        z0 = fmax(kZ0Snow, z0);
-        ustar = fmax(0.01, ustar);
-        const double hs = salt ? 0.08436 * pow(ustar, 1.27) : 0.0;
-
-        const double t = Tc + 273.15;
-        double vx, vy;
-        wind_unit_vector(phi, vx, vy);
-        double Qsalt = 0.0, c_salt = 0.0;
-        if (salt) {
-            const double rho_f = std_dry_air_density(m.zc[p], t);
-            const double mB = 0.16 * 202.0;
-            const double tau_n_ratio = (mB * lambda) / (1.0 + mB * lambda);
-            c_salt = rho_f / (3.29 * ustar) * (1.0 - tau_n_ratio - (ust_th * ust_th) / (ustar * ustar));
-            if (c_salt < 0 || isnan(c_salt)) { c_salt = 0.0; salt = false; }
-            if (c.use_exp_fetch && fetch < 500.0) {
-                c_salt *= 1.0 - exp(-3.0 * fetch / 500.0);
-            } else if (c.use_tanh_fetch && fetch <= 300.0) {
-                const double Lc = 0.5 * tanh(0.1333333333e-1 * 300.0 - 2.0) + 0.5;  // fetch_ref inside tanh, as the reference
-                c_salt *= Lc;
-            }
-            if (c.use_PomLi) {  // Pomeroy & Li 2000 upscaled probability of blowing snow (PBSM3D.cpp:848-866)
-                const double A = f.psh[i];  // hours since the last snowfall
-                const double z10 = 10.0 + sd;
-                const double u10 = z10 < kZUR ? log_scale_wind(uref, kZUR, z10, sd, kZ0Snow) : uref;  // :451-463
-                const double u_mean = 11.2 + 0.365 * Tc + 0.00706 * Tc * Tc + 0.9 * log(A);
-                const double delta = 0.145 * Tc + 0.00196 * Tc * Tc + 4.3;
-                const double z0v = (Nst * dv * height_diff) / 2.0;
-                const double us = u10 / sqrt((1 + 340.0 * z0v));
-                const double Pu10 = 1.0 / (1.0 + exp((sqrt(kPi) * (u_mean - us)) / delta));
-                s.prob[p] = Pu10;
-                c_salt *= Pu10;
-            }
-            const double uhs = 2.8 * ust_th;
-            Qsalt = c_salt * uhs * hs;
-            double mass = 0.0;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                double udotm = vx * nxj[j] + vy * nyj[j];
-                mass += -Ej[j] * Qsalt * udotm;
-            }
-            mass = mass / area * dt;
-            if (mass < 0 && fabs(mass) > swe) { c_salt = 0.0; Qsalt = c_salt * uhs * hs; }  // saltation flag survives
-        }
-        s.Qsalt[p] = Qsalt;
-        s.c_salt[p] = c_salt;
-        s.salt[p] = salt ? 1 : 0;
-
+    // layer-independent pieces of the sublimation model: with Sh = Nu (:1046) the reference's dm/dt (:1105-1123)
+    //     Sh rho_sat D (2 pi' Nu Rg r_z sigma t^2 lambda_t - Ls Mw Qr + Qr Rg t) / (D Ls Sh (Ls Mw - Rg t) rho_sat + lambda_t t^2 Nu Rg)
+    // is  C1 sigma Nu r_z + C2 Qr  with the two per-face constants below (pi' = 6.283185308 / 2 as written there)
+    {
         const double rh = f.rh[i] / 100.0;
         const double es = saturated_vapour_pressure(t);
-        const double dz = c.dz;
-        const double nrm = sqrt(vx * vx + vy * vy);
-        // layer-independent pieces of the sublimation model (same expressions as inside the reference's z loop)
         const double D = 2.06e-5 * pow(t / 273.15, 1.75);
         const double lambda_t = 0.000063 * t + 0.00673;
         const double Ls = 2.838e6, Mw = 18.01, Rg = 8313.0;
         const double rho_sat = (Mw * es) / (Rg * t);
-        const double ulog_den = log((kZUR - (sd + z0)) / z0);
-        double Aj[3], alphaj[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            Aj[j] = Ej[j] * dz;
-            alphaj[j] = c.do_lateral_diff ? Aj[j] * 0.00001 : 0.0;
-        }
-
-        double cp_prev = 0.0;
-        for (int z = 0; z < L; ++z) {
-            const size_t r = (size_t)z * Tp + p;
-            const double cz = z * dz + hs + dz / 2.0;
-            const double hz = cz + sd;
-            double u_z;
-            if (salt && cz < height_diff) u_z = 2.8 * ust_th;
-            else if (cz < height_diff) u_z = 0.01;
-            else if (hz < kZUR) u_z = fmax(0.01, uref * log((hz - (sd + z0)) / z0) / ulog_den);
-            else u_z = fmax(0.01, uref);
-            s.u_z[r] = u_z;
-
-            // x^y for x > 0 as exp(y log x): |y log x| < 40 on every use below, so the result is within ~1e-14
-            // relative of pow() (the parity bar on coefficients is 1e-12) at a fraction of pow()'s fp64 cost
-            const double lcz = log(cz);
-            const double rm = 4.6e-5 * exp(-0.258 * lcz);
-            const double mm_alpha = 4.08 + 12.6 * cz;
-            const double mm = 4.0 / 3.0 * kPi * kRhoIce * rm * rm * rm * (1.0 + 3.0 / mm_alpha + 2.0 / (mm_alpha * mm_alpha));
-            const double lrz3 = log((3.0 * mm) / (4 * kPi * kRhoIce));
-            const double r_z = exp(0.3333333 * lrz3);
-            const double xrz = 0.005 * exp(1.36 * log(u_z));
-            const double omega = c.do_fixed_settling ? c.settling_velocity : 1.1e7 * exp(1.8 * log(r_z));
-            const double Vr = omega + 3.0 * xrz * cos(kPi / 4.0);
-            const double Re = 2.0 * r_z * Vr / 1.88e-5;
-            const double Nu = 1.79 + 0.606 * sqrt(Re);
-            const double Sh = Nu;
-            const double sigma = (rh - 1.0) * (1.019 + 0.027 * lcz);
-            const double Qr = 0.9 * kPi * rm * rm * 120.0;
-            const double dmdtz = Sh * rho_sat * D * (6.283185308 * Nu * Rg * r_z * sigma * t * t * lambda_t - Ls * Mw * Qr + Qr * Rg * t) /
-                                 (D * Ls * Sh * (Ls * Mw - Rg * t) * rho_sat + lambda_t * t * t * Nu * Rg);
-            double csubl = dmdtz / mm;
-            if (!c.do_sublimation) csubl = 0.0;
-            s.csubl[r] = csubl;
-
-            const double lmix = kKappa * (cz + z0) * c.l_max / (kKappa * (cz + z0) + c.l_max);
-            const double w = omega;
-            double diffusion_coeff = c.snow_diffusion_const;
-            if (c.rouault) diffusion_coeff = 1.0 / (1.0 + (1.0 * w * w) / (1.56 * ustar * ustar));
-            const double K = diffusion_coeff * ustar * lmix;
-            const double alpha3 = area * K / dz;
-            const double alpha4 = area * K / dz;
-            const double scl = u_z / nrm;
-            const double ux = vx * scl, uy = vy * scl;
-            const double udotm3 = -w, udotm4 = w;
-            const double Vc = (area * dz / 5.0) * csubl;
-
-            double d = 0.0;
-            double offj[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const double udotm = ux * nxj[j] + uy * nyj[j];
-                double off = 0.0;
-                if (udotm > 0) {
-                    if (has[j]) { d += Vc - Aj[j] * udotm - alphaj[j]; off = alphaj[j]; }
-                    else d += -0.1e-1 * alphaj[j] - 1.0 * Aj[j] * udotm + Vc;
-                } else {
-                    if (has[j]) { d += Vc - alphaj[j]; off = -Aj[j] * udotm + alphaj[j]; }
-                    else d += -0.1e-1 * alphaj[j] - 0.99 * Aj[j] * udotm + Vc;
-                }
-                offj[j] = off;
-                s.lat[((size_t)j * L + z) * Tp + p] = off;
-            }
-            double lo = 0.0, up = 0.0, rhs = 0.0;
-            if (z == 0) {
-                const double alpha4p = area * K / (hs / 2.0 + dz / 2.0);
-                d += Vc - area * udotm4 - alpha4p;
-                rhs = -alpha4p * c_salt;
-                b0 = rhs;
-                s.rhs0[p] = rhs;
-                if (udotm3 > 0) { d += Vc - area * udotm3 - alpha3; up = alpha3; }
-                else { d += Vc - alpha3; up = -area * udotm3 + alpha3; }
-            } else if (z == L - 1) {
-                if (udotm3 > 0) d += Vc - area * udotm3 - alpha3;
-                else d += Vc - alpha3;
-                if (udotm4 > 0) { d += Vc - area * udotm4 - alpha4; lo = alpha4; }
-                else { d += Vc - alpha4; lo = -area * udotm4 + alpha4; }
-            } else {
-                if (udotm3 > 0) { d += Vc - area * udotm3 - alpha3; up = alpha3; }
-                else { d += Vc - alpha3; up = -area * udotm3 + alpha3; }
-                if (udotm4 > 0) { d += Vc - area * udotm4 - alpha4; lo = alpha4; }
-                else { d += Vc - alpha4; lo = -area * udotm4 + alpha4; }
-            }
-            s.diag[r] = d;
-            s.below[r] = lo;
-            s.above[r] = up;
-            // forward elimination of the column block (Thomas): den_z = d_z - lo_z * cp_{z-1}
-            const double inv = 1.0 / (d - lo * cp_prev);
-            cp_prev = up * inv;
-            s.inv[r] = inv;
-            s.cp[r] = cp_prev;
-            s.belowS[r] = lo * inv;
-            s.cp32[r] = (float)cp_prev;
-            s.pack32[r] = make_float4((float)(offj[0] * inv), (float)(offj[1] * inv), (float)(offj[2] * inv), (float)(lo * inv));
-#pragma unroll
-            for (int j = 0; j < 3; ++j) s.latS[((size_t)j * L + z) * Tp + p] = offj[j] * inv;
-            if (z == 0) s.rhsS0[p] = rhs * inv;
-        }
+        const double inv_den = 1.0 / (D * Ls * (Ls * Mw - Rg * t) * rho_sat + lambda_t * t * t * Rg);
+        o.C1p = rho_sat * D * (6.283185308 * Rg * t * t * lambda_t) * inv_den * (rh - 1.0);
+        o.C2 = rho_sat * D * (Rg * t - Ls * Mw) * inv_den;
     }
-    return b0;
+    o.hs = hs;
+    o.height_diff = height_diff;
+    o.u28 = 2.8 * ust_th;
+    o.UQ = uref / log((kZUR - (sd + z0)) / z0);
+    o.uref = uref;
+    o.sd = sd;
+    o.ustar = ustar;
+    o.area = area;
+    o.c_salt = c_salt;
+    const double nrm = sqrt(vx * vx + vy * vy);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        o.Aj[j] = Ej[j] * c.dz;
+        o.g[j] = (vx * nxj[j] + vy * nyj[j]) / nrm;  // u . m_j = u_z g_j  (uvw = u_z v / |v|, :1189-1200)
+    }
+    o.flags = flags;
+    return o;
 }
 
-// Faces [i0, i1) of CHM's order (the order the forcing arrives in, so the step can assemble one chunk while the
-// next chunk's forcing is still crossing PCIe); each thread writes the column of its slot iperm[i].  Within a warp
-// the slots of one colour are consecutive, so every stream is still written in full 128-byte lines.
-// Persistent-style grid (a multiple of the SM count, each block walks 128-face tiles) so the fused reduction
-// folds a bounded number of partials.  red[0] = max|b|, red[1] = sum b^2 over the chunk (this rank).
+// ---- one row: everything of PBSM3D.cpp:946-1348 for (face, z) except the column recurrence
+struct RowCoef64 {
+    double d, lo, up, off[3], rhs;
+};
+__device__ __forceinline__ RowCoef64 assemble_row(const DevConfig& c, const FaceConsts& fc, const LayerConsts& lc, int z, int L,
+                                                  double& u_z_out, double& csubl_out) {
+    const double dz = c.dz;
+    const bool salt = fc.flags & 1;
+    const double cz = lc.cz;
+    double u_z;
+    if (salt && cz < fc.height_diff) u_z = fc.u28;
+    else if (cz < fc.height_diff) u_z = 0.01;
+    else if (cz + fc.sd < kZUR) u_z = fmax(0.01, fc.UQ * lc.ulog);
+    else u_z = fmax(0.01, fc.uref);
+    u_z_out = u_z;
+
+    const double xrz = 0.005 * exp(1.36 * log(u_z));        // :1020
+    const double omega = lc.omega;
+    const double Vr = omega + 3.0 * xrz * cos(kPi / 4.0);   // :1039
+    const double Re = 2.0 * lc.r_z * Vr / 1.88e-5;
+    const double Nu = 1.79 + 0.606 * sqrt(Re);
+    const double dmdtz = fc.C1p * lc.sig * Nu * lc.r_z + fc.C2 * lc.Qr;
+    const double csubl = c.do_sublimation ? dmdtz * lc.inv_mm : 0.0;
+    csubl_out = csubl;
+
+    double diffusion_coeff = c.snow_diffusion_const;
+    if (c.rouault) diffusion_coeff = 1.0 / (1.0 + (1.0 * omega * omega) / (1.56 * fc.ustar * fc.ustar));
+    const double K = diffusion_coeff * fc.ustar * lc.lmix;
+    const double area = fc.area;
+    const double alpha3 = area * K / dz;
+    const double alpha4 = alpha3;
+    const double udotm3 = -omega, udotm4 = omega;
+    const double Vc = (area * dz / 5.0) * csubl;
+
+    RowCoef64 o;
+    double d = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double udotm = u_z * fc.g[j];
+        const double alphaj = c.do_lateral_diff ? fc.Aj[j] * 0.00001 : 0.0;
+        const bool has = fc.flags & (2 << j);
+        double off = 0.0;
+        if (udotm > 0) {
+            if (has) { d += Vc - fc.Aj[j] * udotm - alphaj; off = alphaj; }
+            else d += -0.1e-1 * alphaj - 1.0 * fc.Aj[j] * udotm + Vc;
+        } else {
+            if (has) { d += Vc - alphaj; off = -fc.Aj[j] * udotm + alphaj; }
+            else d += -0.1e-1 * alphaj - 0.99 * fc.Aj[j] * udotm + Vc;
+        }
+        o.off[j] = off;
+    }
+    double lo = 0.0, up = 0.0, rhs = 0.0;
+    if (z == 0) {
+        const double alpha4p = area * K / (fc.hs / 2.0 + dz / 2.0);
+        d += Vc - area * udotm4 - alpha4p;
+        rhs = -alpha4p * fc.c_salt;
+        // the coupling to layer 1; with nLayer == 1 the reference sums it into a column outside the matrix (dropped)
+        if (udotm3 > 0) { d += Vc - area * udotm3 - alpha3; up = alpha3; }
+        else { d += Vc - alpha3; up = -area * udotm3 + alpha3; }
+        if (L == 1) up = 0.0;
+    } else if (z == L - 1) {
+        if (udotm3 > 0) d += Vc - area * udotm3 - alpha3;
+        else d += Vc - alpha3;
+        if (udotm4 > 0) { d += Vc - area * udotm4 - alpha4; lo = alpha4; }
+        else { d += Vc - alpha4; lo = -area * udotm4 + alpha4; }
+    } else {
+        if (udotm3 > 0) { d += Vc - area * udotm3 - alpha3; up = alpha3; }
+        else { d += Vc - alpha3; up = -area * udotm3 + alpha3; }
+        if (udotm4 > 0) { d += Vc - area * udotm4 - alpha4; lo = alpha4; }
+        else { d += Vc - alpha4; lo = -area * udotm4 + alpha4; }
+    }
+    o.d = d; o.lo = lo; o.up = up; o.rhs = rhs;
+    return o;
+}
+__device__ __forceinline__ LayerConsts layer_lookup(const DevConfig& c, const FaceConsts& fc, const double* __restrict__ tab, int z) {
+    // hs > 0 shifts every height (hs is set before the negative-c_salt clamp may clear the saltation flag, so test hs itself)
+    if (fc.hs != 0.0) return layer_consts(c, z * c.dz + fc.hs + c.dz / 2.0, fc.sd);
+    LayerConsts o;
+    const int L = c.L;
+    o.cz = __ldg(tab + z); o.inv_mm = __ldg(tab + L + z); o.r_z = __ldg(tab + 2 * L + z); o.omega = __ldg(tab + 3 * L + z);
+    o.Qr = __ldg(tab + 4 * L + z); o.sig = __ldg(tab + 5 * L + z); o.lmix = __ldg(tab + 6 * L + z); o.ulog = __ldg(tab + 7 * L + z);
+    return o;
+}
+__device__ __forceinline__ void store_row(const SuspSystem& s, size_t r, size_t LTp, const RowCoef64& rc, double den, double inv,
+                                          double cp) {
+    s.den[r] = den;
+    s.cp[r] = cp;
+    const double bS = rc.lo * inv, l0 = rc.off[0] * inv, l1 = rc.off[1] * inv, l2 = rc.off[2] * inv;
+    s.belowS[r] = bS;
+    s.latS[r] = l0; s.latS[LTp + r] = l1; s.latS[2 * LTp + r] = l2;
+    s.cp32[r] = (float)cp;
+    s.pack32[r] = make_float4((float)l0, (float)l1, (float)l2, (float)bS);
+}
+
+// Layer-parallel assembly.  A block of NW warps owns tiles of 32 faces (CHM order, the order the forcing arrives in, so the
+// step can assemble one chunk while the next chunk's forcing is still crossing PCIe); warp z computes the rows of layer z, so
+// the 32 lanes write 32 consecutive faces of every stream of that layer, and no thread walks a column.  Two short serial
+// pieces ride on single warps while the others wait at a barrier (other resident blocks fill the SM meanwhile):
+//     warp 1: the per-face prelude (saltation, wind, sublimation constants) of the NEXT tile       } concurrently
+//     warp 0: the Thomas recurrence den_z = d_z - lo_z cp_{z-1} of this tile's 32 columns (shared) }
+// Non-saltating faces (hs = 0) take everything that depends on the height only from a per-layer table (SuspSystem::ltab): their
+// rows cost one log/exp pair, a square root and the coefficient arithmetic.
+// red[0] = max|b|, red[1] = sum b^2 over the chunk (this rank).
+constexpr int kRecD = 17;  // doubles per face in the shared prelude record
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+assemble_tile_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt, int i0, int i1, double* __restrict__ partial,
+                     int pstride, Scalars* sc, double* __restrict__ red) {
+    extern __shared__ double sm[];
+    const int L = c.L;
+    double* rec = sm;                          // [kRecD][32]
+    int* reci = (int*)(sm + kRecD * 32);       // [2][32]: flags, slot
+    double* colA = sm + kRecD * 32 + 32;       // [L][32] d   -> den
+    double* colB = colA + (size_t)L * 32;      // [L][32] lo  -> 1/den
+    double* colC = colB + (size_t)L * 32;      // [L][32] up  -> cp
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wPre = NW > 1 ? 1 : 0;
+    const int ntiles = (i1 - i0 + 31) / 32;
+    const size_t LTp = (size_t)L * m.Tp;
+    double mx = 0.0, ss = 0.0;
+
+    auto prelude = [&](int tile) {
+        const int i = i0 + tile * 32 + lane;
+        if (i < i1) {
+            const FaceConsts fc = face_prelude(c, m, f, s, dt, m.iperm[i], i);
+            const double v[kRecD] = {fc.hs, fc.height_diff, fc.u28, fc.UQ, fc.uref, fc.sd, fc.C1p, fc.C2, fc.ustar, fc.area, fc.c_salt,
+                                     fc.Aj[0], fc.Aj[1], fc.Aj[2], fc.g[0], fc.g[1], fc.g[2]};
+#pragma unroll
+            for (int k = 0; k < kRecD; ++k) rec[k * 32 + lane] = v[k];
+            reci[lane] = fc.flags;
+            reci[32 + lane] = fc.p;
+        } else {
+            reci[lane] = 0;
+            reci[32 + lane] = 0;
+        }
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles && w == wPre) prelude(tile);
+    __syncthreads();
+    for (; tile < ntiles; tile += gridDim.x) {
+        // ---- rows of layer w of this tile's faces
+        RowCoef64 rc;
+        int p = 0;
+        bool act = false;
+        if (w < L) {
+            FaceConsts fc;
+            fc.flags = reci[lane];
+            p = reci[32 + lane];
+            act = fc.flags & 16;
+            if (act) {
+                fc.hs = rec[lane]; fc.height_diff = rec[32 + lane]; fc.u28 = rec[2 * 32 + lane]; fc.UQ = rec[3 * 32 + lane];
+                fc.uref = rec[4 * 32 + lane]; fc.sd = rec[5 * 32 + lane]; fc.C1p = rec[6 * 32 + lane]; fc.C2 = rec[7 * 32 + lane];
+                fc.ustar = rec[8 * 32 + lane]; fc.area = rec[9 * 32 + lane]; fc.c_salt = rec[10 * 32 + lane];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { fc.Aj[j] = rec[(11 + j) * 32 + lane]; fc.g[j] = rec[(14 + j) * 32 + lane]; }
+                const LayerConsts lc = layer_lookup(c, fc, s.ltab, w);
+                double u_z, csubl;
+                rc = assemble_row(c, fc, lc, w, L, u_z, csubl);
+                const size_t r = (size_t)w * m.Tp + p;
+                s.u_z[r] = u_z;
+                s.csubl[r] = csubl;
+                colA[w * 32 + lane] = rc.d;
+                colB[w * 32 + lane] = rc.lo;
+                colC[w * 32 + lane] = rc.up;
+                if (w == 0) {
+                    mx = fmax(mx, fabs(rc.rhs));
+                    ss += rc.rhs * rc.rhs;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- serial pieces: the column recurrence of this tile (warp 0), the prelude of the block's next tile (warp wPre)
+        if (w == 0 && act) {  // act is this lane's face in every warp (registers: reci is being rewritten by warp wPre)
+            double cp_prev = 0.0;
+            for (int z = 0; z < L; ++z) {
+                const double den = colA[z * 32 + lane] - colB[z * 32 + lane] * cp_prev;
+                const double inv = 1.0 / den;
+                cp_prev = colC[z * 32 + lane] * inv;
+                colA[z * 32 + lane] = den;
+                colB[z * 32 + lane] = inv;
+                colC[z * 32 + lane] = cp_prev;
+            }
+        }
+        if (w == wPre && tile + (int)gridDim.x < ntiles) prelude(tile + gridDim.x);
+        __syncthreads();
+        // ---- scale and store
+        if (act) {
+            const double den = colA[w * 32 + lane], inv = colB[w * 32 + lane], cp = colC[w * 32 + lane];
+            store_row(s, (size_t)w * m.Tp + p, LTp, rc, den, inv, cp);
+            if (w == 0) { s.rhs0[p] = rc.rhs; s.rhsS0[p] = rc.rhs * inv; }
+        }
+        // no barrier: in the next iteration warp w touches only row w of colA..C again, and rec/reci were rewritten before
+        // the barrier above
+    }
+    double o0, o1;
+    if (grid_fold<2>(mx, ss, 1, 0, partial, pstride, &sc->ticket[0], o0, o1)) {
+        if (threadIdx.x == 0) { red[0] = o0; red[1] = o1; }
+    }
+}
+
+// Column-walking variant (one thread per face column): any nLayer, and the cross-check of the tile kernel in the tests
+// (PBSM3D_ASSEMBLY=column).  Same arithmetic, same streams.
 __global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt, int i0, int i1,
                                                        double* __restrict__ partial, int pstride, Scalars* sc,
                                                        double* __restrict__ red) {
     double mx = 0.0, ss = 0.0;
     const int ntiles = (i1 - i0 + 127) / 128;
+    const int L = c.L;
+    const size_t LTp = (size_t)L * m.Tp;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = i0 + tile * 128 + threadIdx.x;
         if (i < i1) {
-            const double b0 = assemble_column(c, m, f, s, dt, m.iperm[i], i);
-            mx = fmax(mx, fabs(b0));
-            ss += b0 * b0;
+            const int p = m.iperm[i];
+            const FaceConsts fc = face_prelude(c, m, f, s, dt, p, i);
+            double cp_prev = 0.0;
+            for (int z = 0; z < L; ++z) {
+                const LayerConsts lc = layer_lookup(c, fc, s.ltab, z);
+                double u_z, csubl;
+                const RowCoef64 rc = assemble_row(c, fc, lc, z, L, u_z, csubl);
+                const size_t r = (size_t)z * m.Tp + p;
+                s.u_z[r] = u_z;
+                s.csubl[r] = csubl;
+                const double den = rc.d - rc.lo * cp_prev;
+                const double inv = 1.0 / den;
+                cp_prev = rc.up * inv;
+                store_row(s, r, LTp, rc, den, inv, cp_prev);
+                if (z == 0) {
+                    s.rhs0[p] = rc.rhs;
+                    s.rhsS0[p] = rc.rhs * inv;
+                    mx = fmax(mx, fabs(rc.rhs));
+                    ss += rc.rhs * rc.rhs;
+                }
+            }
         }
     }
     double o0, o1;
     if (grid_fold<2>(mx, ss, 1, 0, partial, pstride, &sc->ticket[0], o0, o1)) {
         if (threadIdx.x == 0) { red[0] = o0; red[1] = o1; }
+    }
+}
+
+// The reference's own coefficients from what is stored (inspection: pbsm3d_get_suspension_system).
+__global__ void reconstruct_rows_kernel(SuspSystem s, int Tp, int L, double* __restrict__ diag, double* __restrict__ lat,
+                                        double* __restrict__ below, double* __restrict__ above) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Tp) return;
+    const size_t LTp = (size_t)L * Tp;
+    double cp_prev = 0.0;
+    for (int z = 0; z < L; ++z) {
+        const size_t r = (size_t)z * Tp + p;
+        const double den = s.den[r], bS = s.belowS[r], cp = s.cp[r];
+        if (diag) diag[r] = den * (1.0 + bS * cp_prev);
+        if (below) below[r] = bS * den;
+        if (above) above[r] = cp * den;
+        if (lat)
+            for (int j = 0; j < 3; ++j) lat[j * LTp + r] = s.latS[j * LTp + r] * den;
+        cp_prev = cp;
     }
 }
 
@@ -704,16 +933,18 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh 
 }
 
 // ------------------------------------------------------------------------------------ SpMV / residual
-// Row of A·x in the extruded-ELL layout: lateral gathers x[z*S + nbs_j], vertical x[(z±1)*S + p].
+// Row of A·x in the extruded-ELL layout: lateral gathers x[z*S + nbs_j], vertical x[(z±1)*S + p].  With the stored form
+// (A x)_z = den_z [ (1 + belowS_z cp_{z-1}) x_z + belowS_z x_{z-1} + sum_j latS_j x_nb_j + cp_z x_{z+1} ].
 __device__ __forceinline__ double spmv_row(const SuspSystem& s, const DevMesh& m, int L, const double* __restrict__ x, int z, int p) {
     const int Tp = m.Tp, S = m.S;
     const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
-    double acc = s.diag[r] * x[xr + p];
+    const double bS = s.belowS[r];
+    double acc = x[xr + p];
+    if (z > 0) acc += bS * (s.cp[r - Tp] * x[xr + p] + x[xr - S + p]);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) acc += s.lat[((size_t)j * L + z) * Tp + p] * x[xr + m.nbs[(size_t)j * Tp + p]];
-    if (z > 0) acc += s.below[r] * x[xr - S + p];
-    if (z < L - 1) acc += s.above[r] * x[xr + S + p];
-    return acc;
+    for (int j = 0; j < 3; ++j) acc += s.latS[((size_t)j * L + z) * Tp + p] * x[xr + m.nbs[(size_t)j * Tp + p]];
+    if (z < L - 1) acc += s.cp[r] * x[xr + S + p];
+    return acc * s.den[r];
 }
 
 // True residual of the line solver: ||b - A x||_2^2 of this rank into red[0]; with `fused` (single rank) the
@@ -760,17 +991,20 @@ __global__ void __launch_bounds__(128) residual_col_kernel(SuspSystem s, DevMesh
 #pragma unroll
         for (int z = 0; z < LT; ++z) {
             const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
-            g[z] = __ldcs(s.lat + r) * x[xr + n0] + __ldcs(s.lat + (size_t)LT * Tp + r) * x[xr + n1] +
-                   __ldcs(s.lat + (size_t)2 * LT * Tp + r) * x[xr + n2];
+            g[z] = __ldcs(s.latS + r) * x[xr + n0] + __ldcs(s.latS + (size_t)LT * Tp + r) * x[xr + n1] +
+                   __ldcs(s.latS + (size_t)2 * LT * Tp + r) * x[xr + n2];
         }
+        double cp_prev = 0.0;
 #pragma unroll
         for (int z = 0; z < LT; ++z) {
             const size_t r = (size_t)z * Tp + p;
-            double v = g[z] + __ldcs(s.diag + r) * xo[z];
-            if (z > 0) v += __ldcs(s.below + r) * xo[z - 1];
-            if (z < LT - 1) v += __ldcs(s.above + r) * xo[z + 1];
-            v = ((z == 0) ? s.rhs0[p] : 0.0) - v;
+            const double bS = __ldcs(s.belowS + r), cp = __ldcs(s.cp + r);
+            double v = g[z] + xo[z];
+            if (z > 0) v += bS * (cp_prev * xo[z] + xo[z - 1]);
+            if (z < LT - 1) v += cp * xo[z + 1];
+            v = (((z == 0) ? s.rhsS0[p] : 0.0) - v) * __ldcs(s.den + r);
             a += v * v;
+            cp_prev = cp;
         }
     }
     double rr, unused;
@@ -829,7 +1063,7 @@ __global__ void __launch_bounds__(128) thomas_kernel(SuspSystem s, int Tp, int S
     double prev = 0.0;
     for (int z = 0; z < L; ++z) {
         const size_t r = (size_t)z * Tp + p;
-        prev = (v[(size_t)z * S + p] - s.below[r] * prev) * s.inv[r];
+        prev = v[(size_t)z * S + p] / s.den[r] - s.belowS[r] * prev;
         y[(size_t)z * S + p] = prev;
     }
     double xn = prev;
@@ -1551,21 +1785,21 @@ __global__ void __launch_bounds__(128) residual_halo_kernel(SuspSystem s, DevMes
         const int p = tile * 128 + threadIdx.x;
         if (p >= Tp) continue;
         const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
-        double xm = 0.0, xc = x[p];
+        double xm = 0.0, xc = x[p], cp_prev = 0.0;
         for (int z = 0; z < L; ++z) {
             const size_t r = (size_t)z * Tp + p;
             const size_t zS = (size_t)z * S, zG = (size_t)z * hl.nGp;
             const double xp = z < L - 1 ? x[zS + S + p] : 0.0;
-            double v = __ldcs(s.lat + r) * link_gather(hl, x, zS, zG, n0, Tp) +
-                       __ldcs(s.lat + (size_t)L * Tp + r) * link_gather(hl, x, zS, zG, n1, Tp) +
-                       __ldcs(s.lat + (size_t)2 * L * Tp + r) * link_gather(hl, x, zS, zG, n2, Tp);
-            v += __ldcs(s.diag + r) * xc;
-            if (z > 0) v += __ldcs(s.below + r) * xm;
-            if (z < L - 1) v += __ldcs(s.above + r) * xp;
-            v = ((z == 0) ? s.rhs0[p] : 0.0) - v;
+            double v = __ldcs(s.latS + r) * link_gather(hl, x, zS, zG, n0, Tp) +
+                       __ldcs(s.latS + (size_t)L * Tp + r) * link_gather(hl, x, zS, zG, n1, Tp) +
+                       __ldcs(s.latS + (size_t)2 * L * Tp + r) * link_gather(hl, x, zS, zG, n2, Tp);
+            const double bS = __ldcs(s.belowS + r), cp = __ldcs(s.cp + r);
+            v += xc + bS * (cp_prev * xc + xm) + cp * xp;  // belowS = 0 in layer 0, cp = 0 in the top layer
+            v = (((z == 0) ? s.rhsS0[p] : 0.0) - v) * __ldcs(s.den + r);
             a += v * v;
             xm = xc;
             xc = xp;
+            cp_prev = cp;
         }
     }
     double rr, unused;

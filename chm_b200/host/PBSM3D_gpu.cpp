@@ -219,6 +219,7 @@ void PBSM3D_gpu::init(mesh& domain)
     m.stalk_number = (veg && !_c.use_R94_lambda) ? sn.data() : nullptr;
     m.stalk_diameter = (veg && !_c.use_R94_lambda) ? sdv.data() : nullptr;
     m.is_water = water.data();
+    m.is_geographic = domain->is_geographic() ? 1 : 0; // triangulation.cpp:98-101; selects math::gis::distance (core.cpp:809-821)
     if (_fuse && any_wveg && !veg)
     { // PBSM3D's own vegetation is off (disabled, or a face lacks the data) but the providers still see the canopy where it exists
         _c.enable_veg = 0;

@@ -114,6 +114,8 @@ class triangulation
     size_t n_global = 0;
     size_t size_faces() const { return faces.size(); }
     size_t size_global_faces() const { return n_global; }
+    bool is_geographic() const { return geographic; } // triangulation.cpp:98-101
+    bool geographic = false;
     mesh_elem face(size_t i) const { return faces[i].get(); }
 };
 typedef std::shared_ptr<triangulation> mesh;

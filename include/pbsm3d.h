@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PBSM3D_ABI_VERSION 3
+#define PBSM3D_ABI_VERSION 4
 
 enum {
     PBSM3D_OK = 0,
@@ -127,6 +127,10 @@ typedef struct pbsm3d_mesh {
     const double* stalk_number;   /* [n_local] or NULL -> 1   (PBSM3D.cpp:303-312) */
     const double* stalk_diameter; /* [n_local] or NULL -> 0.8 */
     const uint8_t* is_water;      /* [n_local] module_base::is_water(face), NULL = none */
+    int32_t is_geographic;        /* domain->is_geographic(): vertex x/y are longitude/latitude in degrees.  core.cpp:809-821 then
+                                     installs math::gis::distance = distance_latlong (haversine, coordinates.cpp:68-92), which the
+                                     deposition matrix's dx uses (PBSM3D.cpp:1546).  pbsm3d_fetchr refuses such a mesh
+                                     (PBSM3D_ERR_UNSUPPORTED: point_from_bearing_latlong returns (lat, lon) swapped). */
 } pbsm3d_mesh;
 
 /* Multi-GPU: one process per GPU.  NULL or n_ranks==1 means a single-rank run. */
