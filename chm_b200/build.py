@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpbsm3d_b200.so")
 SOURCES = ["pbsm3d_capi.cu"]
-DEPS = ["pbsm3d_capi.cu", "pbsm3d_kernels.cuh", "pbsm3d_physics.cuh", os.path.join("..", "..", "include", "pbsm3d.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [os.path.join("..", "..", "include", "pbsm3d.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -50,11 +50,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nccl = ["-lnccl"]
     if inc:
         nccl = ["-I", inc, "-L", libdir, "-l:libnccl.so.2", "-Xlinker", "-rpath", "-Xlinker", libdir]
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], *nccl]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES], *nccl]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building libpbsm3d_b200.so")
+    os.replace(tmp, LIB)  # atomic: concurrent builders (the ranks of a torchrun job) never load a half-written library
     if verbose:
         sys.stderr.write(res.stderr)
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:

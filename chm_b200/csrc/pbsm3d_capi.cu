@@ -196,6 +196,8 @@ struct pbsm3d_handle {
     int asm_nw = 0, asm_grid = 1;  // assembly: warps per block of the tile kernel (0 = column kernel), persistent grid size
     size_t asm_smem = 0;
     void* asm_fn = nullptr;
+    int asm_threads = 128;
+    FaceRecs recs{};  // per-face records between the prelude kernel and the row kernel
     int pred_n32 = 0;  // leading sweeps of the next solve that may stream fp32 coefficient copies
     bool have_system = false;
     long long n_launch = 0;
@@ -1241,47 +1243,64 @@ int enqueue_finish(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTa
 // Assembly of CHM faces [i0, i1); its {max|b|, sum b^2} go to red[2*chunk ..].
 // The layer-parallel tile kernel runs with one warp per layer (nLayer <= 32; block sizes 4/5/8/10/16/20/32 warps, surplus warps
 // only keep the barriers); deeper columns, or PBSM3D_ASSEMBLY=column, take the column-walking kernel.
-using AsmKernel = void (*)(DevConfig, DevMesh, DevForcing, SuspSystem, double, int, int, double*, int, Scalars*, double*);
-template <int NW, int MINB>
-int setup_assembly_nw(pbsm3d_handle* h) {
-    h->asm_nw = NW;
-    h->asm_fn = (void*)(AsmKernel)assemble_tile_kernel<NW, MINB>;
-    h->asm_smem = (size_t)(kRecD * 32 + 32 + 3 * h->L * 32) * sizeof(double);
-    CU(cudaFuncSetAttribute(assemble_tile_kernel<NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->asm_smem));
+using AsmKernel = void (*)(DevConfig, DevMesh, FaceRecs, SuspSystem, int, int, double*, int, Scalars*, double*);
+int setup_assembly_fn(pbsm3d_handle* h, AsmKernel fn, int nw, int threads) {
+    h->asm_nw = nw;
+    h->asm_fn = (void*)fn;
+    h->asm_threads = threads;
+    h->asm_smem = nw ? (size_t)(3 * h->L * 32) * sizeof(double) : 0;
+    CU(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->asm_smem));
     int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, assemble_tile_kernel<NW, MINB>, NW * 32, h->asm_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)fn, threads, h->asm_smem));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, h->device));
     h->asm_grid = std::max(1, std::min(kRedBlocks, std::max(nb, 1) * prop.multiProcessorCount));
     if (getenv("PBSM3D_VERBOSE"))
-        fprintf(stderr, "[pbsm3d] assembly: tile kernel, %d warps per block, %d blocks per SM, grid %d\n", NW, nb, h->asm_grid);
+        fprintf(stderr, "[pbsm3d] assembly: %s kernel, %d threads per block, %d blocks per SM, grid %d\n", nw ? "tile" : "column", threads,
+                nb, h->asm_grid);
     return 0;
 }
 int setup_assembly(pbsm3d_handle* h) {
     const char* want = getenv("PBSM3D_ASSEMBLY");
-    const char* mb = getenv("PBSM3D_ASM_MINB");  // tuning knob: resident blocks per SM the tile kernel is compiled for
+    const char* mb = getenv("PBSM3D_ASM_MINB");  // tuning knob: resident blocks per SM the kernel is compiled for
     const int minb = mb ? atoi(mb) : 0;
-    h->asm_nw = 0;
-    if ((want && std::string(want) == "column") || h->L > 32) return 0;
     const int L = h->L;
-    if (L <= 4) return setup_assembly_nw<4, 4>(h);
-    if (L <= 5) return setup_assembly_nw<5, 4>(h);
-    if (L <= 8) return setup_assembly_nw<8, 3>(h);
-    if (L <= 10) return minb == 2 ? setup_assembly_nw<10, 2>(h) : (minb == 4 ? setup_assembly_nw<10, 4>(h) : setup_assembly_nw<10, 3>(h));
-    if (L <= 16) return setup_assembly_nw<16, 2>(h);
-    if (L <= 20) return setup_assembly_nw<20, 1>(h);
-    return setup_assembly_nw<32, 1>(h);
+    TRY(h->alloc(&h->recs.d, (size_t)kRecD * h->T));
+    TRY(h->alloc(&h->recs.i, (size_t)2 * h->T));
+    h->recs.T = h->T;
+    const bool column = !(want && std::string(want) == "tile") || L > 32;  // column-walking is the faster one (profiles/r2a)
+    if (column) {  // measured on c2 (profiles/r2a_assembly.md): 3 resident blocks, layer loop unrolled by 2
+        const char* un = getenv("PBSM3D_ASM_UNROLL");
+        const int unr = un ? atoi(un) : 2;
+        if (unr == 2) {
+            if (minb == 4) return setup_assembly_fn(h, assemble_kernel<4, 2>, 0, 128);
+            if (minb == 2) return setup_assembly_fn(h, assemble_kernel<2, 2>, 0, 128);
+            return setup_assembly_fn(h, assemble_kernel<3, 2>, 0, 128);
+        }
+        if (minb == 4) return setup_assembly_fn(h, assemble_kernel<4, 1>, 0, 128);
+        if (minb == 5) return setup_assembly_fn(h, assemble_kernel<5, 1>, 0, 128);
+        if (minb == 6) return setup_assembly_fn(h, assemble_kernel<6, 1>, 0, 128);
+        return setup_assembly_fn(h, assemble_kernel<3, 1>, 0, 128);
+    }
+    if (L <= 4) return setup_assembly_fn(h, assemble_tile_kernel<4, 4>, 4, 128);
+    if (L <= 5) return setup_assembly_fn(h, assemble_tile_kernel<5, 4>, 5, 160);
+    if (L <= 8) return setup_assembly_fn(h, assemble_tile_kernel<8, 3>, 8, 256);
+    if (L <= 10) {
+        if (minb == 2) return setup_assembly_fn(h, assemble_tile_kernel<10, 2>, 10, 320);
+        if (minb == 4) return setup_assembly_fn(h, assemble_tile_kernel<10, 4>, 10, 320);
+        if (minb == 5) return setup_assembly_fn(h, assemble_tile_kernel<10, 5>, 10, 320);
+        return setup_assembly_fn(h, assemble_tile_kernel<10, 3>, 10, 320);
+    }
+    if (L <= 16) return setup_assembly_fn(h, assemble_tile_kernel<16, 2>, 16, 512);
+    if (L <= 20) return setup_assembly_fn(h, assemble_tile_kernel<20, 1>, 20, 640);
+    return setup_assembly_fn(h, assemble_tile_kernel<32, 1>, 32, 1024);
 }
 void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt, int i0, int i1, int chunk) {
-    if (h->asm_nw == 0) {
-        const int ntiles = cdiv((size_t)(i1 - i0), 128);
-        LAUNCH(h, assemble_kernel, std::max(1, std::min(ntiles, kRedBlocks)), 128, h->dc, h->dm, f, h->ss, dt, i0, i1, h->partial,
-               kRedBlocks, h->sc, h->red + 2 * chunk);
-        return;
-    }
-    const int grid = std::max(1, std::min(cdiv((size_t)(i1 - i0), 32), h->asm_grid));
+    LAUNCH(h, face_prelude_kernel, cdiv((size_t)(i1 - i0), 128), 128, h->dc, h->dm, f, h->ss, dt, i0, i1, h->recs);
+    const int per = h->asm_nw ? 32 : 128;
+    const int grid = std::max(1, std::min(cdiv((size_t)(i1 - i0), per), h->asm_grid));
     ++h->n_launch;
-    ((AsmKernel)h->asm_fn)<<<grid, h->asm_nw * 32, h->asm_smem, h->stream>>>(h->dc, h->dm, f, h->ss, dt, i0, i1, h->partial, kRedBlocks,
+    ((AsmKernel)h->asm_fn)<<<grid, h->asm_threads, h->asm_smem, h->stream>>>(h->dc, h->dm, h->recs, h->ss, i0, i1, h->partial, kRedBlocks,
                                                                             h->sc, h->red + 2 * chunk);
 }
 
@@ -2006,6 +2025,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     dc.cutoff = cfg->cutoff;
     dc.snow_diffusion_const = cfg->snow_diffusion_const;
     dc.dz = 5.0 / (double)L;  // susp_depth / nLayer
+    dc.inv_dz = 1.0 / dc.dz;
     dc.l_max = 40.0;
     DevMesh& dm = h->dm;
     dm.T = T;

@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "pbsm3d_physics.cuh"
+#include "pbsm3d_math.cuh"
 
 namespace pbsm3d {
 
@@ -27,6 +28,7 @@ struct DevConfig {
     int use_exp_fetch, use_tanh_fetch, use_R94_lambda, use_PomLi;
     double settling_velocity, eps, min_sd_trans, cutoff, snow_diffusion_const;
     double dz;     // v_edge_height = susp_depth / nLayer (PBSM3D.cpp:225-226)
+    double inv_dz;
     double l_max;  // 40 (PBSM3D.cpp:227)
 };
 
@@ -345,34 +347,37 @@ struct LayerConsts {
     double sig;      // 1.019 + 0.027 ln cz
     double lmix;     // mixing length
     double ulog;     // ln((cz - z0)/z0): the log-profile factor of u_z
+    double ulog136;  // ulog^1.36 (table rows only: xrz = 0.005 u_z^1.36 without a log/exp pair)
 };
-constexpr int kTabN = 8;  // doubles per layer in SuspSystem::ltab (LayerConsts, field order)
+constexpr int kTabN = 9;  // doubles per layer in SuspSystem::ltab (LayerConsts, field order)
 
-// x^y for x > 0 as exp(y log x): |y log x| < 40 on every use below, so the result is within ~1e-14 relative of pow() (the
-// parity bar on coefficients is 1e-12) at a fraction of pow()'s fp64 cost.
+// x^y on this path is exp(y ln x) through pbsm3d_math.cuh (flog/fexp: ~1 ulp, branch-free): |y ln x| < 20 on every use, so
+// the result is within ~2e-15 relative of pow(); the parity bar on coefficients is 1e-12.
 __device__ __forceinline__ LayerConsts layer_consts(const DevConfig& c, double cz, double sd) {
     LayerConsts o;
     o.cz = cz;
-    const double lcz = log(cz);
+    const double lcz = flog(cz);
     const double lrm = -0.258 * lcz;                        // rm = 4.6e-5 cz^-0.258 (:1009)
-    const double rm = 4.6e-5 * exp(lrm);
-    const double mm_alpha = 4.08 + 12.6 * cz;               // :1012
-    const double P = 1.0 + 3.0 / mm_alpha + 2.0 / (mm_alpha * mm_alpha);
+    const double rm = 4.6e-5 * fexp(lrm);
+    const double ia = frcp(4.08 + 12.6 * cz);               // mm_alpha (:1012)
+    const double P = 1.0 + ia * (3.0 + 2.0 * ia);           // 1 + 3/a + 2/a^2
     const double mm = 4.0 / 3.0 * kPi * kRhoIce * rm * rm * rm * P;  // :1013-1014
-    o.inv_mm = 1.0 / mm;
+    o.inv_mm = frcp(mm);
     // r_z = (3 mm / (4 pi rho_p))^0.3333333 (:1017, the literal exponent) = (rm^3 P)^(1/3 - e), e = 1/3 - 0.3333333:
     //     = rm cbrt(P) exp(-e ln(rm^3 P)); the last factor is 1 + O(1e-6), so ln(rm^3 P) is needed to ~1e-9 only.
     {
         const double e = 1.0 / 3.0 - 0.3333333;
-        const double l3 = 3.0 * (log(4.6e-5) + lrm) + (double)__logf((float)P);
+        const double l3 = 3.0 * (-9.986869161475179 /* ln 4.6e-5 */ + lrm) + (double)__logf((float)P);
         const double t = -e * l3;  // |t| < 2e-6: three terms of exp() are exact to 1e-19
-        o.r_z = rm * cbrt(P) * (1.0 + t * (1.0 + t * (0.5 + t * (1.0 / 6.0))));
+        o.r_z = rm * fcbrt_1_15(P) * (1.0 + t * (1.0 + t * (0.5 + t * (1.0 / 6.0))));  // P in (1, 1.46]
     }
-    o.omega = c.do_fixed_settling ? c.settling_velocity : 1.1e7 * exp(1.8 * log(o.r_z));  // :1024-1033
+    o.omega = c.do_fixed_settling ? c.settling_velocity : 1.1e7 * fexp(1.8 * flog(o.r_z));  // :1024-1033
     o.Qr = 0.9 * kPi * rm * rm * 120.0;                     // :1097
     o.sig = 1.019 + 0.027 * lcz;                            // :1095
-    o.lmix = kKappa * (cz + kZ0Snow) * c.l_max / (kKappa * (cz + kZ0Snow) + c.l_max);  // :1156
-    o.ulog = log(((cz + sd) - (sd + kZ0Snow)) / kZ0Snow);   // :970-976 with hz = cz + sd
+    const double kz = kKappa * (cz + kZ0Snow);
+    o.lmix = kz * c.l_max * frcp(kz + c.l_max);             // :1156
+    o.ulog = flog(((cz + sd) - (sd + kZ0Snow)) * (1.0 / kZ0Snow));  // :970-976 with hz = cz + sd
+    o.ulog136 = 0.0;
     return o;
 }
 // Table of LayerConsts for hs = 0 (every non-saltating face: hs = 0, z0 = Z0_SNOW), built once in pbsm3d_create by
@@ -381,15 +386,15 @@ __global__ void layer_table_kernel(DevConfig c, double* __restrict__ tab) {
     const int z = threadIdx.x;
     if (z >= c.L) return;
     const LayerConsts o = layer_consts(c, z * c.dz + 0.0 + c.dz / 2.0, 0.0);
-    const double v[kTabN] = {o.cz, o.inv_mm, o.r_z, o.omega, o.Qr, o.sig, o.lmix, o.ulog};
+    const double v[kTabN] = {o.cz, o.inv_mm, o.r_z, o.omega, o.Qr, o.sig, o.lmix, o.ulog, fpow(o.ulog, 1.36)};
     for (int k = 0; k < kTabN; ++k) tab[k * c.L + z] = v[k];
 }
 
 // ---- per-face part: saltation (PBSM3D.cpp:436-925) and the factors of the layer loop that do not depend on z
 struct FaceConsts {
-    double hs, height_diff, u28 /* 2.8 u*_t */, UQ /* U_R / ln((Z_UR - (sd+z0))/z0) */, uref, sd;
+    double hs, height_diff, u28 /* 2.8 u*_t */, UQ /* U_R / ln((Z_UR - (sd+z0))/z0) */, UQ136 /* 0.005 UQ^1.36 */, uref, sd;
     double C1p, C2;       // dm/dt = C1p sig Nu r_z + C2 Qr   (the reference's expression :1105-1123 with Sh = Nu cancelled)
-    double ustar, area, c_salt;
+    double ustar, area, aod /* area / dz */, a4p /* area / (hs/2 + dz/2) */, v5 /* area dz / 5 */, c_salt;
     double Aj[3], g[3];   // lateral face areas E_j dz; unit wind . edge normal
     int flags;            // bit 0 saltation, bits 1-3 neighbour j present, bit 4 active (a real face)
     int p;                // slot
@@ -432,20 +437,20 @@ __device__ __forceinline__ FaceConsts face_prelude(const DevConfig& c, const Dev
     double lambda = 0.0, ustar = 1.3;
     if (height_diff <= c.cutoff && sd >= c.min_sd_trans && !water) {
         lambda = c.use_R94_lambda ? 0.5 * LAI * height_diff : Nst * dv * height_diff;
-        ustar = u2 * kKappa / log(2.0 / 0.0002);
+        ustar = u2 * kKappa / 9.210340371976184 /* ln(2/0.0002) */;
         if (ustar >= ust_th) salt = true;
     }
     const double z0 = kZ0Snow;
-    if (!salt) ustar = fmax(0.01, kKappa * uref / log(kZUR / z0));
+    if (!salt) ustar = fmax(0.01, kKappa * uref / 8.517193191416238 /* ln(Z_UR/z0) */);
     ustar = fmax(0.01, ustar);
-    const double hs = salt ? 0.08436 * pow(ustar, 1.27) : 0.0;
+    const double hs = salt ? 0.08436 * fpow(ustar, 1.27) : 0.0;  // ustar^1.27 (:752); see layer_consts on exp(y ln x)
 
     const double t = Tc + 273.15;
     double vx, vy;
     wind_unit_vector(phi, vx, vy);
     double Qsalt = 0.0, c_salt = 0.0;
     if (salt) {
-        const double rho_f = std_dry_air_density(m.zc[p], t);
+        const double rho_f = std_dry_air_density_fast(m.zc[p], t);
         const double mB = 0.16 * 202.0;
         const double tau_n_ratio = (mB * lambda) / (1.0 + mB * lambda);
         c_salt = rho_f / (3.29 * ustar) * (1.0 - tau_n_ratio - (ust_th * ust_th) / (ustar * ustar));
@@ -488,30 +493,34 @@ __device__ __forceinline__ FaceConsts face_prelude(const DevConfig& c, const Dev
     //     Sh rho_sat D (2 pi' Nu Rg r_z sigma t^2 lambda_t - Ls Mw Qr + Qr Rg t) / (D Ls Sh (Ls Mw - Rg t) rho_sat + lambda_t t^2 Nu Rg)
     // is  C1 sigma Nu r_z + C2 Qr  with the two per-face constants below (pi' = 6.283185308 / 2 as written there)
     {
-        const double rh = f.rh[i] / 100.0;
-        const double es = saturated_vapour_pressure(t);
-        const double D = 2.06e-5 * pow(t / 273.15, 1.75);
+        const double rh = f.rh[i] * 0.01;
+        const double es = 611.21 * fexp((17.502 * Tc) * frcp(240.97 + Tc));  // saturatedVapourPressure, Kelvin >= 0 branch (Atmosphere.cpp:62-80)
+        const double D = 2.06e-5 * fpow(t * (1.0 / 273.15), 1.75);
         const double lambda_t = 0.000063 * t + 0.00673;
         const double Ls = 2.838e6, Mw = 18.01, Rg = 8313.0;
-        const double rho_sat = (Mw * es) / (Rg * t);
-        const double inv_den = 1.0 / (D * Ls * (Ls * Mw - Rg * t) * rho_sat + lambda_t * t * t * Rg);
+        const double rho_sat = (Mw * es) * frcp(Rg * t);
+        const double inv_den = frcp(D * Ls * (Ls * Mw - Rg * t) * rho_sat + lambda_t * t * t * Rg);
         o.C1p = rho_sat * D * (6.283185308 * Rg * t * t * lambda_t) * inv_den * (rh - 1.0);
         o.C2 = rho_sat * D * (Rg * t - Ls * Mw) * inv_den;
     }
     o.hs = hs;
     o.height_diff = height_diff;
     o.u28 = 2.8 * ust_th;
-    o.UQ = uref / log((kZUR - (sd + z0)) / z0);
+    o.UQ = uref * frcp(flog((kZUR - (sd + z0)) * (1.0 / kZ0Snow)));
+    o.UQ136 = o.UQ > 0 ? 0.005 * fpow(o.UQ, 1.36) : 0.0;
     o.uref = uref;
     o.sd = sd;
     o.ustar = ustar;
     o.area = area;
+    o.aod = area * c.inv_dz;
+    o.a4p = area * frcp(hs / 2.0 + c.dz / 2.0);
+    o.v5 = area * c.dz / 5.0;
     o.c_salt = c_salt;
-    const double nrm = sqrt(vx * vx + vy * vy);
+    const double inrm = frcp(fsqrt(vx * vx + vy * vy));
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         o.Aj[j] = Ej[j] * c.dz;
-        o.g[j] = (vx * nxj[j] + vy * nyj[j]) / nrm;  // u . m_j = u_z g_j  (uvw = u_z v / |v|, :1189-1200)
+        o.g[j] = (vx * nxj[j] + vy * nyj[j]) * inrm;  // u . m_j = u_z g_j  (uvw = u_z v / |v|, :1189-1200)
     }
     o.flags = flags;
     return o;
@@ -523,21 +532,25 @@ struct RowCoef64 {
 };
 __device__ __forceinline__ RowCoef64 assemble_row(const DevConfig& c, const FaceConsts& fc, const LayerConsts& lc, int z, int L,
                                                   double& u_z_out, double& csubl_out) {
-    const double dz = c.dz;
     const bool salt = fc.flags & 1;
     const double cz = lc.cz;
-    double u_z;
-    if (salt && cz < fc.height_diff) u_z = fc.u28;
-    else if (cz < fc.height_diff) u_z = 0.01;
-    else if (cz + fc.sd < kZUR) u_z = fmax(0.01, fc.UQ * lc.ulog);
-    else u_z = fmax(0.01, fc.uref);
+    double u_z, xrz;  // xrz = 0.005 u_z^1.36 (:1020)
+    if (cz >= fc.height_diff && cz + fc.sd < kZUR && fc.UQ * lc.ulog >= 0.01) {  // the log profile, not clamped: the common case
+        u_z = fc.UQ * lc.ulog;
+        xrz = fc.UQ136 * (lc.ulog136 != 0.0 ? lc.ulog136 : fpow(lc.ulog, 1.36));
+    } else {
+        if (salt && cz < fc.height_diff) u_z = fc.u28;
+        else if (cz < fc.height_diff) u_z = 0.01;
+        else if (cz + fc.sd < kZUR) u_z = fmax(0.01, fc.UQ * lc.ulog);
+        else u_z = fmax(0.01, fc.uref);
+        xrz = 0.005 * fpow(u_z, 1.36);
+    }
     u_z_out = u_z;
 
-    const double xrz = 0.005 * exp(1.36 * log(u_z));        // :1020
     const double omega = lc.omega;
-    const double Vr = omega + 3.0 * xrz * cos(kPi / 4.0);   // :1039
-    const double Re = 2.0 * lc.r_z * Vr / 1.88e-5;
-    const double Nu = 1.79 + 0.606 * sqrt(Re);
+    const double Vr = omega + 3.0 * xrz * 0.70710678118654757 /* cos(pi/4) */;  // :1039
+    const double Re = 2.0 * lc.r_z * Vr * (1.0 / 1.88e-5);
+    const double Nu = 1.79 + 0.606 * fsqrt(Re);
     const double dmdtz = fc.C1p * lc.sig * Nu * lc.r_z + fc.C2 * lc.Qr;
     const double csubl = c.do_sublimation ? dmdtz * lc.inv_mm : 0.0;
     csubl_out = csubl;
@@ -546,10 +559,10 @@ __device__ __forceinline__ RowCoef64 assemble_row(const DevConfig& c, const Face
     if (c.rouault) diffusion_coeff = 1.0 / (1.0 + (1.0 * omega * omega) / (1.56 * fc.ustar * fc.ustar));
     const double K = diffusion_coeff * fc.ustar * lc.lmix;
     const double area = fc.area;
-    const double alpha3 = area * K / dz;
+    const double alpha3 = fc.aod * K;  // area K / dz
     const double alpha4 = alpha3;
     const double udotm3 = -omega, udotm4 = omega;
-    const double Vc = (area * dz / 5.0) * csubl;
+    const double Vc = fc.v5 * csubl;
 
     RowCoef64 o;
     double d = 0.0;
@@ -570,7 +583,7 @@ __device__ __forceinline__ RowCoef64 assemble_row(const DevConfig& c, const Face
     }
     double lo = 0.0, up = 0.0, rhs = 0.0;
     if (z == 0) {
-        const double alpha4p = area * K / (fc.hs / 2.0 + dz / 2.0);
+        const double alpha4p = fc.a4p * K;  // area K / (hs/2 + dz/2)
         d += Vc - area * udotm4 - alpha4p;
         rhs = -alpha4p * fc.c_salt;
         // the coupling to layer 1; with nLayer == 1 the reference sums it into a column outside the matrix (dropped)
@@ -598,6 +611,7 @@ __device__ __forceinline__ LayerConsts layer_lookup(const DevConfig& c, const Fa
     const int L = c.L;
     o.cz = __ldg(tab + z); o.inv_mm = __ldg(tab + L + z); o.r_z = __ldg(tab + 2 * L + z); o.omega = __ldg(tab + 3 * L + z);
     o.Qr = __ldg(tab + 4 * L + z); o.sig = __ldg(tab + 5 * L + z); o.lmix = __ldg(tab + 6 * L + z); o.ulog = __ldg(tab + 7 * L + z);
+    o.ulog136 = __ldg(tab + 8 * L + z);
     return o;
 }
 __device__ __forceinline__ void store_row(const SuspSystem& s, size_t r, size_t LTp, const RowCoef64& rc, double den, double inv,
@@ -611,105 +625,107 @@ __device__ __forceinline__ void store_row(const SuspSystem& s, size_t r, size_t 
     s.pack32[r] = make_float4((float)l0, (float)l1, (float)l2, (float)bS);
 }
 
-// Layer-parallel assembly.  A block of NW warps owns tiles of 32 faces (CHM order, the order the forcing arrives in, so the
+// Per-face records between the prelude kernel and the row kernels: SoA [kRecD][T] doubles + [2][T] ints, CHM face order.
+constexpr int kRecD = 21;
+struct FaceRecs {
+    double* d;   // [kRecD][T]
+    int* i;      // [2][T]: flags, slot
+    int T;
+};
+__device__ __forceinline__ void store_rec(const FaceRecs& R, int i, const FaceConsts& fc) {
+    const double v[kRecD] = {fc.hs, fc.height_diff, fc.u28, fc.UQ, fc.uref, fc.sd, fc.C1p, fc.C2, fc.ustar, fc.area, fc.c_salt,
+                             fc.Aj[0], fc.Aj[1], fc.Aj[2], fc.g[0], fc.g[1], fc.g[2], fc.UQ136, fc.aod, fc.a4p, fc.v5};
+#pragma unroll
+    for (int k = 0; k < kRecD; ++k) R.d[(size_t)k * R.T + i] = v[k];
+    R.i[i] = fc.flags;
+    R.i[R.T + i] = fc.p;
+}
+__device__ __forceinline__ FaceConsts load_rec(const FaceRecs& R, int i) {
+    FaceConsts fc;
+    const double* d = R.d + i;
+    const size_t T = R.T;
+    fc.hs = d[0]; fc.height_diff = d[T]; fc.u28 = d[2 * T]; fc.UQ = d[3 * T]; fc.uref = d[4 * T]; fc.sd = d[5 * T];
+    fc.C1p = d[6 * T]; fc.C2 = d[7 * T]; fc.ustar = d[8 * T]; fc.area = d[9 * T]; fc.c_salt = d[10 * T];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { fc.Aj[j] = d[(11 + j) * T]; fc.g[j] = d[(14 + j) * T]; }
+    fc.UQ136 = d[17 * T]; fc.aod = d[18 * T]; fc.a4p = d[19 * T]; fc.v5 = d[20 * T];
+    fc.flags = R.i[i];
+    fc.p = R.i[T + i];
+    return fc;
+}
+
+// Kernel 1 of the assembly: one thread per CHM face (coalesced forcing reads): saltation, Qsalt/c_salt, the per-face factors
+// of the layer loop, and the two global facts of the right-hand side (b is non-zero in layer 0 only, and known here:
+// b0 = -alpha4' c_salt needs K of layer 0, so the row kernel reports it; this kernel leaves red alone).
+__global__ void __launch_bounds__(128) face_prelude_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt, int i0, int i1,
+                                                          FaceRecs R) {
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    store_rec(R, i, face_prelude(c, m, f, s, dt, m.iperm[i], i));
+}
+
+// Kernel 2, layer-parallel.  A block of NW warps owns tiles of 32 faces (CHM order, the order the forcing arrives in, so the
 // step can assemble one chunk while the next chunk's forcing is still crossing PCIe); warp z computes the rows of layer z, so
-// the 32 lanes write 32 consecutive faces of every stream of that layer, and no thread walks a column.  Two short serial
-// pieces ride on single warps while the others wait at a barrier (other resident blocks fill the SM meanwhile):
-//     warp 1: the per-face prelude (saltation, wind, sublimation constants) of the NEXT tile       } concurrently
-//     warp 0: the Thomas recurrence den_z = d_z - lo_z cp_{z-1} of this tile's 32 columns (shared) }
-// Non-saltating faces (hs = 0) take everything that depends on the height only from a per-layer table (SuspSystem::ltab): their
-// rows cost one log/exp pair, a square root and the coefficient arithmetic.
+// the 32 lanes write 32 consecutive faces of every stream of that layer and no thread walks a column; the per-face record
+// is read by every warp of the block (one DRAM read, L1 hits after that).  The one serial piece, the Thomas recurrence
+// den_z = d_z - lo_z cp_{z-1} over the tile's 32 columns, runs on warp 0 out of shared memory between two barriers.
+// Faces with hs = 0 (all non-saltating ones) take everything that depends on the height only from a per-layer table
+// (SuspSystem::ltab): their rows cost one log/exp pair, a square root and the coefficient arithmetic.
 // red[0] = max|b|, red[1] = sum b^2 over the chunk (this rank).
-constexpr int kRecD = 17;  // doubles per face in the shared prelude record
 template <int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
-assemble_tile_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt, int i0, int i1, double* __restrict__ partial,
-                     int pstride, Scalars* sc, double* __restrict__ red) {
+assemble_tile_kernel(DevConfig c, DevMesh m, FaceRecs R, SuspSystem s, int i0, int i1, double* __restrict__ partial, int pstride,
+                     Scalars* sc, double* __restrict__ red) {
     extern __shared__ double sm[];
     const int L = c.L;
-    double* rec = sm;                          // [kRecD][32]
-    int* reci = (int*)(sm + kRecD * 32);       // [2][32]: flags, slot
-    double* colA = sm + kRecD * 32 + 32;       // [L][32] d   -> den
+    double* colA = sm;                         // [L][32] d   -> den
     double* colB = colA + (size_t)L * 32;      // [L][32] lo  -> 1/den
     double* colC = colB + (size_t)L * 32;      // [L][32] up  -> cp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int wPre = NW > 1 ? 1 : 0;
     const int ntiles = (i1 - i0 + 31) / 32;
     const size_t LTp = (size_t)L * m.Tp;
     double mx = 0.0, ss = 0.0;
-
-    auto prelude = [&](int tile) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = i0 + tile * 32 + lane;
-        if (i < i1) {
-            const FaceConsts fc = face_prelude(c, m, f, s, dt, m.iperm[i], i);
-            const double v[kRecD] = {fc.hs, fc.height_diff, fc.u28, fc.UQ, fc.uref, fc.sd, fc.C1p, fc.C2, fc.ustar, fc.area, fc.c_salt,
-                                     fc.Aj[0], fc.Aj[1], fc.Aj[2], fc.g[0], fc.g[1], fc.g[2]};
-#pragma unroll
-            for (int k = 0; k < kRecD; ++k) rec[k * 32 + lane] = v[k];
-            reci[lane] = fc.flags;
-            reci[32 + lane] = fc.p;
-        } else {
-            reci[lane] = 0;
-            reci[32 + lane] = 0;
-        }
-    };
-    int tile = blockIdx.x;
-    if (tile < ntiles && w == wPre) prelude(tile);
-    __syncthreads();
-    for (; tile < ntiles; tile += gridDim.x) {
-        // ---- rows of layer w of this tile's faces
+        const bool act = i < i1 && w < L;
         RowCoef64 rc;
         int p = 0;
-        bool act = false;
-        if (w < L) {
-            FaceConsts fc;
-            fc.flags = reci[lane];
-            p = reci[32 + lane];
-            act = fc.flags & 16;
-            if (act) {
-                fc.hs = rec[lane]; fc.height_diff = rec[32 + lane]; fc.u28 = rec[2 * 32 + lane]; fc.UQ = rec[3 * 32 + lane];
-                fc.uref = rec[4 * 32 + lane]; fc.sd = rec[5 * 32 + lane]; fc.C1p = rec[6 * 32 + lane]; fc.C2 = rec[7 * 32 + lane];
-                fc.ustar = rec[8 * 32 + lane]; fc.area = rec[9 * 32 + lane]; fc.c_salt = rec[10 * 32 + lane];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) { fc.Aj[j] = rec[(11 + j) * 32 + lane]; fc.g[j] = rec[(14 + j) * 32 + lane]; }
-                const LayerConsts lc = layer_lookup(c, fc, s.ltab, w);
-                double u_z, csubl;
-                rc = assemble_row(c, fc, lc, w, L, u_z, csubl);
-                const size_t r = (size_t)w * m.Tp + p;
-                s.u_z[r] = u_z;
-                s.csubl[r] = csubl;
-                colA[w * 32 + lane] = rc.d;
-                colB[w * 32 + lane] = rc.lo;
-                colC[w * 32 + lane] = rc.up;
-                if (w == 0) {
-                    mx = fmax(mx, fabs(rc.rhs));
-                    ss += rc.rhs * rc.rhs;
-                }
+        if (act) {
+            const FaceConsts fc = load_rec(R, i);
+            p = fc.p;
+            const LayerConsts lc = layer_lookup(c, fc, s.ltab, w);
+            double u_z, csubl;
+            rc = assemble_row(c, fc, lc, w, L, u_z, csubl);
+            const size_t r = (size_t)w * m.Tp + p;
+            s.u_z[r] = u_z;
+            s.csubl[r] = csubl;
+            colA[w * 32 + lane] = rc.d;
+            colB[w * 32 + lane] = rc.lo;
+            colC[w * 32 + lane] = rc.up;
+            if (w == 0) {
+                mx = fmax(mx, fabs(rc.rhs));
+                ss += rc.rhs * rc.rhs;
             }
         }
         __syncthreads();
-        // ---- serial pieces: the column recurrence of this tile (warp 0), the prelude of the block's next tile (warp wPre)
-        if (w == 0 && act) {  // act is this lane's face in every warp (registers: reci is being rewritten by warp wPre)
+        if (w == 0 && act) {
             double cp_prev = 0.0;
             for (int z = 0; z < L; ++z) {
                 const double den = colA[z * 32 + lane] - colB[z * 32 + lane] * cp_prev;
-                const double inv = 1.0 / den;
+                const double inv = frcp(den);
                 cp_prev = colC[z * 32 + lane] * inv;
                 colA[z * 32 + lane] = den;
                 colB[z * 32 + lane] = inv;
                 colC[z * 32 + lane] = cp_prev;
             }
         }
-        if (w == wPre && tile + (int)gridDim.x < ntiles) prelude(tile + gridDim.x);
         __syncthreads();
-        // ---- scale and store
         if (act) {
             const double den = colA[w * 32 + lane], inv = colB[w * 32 + lane], cp = colC[w * 32 + lane];
             store_row(s, (size_t)w * m.Tp + p, LTp, rc, den, inv, cp);
             if (w == 0) { s.rhs0[p] = rc.rhs; s.rhsS0[p] = rc.rhs * inv; }
         }
-        // no barrier: in the next iteration warp w touches only row w of colA..C again, and rec/reci were rewritten before
-        // the barrier above
+        // no barrier: in the next iteration warp w writes only row w of colA..C before the next barrier
     }
     double o0, o1;
     if (grid_fold<2>(mx, ss, 1, 0, partial, pstride, &sc->ticket[0], o0, o1)) {
@@ -717,11 +733,12 @@ assemble_tile_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double 
     }
 }
 
-// Column-walking variant (one thread per face column): any nLayer, and the cross-check of the tile kernel in the tests
-// (PBSM3D_ASSEMBLY=column).  Same arithmetic, same streams.
-__global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt, int i0, int i1,
-                                                       double* __restrict__ partial, int pstride, Scalars* sc,
-                                                       double* __restrict__ red) {
+// Kernel 2, column-walking variant (one thread per face column): any nLayer, and the cross-check of the tile kernel in the
+// tests (PBSM3D_ASSEMBLY=column).  Same arithmetic, same streams.
+template <int MINB, int UNR>
+__global__ void __launch_bounds__(128, MINB) assemble_kernel(DevConfig c, DevMesh m, FaceRecs R, SuspSystem s, int i0, int i1,
+                                                             double* __restrict__ partial, int pstride, Scalars* sc,
+                                                             double* __restrict__ red) {
     double mx = 0.0, ss = 0.0;
     const int ntiles = (i1 - i0 + 127) / 128;
     const int L = c.L;
@@ -729,9 +746,10 @@ __global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, D
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = i0 + tile * 128 + threadIdx.x;
         if (i < i1) {
-            const int p = m.iperm[i];
-            const FaceConsts fc = face_prelude(c, m, f, s, dt, p, i);
+            const FaceConsts fc = load_rec(R, i);
+            const int p = fc.p;
             double cp_prev = 0.0;
+#pragma unroll UNR
             for (int z = 0; z < L; ++z) {
                 const LayerConsts lc = layer_lookup(c, fc, s.ltab, z);
                 double u_z, csubl;
@@ -740,7 +758,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(DevConfig c, DevMesh m, D
                 s.u_z[r] = u_z;
                 s.csubl[r] = csubl;
                 const double den = rc.d - rc.lo * cp_prev;
-                const double inv = 1.0 / den;
+                const double inv = frcp(den);
                 cp_prev = rc.up * inv;
                 store_row(s, r, LTp, rc, den, inv, cp_prev);
                 if (z == 0) {

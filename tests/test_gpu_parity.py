@@ -211,7 +211,7 @@ def test_error_paths_on_device(granger):
     with pytest.raises(capi.Pbsm3dError, match="out of bound neighbors"):
         capi.Handle(capi.default_config(nLayer=5), bad)
     with pytest.raises(capi.Pbsm3dError, match="nLayer"):
-        capi.Handle(capi.default_config(nLayer=1), granger)
+        capi.Handle(capi.default_config(nLayer=0), granger)
     h = capi.Handle(capi.default_config(nLayer=5, max_iterations=3, solver=capi.SOLVER_LINE), granger)
     geo = granger.geometry()
     with pytest.raises(capi.Pbsm3dError) as e:
