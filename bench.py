@@ -106,6 +106,17 @@ def sweep_bytes_per_row(L: int, fp32_streams: bool = False) -> float:
     return (36.0 if fp32_streams else 56.0) + 20.0 / L
 
 
+def persistent_solve_bytes(st, T, L):
+    """Algorithmic HBM bytes of ONE launch of gs_persistent_kernel (the whole suspension solve of a step): per row and sweep
+    30 B while the iterate is stored in fp32 (20 B fp32 coefficient copies + x in/out 2x4 + 2), 38 B with fp64 x, 58 B on fp64
+    coefficients; 58 B per residual check (3 latS + belowS + cp + den + x, + slots/rhs amortised); 12 B once for the
+    fp32 -> fp64 conversion of the iterate; 4 B for zeroing the fp32 iterate."""
+    n, n32, nx = st["sweeps_timed"], st["sweeps_timed_fp32"], st["sweeps_fp32_x"]
+    per_row = nx * (28.0 + 20.0 / L) + (n32 - nx) * (36.0 + 20.0 / L) + (n - n32) * (56.0 + 20.0 / L) \
+        + st["residual_checks"] * (56.0 + 20.0 / L) + (16.0 if nx > 0 else 0.0)
+    return per_row * T * L
+
+
 # ------------------------------------------------------------------------------------------ CPU reference arm
 N_FORCING = 3  # distinct synthetic forcing fields cycled over the steps (iteration counts differ from step to step)
 
@@ -266,6 +277,7 @@ def main():
     if rank == 0:
         sampler.start()
     ev_ms, launches, sweep_ms, sweeps, sweep32_ms, sweeps32 = 0.0, 0, 0.0, 0, 0.0, 0
+    solve_bytes, solve_launches, sweeps_x32, checks = 0.0, 0, 0, 0
     phases = {"ms_assembly": 0.0, "ms_suspension_solve": 0.0, "ms_flux_and_halo": 0.0, "ms_deposition": 0.0}
     t0 = time.perf_counter()
     syncs, susp_its, dep_its = 0, [], []
@@ -280,6 +292,11 @@ def main():
         sweeps += st["sweeps_timed"]
         sweep32_ms += st["ms_line_sweeps_fp32"]
         sweeps32 += st["sweeps_timed_fp32"]
+        if st.get("persistent_kernels") and st["suspension_present"]:
+            solve_bytes += persistent_solve_bytes(st, T, NLAYER)
+            solve_launches += 1
+            sweeps_x32 += st["sweeps_fp32_x"]
+            checks += st["residual_checks"]
         for k in phases:
             phases[k] += st[k]
     barrier()
@@ -349,9 +366,10 @@ def main():
     total_rows = G * NLAYER
     value = total_rows / (ms_step * 1e-3)
     e2e = total_rows / (e2e_ms * 1e-3)
-    # ---- roofline of the dominant kernel (line sweep), timed live inside the timed steps with CUDA events
+    # ---- roofline of the dominant kernel, timed live inside the timed steps with CUDA events
     peak, peak_src = measured_peak_gbs()
-    # the dominant kernel is the sweep on fp32-rounded coefficient streams when the step used it (most sweeps do), else the fp64 one
+    persistent = bool(st.get("persistent_kernels"))
+    # per-pass path: the dominant kernel is the sweep on fp32-rounded coefficient streams when the step used it (most sweeps do)
     use32 = sweeps32 > 0
     n_dom = sweeps32 if use32 else sweeps
     avg_sweep_ms = (sweep32_ms if use32 else sweep_ms) / max(n_dom, 1)
@@ -367,6 +385,30 @@ def main():
             traffic, traffic32 = tj.get("dram_bytes_per_launch"), tj.get("dram_bytes_per_launch_fp32_streams")
         except Exception:
             traffic = traffic32 = None
+    if persistent and solve_launches:
+        ach_p = solve_bytes / (sweep_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm",
+                    "kernel": "gs_persistent_kernel<10> (one cooperative launch = the whole suspension solve of a step: line "
+                              "Gauss-Seidel sweeps in three storage phases + residual checks, grid barriers between colour passes)",
+                    "achieved": ach_p, "peak": peak, "unit": "GB/s", "frac": ach_p / peak, "traffic": traffic, "peak_source": peak_src,
+                    "bytes_per_launch": solve_bytes / solve_launches, "avg_launch_ms": sweep_ms / solve_launches,
+                    "launches_timed": int(solve_launches), "share_of_step": sweep_ms / max(ev_ms, 1e-9),
+                    "per_launch": {"sweeps": sweeps / solve_launches, "of_which_fp32_coefficients": sweeps32 / solve_launches,
+                                   "of_which_fp32_x": sweeps_x32 / solve_launches, "residual_checks": checks / solve_launches},
+                    "bytes_per_row": {"fp32_x_sweep": 28.0 + 20.0 / NLAYER, "fp32_coefficient_sweep": 36.0 + 20.0 / NLAYER,
+                                      "fp64_sweep": 56.0 + 20.0 / NLAYER, "residual_check": 56.0 + 20.0 / NLAYER}}
+    else:
+        roofline = {"bound": "hbm",
+                    "kernel": ("gs_sweep_kernel<10, float> (fp32-rounded coefficient streams, fp64 x and arithmetic; " if use32
+                               else "gs_sweep_kernel<10, double> (") + "one full sweep = all colour passes)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic if not use32 else traffic32, "peak_source": peak_src,
+                    "bytes_per_launch": row_bytes * T * NLAYER, "avg_launch_ms": avg_sweep_ms,
+                    "launches_timed": int(n_dom), "share_of_step": (sweep32_ms if use32 else sweep_ms) / max(ev_ms, 1e-9),
+                    "fp64_stream_sweeps": {"launches_timed": int(sweeps - sweeps32), "avg_launch_ms": avg64_ms, "achieved": ach64,
+                                           "frac": (ach64 / peak) if ach64 else None,
+                                           "bytes_per_launch": sweep_bytes_per_row(NLAYER) * T * NLAYER,
+                                           "share_of_step": (sweep_ms - sweep32_ms) / max(ev_ms, 1e-9)}}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -391,17 +433,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * 8 * T * world,
                     "d2h_bytes_per_step": 8 * 8 * T * world},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm",
-                         "kernel": ("gs_sweep_kernel<10, float> (fp32-rounded coefficient streams, fp64 x and arithmetic; " if use32
-                                    else "gs_sweep_kernel<10, double> (") + "one full sweep = all colour passes)",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic if not use32 else traffic32, "peak_source": peak_src,
-                         "bytes_per_launch": row_bytes * T * NLAYER, "avg_launch_ms": avg_sweep_ms,
-                         "launches_timed": int(n_dom), "share_of_step": (sweep32_ms if use32 else sweep_ms) / max(ev_ms, 1e-9),
-                         "fp64_stream_sweeps": {"launches_timed": int(sweeps - sweeps32), "avg_launch_ms": avg64_ms, "achieved": ach64,
-                                                "frac": (ach64 / peak) if ach64 else None,
-                                                "bytes_per_launch": sweep_bytes_per_row(NLAYER) * T * NLAYER,
-                                                "share_of_step": (sweep_ms - sweep32_ms) / max(ev_ms, 1e-9)}},
+            "roofline": roofline,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == "c2":

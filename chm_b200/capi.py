@@ -73,6 +73,7 @@ class Stats(C.Structure):
         ("ms_flux_and_halo", C.c_float), ("ms_deposition", C.c_float), ("ms_total", C.c_float), ("ms_line_sweeps", C.c_float),
         ("sweeps_timed", C.c_int32), ("sweeps_timed_fp32", C.c_int32), ("ms_line_sweeps_fp32", C.c_float), ("n_colours", C.c_int32), ("deposition_solver_used", C.c_int32), ("host_syncs", C.c_int32),
         ("halo_exchanges", C.c_int32), ("halo_transport", C.c_int32), ("halo_fused", C.c_int32),
+        ("residual_checks", C.c_int32), ("sweeps_fp32_x", C.c_int32), ("persistent_kernels", C.c_int32),
     ]
 
     def asdict(self):

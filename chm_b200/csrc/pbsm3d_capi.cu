@@ -193,6 +193,15 @@ struct pbsm3d_handle {
     cudaEvent_t ev[6] = {nullptr};
     cudaEvent_t ev_sw[3] = {nullptr};
     int sweeps_timed = 0, sweeps_timed32 = 0;
+    // persistent (cooperative) solver kernels: single rank
+    bool persistent = false;
+    unsigned* grid_bar = nullptr;       // [2] grid-barrier counters (suspension, deposition)
+    int gs_grid = 0, sor_grid = 0;
+    void* gs_fn = nullptr;
+    const void* sor_fn = nullptr;
+    int sor_threads = 1024;
+    int plan_n32 = 0, plan_nx32 = 0;
+    float* xf = nullptr;                // [L][S] fp32 storage of the iterate for the sweeps furthest from convergence
     int asm_nw = 0, asm_grid = 1;  // assembly: warps per block of the tile kernel (0 = column kernel), persistent grid size
     size_t asm_smem = 0;
     void* asm_fn = nullptr;
@@ -757,6 +766,103 @@ int enqueue_check(pbsm3d_handle* h, int it_now) {
     return 0;
 }
 
+// ---- single rank: a whole solve is one cooperative launch (gs_persistent_kernel / sor_persistent_kernel)
+using GsKernel = void (*)(SuspSystem, DevMesh, int, ColourRanges, double*, float*, Scalars*, double*, SolvePlan, unsigned*);
+ColourRanges colour_ranges(const pbsm3d_handle* h) {
+    ColourRanges cr;
+    std::memset(&cr, 0, sizeof(cr));
+    for (int c = 0; c < h->n_colours; ++c)
+        if (h->ccount[c] > 0) { cr.start[cr.n] = h->cstart[c]; cr.end[cr.n] = h->cstart[c] + h->ccount[c]; ++cr.n; }
+    return cr;
+}
+int setup_persistent(pbsm3d_handle* h) {
+    const char* env = getenv("PBSM3D_PERSISTENT");
+    h->persistent = false;
+    if (h->n_ranks > 1 || (env && atoi(env) == 0)) return 0;
+    int coop = 0;
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    if (!coop) return 0;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    GsKernel fn;
+    switch (h->L) {
+        case 5: fn = gs_persistent_kernel<5>; break;
+        case 10: fn = gs_persistent_kernel<10>; break;
+        case 15: fn = gs_persistent_kernel<15>; break;
+        case 20: fn = gs_persistent_kernel<20>; break;
+        default: fn = gs_persistent_kernel<0>; break;
+    }
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)fn, kGsThreads, 0));
+    h->gs_fn = (void*)fn;
+    h->gs_grid = std::min(kRedBlocks, std::max(nb, 1) * prop.multiProcessorCount);
+    {
+        const char* v = getenv("PBSM3D_SOR_VARIANT");  // tuning knob: threads per block / faces in flight per thread
+        const int var = v ? atoi(v) : 2;  // measured on c2: 512 threads x 4 faces in flight (profiles/r2b)
+        const bool stream = (size_t)h->Tp * 60 > ((size_t)80 << 20);  // working set beyond what stays in the 126 MB L2
+        const void* fn;
+        if (var == 1) { h->sor_threads = 1024; fn = stream ? (const void*)sor_persistent_kernel<true, 1024, 2> : (const void*)sor_persistent_kernel<false, 1024, 2>; }
+        else if (var == 2) { h->sor_threads = 512; fn = stream ? (const void*)sor_persistent_kernel<true, 512, 4> : (const void*)sor_persistent_kernel<false, 512, 4>; }
+        else if (var == 3) { h->sor_threads = 512; fn = stream ? (const void*)sor_persistent_kernel<true, 512, 8> : (const void*)sor_persistent_kernel<false, 512, 8>; }
+        else if (var == 2) { h->sor_threads = 512; fn = stream ? (const void*)sor_persistent_kernel<true, 512, 4> : (const void*)sor_persistent_kernel<false, 512, 4>; }
+        else { h->sor_threads = 1024; fn = stream ? (const void*)sor_persistent_kernel<true, 1024, 4> : (const void*)sor_persistent_kernel<false, 1024, 4>; }
+        h->sor_fn = fn;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, h->sor_threads, 0));
+        h->sor_grid = std::min(kRedBlocks, std::max(nb, 1) * prop.multiProcessorCount);
+    }
+    TRY(h->alloc_zero(&h->grid_bar, 2));
+    if (h->cfg.fp32_sweep_streams && (h->L == 5 || h->L == 10 || h->L == 15 || h->L == 20)) TRY(h->alloc_zero(&h->xf, h->NS));
+    h->persistent = true;
+    if (getenv("PBSM3D_VERBOSE"))
+        fprintf(stderr, "[pbsm3d] persistent solver kernels: sweep grid %d x %d, SOR grid %d x %d\n", h->gs_grid, kGsThreads, h->sor_grid,
+                h->sor_threads);
+    return 0;
+}
+int line_enqueue_persistent(pbsm3d_handle* h) {
+    const int maxit = h->cfg.max_iterations;
+    const bool known = h->pred_sweeps > 0;
+    SolvePlan pl;
+    pl.check_first = std::max(1, std::min(known ? h->pred_sweeps : 8, maxit));
+    pl.check_every = known ? 1 : 4;
+    pl.n32 = (known && h->cfg.fp32_sweep_streams) ? std::max(0, std::min(h->pred_n32, pl.check_first - 3)) : 0;
+    // the iterate itself stays in fp32 storage until 10 sweeps before the predicted end (never past the fp32-coefficient phase)
+    const char* nox = getenv("PBSM3D_FP32_X");
+    pl.nx32 = (h->xf && !(nox && atoi(nox) == 0)) ? std::max(0, std::min(pl.n32, pl.check_first - 10)) : 0;
+    pl.maxit = maxit;
+    pl.tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    h->plan_n32 = pl.n32;
+    h->plan_nx32 = pl.nx32;
+    ColourRanges cr = colour_ranges(h);
+    unsigned* bar = h->grid_bar;
+    CU(cudaMemsetAsync(bar, 0, sizeof(unsigned), h->stream));
+    int L = h->L;
+    void* args[] = {&h->ss, &h->dm, &L, &cr, &h->x, &h->xf, &h->sc, &h->partial, &pl, &bar};
+    CU(cudaEventRecord(h->ev_sw[0], h->stream));
+    ++h->n_launch;
+    CU(cudaLaunchCooperativeKernel((const void*)h->gs_fn, dim3(h->gs_grid), dim3(kGsThreads), args, 0, h->stream));
+    CU(cudaEventRecord(h->ev_sw[1], h->stream));
+    CU(cudaEventRecord(h->ev_sw[2], h->stream));
+    return 0;
+}
+int sor_enqueue_persistent(pbsm3d_handle* h) {
+    const int maxit = std::min(h->cfg.max_iterations, 6 * h->sor_kest + 64);
+    const bool known = h->pred_sor > 0;
+    SolvePlan pl;
+    pl.n32 = pl.nx32 = 0;
+    pl.check_first = std::max(1, std::min(maxit, known ? h->pred_sor : h->sor_kest));
+    pl.check_every = known ? 1 : 4;
+    pl.maxit = maxit;
+    pl.tol2 = h->cfg.tolerance * h->cfg.tolerance;
+    ColourRanges cr = colour_ranges(h);
+    unsigned* bar = h->grid_bar + 1;
+    CU(cudaMemsetAsync(bar, 0, sizeof(unsigned), h->stream));
+    void* args[] = {&h->dm, &h->offS, &h->drhsS, &h->ddiag, &h->qA, &h->sor_omega, &cr, &h->sc, &h->partial, &pl, &bar};
+    ++h->n_launch;
+    CU(cudaLaunchCooperativeKernel(h->sor_fn, dim3(h->sor_grid), dim3(h->sor_threads), args, 0, h->stream));
+    h->sor_enqueued = maxit;  // replaced by the executed count (Scalars::dep_sweeps) once the step has synchronised
+    return 0;
+}
+
 // Optimistic part: a predicted number of sweeps, a check, and a few short speculative rounds (no-ops once converged).
 int line_enqueue_initial(pbsm3d_handle* h, int* total_out) {
     const int maxit = h->cfg.max_iterations;
@@ -1211,7 +1317,9 @@ int enqueue_tail(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTarg
     CU(cudaEventRecord(h->ev[3], s));
     // deposition solve (x0 = 0)
     CU(cudaMemsetAsync(h->qA, 0, (size_t)h->S * sizeof(double), s));
-    if (use_sor(h)) {
+    if (use_sor(h) && h->persistent) {
+        TRY(sor_enqueue_persistent(h));
+    } else if (use_sor(h)) {
         TRY(enqueue_sor_initial(h));
     } else if (use_chebyshev(h)) {
         CU(cudaMemsetAsync(h->qB, 0, (size_t)h->S * sizeof(double), s));  // q_{-1}: multiplied by a_0 = 0, must be finite
@@ -1491,7 +1599,9 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
     bool line = (solver == PBSM3D_SOLVER_AUTO || solver == PBSM3D_SOLVER_LINE);
     h->sweeps_timed = 0;
     h->sweeps_timed32 = 0;
-    if (line) {
+    if (line && h->persistent) {
+        TRY(line_enqueue_persistent(h));
+    } else if (line) {
         TRY(l2_window(h, h->x, h->NS * sizeof(double)));
         TRY(line_enqueue_initial(h, &total));
         TRY(l2_window(h, nullptr, 0));
@@ -1535,9 +1645,13 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
 
     // ---- what actually happened
     bool redo_tail = false;
+    if (line && h->persistent && h->h_sc->susp_present) {
+        h->sweeps_timed = h->h_sc->susp_sweeps;
+        h->sweeps_timed32 = std::min(h->plan_n32, h->h_sc->susp_sweeps);
+    }
     if (line && h->h_sc->susp_present && !h->h_sc->susp_ok) {
         bool conv = false;
-        TRY(line_continue(h, total, solver == PBSM3D_SOLVER_AUTO, &conv));
+        if (!h->persistent) TRY(line_continue(h, total, solver == PBSM3D_SOLVER_AUTO, &conv));
         if (!conv && solver == PBSM3D_SOLVER_AUTO) {
             TRY(solve_bicgstab(h, &conv));
             if (conv) {
@@ -1580,6 +1694,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
     bool cheb = !sor && use_chebyshev(h);
     int dep_used = sor ? PBSM3D_DEP_SOR : (cheb ? PBSM3D_DEP_CHEBYSHEV : PBSM3D_DEP_CG);
     while (h->h_sc->tail_done && h->h_sc->dep_present && !h->h_sc->dep_ok) {
+        if (sor && h->persistent) h->sor_enqueued = std::max(h->h_sc->dep_sweeps, std::min(maxit, 6 * h->sor_kest + 64));  // it ran to its bound
         if (sor) {
             const bool gave_up = h->h_sc->done == 2 || h->sor_enqueued >= std::min(maxit, 6 * h->sor_kest + 64);
             if (gave_up && h->cfg.deposition_solver == PBSM3D_DEP_SOR)
@@ -1649,6 +1764,9 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
         CU(cudaEventElapsedTime(&st->ms_line_sweeps, h->ev_sw[0], h->ev_sw[1]));
         CU(cudaEventElapsedTime(&st->ms_line_sweeps_fp32, h->ev_sw[0], h->ev_sw[2]));
     }
+    st->residual_checks = h->h_sc->n_checks;
+    st->sweeps_fp32_x = h->persistent ? std::min(h->plan_nx32, h->sweeps_timed) : 0;
+    st->persistent_kernels = h->persistent ? 1 : 0;
     st->sweeps_timed = h->sweeps_timed;
     st->sweeps_timed_fp32 = h->sweeps_timed32;
     st->n_colours = h->n_colours;
@@ -2053,6 +2171,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
         h->ss.ltab = tab;
     }
     TRY(setup_assembly(h));
+    TRY(setup_persistent(h));
     LAUNCH(h, assemble_pads_kernel, cdiv(Tp, 256), 256, h->dm, h->ss, L);
     if (h->n_ranks > 1) TRY(setup_comm(h, iperm));
     CU(cudaStreamSynchronize(h->stream));

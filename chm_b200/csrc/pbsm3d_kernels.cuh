@@ -87,6 +87,8 @@ struct Scalars {
     int susp_present, dep_present;
     int susp_done, susp_iters;        // line solver: converged flag and the sweep count at detection
     int susp_ok;                      // suspension phase finished (converged, or nothing to solve)
+    int susp_sweeps, susp_stalled;    // persistent solve: sweeps executed; 1 = it stopped contracting (hand over to BiCGStab)
+    int dep_sweeps;                   // persistent deposition solve: sweeps executed
     int dep_ok;                       // deposition solve finished (converged)
     int tail_done;                    // flux/deposition-rhs ran on a finished suspension solve
     int drift_done;
@@ -838,6 +840,7 @@ __global__ void flags_kernel(int stage, Scalars* sc, const double* __restrict__ 
             sc->susp_iters = 0;
             sc->susp_rr = 0.0;
             sc->n_checks = 0;
+            sc->susp_sweeps = 0; sc->susp_stalled = 0; sc->dep_sweeps = 0;
             sc->dep_present = 0; sc->dep_ok = 0; sc->tail_done = 0; sc->drift_done = 0;
             sc->done = 0; sc->iters = 0; sc->dep_rhs_max = 0.0; sc->rr = 0.0; sc->bnorm2 = 0.0;
         } break;
@@ -904,14 +907,12 @@ template <typename CT> __device__ __forceinline__ CT load_cp(const SuspSystem& s
 template <> __device__ __forceinline__ double load_cp<double>(const SuspSystem& s, size_t r) { return __ldcs(s.cp + r); }
 template <> __device__ __forceinline__ float load_cp<float>(const SuspSystem& s, size_t r) { return __ldcs(s.cp32 + r); }
 
-template <int LT, typename CT>
-__global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh m, int Lrt, int p0, int p1, double* x,
-                                                          const Scalars* __restrict__ sc) {
-    if (sc->susp_done) return;
+// One face column of a colour pass: x_p <- T_p^{-1} (b_p - A_lat[p,:] x), in place.  XT is the STORAGE type of x: double, or
+// float for the sweeps furthest from convergence (gs_persistent_kernel); the arithmetic is fp64 either way.
+template <int LT, typename CT, typename XT>
+__device__ __forceinline__ void gs_column(const SuspSystem& s, const DevMesh& m, int Lrt, int p, XT* x) {
     const int Tp = m.Tp, S = m.S;
     const int L = LT > 0 ? LT : Lrt;
-    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= p1) return;
     const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
     const size_t LTp = (size_t)L * Tp;
     if (LT > 0) {
@@ -921,7 +922,7 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh 
         for (int z = 0; z < LT; ++z) {
             const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
             const RowCoef<CT> c = load_row<CT>(s, r, LTp);
-            g[z] = -((double)c.l0 * x[xr + n0] + (double)c.l1 * x[xr + n1] + (double)c.l2 * x[xr + n2]);
+            g[z] = -((double)c.l0 * (double)x[xr + n0] + (double)c.l1 * (double)x[xr + n1] + (double)c.l2 * (double)x[xr + n2]);
             bl[z] = c.bl;
         }
 #pragma unroll
@@ -930,23 +931,191 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh 
         g[0] = y;
 #pragma unroll
         for (int z = 1; z < LT; ++z) { y = g[z] - (double)bl[z] * y; g[z] = y; }
-        x[(size_t)(LT - 1) * S + p] = y;
+        x[(size_t)(LT - 1) * S + p] = (XT)y;
 #pragma unroll
-        for (int z = LT - 2; z >= 0; --z) { y = g[z] - (double)cu[z] * y; x[(size_t)z * S + p] = y; }
+        for (int z = LT - 2; z >= 0; --z) { y = g[z] - (double)cu[z] * y; x[(size_t)z * S + p] = (XT)y; }
     } else {
+        // runtime layer count: the own column of x is the scratch of the forward pass (fp64 x only)
         double y = 0.0;
         for (int z = 0; z < L; ++z) {
             const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
             const RowCoef<CT> c = load_row<CT>(s, r, LTp);
-            double g = -((double)c.l0 * x[xr + n0] + (double)c.l1 * x[xr + n1] + (double)c.l2 * x[xr + n2]);
+            double g = -((double)c.l0 * (double)x[xr + n0] + (double)c.l1 * (double)x[xr + n1] + (double)c.l2 * (double)x[xr + n2]);
             if (z == 0) g += s.rhsS0[p];
             y = g - (double)c.bl * y;
-            x[xr + p] = y;
+            x[xr + p] = (XT)y;
         }
         for (int z = L - 2; z >= 0; --z) {
-            y = x[(size_t)z * S + p] - (double)load_cp<CT>(s, (size_t)z * Tp + p) * y;
-            x[(size_t)z * S + p] = y;
+            y = (double)x[(size_t)z * S + p] - (double)load_cp<CT>(s, (size_t)z * Tp + p) * y;
+            x[(size_t)z * S + p] = (XT)y;
         }
+    }
+}
+
+template <int LT, typename CT>
+__global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh m, int Lrt, int p0, int p1, double* x,
+                                                          const Scalars* __restrict__ sc) {
+    if (sc->susp_done) return;
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    gs_column<LT, CT, double>(s, m, Lrt, p, x);
+}
+
+__device__ __forceinline__ double spmv_row(const SuspSystem& s, const DevMesh& m, int L, const double* __restrict__ x, int z, int p);
+
+// ------------------------------------------------------------------- persistent (cooperative) solver kernels
+// On one rank a whole solve is ONE cooperative launch: the grid is sized to be co-resident (occupancy x SM count), every
+// block walks its share of each colour class, and a grid-wide barrier (one atomic arrive + an acquire spin per block)
+// separates the colour passes.  The stopping rule ||b - A x||_2 <= tol ||b||_2 is evaluated inside the kernel at the sweeps
+// the host's schedule names (first check at the predicted sweep count, then every `check_every` sweeps): every block folds
+// the same per-block partial sums in the same order, so all blocks take the same decision and leave the loop together.
+// This replaces ~60 (suspension) and ~150 (deposition) launches per step, and the guarded no-op launches of a calm step.
+struct ColourRanges {
+    int n;
+    int start[8], end[8];
+};
+struct SolvePlan {
+    int nx32;         // leading sweeps that also keep the iterate in fp32 storage (suspension only; <= n32)
+    int n32;          // leading sweeps that stream the fp32-rounded coefficient copies (suspension only)
+    int check_first;  // first residual check after this many sweeps
+    int check_every;
+    int maxit;
+    double tol2;
+};
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// `ctr` is zeroed by the host before the launch; `target` is the block's private running count.
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();  // release: every write of this block (ordered before thread 0 by the barrier above)
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_gpu_u32(ctr) < target) {}
+        __threadfence();  // and drop what this SM's L1 still holds of the arrays the other blocks just wrote
+    }
+    __syncthreads();
+}
+// Sum of the per-block partials in index order: identical bits in every block.
+__device__ __forceinline__ double fold_partials(const double* partial, int n) {
+    double a = 0.0;
+    for (int b = threadIdx.x; b < n; b += blockDim.x) a += __ldcg(partial + b);
+    __shared__ double bcast;
+    a = block_sum(a);
+    if (threadIdx.x == 0) bcast = a;
+    __syncthreads();
+    return bcast;
+}
+
+template <int LT>
+__device__ __forceinline__ double residual_column(const SuspSystem& s, const DevMesh& m, const double* x, int p) {
+    const int Tp = m.Tp, S = m.S;
+    const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
+    double xo[LT], g[LT], a = 0.0;
+#pragma unroll
+    for (int z = 0; z < LT; ++z) xo[z] = x[(size_t)z * S + p];
+#pragma unroll
+    for (int z = 0; z < LT; ++z) {
+        const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
+        g[z] = __ldcs(s.latS + r) * x[xr + n0] + __ldcs(s.latS + (size_t)LT * Tp + r) * x[xr + n1] +
+               __ldcs(s.latS + (size_t)2 * LT * Tp + r) * x[xr + n2];
+    }
+    double cp_prev = 0.0;
+#pragma unroll
+    for (int z = 0; z < LT; ++z) {
+        const size_t r = (size_t)z * Tp + p;
+        const double bS = __ldcs(s.belowS + r), cp = __ldcs(s.cp + r);
+        double v = g[z] + xo[z];
+        if (z > 0) v += bS * (cp_prev * xo[z] + xo[z - 1]);
+        if (z < LT - 1) v += cp * xo[z + 1];
+        v = (((z == 0) ? s.rhsS0[p] : 0.0) - v) * __ldcs(s.den + r);
+        a += v * v;
+        cp_prev = cp;
+    }
+    return a;
+}
+
+// The suspension solve: multicolour line Gauss-Seidel sweeps + residual checks, one launch.
+// Writes the same control-block fields as the per-pass path (susp_done / susp_iters / susp_rr / rr_hist) plus
+// susp_stalled when the sweeps stop contracting (rate > 0.97 after 64 sweeps): the host then hands over to BiCGStab.
+// Three phases of one solve (sweep numbers from the host's schedule, which carries iteration COUNTS only from the previous step):
+//     [0, nx32)     x stored in fp32 (xf), fp32-rounded coefficient copies   30 B/row
+//     [nx32, n32)   x in fp64, fp32-rounded coefficient copies               38 B/row
+//     [n32, ...)    x in fp64, fp64 coefficients                             58 B/row, and every residual check
+// fp32 storage of the iterate perturbs each sweep's result by <= 6e-8 relative; the iteration contracts (rho ~ 0.5), so the
+// error it leaves when the iterate moves to fp64 (one conversion pass) is ~1e-7 ||x|| and the following fp64-x sweeps remove
+// it at the usual rate (tests/models/fp32_x_model.py: the sweep count does not change when the switch is >= 10 sweeps before
+// the end).  All arithmetic, the right-hand side and the stopping rule are fp64 throughout.
+constexpr int kGsThreads = 512;
+template <int LT>
+__global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem s, DevMesh m, int Lrt, ColourRanges cr, double* x, float* xf,
+                                                                      Scalars* sc, double* __restrict__ partial, SolvePlan pl, unsigned* bar) {
+    if (sc->susp_done) return;  // uniform: nobody writes it before the first grid barrier
+    const int L = LT > 0 ? LT : Lrt;
+    const double bnorm2 = sc->susp_bnorm2;
+    unsigned target = 0;
+    int it = 0, n_checks = 0, converged = 0, stalled = 0;
+    double rr = 0.0, prev_rr = bnorm2;
+    int prev_it = 0;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nx32 = (LT > 0 && xf) ? pl.nx32 : 0;
+    if (nx32 > 0) {  // x0 = 0 in the fp32 copy (ghost tails included)
+        const size_t NS = (size_t)L * m.S;
+        for (size_t k = t0; k < NS; k += stride) xf[k] = 0.f;
+        grid_barrier(bar, target);
+    }
+    while (it < pl.maxit) {
+        const int phase = it < nx32 ? 0 : (it < pl.n32 ? 1 : 2);
+        for (int c = 0; c < cr.n; ++c) {
+            if (phase == 0) for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) gs_column<LT, float, float>(s, m, L, p, xf);
+            else if (phase == 1) for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) gs_column<LT, float, double>(s, m, L, p, x);
+            else for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) gs_column<LT, double, double>(s, m, L, p, x);
+            grid_barrier(bar, target);
+        }
+        ++it;
+        if (it == nx32) {  // the iterate moves to fp64
+            const size_t NS = (size_t)L * m.S;
+            for (size_t k = t0; k < NS; k += stride) x[k] = (double)xf[k];
+            grid_barrier(bar, target);
+        }
+        const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
+        if (!check) continue;
+        double a = 0.0;
+        if (LT > 0) {
+            for (int p = t0; p < m.Tp; p += stride) a += residual_column<(LT > 0 ? LT : 1)>(s, m, x, p);
+        } else {
+            for (int p = t0; p < m.Tp; p += stride)
+                for (int z = 0; z < L; ++z) {
+                    const double v = ((z == 0) ? s.rhs0[p] : 0.0) - spmv_row(s, m, L, x, z, p);
+                    a += v * v;
+                }
+        }
+        a = block_sum(a);
+        if (threadIdx.x == 0) partial[blockIdx.x] = a;
+        grid_barrier(bar, target);
+        rr = fold_partials(partial, gridDim.x);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (n_checks < 16) { sc->rr_hist[n_checks] = rr; sc->it_hist[n_checks] = it; }
+        }
+        ++n_checks;
+        if (rr <= pl.tol2 * bnorm2) { converged = 1; break; }
+        if (!(rr == rr) || rr > 1e60 * bnorm2) { stalled = 1; break; }
+        if (it >= 64 && it > prev_it && rr > 0.0 && prev_rr > 0.0) {  // contraction per sweep of ||r|| worse than 0.97: crawling
+            const double lim = exp(2.0 * (it - prev_it) * log(0.97));
+            if (rr > lim * prev_rr) { stalled = 1; break; }
+        }
+        prev_rr = rr;
+        prev_it = it;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->susp_rr = rr;
+        sc->n_checks = n_checks;
+        sc->susp_sweeps = it;
+        sc->susp_stalled = stalled;
+        if (converged) { sc->susp_done = 1; sc->susp_iters = it; sc->susp_ok = 1; }
     }
 }
 
@@ -1348,6 +1517,80 @@ __global__ void __launch_bounds__(kRedThreads) dep_residual_kernel(DevMesh m, co
     double o0, unused;
     if (grid_fold<1>(rr, 0.0, 0, 0, partial, pstride, &sc->ticket[3], o0, unused)) {
         if (threadIdx.x == 0) { red[0] = o0; if (fused) sor_check(sc, o0, k, tol2); }
+    }
+}
+
+// The deposition solve as one cooperative launch: multicolour SOR sweeps with a grid barrier between the colour passes and the
+// stopping rule ||b - A q|| <= tol ||b|| evaluated in the kernel (see gs_persistent_kernel).  STREAM: the working set does not fit
+// the L2, coefficient streams are read with the evict-first hint; otherwise they stay resident in the 126 MB L2 across the sweeps.
+template <bool STREAM, int NT, int B>  // NT threads per block (one block per SM), B faces per thread in flight
+__global__ void __launch_bounds__(NT, 1) sor_persistent_kernel(DevMesh m, const double* __restrict__ offS, const double* __restrict__ bS,
+                                                                        const double* __restrict__ ddiag, double* q, double omega,
+                                                                        ColourRanges cr, Scalars* sc, double* __restrict__ partial,
+                                                                        SolvePlan pl, unsigned* bar) {
+    if (!sc->tail_done || !sc->dep_present || sc->done) return;  // uniform: written only after the last grid barrier
+    const int Tp = m.Tp;
+    const double bnorm2 = sc->bnorm2;
+    unsigned target = 0;
+    int it = 0, done = 0;
+    double rr = bnorm2;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    // a pass is latency-bound (two dependent L2 round trips per face): B independent faces per thread are in flight at once
+    while (it < pl.maxit) {
+        for (int c = 0; c < cr.n; ++c) {
+            const int end = cr.end[c];
+            for (int base = cr.start[c] + t0; base < end; base += B * stride) {
+                double qp[B], z[B], o[B][3];
+                int n[B][3];
+#pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    const int p = base + k * stride;
+                    if (p < end) {
+                        qp[k] = q[p];
+                        z[k] = bS[p] - qp[k];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            n[k][j] = m.nbs[(size_t)j * Tp + p];
+                            o[k][j] = STREAM ? __ldcs(offS + (size_t)j * Tp + p) : offS[(size_t)j * Tp + p];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < B; ++k)
+                    if (base + k * stride < end) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) z[k] -= o[k][j] * q[n[k][j]];
+                    }
+#pragma unroll
+                for (int k = 0; k < B; ++k)
+                    if (base + k * stride < end) q[base + k * stride] = qp[k] + omega * z[k];
+            }
+            grid_barrier(bar, target);
+        }
+        ++it;
+        const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
+        if (!check) continue;
+        double a = 0.0;
+        for (int p = t0; p < Tp; p += stride) {
+            double z = bS[p] - q[p];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) z -= offS[(size_t)j * Tp + p] * q[m.nbs[(size_t)j * Tp + p]];
+            const double r = z * ddiag[p];
+            a += r * r;
+        }
+        a = block_sum(a);
+        if (threadIdx.x == 0) partial[blockIdx.x] = a;
+        grid_barrier(bar, target);
+        rr = fold_partials(partial, gridDim.x);
+        if (rr <= pl.tol2 * bnorm2) { done = 1; break; }
+        if (!(rr == rr) || rr > 1e60 * bnorm2) { done = 2; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->rr = rr;
+        sc->dep_sweeps = it;
+        sc->iters = it;
+        if (done == 1) { sc->done = 1; sc->dep_ok = 1; sc->dep_buf = 0; }
+        else if (done == 2) sc->done = 2;
     }
 }
 

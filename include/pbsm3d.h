@@ -196,6 +196,10 @@ typedef struct pbsm3d_stats {
     int32_t halo_transport;          /* PBSM3D_HALO_NONE / _NCCL / _PEER */
     int32_t halo_fused;              /* of halo_exchanges: carried by the solver kernels themselves (direct stores into the
                                         partner's ghost buffer from the producing kernel; no pack/unpack launch) */
+    int32_t residual_checks;         /* evaluations of ||b - A x|| of the suspension system in this step */
+    int32_t sweeps_fp32_x;           /* of sweeps_timed_fp32: the leading ones that also kept the iterate x in fp32 STORAGE */
+    int32_t persistent_kernels;      /* 1: each solve ran as one cooperative launch (single rank); then ms_line_sweeps is the
+                                        duration of that launch = sweeps_timed sweeps + residual_checks checks */
 } pbsm3d_stats;
 
 typedef struct pbsm3d_handle pbsm3d_handle;

@@ -50,7 +50,7 @@ def test_struct_layouts_match_header(lib, tmp_path):
     """The ctypes mirrors against the C compiler's view of include/pbsm3d.h: sizes and the offset of every struct's last field."""
     import subprocess
     probes = {"pbsm3d_forcing": (capi.Forcing, "fetch"), "pbsm3d_outputs": (capi.Outputs, "pbsm_more_than_avail"),
-              "pbsm3d_comm": (capi.Comm, None), "pbsm3d_stats": (capi.Stats, "halo_fused"), "pbsm3d_mesh": (capi.Mesh, None),
+              "pbsm3d_comm": (capi.Comm, None), "pbsm3d_stats": (capi.Stats, "persistent_kernels"), "pbsm3d_mesh": (capi.Mesh, None),
               "pbsm3d_config": (capi.Config, "fp32_sweep_streams"), "pbsm3d_wind_config": (capi.WindConfig, "fetch_I")}
     lines = []
     for cname, (_, last) in probes.items():
