@@ -804,7 +804,6 @@ int setup_persistent(pbsm3d_handle* h) {
         if (var == 1) { h->sor_threads = 1024; fn = stream ? (const void*)sor_persistent_kernel<true, 1024, 2> : (const void*)sor_persistent_kernel<false, 1024, 2>; }
         else if (var == 2) { h->sor_threads = 512; fn = stream ? (const void*)sor_persistent_kernel<true, 512, 4> : (const void*)sor_persistent_kernel<false, 512, 4>; }
         else if (var == 3) { h->sor_threads = 512; fn = stream ? (const void*)sor_persistent_kernel<true, 512, 8> : (const void*)sor_persistent_kernel<false, 512, 8>; }
-        else if (var == 2) { h->sor_threads = 512; fn = stream ? (const void*)sor_persistent_kernel<true, 512, 4> : (const void*)sor_persistent_kernel<false, 512, 4>; }
         else { h->sor_threads = 1024; fn = stream ? (const void*)sor_persistent_kernel<true, 1024, 4> : (const void*)sor_persistent_kernel<false, 1024, 4>; }
         h->sor_fn = fn;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, h->sor_threads, 0));
