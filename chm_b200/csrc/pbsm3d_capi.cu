@@ -1372,9 +1372,9 @@ int setup_assembly(pbsm3d_handle* h) {
     const char* mb = getenv("PBSM3D_ASM_MINB");  // tuning knob: resident blocks per SM the kernel is compiled for
     const int minb = mb ? atoi(mb) : 0;
     const int L = h->L;
-    TRY(h->alloc(&h->recs.d, (size_t)kRecD * h->T));
-    TRY(h->alloc(&h->recs.i, (size_t)2 * h->T));
-    h->recs.T = h->T;
+    TRY(h->alloc(&h->recs.d, (size_t)kRecD * h->Tp));
+    TRY(h->alloc_zero(&h->recs.i, (size_t)h->Tp));
+    h->recs.T = h->Tp;
     const bool column = !(want && std::string(want) == "tile") || L > 32;  // column-walking is the faster one (profiles/r2a)
     if (column) {  // measured on c2 (profiles/r2a_assembly.md): 3 resident blocks, layer loop unrolled by 2
         const char* un = getenv("PBSM3D_ASM_UNROLL");
@@ -1402,13 +1402,21 @@ int setup_assembly(pbsm3d_handle* h) {
     if (L <= 20) return setup_assembly_fn(h, assemble_tile_kernel<20, 1>, 20, 640);
     return setup_assembly_fn(h, assemble_tile_kernel<32, 1>, 32, 1024);
 }
-void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt, int i0, int i1, int chunk) {
+// prelude of CHM faces [i0, i1) (one forcing chunk)
+void launch_prelude(pbsm3d_handle* h, const DevForcing& f, double dt, int i0, int i1) {
     LAUNCH(h, face_prelude_kernel, cdiv((size_t)(i1 - i0), 128), 128, h->dc, h->dm, f, h->ss, dt, i0, i1, h->recs);
+}
+// rows of all slots; {max|b|, sum b^2} of this rank go to red[0..1]
+void launch_rows(pbsm3d_handle* h) {
     const int per = h->asm_nw ? 32 : 128;
-    const int grid = std::max(1, std::min(cdiv((size_t)(i1 - i0), per), h->asm_grid));
+    const int grid = std::max(1, std::min(cdiv((size_t)h->Tp, per), h->asm_grid));
     ++h->n_launch;
-    ((AsmKernel)h->asm_fn)<<<grid, h->asm_threads, h->asm_smem, h->stream>>>(h->dc, h->dm, h->recs, h->ss, i0, i1, h->partial, kRedBlocks,
-                                                                            h->sc, h->red + 2 * chunk);
+    ((AsmKernel)h->asm_fn)<<<grid, h->asm_threads, h->asm_smem, h->stream>>>(h->dc, h->dm, h->recs, h->ss, 0, h->Tp, h->partial, kRedBlocks,
+                                                                            h->sc, h->red);
+}
+void launch_assembly(pbsm3d_handle* h, const DevForcing& f, double dt) {
+    launch_prelude(h, f, dt, 0, h->T);
+    launch_rows(h);
 }
 
 // One PBSM3D::run with device-resident forcing (reference PBSM3D.cpp:400-1748, phases A–I of SURVEY §3.2).
@@ -1571,19 +1579,17 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
         if (derive_u2) TRY(enqueue_scale_wind_vert(h, &h->wind_cfg, f.U_R, f.sd, h->forcing_buf[1]));
         if (derive_fetch) TRY(enqueue_fetchr(h, &h->wind_cfg, f.vw_dir, h->forcing_buf[7]));
     }
-    for (int c = 0; c < nch; ++c) {
+    for (int c = 0; c < nch; ++c) {  // the per-face prelude of each forcing chunk as it lands
         if (host_in) CU(cudaStreamWaitEvent(s, h->ev_in[c], 0));
-        launch_assembly(h, f, dt, (int)((size_t)T * c / nch), (int)((size_t)T * (c + 1) / nch), c);
+        launch_prelude(h, f, dt, (int)((size_t)T * c / nch), (int)((size_t)T * (c + 1) / nch));
     }
+    launch_rows(h);
     h->have_system = true;
     if (h->n_ranks > 1) {
-        LAUNCH(h, flags_kernel, 1, 1, FLAGS_COMBINE, h->sc, h->red, nch, tol2);
         TRY(allreduce(h, h->red, 1, true));
         TRY(allreduce(h, h->red + 1, 1, false));
-        LAUNCH(h, flags_kernel, 1, 1, FLAGS_SUSP, h->sc, h->red, 1, tol2);
-    } else {
-        LAUNCH(h, flags_kernel, 1, 1, FLAGS_SUSP, h->sc, h->red, nch, tol2);
     }
+    LAUNCH(h, flags_kernel, 1, 1, FLAGS_SUSP, h->sc, h->red, 1, tol2);
     CU(cudaEventRecord(h->ev[1], s));
     // outputs that are final early leave on their own stream while the solves run (host-buffer entry point)
     const bool early = out && host_in;
@@ -2385,7 +2391,7 @@ int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms) {
                     TRY(enqueue_sweeps(h, 1));
                     break;
                 case 1: launch_residual(h, 0, tol2, 0); break;
-                case 2: launch_assembly(h, h->last_forcing, h->last_dt, 0, h->T, 0); break;
+                case 2: launch_assembly(h, h->last_forcing, h->last_dt); break;
                 case 3:
                     LAUNCH(h, cg_spmv_kernel, red_grid(h->Tp), kRedThreads, h->dm, h->ddiag, h->doff, h->cg_p, h->cg_Ap, h->partial,
                            kRedBlocks, nullptr, h->red, tol2, 0);

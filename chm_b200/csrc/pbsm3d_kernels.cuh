@@ -627,12 +627,13 @@ __device__ __forceinline__ void store_row(const SuspSystem& s, size_t r, size_t 
     s.pack32[r] = make_float4((float)l0, (float)l1, (float)l2, (float)bS);
 }
 
-// Per-face records between the prelude kernel and the row kernels: SoA [kRecD][T] doubles + [2][T] ints, CHM face order.
+// Per-face records between the prelude kernel and the row kernels: SoA [kRecD][Tp] doubles + [Tp] ints, SLOT order (so the row
+// kernels read records and write every stream fully coalesced whatever the number of colours).
 constexpr int kRecD = 21;
 struct FaceRecs {
-    double* d;   // [kRecD][T]
-    int* i;      // [2][T]: flags, slot
-    int T;
+    double* d;   // [kRecD][Tp]
+    int* i;      // [Tp] flags (0 on padding slots: never written by the prelude, zeroed at create)
+    int T;       // = Tp, the stride
 };
 __device__ __forceinline__ void store_rec(const FaceRecs& R, int i, const FaceConsts& fc) {
     const double v[kRecD] = {fc.hs, fc.height_diff, fc.u28, fc.UQ, fc.uref, fc.sd, fc.C1p, fc.C2, fc.ustar, fc.area, fc.c_salt,
@@ -640,7 +641,6 @@ __device__ __forceinline__ void store_rec(const FaceRecs& R, int i, const FaceCo
 #pragma unroll
     for (int k = 0; k < kRecD; ++k) R.d[(size_t)k * R.T + i] = v[k];
     R.i[i] = fc.flags;
-    R.i[R.T + i] = fc.p;
 }
 __device__ __forceinline__ FaceConsts load_rec(const FaceRecs& R, int i) {
     FaceConsts fc;
@@ -652,22 +652,22 @@ __device__ __forceinline__ FaceConsts load_rec(const FaceRecs& R, int i) {
     for (int j = 0; j < 3; ++j) { fc.Aj[j] = d[(11 + j) * T]; fc.g[j] = d[(14 + j) * T]; }
     fc.UQ136 = d[17 * T]; fc.aod = d[18 * T]; fc.a4p = d[19 * T]; fc.v5 = d[20 * T];
     fc.flags = R.i[i];
-    fc.p = R.i[T + i];
+    fc.p = i;
     return fc;
 }
 
-// Kernel 1 of the assembly: one thread per CHM face (coalesced forcing reads): saltation, Qsalt/c_salt, the per-face factors
-// of the layer loop, and the two global facts of the right-hand side (b is non-zero in layer 0 only, and known here:
-// b0 = -alpha4' c_salt needs K of layer 0, so the row kernel reports it; this kernel leaves red alone).
+// Kernel 1 of the assembly: one thread per CHM face (coalesced forcing reads; runs per forcing chunk as the chunks land from the
+// host): saltation, Qsalt/c_salt and the per-face factors of the layer loop, written to the face's SLOT (the partial sectors of
+// neighbouring faces merge in L2).
 __global__ void __launch_bounds__(128) face_prelude_kernel(DevConfig c, DevMesh m, DevForcing f, SuspSystem s, double dt, int i0, int i1,
                                                           FaceRecs R) {
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= i1) return;
-    store_rec(R, i, face_prelude(c, m, f, s, dt, m.iperm[i], i));
+    const int p = m.iperm[i];
+    store_rec(R, p, face_prelude(c, m, f, s, dt, p, i));
 }
 
-// Kernel 2, layer-parallel.  A block of NW warps owns tiles of 32 faces (CHM order, the order the forcing arrives in, so the
-// step can assemble one chunk while the next chunk's forcing is still crossing PCIe); warp z computes the rows of layer z, so
+// Kernel 2, layer-parallel.  A block of NW warps owns tiles of 32 consecutive slots; warp z computes the rows of layer z, so
 // the 32 lanes write 32 consecutive faces of every stream of that layer and no thread walks a column; the per-face record
 // is read by every warp of the block (one DRAM read, L1 hits after that).  The one serial piece, the Thomas recurrence
 // den_z = d_z - lo_z cp_{z-1} over the tile's 32 columns, runs on warp 0 out of shared memory between two barriers.
@@ -688,8 +688,8 @@ assemble_tile_kernel(DevConfig c, DevMesh m, FaceRecs R, SuspSystem s, int i0, i
     const size_t LTp = (size_t)L * m.Tp;
     double mx = 0.0, ss = 0.0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int i = i0 + tile * 32 + lane;
-        const bool act = i < i1 && w < L;
+        const int i = i0 + tile * 32 + lane;  // a slot
+        const bool act = i < i1 && w < L && (R.i[i] & 16);
         RowCoef64 rc;
         int p = 0;
         if (act) {
@@ -746,8 +746,8 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(DevConfig c, DevMes
     const int L = c.L;
     const size_t LTp = (size_t)L * m.Tp;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int i = i0 + tile * 128 + threadIdx.x;
-        if (i < i1) {
+        const int i = i0 + tile * 128 + threadIdx.x;  // a slot
+        if (i < i1 && (R.i[i] & 16)) {
             const FaceConsts fc = load_rec(R, i);
             const int p = fc.p;
             double cp_prev = 0.0;
