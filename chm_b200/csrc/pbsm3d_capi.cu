@@ -156,7 +156,8 @@ struct pbsm3d_handle {
     double** stage_remote[2] = {nullptr, nullptr};  // [parity][n_send] where each send entry lands on its partner
     double* stage_local[2] = {nullptr, nullptr};
     unsigned* halo_ticket = nullptr;
-    unsigned long long halo_epoch = 0, ar_epoch = 0;
+    unsigned long long halo_epoch = 0;
+    unsigned long long* d_ar_epoch = nullptr;       // device-resident all-reduce counter (PeerTable::ar_epoch)
     int halo_ops = 0;                               // halo exchanges enqueued by the step in flight
     // halos carried by the solver kernels themselves (HaloLink): x of the line sweeps, q of the Chebyshev iteration
     bool fused_halo = false;
@@ -195,6 +196,8 @@ struct pbsm3d_handle {
     int sweeps_timed = 0, sweeps_timed32 = 0;
     // persistent (cooperative) solver kernels: single rank
     bool persistent = false;
+    bool sor_persistent = false;        // the deposition solve too: only while its working set stays in the L2 (else per-pass launches
+                                        // stream better: 17 vs 21 ms on 10 M faces, profiles/r2b)
     unsigned* grid_bar = nullptr;       // [2] grid-barrier counters (suspension, deposition)
     int gs_grid = 0, sor_grid = 0;
     void* gs_fn = nullptr;
@@ -245,8 +248,7 @@ inline bool fused(const pbsm3d_handle* h) { return h->n_ranks == 1; }
 int allreduce(pbsm3d_handle* h, double* buf, int n, bool is_max) {
     if (h->n_ranks == 1) return 0;
     if (h->peer) {
-        ++h->ar_epoch;
-        LAUNCH(h, peer_allreduce_kernel, 1, 32, buf, n, is_max ? 1 : 0, h->d_pt, h->ar_epoch);
+        LAUNCH(h, peer_allreduce_kernel, 1, 32, buf, n, is_max ? 1 : 0, h->d_pt);
         return 0;
     }
     NC(ncclAllReduce(buf, buf, n, ncclDouble, is_max ? ncclMax : ncclSum, h->comm, h->stream));
@@ -456,6 +458,8 @@ int setup_peer(pbsm3d_handle* h, const std::vector<int>& M, const std::vector<in
     pt.ar_slots_local = (double*)(h->arena + kArenaArSlots);
     pt.ar_flag_local = (unsigned long long*)(h->arena + kArenaArFlag);
     pt.error = &h->sc->peer_error;
+    TRY(h->alloc_zero(&h->d_ar_epoch, 1));
+    pt.ar_epoch = h->d_ar_epoch;
     const char* to = getenv("PBSM3D_PEER_TIMEOUT_MS");
     pt.timeout_ns = (unsigned long long)(to ? std::max(1L, atol(to)) : 20000L) * 1000000ull;
     TRY(h->alloc(&h->d_pt, 1));
@@ -766,7 +770,8 @@ int enqueue_check(pbsm3d_handle* h, int it_now) {
     return 0;
 }
 
-// ---- single rank: a whole solve is one cooperative launch (gs_persistent_kernel / sor_persistent_kernel)
+// ---- a whole solve is one cooperative launch (gs_persistent_kernel / sor_persistent_kernel; across ranks their _halo variants)
+SorLink sor_link(const pbsm3d_handle* h);
 using GsKernel = void (*)(SuspSystem, DevMesh, int, ColourRanges, double*, float*, Scalars*, double*, SolvePlan, unsigned*);
 ColourRanges colour_ranges(const pbsm3d_handle* h) {
     ColourRanges cr;
@@ -775,47 +780,80 @@ ColourRanges colour_ranges(const pbsm3d_handle* h) {
         if (h->ccount[c] > 0) { cr.start[cr.n] = h->cstart[c]; cr.end[cr.n] = h->cstart[c] + h->ccount[c]; ++cr.n; }
     return cr;
 }
+using GsHaloKernel = void (*)(SuspSystem, DevMesh, int, ColourRanges, double*, float*, Scalars*, double*, double*, SolvePlan, unsigned*, XHalo);
 int setup_persistent(pbsm3d_handle* h) {
     const char* env = getenv("PBSM3D_PERSISTENT");
     h->persistent = false;
-    if (h->n_ranks > 1 || (env && atoi(env) == 0)) return 0;
+    if (env && atoi(env) == 0) return 0;
+    const bool multi = h->n_ranks > 1;
+    if (multi && !(h->peer && h->fused_halo)) return 0;  // across ranks the persistent kernels live on the in-kernel halos
     int coop = 0;
     CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     if (!coop) return 0;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, h->device));
-    GsKernel fn;
-    switch (h->L) {
-        case 5: fn = gs_persistent_kernel<5>; break;
-        case 10: fn = gs_persistent_kernel<10>; break;
-        case 15: fn = gs_persistent_kernel<15>; break;
-        case 20: fn = gs_persistent_kernel<20>; break;
-        default: fn = gs_persistent_kernel<0>; break;
+    const void* fn;
+    if (multi) {
+        GsHaloKernel f;
+        switch (h->L) {
+            case 5: f = gs_persistent_halo_kernel<5>; break;
+            case 10: f = gs_persistent_halo_kernel<10>; break;
+            case 15: f = gs_persistent_halo_kernel<15>; break;
+            case 20: f = gs_persistent_halo_kernel<20>; break;
+            default: f = gs_persistent_halo_kernel<0>; break;
+        }
+        fn = (const void*)f;
+    } else {
+        GsKernel f;
+        switch (h->L) {
+            case 5: f = gs_persistent_kernel<5>; break;
+            case 10: f = gs_persistent_kernel<10>; break;
+            case 15: f = gs_persistent_kernel<15>; break;
+            case 20: f = gs_persistent_kernel<20>; break;
+            default: f = gs_persistent_kernel<0>; break;
+        }
+        fn = (const void*)f;
     }
     int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)fn, kGsThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kGsThreads, 0));
     h->gs_fn = (void*)fn;
     h->gs_grid = std::min(kRedBlocks, std::max(nb, 1) * prop.multiProcessorCount);
     {
         const char* v = getenv("PBSM3D_SOR_VARIANT");  // tuning knob: threads per block / faces in flight per thread
         const int var = v ? atoi(v) : 2;  // measured on c2: 512 threads x 4 faces in flight (profiles/r2b)
         const bool stream = (size_t)h->Tp * 60 > ((size_t)80 << 20);  // working set beyond what stays in the 126 MB L2
-        const void* fn;
-        if (var == 1) { h->sor_threads = 1024; fn = stream ? (const void*)sor_persistent_kernel<true, 1024, 2> : (const void*)sor_persistent_kernel<false, 1024, 2>; }
-        else if (var == 2) { h->sor_threads = 512; fn = stream ? (const void*)sor_persistent_kernel<true, 512, 4> : (const void*)sor_persistent_kernel<false, 512, 4>; }
-        else if (var == 3) { h->sor_threads = 512; fn = stream ? (const void*)sor_persistent_kernel<true, 512, 8> : (const void*)sor_persistent_kernel<false, 512, 8>; }
-        else { h->sor_threads = 1024; fn = stream ? (const void*)sor_persistent_kernel<true, 1024, 4> : (const void*)sor_persistent_kernel<false, 1024, 4>; }
-        h->sor_fn = fn;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, h->sor_threads, 0));
+        const void* sf;
+        if (multi) { h->sor_threads = 512; sf = stream ? (const void*)sor_persistent_halo_kernel<true, 512, 4> : (const void*)sor_persistent_halo_kernel<false, 512, 4>; }
+        else if (var == 1) { h->sor_threads = 1024; sf = stream ? (const void*)sor_persistent_kernel<true, 1024, 2> : (const void*)sor_persistent_kernel<false, 1024, 2>; }
+        else if (var == 3) { h->sor_threads = 512; sf = stream ? (const void*)sor_persistent_kernel<true, 512, 8> : (const void*)sor_persistent_kernel<false, 512, 8>; }
+        else if (var == 4) { h->sor_threads = 1024; sf = stream ? (const void*)sor_persistent_kernel<true, 1024, 4> : (const void*)sor_persistent_kernel<false, 1024, 4>; }
+        else { h->sor_threads = 512; sf = stream ? (const void*)sor_persistent_kernel<true, 512, 4> : (const void*)sor_persistent_kernel<false, 512, 4>; }
+        h->sor_fn = sf;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sf, h->sor_threads, 0));
         h->sor_grid = std::min(kRedBlocks, std::max(nb, 1) * prop.multiProcessorCount);
+    }
+    if (multi) {  // the boundary columns of a colour must fit the first grid-stride iteration
+        for (int c = 0; c < h->n_colours; ++c)
+            if (h->nb[c] > h->gs_grid * kGsThreads || h->nb[c] > h->sor_grid * h->sor_threads) return 0;
     }
     TRY(h->alloc_zero(&h->grid_bar, 2));
     if (h->cfg.fp32_sweep_streams && (h->L == 5 || h->L == 10 || h->L == 15 || h->L == 20)) TRY(h->alloc_zero(&h->xf, h->NS));
     h->persistent = true;
+    {
+        const char* sp = getenv("PBSM3D_SOR_PERSISTENT");
+        h->sor_persistent = sp ? atoi(sp) != 0 : (size_t)h->Tp * 60 <= ((size_t)80 << 20);
+    }
     if (getenv("PBSM3D_VERBOSE"))
-        fprintf(stderr, "[pbsm3d] persistent solver kernels: sweep grid %d x %d, SOR grid %d x %d\n", h->gs_grid, kGsThreads, h->sor_grid,
-                h->sor_threads);
+        fprintf(stderr, "[pbsm3d] persistent solver kernels%s: sweep grid %d x %d, SOR grid %d x %d\n", multi ? " (halos inside)" : "",
+                h->gs_grid, kGsThreads, h->sor_grid, h->sor_threads);
     return 0;
+}
+// colour ranges in the order colour_ranges() emits them, with the boundary bookkeeping of each
+template <typename H>
+void fill_boundary(const pbsm3d_handle* h, H& x) {
+    int k = 0;
+    for (int c = 0; c < h->n_colours; ++c)
+        if (h->ccount[c] > 0) { x.nb[k] = h->nb[c]; x.boff[k] = h->boff[c]; ++k; }
 }
 int line_enqueue_persistent(pbsm3d_handle* h) {
     const int maxit = h->cfg.max_iterations;
@@ -835,10 +873,28 @@ int line_enqueue_persistent(pbsm3d_handle* h) {
     unsigned* bar = h->grid_bar;
     CU(cudaMemsetAsync(bar, 0, sizeof(unsigned), h->stream));
     int L = h->L;
-    void* args[] = {&h->ss, &h->dm, &L, &cr, &h->x, &h->xf, &h->sc, &h->partial, &pl, &bar};
     CU(cudaEventRecord(h->ev_sw[0], h->stream));
     ++h->n_launch;
-    CU(cudaLaunchCooperativeKernel((const void*)h->gs_fn, dim3(h->gs_grid), dim3(kGsThreads), args, 0, h->stream));
+    if (h->n_ranks > 1) {
+        XHalo xh;
+        std::memset(&xh, 0, sizeof(xh));
+        xh.pt = h->d_pt;
+        xh.flag_remote = h->xflag_remote;
+        xh.flag_local = h->xflag_local;
+        xh.bptr = h->bptr;
+        xh.rstride = h->rstride;
+        for (int b = 0; b < 3; ++b) { xh.remote[b] = h->x_remote[b]; xh.ghost[b] = h->xg[b]; }
+        xh.g_zero = h->g_zero;
+        xh.nGp = h->nGp;
+        xh.e0 = h->xh_epoch;
+        fill_boundary(h, xh);
+        void* args[] = {&h->ss, &h->dm, &L, &cr, &h->x, &h->xf, &h->sc, &h->partial, &h->red, &pl, &bar, &xh};
+        CU(cudaLaunchCooperativeKernel((const void*)h->gs_fn, dim3(h->gs_grid), dim3(kGsThreads), args, 0, h->stream));
+        h->x_first = false;
+    } else {
+        void* args[] = {&h->ss, &h->dm, &L, &cr, &h->x, &h->xf, &h->sc, &h->partial, &pl, &bar};
+        CU(cudaLaunchCooperativeKernel((const void*)h->gs_fn, dim3(h->gs_grid), dim3(kGsThreads), args, 0, h->stream));
+    }
     CU(cudaEventRecord(h->ev_sw[1], h->stream));
     CU(cudaEventRecord(h->ev_sw[2], h->stream));
     return 0;
@@ -855,9 +911,24 @@ int sor_enqueue_persistent(pbsm3d_handle* h) {
     ColourRanges cr = colour_ranges(h);
     unsigned* bar = h->grid_bar + 1;
     CU(cudaMemsetAsync(bar, 0, sizeof(unsigned), h->stream));
-    void* args[] = {&h->dm, &h->offS, &h->drhsS, &h->ddiag, &h->qA, &h->sor_omega, &cr, &h->sc, &h->partial, &pl, &bar};
     ++h->n_launch;
-    CU(cudaLaunchCooperativeKernel(h->sor_fn, dim3(h->sor_grid), dim3(h->sor_threads), args, 0, h->stream));
+    if (h->n_ranks > 1) {
+        QHalo qh;
+        std::memset(&qh, 0, sizeof(qh));
+        qh.sl = sor_link(h);
+        qh.e0 = h->sor_epoch;
+        qh.n_ranks = h->n_ranks;
+        qh.rank = h->rank;
+        fill_boundary(h, qh);
+        int k = 0;
+        for (int c = 0; c < h->n_colours; ++c)
+            if (h->ccount[c] > 0) qh.colour_of[k++] = c;
+        void* args[] = {&h->dm, &h->offS, &h->drhsS, &h->ddiag, &h->qA, &h->sor_omega, &cr, &h->sc, &h->partial, &h->red, &pl, &bar, &qh};
+        CU(cudaLaunchCooperativeKernel(h->sor_fn, dim3(h->sor_grid), dim3(h->sor_threads), args, 0, h->stream));
+    } else {
+        void* args[] = {&h->dm, &h->offS, &h->drhsS, &h->ddiag, &h->qA, &h->sor_omega, &cr, &h->sc, &h->partial, &pl, &bar};
+        CU(cudaLaunchCooperativeKernel(h->sor_fn, dim3(h->sor_grid), dim3(h->sor_threads), args, 0, h->stream));
+    }
     h->sor_enqueued = maxit;  // replaced by the executed count (Scalars::dep_sweeps) once the step has synchronised
     return 0;
 }
@@ -1316,7 +1387,7 @@ int enqueue_tail(pbsm3d_handle* h, const DevForcing& f, double dt, const OutTarg
     CU(cudaEventRecord(h->ev[3], s));
     // deposition solve (x0 = 0)
     CU(cudaMemsetAsync(h->qA, 0, (size_t)h->S * sizeof(double), s));
-    if (use_sor(h) && h->persistent) {
+    if (use_sor(h) && h->persistent && h->sor_persistent) {
         TRY(sor_enqueue_persistent(h));
     } else if (use_sor(h)) {
         TRY(enqueue_sor_initial(h));
@@ -1650,6 +1721,22 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
 
     // ---- what actually happened
     bool redo_tail = false;
+    bool sor_counted = false;
+    auto count_persistent_halos = [&](bool with_x) {  // sweep numbers of the in-kernel halo channels advance by what was executed
+        if (!(h->persistent && h->n_ranks > 1)) return;
+        if (with_x && line && h->h_sc->susp_sweeps > 0) {
+            h->xh_epoch += (unsigned long long)h->h_sc->susp_sweeps;
+            h->halo_ops += h->h_sc->susp_sweeps;
+            h->halo_fused_ops += h->h_sc->susp_sweeps;
+        }
+        if (!sor_counted && h->h_sc->dep_sweeps > 0) {
+            h->sor_epoch += (unsigned long long)h->h_sc->dep_sweeps;
+            h->halo_ops += h->h_sc->dep_sweeps;
+            h->halo_fused_ops += h->h_sc->dep_sweeps;
+            sor_counted = true;
+        }
+    };
+    count_persistent_halos(true);
     if (line && h->persistent && h->h_sc->susp_present) {
         h->sweeps_timed = h->h_sc->susp_sweeps;
         h->sweeps_timed32 = std::min(h->plan_n32, h->h_sc->susp_sweeps);
@@ -1693,13 +1780,14 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
         TRY(enqueue_tail(h, f, dt, nullptr, n_cg));
         TRY(enqueue_finish(h, f, dt, out, 0x1ffu));
         TRY(sync_stream(h));
+        count_persistent_halos(false);
     }
     // deposition solve still open?
     bool sor = use_sor(h);
     bool cheb = !sor && use_chebyshev(h);
     int dep_used = sor ? PBSM3D_DEP_SOR : (cheb ? PBSM3D_DEP_CHEBYSHEV : PBSM3D_DEP_CG);
     while (h->h_sc->tail_done && h->h_sc->dep_present && !h->h_sc->dep_ok) {
-        if (sor && h->persistent) h->sor_enqueued = std::max(h->h_sc->dep_sweeps, std::min(maxit, 6 * h->sor_kest + 64));  // it ran to its bound
+        if (sor && h->persistent && h->sor_persistent) h->sor_enqueued = std::max(h->h_sc->dep_sweeps, std::min(maxit, 6 * h->sor_kest + 64));  // it ran to its bound
         if (sor) {
             const bool gave_up = h->h_sc->done == 2 || h->sor_enqueued >= std::min(maxit, 6 * h->sor_kest + 64);
             if (gave_up && h->cfg.deposition_solver == PBSM3D_DEP_SOR)
@@ -2176,9 +2264,9 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
         h->ss.ltab = tab;
     }
     TRY(setup_assembly(h));
-    TRY(setup_persistent(h));
     LAUNCH(h, assemble_pads_kernel, cdiv(Tp, 256), 256, h->dm, h->ss, L);
     if (h->n_ranks > 1) TRY(setup_comm(h, iperm));
+    TRY(setup_persistent(h));  // after the transport is known: across ranks the persistent kernels need the in-kernel halos
     CU(cudaStreamSynchronize(h->stream));
     if (cfg->deposition_solver != PBSM3D_DEP_CG) TRY(estimate_spectrum(h));
     CU(cudaStreamSynchronize(h->stream));

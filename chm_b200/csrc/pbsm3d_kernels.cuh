@@ -909,8 +909,14 @@ template <> __device__ __forceinline__ float load_cp<float>(const SuspSystem& s,
 
 // One face column of a colour pass: x_p <- T_p^{-1} (b_p - A_lat[p,:] x), in place.  XT is the STORAGE type of x: double, or
 // float for the sweeps furthest from convergence (gs_persistent_kernel); the arithmetic is fp64 either way.
-template <int LT, typename CT, typename XT>
-__device__ __forceinline__ void gs_column(const SuspSystem& s, const DevMesh& m, int Lrt, int p, XT* x) {
+template <typename XT>
+__device__ __forceinline__ double halo_gather(const XT* x, const double* ghost, size_t zS, size_t zG, int n, int Tp) {
+    return n < Tp ? (double)x[zS + n] : ghost[zG + (n - Tp)];
+}
+// HALO: neighbour slots >= Tp are ghost faces, read from `ghost` [L][nGp] (fp64 whatever XT is); else every neighbour is in x.
+template <int LT, typename CT, typename XT, bool HALO = false>
+__device__ __forceinline__ void gs_column(const SuspSystem& s, const DevMesh& m, int Lrt, int p, XT* x, const double* ghost = nullptr,
+                                          int nGp = 0) {
     const int Tp = m.Tp, S = m.S;
     const int L = LT > 0 ? LT : Lrt;
     const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
@@ -920,9 +926,13 @@ __device__ __forceinline__ void gs_column(const SuspSystem& s, const DevMesh& m,
         CT bl[LT > 0 ? LT : 1], cu[LT > 0 ? LT : 1];
 #pragma unroll
         for (int z = 0; z < LT; ++z) {
-            const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
+            const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S, zG = (size_t)z * nGp;
             const RowCoef<CT> c = load_row<CT>(s, r, LTp);
-            g[z] = -((double)c.l0 * (double)x[xr + n0] + (double)c.l1 * (double)x[xr + n1] + (double)c.l2 * (double)x[xr + n2]);
+            if (HALO)
+                g[z] = -((double)c.l0 * halo_gather(x, ghost, xr, zG, n0, Tp) + (double)c.l1 * halo_gather(x, ghost, xr, zG, n1, Tp) +
+                         (double)c.l2 * halo_gather(x, ghost, xr, zG, n2, Tp));
+            else
+                g[z] = -((double)c.l0 * (double)x[xr + n0] + (double)c.l1 * (double)x[xr + n1] + (double)c.l2 * (double)x[xr + n2]);
             bl[z] = c.bl;
         }
 #pragma unroll
@@ -938,9 +948,14 @@ __device__ __forceinline__ void gs_column(const SuspSystem& s, const DevMesh& m,
         // runtime layer count: the own column of x is the scratch of the forward pass (fp64 x only)
         double y = 0.0;
         for (int z = 0; z < L; ++z) {
-            const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S;
+            const size_t r = (size_t)z * Tp + p, xr = (size_t)z * S, zG = (size_t)z * nGp;
             const RowCoef<CT> c = load_row<CT>(s, r, LTp);
-            double g = -((double)c.l0 * (double)x[xr + n0] + (double)c.l1 * (double)x[xr + n1] + (double)c.l2 * (double)x[xr + n2]);
+            double g;
+            if (HALO)
+                g = -((double)c.l0 * halo_gather(x, ghost, xr, zG, n0, Tp) + (double)c.l1 * halo_gather(x, ghost, xr, zG, n1, Tp) +
+                      (double)c.l2 * halo_gather(x, ghost, xr, zG, n2, Tp));
+            else
+                g = -((double)c.l0 * (double)x[xr + n0] + (double)c.l1 * (double)x[xr + n1] + (double)c.l2 * (double)x[xr + n2]);
             if (z == 0) g += s.rhsS0[p];
             y = g - (double)c.bl * y;
             x[xr + p] = (XT)y;
@@ -1789,6 +1804,7 @@ struct PeerTable {
     double* ar_slots_local;                           // [2][kMaxRanks][4]
     unsigned long long* ar_flag_local;                // [kMaxRanks]
     int* error;                                       // sticky: 1 = a wait timed out (peer died / protocol bug)
+    unsigned long long* ar_epoch;                     // device-resident count of the all-reduces done so far
     unsigned long long timeout_ns;
 };
 
@@ -1865,12 +1881,17 @@ __global__ void __launch_bounds__(256) halo_wait_unpack_kernel(int nG, int nl, i
 // All-reduce of n <= 4 doubles over all ranks through peer memory, in place in red[]: lane q stores my values into
 // rank q's slot [parity][me], raises rank q's flag, then waits for rank q's values; lane 0 folds the P slots in
 // RANK ORDER, so every rank gets the same bits and the result does not depend on arrival order.  One warp.
-__global__ void peer_allreduce_kernel(double* red, int n, int is_max, const PeerTable* __restrict__ pt, unsigned long long epoch) {
-    const int q = threadIdx.x, P = pt->n_ranks, me = pt->me;
+// The epoch is a device-resident counter (every rank runs the same sequence of all-reduces, so the counters agree):
+// kernels that decide on the device how many reductions they need (the persistent solves) need no host bookkeeping.
+__device__ __forceinline__ void peer_allreduce_warp(double* red, int n, int is_max, const PeerTable* __restrict__ pt) {
+    const int q = threadIdx.x & 31, P = pt->n_ranks, me = pt->me;
+    unsigned long long epoch = 0;
+    if (q == 0) epoch = *pt->ar_epoch + 1;
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
     const int parity = (int)(epoch & 1ull);
     if (q < P) {
         double* dst = pt->ar_slots_remote[q] + ((size_t)parity * kMaxRanks + me) * 4;
-        for (int i = 0; i < n; ++i) dst[i] = red[i];
+        for (int i = 0; i < n; ++i) dst[i] = __ldcg(red + i);
         __threadfence_system();
         st_release_sys(pt->ar_flag_remote[q], epoch);
         peer_wait(pt->ar_flag_local + q, epoch, pt);
@@ -1886,7 +1907,12 @@ __global__ void peer_allreduce_kernel(double* red, int n, int is_max, const Peer
             }
             red[i] = acc;
         }
+        *pt->ar_epoch = epoch;
     }
+    __syncwarp();
+}
+__global__ void peer_allreduce_kernel(double* red, int n, int is_max, const PeerTable* __restrict__ pt) {
+    peer_allreduce_warp(red, n, is_max, pt);
 }
 
 // ------------------------------------------------------- halos carried by the solver kernels themselves
@@ -2249,6 +2275,257 @@ __global__ void __launch_bounds__(kRedThreads) dep_residual_halo_kernel(const __
     double o0, unused;
     if (grid_fold<1>(rr, 0.0, 0, 0, partial, pstride, &sc->ticket[3], o0, unused)) {
         if (threadIdx.x == 0) red[0] = o0;
+    }
+}
+
+// ---------------------------------------------------------------- persistent solver kernels across ranks
+// gs_persistent_kernel / sor_persistent_kernel with the halos of §"halos carried by the solver kernels themselves" inside the
+// loop: per colour pass the blocks that own boundary columns wait for the partners' counters, read ghosts from the generation
+// buffer of this sweep, and store their new values straight into the partners' next generation; the residual checks all-reduce
+// through peer memory from inside the kernel (peer_allreduce_warp), so every rank takes the same decision at the same sweep.
+// Sweep numbers (generation / tag arithmetic) start from a base the host advances by the executed count after the step.
+struct XHalo {
+    const PeerTable* pt;
+    unsigned long long* const* flag_remote;
+    const unsigned long long* flag_local;
+    const int* bptr;
+    const int* rstride;
+    double* const* remote[3];   // [generation][entry]
+    const double* ghost[3];     // my ghost buffers
+    const double* g_zero;
+    int nGp;
+    unsigned long long e0;      // number of the first sweep of this solve
+    int nb[8], boff[8];         // boundary columns of each colour range (first in the range) and their offset in bptr
+};
+template <int LT>
+__global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspSystem s, DevMesh m, int Lrt, ColourRanges cr, double* x, float* xf,
+                                                                           Scalars* sc, double* __restrict__ partial, double* red,
+                                                                           SolvePlan pl, unsigned* bar, const __grid_constant__ XHalo xh) {
+    if (sc->susp_done) return;
+    const int L = LT > 0 ? LT : Lrt;
+    const int Tp = m.Tp, S = m.S;
+    const double bnorm2 = sc->susp_bnorm2;
+    unsigned target = 0;
+    int it = 0, n_checks = 0, converged = 0, stalled = 0;
+    double rr = 0.0, prev_rr = bnorm2;
+    int prev_it = 0;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nx32 = (LT > 0 && xf) ? pl.nx32 : 0;
+    if (nx32 > 0) {
+        const size_t NS = (size_t)L * S;
+        for (size_t k = t0; k < NS; k += stride) xf[k] = 0.f;
+        grid_barrier(bar, target);
+    }
+    while (it < pl.maxit) {
+        const int phase = it < nx32 ? 0 : (it < pl.n32 ? 1 : 2);
+        const unsigned long long e = xh.e0 + (unsigned long long)it;
+        HaloLink hl;
+        hl.pt = xh.pt; hl.flag_remote = xh.flag_remote; hl.flag_local = xh.flag_local; hl.bptr = xh.bptr; hl.rstride = xh.rstride;
+        hl.remote = xh.remote[(e + 1) % 3];
+        hl.ghost = it == 0 ? xh.g_zero : xh.ghost[e % 3];
+        hl.nGp = xh.nGp;
+        hl.wait_epoch = e;
+        for (int c = 0; c < cr.n; ++c) {
+            hl.signal_epoch = (c == cr.n - 1) ? e + 1 : 0;
+            const int nbc = xh.nb[c];
+            const int nbb = max(1, (nbc + (int)blockDim.x - 1) / (int)blockDim.x);  // blocks that own boundary columns
+            const bool bblock = (int)blockIdx.x < nbb;
+            if (bblock) link_wait(hl);
+            for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) {
+                const int i = p - cr.start[c];
+                if (i < nbc) {
+                    if (phase == 0) gs_column<LT, float, float, true>(s, m, L, p, xf, hl.ghost, hl.nGp);
+                    else if (phase == 1) gs_column<LT, float, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
+                    else gs_column<LT, double, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
+                    const int e0 = hl.bptr[xh.boff[c] + i], e1 = hl.bptr[xh.boff[c] + i + 1];
+                    for (int k = e0; k < e1; ++k) {
+                        double* dst = hl.remote[k];
+                        const int st = hl.rstride[k];
+                        for (int z = 0; z < L; ++z) dst[(size_t)z * st] = phase == 0 ? (double)xf[(size_t)z * S + p] : x[(size_t)z * S + p];
+                    }
+                } else {
+                    if (phase == 0) gs_column<LT, float, float>(s, m, L, p, xf);
+                    else if (phase == 1) gs_column<LT, float, double>(s, m, L, p, x);
+                    else gs_column<LT, double, double>(s, m, L, p, x);
+                }
+            }
+            if (bblock) link_signal(hl, nbb);
+            grid_barrier(bar, target);
+        }
+        ++it;
+        if (it == nx32) {
+            const size_t NS = (size_t)L * S;
+            for (size_t k = t0; k < NS; k += stride) x[k] = (double)xf[k];
+            grid_barrier(bar, target);
+        }
+        const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
+        if (!check) continue;
+        // ---- ||b - A x||^2 with the ghosts the next sweep would read
+        {
+            const unsigned long long en = xh.e0 + (unsigned long long)it;
+            hl.ghost = xh.ghost[en % 3];
+            hl.wait_epoch = en;
+            link_wait(hl);
+        }
+        double a = 0.0;
+        for (int p = t0; p < Tp; p += stride) {
+            const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
+            double xm = 0.0, xc = x[p], cp_prev = 0.0;
+            for (int z = 0; z < L; ++z) {
+                const size_t r = (size_t)z * Tp + p;
+                const size_t zS = (size_t)z * S, zG = (size_t)z * hl.nGp;
+                const double xp = z < L - 1 ? x[zS + S + p] : 0.0;
+                double v = __ldcs(s.latS + r) * halo_gather(x, hl.ghost, zS, zG, n0, Tp) +
+                           __ldcs(s.latS + (size_t)L * Tp + r) * halo_gather(x, hl.ghost, zS, zG, n1, Tp) +
+                           __ldcs(s.latS + (size_t)2 * L * Tp + r) * halo_gather(x, hl.ghost, zS, zG, n2, Tp);
+                const double bS = __ldcs(s.belowS + r), cp = __ldcs(s.cp + r);
+                v += xc + bS * (cp_prev * xc + xm) + cp * xp;
+                v = (((z == 0) ? s.rhsS0[p] : 0.0) - v) * __ldcs(s.den + r);
+                a += v * v;
+                xm = xc;
+                xc = xp;
+                cp_prev = cp;
+            }
+        }
+        a = block_sum(a);
+        if (threadIdx.x == 0) partial[blockIdx.x] = a;
+        grid_barrier(bar, target);
+        const double rloc = fold_partials(partial, gridDim.x);
+        if (blockIdx.x == 0 && threadIdx.x < 32) {  // the sum over ranks
+            if (threadIdx.x == 0) red[0] = rloc;
+            __syncwarp();
+            peer_allreduce_warp(red, 1, 0, xh.pt);
+            __threadfence();
+        }
+        grid_barrier(bar, target);
+        rr = __ldcg(red);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (n_checks < 16) { sc->rr_hist[n_checks] = rr; sc->it_hist[n_checks] = it; }
+        }
+        ++n_checks;
+        if (rr <= pl.tol2 * bnorm2) { converged = 1; break; }
+        if (!(rr == rr) || rr > 1e60 * bnorm2) { stalled = 1; break; }
+        if (it >= 64 && it > prev_it && rr > 0.0 && prev_rr > 0.0) {
+            const double lim = exp(2.0 * (it - prev_it) * log(0.97));
+            if (rr > lim * prev_rr) { stalled = 1; break; }
+        }
+        prev_rr = rr;
+        prev_it = it;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->susp_rr = rr;
+        sc->n_checks = n_checks;
+        sc->susp_sweeps = it;
+        sc->susp_stalled = stalled;
+        if (converged) { sc->susp_done = 1; sc->susp_iters = it; sc->susp_ok = 1; }
+    }
+}
+
+// Multicolour SOR across ranks, one launch per solve: sor_pass_halo_kernel's (colour, rank) order and tagged ghost entries inside
+// the persistent loop.  Sweep k of this solve carries tag e0 + k + 1.
+struct QHalo {
+    SorLink sl;
+    unsigned long long e0;
+    int n_ranks, rank;
+    int nb[8], boff[8], colour_of[8];  // boundary faces of each (non-empty) colour range; its colour number (for the key)
+};
+template <bool STREAM, int NT, int B>
+__global__ void __launch_bounds__(NT, 1) sor_persistent_halo_kernel(const __grid_constant__ DevMesh m, const double* __restrict__ offS,
+                                                                    const double* __restrict__ bS, const double* __restrict__ ddiag, double* q,
+                                                                    double omega, ColourRanges cr, Scalars* sc, double* __restrict__ partial,
+                                                                    double* red, SolvePlan pl, unsigned* bar, const __grid_constant__ QHalo qh) {
+    if (!sc->tail_done || !sc->dep_present || sc->done) return;
+    const int Tp = m.Tp;
+    const double bnorm2 = sc->bnorm2;
+    unsigned target = 0;
+    int it = 0, done = 0;
+    double rr = bnorm2;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    while (it < pl.maxit) {
+        const unsigned long long e = qh.e0 + (unsigned long long)it + 1ull;
+        const int first = it == 0 ? 1 : 0;
+        for (int c = 0; c < cr.n; ++c) {
+            const int start = cr.start[c], end = cr.end[c], nbc = qh.nb[c];
+            const int my_key = qh.colour_of[c] * qh.n_ranks + qh.rank;
+            // boundary faces (first in the class): the only ones with ghost neighbours
+            for (int i = t0; i < nbc; i += stride) {
+                const int p = start + i;
+                const double qp = q[p];
+                double z = bS[p] - qp;
+                int n[3];
+                double o[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { n[j] = m.nbs[(size_t)j * Tp + p]; o[j] = offS[(size_t)j * Tp + p]; }
+                const int k0 = qh.sl.tl.bptr[qh.boff[c] + i], k1 = qh.sl.tl.bptr[qh.boff[c] + i + 1];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) z -= o[j] * (n[j] < Tp ? q[n[j]] : sor_ghost(qh.sl, n[j] - Tp, my_key, e, first));
+                const double qn = qp + omega * z;
+                q[p] = qn;
+                for (int k = k0; k < k1; ++k) tagged_write(qh.sl.tl.remote[k], qn, e);
+            }
+            for (int base = start + nbc + t0; base < end; base += B * stride) {
+                double qp[B], z[B], o[B][3];
+                int n[B][3];
+#pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    const int p = base + k * stride;
+                    if (p < end) {
+                        qp[k] = q[p];
+                        z[k] = bS[p] - qp[k];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            n[k][j] = m.nbs[(size_t)j * Tp + p];
+                            o[k][j] = STREAM ? __ldcs(offS + (size_t)j * Tp + p) : offS[(size_t)j * Tp + p];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < B; ++k)
+                    if (base + k * stride < end) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) z[k] -= o[k][j] * q[n[k][j]];
+                    }
+#pragma unroll
+                for (int k = 0; k < B; ++k)
+                    if (base + k * stride < end) q[base + k * stride] = qp[k] + omega * z[k];
+            }
+            grid_barrier(bar, target);
+        }
+        ++it;
+        const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
+        if (!check) continue;
+        double a = 0.0;
+        for (int p = t0; p < Tp; p += stride) {  // every ghost entry carries tag e after sweep e
+            double z = bS[p] - q[p];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int n = m.nbs[(size_t)j * Tp + p];
+                z -= offS[(size_t)j * Tp + p] * (n < Tp ? q[n] : tagged_read(qh.sl.tl.ghost + (n - Tp), e, qh.sl.tl.pt));
+            }
+            const double r = z * ddiag[p];
+            a += r * r;
+        }
+        a = block_sum(a);
+        if (threadIdx.x == 0) partial[blockIdx.x] = a;
+        grid_barrier(bar, target);
+        const double rloc = fold_partials(partial, gridDim.x);
+        if (blockIdx.x == 0 && threadIdx.x < 32) {
+            if (threadIdx.x == 0) red[0] = rloc;
+            __syncwarp();
+            peer_allreduce_warp(red, 1, 0, qh.sl.tl.pt);
+            __threadfence();
+        }
+        grid_barrier(bar, target);
+        rr = __ldcg(red);
+        if (rr <= pl.tol2 * bnorm2) { done = 1; break; }
+        if (!(rr == rr) || rr > 1e60 * bnorm2) { done = 2; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->rr = rr;
+        sc->dep_sweeps = it;
+        sc->iters = it;
+        if (done == 1) { sc->done = 1; sc->dep_ok = 1; sc->dep_buf = 0; }
+        else if (done == 2) sc->done = 2;
     }
 }
 
