@@ -834,7 +834,7 @@ int setup_persistent(pbsm3d_handle* h) {
     }
     if (multi) {  // the boundary columns of a colour must fit the first grid-stride iteration
         for (int c = 0; c < h->n_colours; ++c)
-            if (h->nb[c] > h->gs_grid * kGsThreads || h->nb[c] > h->sor_grid * h->sor_threads) return 0;
+            if (h->nb[c] > h->gs_grid / 2 * kGsThreads || h->nb[c] > h->sor_grid / 2 * h->sor_threads) return 0;
     }
     TRY(h->alloc_zero(&h->grid_bar, 2));
     if (h->cfg.fp32_sweep_streams && (h->L == 5 || h->L == 10 || h->L == 15 || h->L == 20)) TRY(h->alloc_zero(&h->xf, h->NS));

@@ -2328,12 +2328,15 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
         for (int c = 0; c < cr.n; ++c) {
             hl.signal_epoch = (c == cr.n - 1) ? e + 1 : 0;
             const int nbc = xh.nb[c];
-            const int nbb = max(1, (nbc + (int)blockDim.x - 1) / (int)blockDim.x);  // blocks that own boundary columns
+            // The first nbb blocks own the boundary columns and nothing else: they wait for the partners, update, store to the
+            // partners and release -- a few microseconds of NVLink latency that the other blocks, which split the interior columns
+            // among themselves, never see (with a static share of the interior on top they would hold every pass back).
+            const int nbb = max(1, (nbc + (int)blockDim.x - 1) / (int)blockDim.x);
             const bool bblock = (int)blockIdx.x < nbb;
-            if (bblock) link_wait(hl);
-            for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) {
-                const int i = p - cr.start[c];
-                if (i < nbc) {
+            if (bblock) {
+                link_wait(hl);
+                for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nbc; i += nbb * blockDim.x) {
+                    const int p = cr.start[c] + i;
                     if (phase == 0) gs_column<LT, float, float, true>(s, m, L, p, xf, hl.ghost, hl.nGp);
                     else if (phase == 1) gs_column<LT, float, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
                     else gs_column<LT, double, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
@@ -2343,13 +2346,16 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
                         const int st = hl.rstride[k];
                         for (int z = 0; z < L; ++z) dst[(size_t)z * st] = phase == 0 ? (double)xf[(size_t)z * S + p] : x[(size_t)z * S + p];
                     }
-                } else {
+                }
+                link_signal(hl, nbb);
+            } else {
+                const int strideI = ((int)gridDim.x - nbb) * blockDim.x;
+                for (int p = cr.start[c] + nbc + ((int)blockIdx.x - nbb) * (int)blockDim.x + (int)threadIdx.x; p < cr.end[c]; p += strideI) {
                     if (phase == 0) gs_column<LT, float, float>(s, m, L, p, xf);
                     else if (phase == 1) gs_column<LT, float, double>(s, m, L, p, x);
                     else gs_column<LT, double, double>(s, m, L, p, x);
                 }
             }
-            if (bblock) link_signal(hl, nbb);
             grid_barrier(bar, target);
         }
         ++it;
@@ -2447,8 +2453,11 @@ __global__ void __launch_bounds__(NT, 1) sor_persistent_halo_kernel(const __grid
         for (int c = 0; c < cr.n; ++c) {
             const int start = cr.start[c], end = cr.end[c], nbc = qh.nb[c];
             const int my_key = qh.colour_of[c] * qh.n_ranks + qh.rank;
-            // boundary faces (first in the class): the only ones with ghost neighbours
-            for (int i = t0; i < nbc; i += stride) {
+            // boundary faces (first in the class, the only ones with ghost neighbours) belong to the first nbb blocks, which do
+            // nothing else in this pass; the other blocks split the interior
+            const int nbb = max(1, (nbc + NT - 1) / NT);
+            if ((int)blockIdx.x < nbb)
+            for (int i = blockIdx.x * NT + threadIdx.x; i < nbc; i += nbb * NT) {
                 const int p = start + i;
                 const double qp = q[p];
                 double z = bS[p] - qp;
@@ -2463,12 +2472,14 @@ __global__ void __launch_bounds__(NT, 1) sor_persistent_halo_kernel(const __grid
                 q[p] = qn;
                 for (int k = k0; k < k1; ++k) tagged_write(qh.sl.tl.remote[k], qn, e);
             }
-            for (int base = start + nbc + t0; base < end; base += B * stride) {
+            const int strideI = ((int)gridDim.x - nbb) * NT;
+            if ((int)blockIdx.x >= nbb)
+            for (int base = start + nbc + ((int)blockIdx.x - nbb) * NT + (int)threadIdx.x; base < end; base += B * strideI) {
                 double qp[B], z[B], o[B][3];
                 int n[B][3];
 #pragma unroll
                 for (int k = 0; k < B; ++k) {
-                    const int p = base + k * stride;
+                    const int p = base + k * strideI;
                     if (p < end) {
                         qp[k] = q[p];
                         z[k] = bS[p] - qp[k];
@@ -2481,13 +2492,13 @@ __global__ void __launch_bounds__(NT, 1) sor_persistent_halo_kernel(const __grid
                 }
 #pragma unroll
                 for (int k = 0; k < B; ++k)
-                    if (base + k * stride < end) {
+                    if (base + k * strideI < end) {
 #pragma unroll
                         for (int j = 0; j < 3; ++j) z[k] -= o[k][j] * q[n[k][j]];
                     }
 #pragma unroll
                 for (int k = 0; k < B; ++k)
-                    if (base + k * stride < end) q[base + k * stride] = qp[k] + omega * z[k];
+                    if (base + k * strideI < end) q[base + k * strideI] = qp[k] + omega * z[k];
             }
             grid_barrier(bar, target);
         }
