@@ -24,7 +24,7 @@ c_uint8_p = C.POINTER(C.c_uint8)
 SOLVER_AUTO, SOLVER_LINE, SOLVER_BICGSTAB = 0, 1, 2
 DEP_AUTO, DEP_CG, DEP_CHEBYSHEV, DEP_SOR = 0, 1, 2, 3
 HALO_NONE, HALO_NCCL, HALO_PEER = 0, 1, 2
-ABI_VERSION = 4  # include/pbsm3d.h PBSM3D_ABI_VERSION
+ABI_VERSION = 5  # include/pbsm3d.h PBSM3D_ABI_VERSION
 ERR_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "NOCONVERGE"}
 
 
@@ -86,6 +86,20 @@ class WindConfig(C.Structure):
                 ("fetch_max_distance", C.c_double), ("fetch_I", C.c_double)]
 
 
+SNOWPACK_FIELDS = ("z_s", "m_s", "rho", "layer_count", "z_s_0", "z_s_l", "m_s_0", "m_s_l", "cc_s", "cc_s_0", "cc_s_l", "T_s", "T_s_0", "T_s_l",
+                   "h2o_total", "h2o_vol", "h2o", "h2o_max", "h2o_sat")
+
+
+class Snowpack(C.Structure):
+    """pbsm3d_snowpack: SoA view of snobal's per-face `sno` members (third_party/snobal/sno.h)."""
+    _fields_ = [(n, c_int32_p if n == "layer_count" else c_double_p) for n in SNOWPACK_FIELDS]
+
+
+class SnobalConfig(C.Structure):
+    """pbsm3d_snobal_config (snobal.cpp:83,101,190)."""
+    _fields_ = [("drift_density", C.c_double), ("threshold", C.c_double), ("max_active_layer", C.c_double)]
+
+
 FORCING_NAMES = [n for n, _ in Forcing._fields_]
 OUTPUT_NAMES = [n for n, _ in Outputs._fields_]
 # what the default path reads / writes (p_snow_hours and blowingsnow_probability belong to use_PomLi_probability)
@@ -116,6 +130,10 @@ SYMBOLS = {
     "pbsm3d_scale_wind_vert": (C.c_int, [C.c_void_p, C.POINTER(WindConfig), c_double_p, c_double_p, c_double_p, C.c_int]),
     "pbsm3d_fetchr": (C.c_int, [C.c_void_p, C.POINTER(WindConfig), c_double_p, c_double_p, C.c_int]),
     "pbsm3d_set_providers": (C.c_int, [C.c_void_p, C.POINTER(WindConfig)]),
+    "pbsm3d_snobal_config_defaults": (None, [C.POINTER(SnobalConfig)]),
+    "pbsm3d_apply_drift": (C.c_int, [C.c_void_p, C.POINTER(SnobalConfig), C.POINTER(Snowpack), c_double_p, c_double_p, c_double_p, C.c_int]),
+    "pbsm3d_apply_avalanche": (C.c_int, [C.c_void_p, C.POINTER(SnobalConfig), C.POINTER(Snowpack), c_double_p, c_double_p, c_double_p,
+                                         c_double_p, C.c_int]),
 }
 
 _lib = None
@@ -292,6 +310,40 @@ class Handle:
     def set_providers(self, cfg: Optional[WindConfig]):
         """Fuse the providers into step(): U_2m_above_srf / fetch left out of the forcing are derived on the device."""
         _check(self.lib, self.lib.pbsm3d_set_providers(self.h, C.byref(cfg) if cfg is not None else None))
+
+    # ------------------------------------------------------------------ the consumer of drift_mass (snobal's _adj_snow)
+    def _snowpack(self, state: Dict[str, np.ndarray]):
+        arrs = {}
+        pk = Snowpack()
+        for n in SNOWPACK_FIELDS:
+            a = np.array(state[n], dtype=np.int32 if n == "layer_count" else np.float64, copy=True)
+            if a.shape != (self.T,):
+                raise ValueError(f"snowpack field {n} must be [{self.T}]")
+            arrs[n] = a
+            setattr(pk, n, a.ctypes.data_as(c_int32_p if n == "layer_count" else c_double_p))
+        return pk, arrs
+
+    def apply_drift(self, state: Dict[str, np.ndarray], drift_mass=None, cfg: Optional[SnobalConfig] = None):
+        """snobal.cpp:363-387 for every face on the device.  drift_mass None = the handle's own (last step's, device-resident).
+        Returns the new state (the input is not modified) with two extra keys `swe`, `snowdepthavg`."""
+        pk, arrs = self._snowpack(state)
+        dm = None if drift_mass is None else np.ascontiguousarray(drift_mass, dtype=np.float64)
+        swe, sd = np.empty(self.T), np.empty(self.T)
+        _check(self.lib, self.lib.pbsm3d_apply_drift(self.h, C.byref(cfg) if cfg is not None else None, C.byref(pk), _dp(dm), _dp(swe),
+                                                     _dp(sd), 0))
+        arrs.update(swe=swe, snowdepthavg=sd)
+        return arrs
+
+    def apply_avalanche(self, state: Dict[str, np.ndarray], delta_snowdepth, delta_mass, cfg: Optional[SnobalConfig] = None):
+        """snobal.cpp:389-408 for every face on the device (snow_slide's volumes / the handle's face areas)."""
+        pk, arrs = self._snowpack(state)
+        dv = np.ascontiguousarray(delta_snowdepth, dtype=np.float64)
+        dm = np.ascontiguousarray(delta_mass, dtype=np.float64)
+        swe, sd = np.empty(self.T), np.empty(self.T)
+        _check(self.lib, self.lib.pbsm3d_apply_avalanche(self.h, C.byref(cfg) if cfg is not None else None, C.byref(pk), _dp(dv), _dp(dm),
+                                                         _dp(swe), _dp(sd), 0))
+        arrs.update(swe=swe, snowdepthavg=sd)
+        return arrs
 
     # ------------------------------------------------------------------ inspection
     def geometry(self):

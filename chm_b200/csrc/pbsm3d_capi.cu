@@ -25,6 +25,7 @@
 
 #include "pbsm3d_kernels.cuh"
 #include "pbsm3d_wind.cuh"
+#include "pbsm3d_snobal.cuh"
 
 using namespace pbsm3d;
 
@@ -213,6 +214,7 @@ struct pbsm3d_handle {
     int pred_n32 = 0;  // leading sweeps of the next solve that may stream fp32 coefficient copies
     bool have_system = false;
     long long n_launch = 0;
+    double* sno_stage = nullptr;  // [23][T] staging of a host-side snowpack (pbsm3d_apply_drift / _avalanche with host buffers)
 
     template <typename U>
     int alloc(U** p, size_t n) {
@@ -2459,6 +2461,85 @@ int pbsm3d_set_providers(pbsm3d_handle* h, const pbsm3d_wind_config* wc) {
     h->providers_on = wc != nullptr;
     if (wc) h->wind_cfg = *wc;
     return 0;
+}
+
+// ---- the consumer of drift_mass: snobal's snowpack mass adjustment -----------------------
+void pbsm3d_snobal_config_defaults(pbsm3d_snobal_config* c) {
+    if (!c) return;
+    c->drift_density = 300.0;    // snobal.cpp:83
+    c->threshold = 0.2;          // snobal.cpp:190
+    c->max_active_layer = 0.1;   // snobal.cpp:101
+}
+
+static int adj_snow_call(pbsm3d_handle* h, const pbsm3d_snobal_config* cfg, const pbsm3d_snowpack* pk, int mode, const double* a,
+                         const double* b, double* swe_out, double* depth_out, int device_ptrs) {
+    if (!h || !pk) return fail(PBSM3D_ERR_INVALID, "null argument");
+    double* const* fields[19] = {&pk->z_s, &pk->m_s, &pk->rho, nullptr, &pk->z_s_0, &pk->z_s_l, &pk->m_s_0, &pk->m_s_l, &pk->cc_s,
+                                 &pk->cc_s_0, &pk->cc_s_l, &pk->T_s, &pk->T_s_0, &pk->T_s_l, &pk->h2o_total, &pk->h2o_vol, &pk->h2o,
+                                 &pk->h2o_max, &pk->h2o_sat};
+    for (int k = 0; k < 19; ++k)
+        if (k == 3 ? pk->layer_count == nullptr : *fields[k] == nullptr) return fail(PBSM3D_ERR_INVALID, "snowpack: every state array is required");
+    if (mode == 1 && (!a || !b)) return fail(PBSM3D_ERR_INVALID, "apply_avalanche: both delta arrays are required");
+    pbsm3d_snobal_config local;
+    if (!cfg) { pbsm3d_snobal_config_defaults(&local); cfg = &local; }
+    if (!(cfg->drift_density > 0)) return fail(PBSM3D_ERR_INVALID, "drift_density must be positive");
+    CU(cudaSetDevice(h->device));
+    const int T = h->T;
+    const size_t n = (size_t)T, bytes = n * sizeof(double);
+    SnowpackPtrs p;
+    double* dptr[19];
+    const double *da = a, *db = b;
+    double *dswe = swe_out, *ddepth = depth_out;
+    int a_slots = 0;
+    if (mode == 0 && !a) {  // the handle's own drift_mass (slot order), left on the device by the last step
+        da = h->drift_mass;
+        a_slots = 1;
+    }
+    if (!device_ptrs) {
+        if (!h->sno_stage) TRY(h->alloc(&h->sno_stage, 23 * n));
+        for (int k = 0; k < 19; ++k) {
+            dptr[k] = h->sno_stage + k * n;
+            if (k == 3) CU(cudaMemcpyAsync(dptr[k], pk->layer_count, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+            else CU(cudaMemcpyAsync(dptr[k], *fields[k], bytes, cudaMemcpyHostToDevice, h->stream));
+        }
+        if (a) { CU(cudaMemcpyAsync(h->sno_stage + 19 * n, a, bytes, cudaMemcpyHostToDevice, h->stream)); da = h->sno_stage + 19 * n; }
+        if (b) { CU(cudaMemcpyAsync(h->sno_stage + 20 * n, b, bytes, cudaMemcpyHostToDevice, h->stream)); db = h->sno_stage + 20 * n; }
+        dswe = swe_out ? h->sno_stage + 21 * n : nullptr;
+        ddepth = depth_out ? h->sno_stage + 22 * n : nullptr;
+    } else {
+        for (int k = 0; k < 19; ++k) dptr[k] = k == 3 ? (double*)pk->layer_count : *fields[k];
+    }
+    p.z_s = dptr[0]; p.m_s = dptr[1]; p.rho = dptr[2]; p.layer_count = (int*)dptr[3];
+    p.z_s_0 = dptr[4]; p.z_s_l = dptr[5]; p.m_s_0 = dptr[6]; p.m_s_l = dptr[7];
+    p.cc_s = dptr[8]; p.cc_s_0 = dptr[9]; p.cc_s_l = dptr[10];
+    p.T_s = dptr[11]; p.T_s_0 = dptr[12]; p.T_s_l = dptr[13];
+    p.h2o_total = dptr[14]; p.h2o_vol = dptr[15]; p.h2o = dptr[16]; p.h2o_max = dptr[17]; p.h2o_sat = dptr[18];
+    const SnobalConst kc{cfg->drift_density, cfg->threshold, cfg->max_active_layer};
+    if (mode == 0)
+        LAUNCH(h, snobal_adj_snow_kernel<0>, cdiv(T, 256), 256, T, p, kc, da, db, h->iperm, a_slots, h->area, dswe, ddepth);
+    else
+        LAUNCH(h, snobal_adj_snow_kernel<1>, cdiv(T, 256), 256, T, p, kc, da, db, h->iperm, 0, h->area, dswe, ddepth);
+    if (!device_ptrs) {
+        for (int k = 0; k < 19; ++k) {
+            if (k == 3) CU(cudaMemcpyAsync(pk->layer_count, dptr[k], n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            else CU(cudaMemcpyAsync(*fields[k], dptr[k], bytes, cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (swe_out) CU(cudaMemcpyAsync(swe_out, dswe, bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (depth_out) CU(cudaMemcpyAsync(depth_out, ddepth, bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    TRY(sync_stream(h));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pbsm3d_apply_drift(pbsm3d_handle* h, const pbsm3d_snobal_config* cfg, const pbsm3d_snowpack* pack, const double* drift_mass,
+                       double* swe_out, double* snowdepth_out, int device_ptrs) {
+    return adj_snow_call(h, cfg, pack, 0, drift_mass, nullptr, swe_out, snowdepth_out, device_ptrs);
+}
+int pbsm3d_apply_avalanche(pbsm3d_handle* h, const pbsm3d_snobal_config* cfg, const pbsm3d_snowpack* pack,
+                           const double* delta_avalanche_snowdepth, const double* delta_avalanche_mass, double* swe_out,
+                           double* snowdepth_out, int device_ptrs) {
+    return adj_snow_call(h, cfg, pack, 1, delta_avalanche_snowdepth, delta_avalanche_mass, swe_out, snowdepth_out, device_ptrs);
 }
 
 int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms) {

@@ -20,6 +20,8 @@
  *   scale_wind_vert::run(mesh&)        scale_wind_vert.cpp:167-229  pbsm3d_scale_wind_vert   } the providers of two PBSM3D inputs,
  *   fetchr::run(face), every face      fetchr.cpp:54-119            pbsm3d_fetchr            } optionally fused into the step
  *                                                                   (pbsm3d_set_providers)
+ *   snobal::run, drift_mass hook       snobal.cpp:363-387 -> sno::_adj_snow (sno.cpp:2527-2575)   pbsm3d_apply_drift     } the consumers of
+ *   snobal::run, avalanche hook        snobal.cpp:389-408 -> sno::_adj_snow                       pbsm3d_apply_avalanche } PBSM3D's / snow_slide's output
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
  * code on failure with a message available from pbsm3d_last_error() (the adaptor turns it into
@@ -38,7 +40,7 @@
 extern "C" {
 #endif
 
-#define PBSM3D_ABI_VERSION 4
+#define PBSM3D_ABI_VERSION 5
 
 enum {
     PBSM3D_OK = 0,
@@ -274,6 +276,39 @@ int pbsm3d_fetchr(pbsm3d_handle* h, const pbsm3d_wind_config* cfg, const double*
  * and (with exp/tanh fetch on) forcing->fetch == NULL and derive them on the device before the assembly, so the two arrays
  * never cross PCIe.  cfg NULL switches the fusion off again. */
 int pbsm3d_set_providers(pbsm3d_handle* h, const pbsm3d_wind_config* cfg);
+
+/* ---- the consumer of PBSM3D's output: snobal's snowpack mass adjustment on the device ----
+ * snobal::run (src/modules/snobal.cpp:363-387) hands each face's drift_mass to sno::_adj_snow (third_party/snobal/sno.cpp:2527-2575,
+ * with _adj_layers :2617-2696, _calc_layers :2366-2405, _layer_mass :1564-1580, _cold_content :2321-2329): erosion removes depth at
+ * the pack's own density, deposition adds depth at `drift_density`; layers are re-partitioned, a pack that falls below the mass
+ * threshold becomes liquid water.  The per-face snowpack state is the caller's (snobal's `sno` members of the same names), SoA,
+ * each [n_local] in CHM face order; every field is read and written in place.  Bit-identical to the compiled sno.cpp. */
+typedef struct pbsm3d_snowpack {
+    double *z_s, *m_s, *rho;   /* total depth (m), specific mass (kg/m^2), density */
+    int32_t* layer_count;      /* 0, 1 or 2 */
+    double *z_s_0, *z_s_l, *m_s_0, *m_s_l;      /* surface / lower layer depth and mass */
+    double *cc_s, *cc_s_0, *cc_s_l;             /* cold contents (J/m^2) */
+    double *T_s, *T_s_0, *T_s_l;                /* temperatures (K) */
+    double *h2o_total, *h2o_vol, *h2o, *h2o_max, *h2o_sat;
+} pbsm3d_snowpack;
+typedef struct pbsm3d_snobal_config {
+    double drift_density;      /* "drift_density", 300 kg/m^3 (snobal.cpp:83) */
+    double threshold;          /* tstep_info[SMALL_TSTEP].threshold, 0.2 kg/m^2 (snobal.cpp:190): minimum mass of a layer */
+    double max_active_layer;   /* "max_active_layer" = sno::max_z_s_0, 0.1 m (snobal.cpp:101) */
+} pbsm3d_snobal_config;
+void pbsm3d_snobal_config_defaults(pbsm3d_snobal_config* cfg);
+/* drift_mass [n_local]: NULL = the handle's own device-resident drift_mass of the last pbsm3d_step (it then never crosses PCIe);
+ * -9999 / NaN count as 0 (module_base::is_nan).  swe_out / snowdepth_out [n_local] (each may be NULL) receive m_s and z_s, the two
+ * face variables snobal hands back to PBSM3D's next step (snobal.cpp:468,491).  device_ptrs: 0 = every pointer (inside `pack`
+ * too) is a host buffer, 1 = device buffers.  cfg NULL = defaults. */
+int pbsm3d_apply_drift(pbsm3d_handle* h, const pbsm3d_snobal_config* cfg, const pbsm3d_snowpack* pack, const double* drift_mass,
+                       double* swe_out, double* snowdepth_out, int device_ptrs);
+/* The same adjustment for snow_slide's output (snobal.cpp:389-408): delta_avalanche_snowdepth is a VOLUME (m^3) and
+ * delta_avalanche_mass a water-equivalent volume (m^3) per face; _adj_snow(volume / area, swe volume / area * 1000) with the
+ * handle's face areas. */
+int pbsm3d_apply_avalanche(pbsm3d_handle* h, const pbsm3d_snobal_config* cfg, const pbsm3d_snowpack* pack,
+                           const double* delta_avalanche_snowdepth, const double* delta_avalanche_mass, double* swe_out,
+                           double* snowdepth_out, int device_ptrs);
 
 /* Stand-alone kernels for measurement (bench.py roofline line, ncu): run `reps` launches of the named kernel on
  * the last assembled system and return the mean CUDA-event time per launch in milliseconds.
