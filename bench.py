@@ -644,8 +644,11 @@ def main():
             traffic_src = tj.get("source")
             if persistent:
                 traffic = tj.get("dram_bytes_per_launch_persistent")
+                traffic_src = (tj.get("persistent") or {}).get("source", traffic_src)
         except Exception:
             traffic = traffic32 = None
+    if not (T == 1002528 and nl == 10):  # the ncu captures are of config c2 on one GPU; no figure for other shapes
+        traffic = traffic32 = None
     if persistent and acc["solve_launches"]:
         nlch = acc["solve_launches"]
         ach_p = acc["solve_bytes"] / (sweep_ms * 1e-3) / 1e9
@@ -685,7 +688,7 @@ def main():
         roofline["assembly"] = {"kernels": "face_prelude_kernel + assemble_kernel, stand-alone (mean of 20 launch pairs, CUDA events)",
                                 "ms": asm_ms, "algorithmic_bytes": ab, "achieved": ab / (asm_ms * 1e-3) / 1e9,
                                 "frac": ab / (asm_ms * 1e-3) / 1e9 / peak,
-                                "note": "fp64-issue bound, not HBM bound (profiles/r2a_assembly.md)"}
+                                "note": "fp64-issue bound, not HBM bound (profiles/r2c_summary.md)"}
 
     # ---- N > 1: the partitioned solve checked off the library
     parity = None

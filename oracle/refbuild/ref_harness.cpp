@@ -1,6 +1,7 @@
 // Harness around the UNMODIFIED reference sources (compiled where they lie under /root/reference by oracle/refbuild/Makefile):
 //     src/modules/PBSM3D.cpp   src/math/coordinates.cpp   src/physics/Atmosphere.cpp
 //     src/modules/scale_wind_vert.cpp   src/modules/fetchr.cpp        (the two per-face providers of PBSM3D inputs)
+//     src/modules/snow_slide.cpp                                       (gravitational redistribution)
 // against the stand-in headers in stubs/.  This file holds (1) the stand-in NearestNeighborProblem implementation
 // (pattern + numbering of LinearAlgebra.cpp:31-152; Solve() = a registered sparse direct solve) and (2) a small C API
 // that builds a CHM-like mesh from flat arrays, runs PBSM3D::init/run and reads variables / assembled systems back.
@@ -8,6 +9,7 @@
 #include "PBSM3D.hpp"
 #include "fetchr.hpp"
 #include "scale_wind_vert.hpp"
+#include "snow_slide.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -122,6 +124,7 @@ struct Harness {
     std::unique_ptr<PBSM3D> mod;
     math::LinearAlgebra::NearestNeighborProblem* nnp[2] = {nullptr, nullptr};
     netcdf chk;
+    std::unique_ptr<snow_slide> slide;
 };
 
 void parse_kv(const char* text, ptree_stub& out)
@@ -308,6 +311,80 @@ int chmref_run_fetchr(void* hv, const char* cfg_kv)
         return 1;
     }
 }
+
+// ---- snow_slide (src/modules/snow_slide.cpp, compiled unmodified; USE_MPI undefined, so its exchanges are compiled out) ----
+// Ghost faces for a rank-local view: face k of the nG ghosts hangs off owned face attach_face[k] as neighbour attach_edge[k]
+// (is_ghost = true; not part of domain->face(i)).  vx,vy,vz [nG][3]; area [nG] (NaN = compute from the vertices).
+int chmref_add_ghosts(void* hv, int nG, const double* vx, const double* vy, const double* vz, const double* area,
+                      const int* attach_face, const int* attach_edge)
+{
+    auto h = static_cast<Harness*>(hv);
+    for (int k = 0; k < nG; ++k) {
+        auto f = new face_stub;
+        f->_domain = h->domain.get();
+        f->is_ghost = f->_is_ghost = true;
+        for (int j = 0; j < 3; ++j) { f->vx[j] = vx[3 * k + j]; f->vy[j] = vy[3 * k + j]; f->vz[j] = vz[3 * k + j]; }
+        if (!std::isnan(area[k])) f->_parameters["area"] = area[k];
+        h->domain->_ghosts.emplace_back(f);
+        h->domain->_faces[attach_face[k]]->_neigh[attach_edge[k]] = f;
+    }
+    return 0;
+}
+int chmref_set_ghost_var(void* hv, const char* name, const double* vals)
+{
+    auto h = static_cast<Harness*>(hv);
+    for (std::size_t i = 0; i < h->domain->_ghosts.size(); ++i) (*h->domain->_ghosts[i])[name] = vals[i];
+    return 0;
+}
+int chmref_get_ghost_var(void* hv, const char* name, double* out)
+{
+    auto h = static_cast<Harness*>(hv);
+    for (std::size_t i = 0; i < h->domain->_ghosts.size(); ++i) out[i] = (*h->domain->_ghosts[i])[name];
+    return 0;
+}
+int chmref_slide_init(void* hv, const char* cfg_kv)
+{
+    auto h = static_cast<Harness*>(hv);
+    try {
+        config_file cfg;
+        parse_kv(cfg_kv, cfg);
+        h->slide.reset(new snow_slide(cfg));
+        h->slide->global_param = h->glob;
+        h->slide->ID = 9;  // module-data slot distinct from PBSM3D's and scale_wind_vert's
+        h->slide->init(h->domain);
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return 1;
+    }
+}
+int chmref_slide_run(void* hv)
+{
+    auto h = static_cast<Harness*>(hv);
+    try {
+        h->slide->run(h->domain);
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return 1;
+    }
+}
+int chmref_slide_n_depends(void* hv) { return (int)static_cast<Harness*>(hv)->slide->_depends.size(); }
+const char* chmref_slide_depend(void* hv, int i) { return static_cast<Harness*>(hv)->slide->_depends.at(i).c_str(); }
+int chmref_slide_n_provides(void* hv) { return (int)static_cast<Harness*>(hv)->slide->_provides.size(); }
+const char* chmref_slide_provide(void* hv, int i) { return static_cast<Harness*>(hv)->slide->_provides.at(i).c_str(); }
+// checkpoint round trip through snow_slide::checkpoint / load_checkpoint (snow_slide.cpp:59-93): 4 arrays [T]
+int chmref_slide_checkpoint(void* hv, double* out4)
+{
+    auto h = static_cast<Harness*>(hv);
+    h->slide->checkpoint(h->domain, h->chk);
+    const char* names[4] = {"snow_slide:delta_avalanche_snowdepth", "snow_slide:delta_avalanche_mass", "snow_slide:delta_avalanche_snowdepth_sum",
+                            "snow_slide:delta_avalanche_mass_sum"};
+    const std::size_t T = h->domain->size_faces();
+    for (int k = 0; k < 4; ++k) std::memcpy(out4 + k * T, h->chk.vars.at(names[k]).data(), T * sizeof(double));
+    return 0;
+}
+double chmref_face_slope(void* hv, int i) { return static_cast<Harness*>(hv)->domain->face(i)->slope(); }
 
 // The interpolant scale_wind_vert uses (stubs/interpolation.hpp, a restatement of TPSpline.cpp): n samples (x,y,v), one query.
 double chmref_tpspline(int n, const double* xyv, const double* query)

@@ -35,7 +35,9 @@ public:
     virtual void checkpoint(mesh&, netcdf&) {}
     virtual void load_checkpoint(mesh&, netcdf&) {}
 
+    enum class SpatialType { local, neighbor, distance };  // module_base.hpp:77
     void depends(const std::string& n) { _depends.push_back(n); }
+    void depends(const std::string& n, SpatialType) { _depends.push_back(n); }
     void provides(const std::string& n) { _provides.push_back(n); }
     void provides_vector(const std::string& n) { _vectors.push_back(n); }
     // module_base.hpp:416-435: an optional input counts as found when another module provides it; the harness says which

@@ -5,6 +5,7 @@
 //   face::get_area                                triangulation.hpp:1830-1856
 //   face::has_vegetation / veg_attribute          triangulation.hpp:1656-1697
 //   variable store default -9999                  triangulation.cpp:2536-2560
+//   face::normal / slope (snow_slide)             triangulation.hpp:1501-1523, 1549-1574 (CGAL::unit_normal, arma::norm_dot)
 // Test infrastructure (oracle/), never linked into the product.
 #pragma once
 #include <CGAL/Exact_predicates_inexact_constructions_kernel.h>
@@ -124,6 +125,23 @@ public:
     double edge_length(int i) const { return CGAL::sqrt(edge(i).squared_length()); }
     Point_3 center() const { return Point_3((vx[0] + vx[1] + vx[2]) / 3, (vy[0] + vy[1] + vy[2]) / 3, (vz[0] + vz[1] + vz[2]) / 3); }
     double get_z() const { return center().z(); }
+    // CGAL::unit_normal(p, q, r) = cross(q - p, r - p) / |.|  (projected mesh; the geographic branch scales x, y by 1e5)
+    Vector_3 normal() const
+    {
+        const double ax = vx[1] - vx[0], ay = vy[1] - vy[0], az = vz[1] - vz[0];
+        const double bx = vx[2] - vx[0], by = vy[2] - vy[0], bz = vz[2] - vz[0];
+        const double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+        const double len = CGAL::sqrt(nx * nx + ny * ny + nz * nz);
+        return Vector_3(nx / len, ny / len, nz / len);
+    }
+    // acos(arma::norm_dot(normal, (0,0,1))), norm_dot(a,b) = dot(a,b) / (norm(a) norm(b))
+    double slope() const
+    {
+        const Vector_3 n = normal();
+        const double dot = n.x() * 0.0 + n.y() * 0.0 + n.z() * 1.0;
+        const double na = std::sqrt(n.x() * n.x() + n.y() * n.y() + n.z() * n.z()), nb = std::sqrt(0.0 * 0.0 + 0.0 * 0.0 + 1.0 * 1.0);
+        return std::acos(dot / (na * nb));
+    }
     double get_x() const { return center().x(); }  // triangulation.hpp:1755-1771
     double get_y() const { return center().y(); }
     // triangulation.hpp:1543-1546 -> triangulation.cpp:170-186: nearest face CENTRE to the point `distance` along `azimuth`
@@ -154,6 +172,8 @@ public:
     std::size_t size_faces() const { return _faces.size(); }
     std::size_t size_global_faces() const { return _n_global; }
     void ghost_neighbors_communicate_variable(const std::string&) {}  // single rank in the harness: nothing to exchange
+    void ghost_to_neighbors_communicate_variable(const std::string&) {}
+    std::vector<std::unique_ptr<face_stub>> _ghosts;  // is_ghost faces hanging off owned faces (snow_slide harness): not in _faces
     void print_ghost_neighbor_info() {}
 };
 typedef std::shared_ptr<triangulation> mesh;
