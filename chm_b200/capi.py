@@ -24,7 +24,7 @@ c_uint8_p = C.POINTER(C.c_uint8)
 SOLVER_AUTO, SOLVER_LINE, SOLVER_BICGSTAB = 0, 1, 2
 DEP_AUTO, DEP_CG, DEP_CHEBYSHEV, DEP_SOR = 0, 1, 2, 3
 HALO_NONE, HALO_NCCL, HALO_PEER = 0, 1, 2
-ABI_VERSION = 5  # include/pbsm3d.h PBSM3D_ABI_VERSION
+ABI_VERSION = 6  # include/pbsm3d.h PBSM3D_ABI_VERSION
 ERR_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "NOCONVERGE"}
 
 
@@ -100,6 +100,16 @@ class SnobalConfig(C.Structure):
     _fields_ = [("drift_density", C.c_double), ("threshold", C.c_double), ("max_active_layer", C.c_double)]
 
 
+class SlideConfig(C.Structure):
+    """pbsm3d_slide_config (snow_slide.cpp:33,409-410)."""
+    _fields_ = [("avalache_mult", C.c_double), ("avalache_pow", C.c_double), ("use_vertical_snow", C.c_int32)]
+
+
+class SlideStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("wavefront_rounds", C.c_int32), ("faces_fired", C.c_int32), ("ms_device", C.c_float)]
+
+
+SLIDE_OUTPUTS = ("delta_avalanche_snowdepth", "delta_avalanche_mass", "delta_avalanche_snowdepth_sum", "delta_avalanche_mass_sum", "maxDepth")
 FORCING_NAMES = [n for n, _ in Forcing._fields_]
 OUTPUT_NAMES = [n for n, _ in Outputs._fields_]
 # what the default path reads / writes (p_snow_hours and blowingsnow_probability belong to use_PomLi_probability)
@@ -130,6 +140,11 @@ SYMBOLS = {
     "pbsm3d_scale_wind_vert": (C.c_int, [C.c_void_p, C.POINTER(WindConfig), c_double_p, c_double_p, c_double_p, C.c_int]),
     "pbsm3d_fetchr": (C.c_int, [C.c_void_p, C.POINTER(WindConfig), c_double_p, c_double_p, C.c_int]),
     "pbsm3d_set_providers": (C.c_int, [C.c_void_p, C.POINTER(WindConfig)]),
+    "pbsm3d_slide_config_defaults": (None, [C.POINTER(SlideConfig)]),
+    "pbsm3d_slide_init": (C.c_int, [C.c_void_p, C.POINTER(SlideConfig)]),
+    "pbsm3d_slide_run": (C.c_int, [C.c_void_p] + [c_double_p] * 8 + [C.POINTER(SlideStats), C.c_int]),
+    "pbsm3d_slide_get_state": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
+    "pbsm3d_slide_set_state": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
     "pbsm3d_snobal_config_defaults": (None, [C.POINTER(SnobalConfig)]),
     "pbsm3d_apply_drift": (C.c_int, [C.c_void_p, C.POINTER(SnobalConfig), C.POINTER(Snowpack), c_double_p, c_double_p, c_double_p, C.c_int]),
     "pbsm3d_apply_avalanche": (C.c_int, [C.c_void_p, C.POINTER(SnobalConfig), C.POINTER(Snowpack), c_double_p, c_double_p, c_double_p,
@@ -344,6 +359,37 @@ class Handle:
                                                          _dp(swe), _dp(sd), 0))
         arrs.update(swe=swe, snowdepthavg=sd)
         return arrs
+
+    # ------------------------------------------------------------------ snow_slide
+    def slide_init(self, **cfg_overrides):
+        """snow_slide::init (maxDepth per face; the running sums start at 0)."""
+        cfg = SlideConfig()
+        self.lib.pbsm3d_slide_config_defaults(C.byref(cfg))
+        for k, v in cfg_overrides.items():
+            if not hasattr(cfg, k):
+                raise KeyError(f"unknown snow_slide config key {k}")
+            setattr(cfg, k, type(getattr(cfg, k))(v))
+        _check(self.lib, self.lib.pbsm3d_slide_init(self.h, C.byref(cfg)))
+
+    def slide_run(self, snowdepthavg, snowdepthavg_vert, swe):
+        """snow_slide::run on host arrays [T].  Returns (outputs dict, stats dict)."""
+        ins = [np.ascontiguousarray(a, dtype=np.float64) for a in (snowdepthavg, snowdepthavg_vert, swe)]
+        for a in ins:
+            if a.shape != (self.T,):
+                raise ValueError(f"snow_slide inputs must be [{self.T}]")
+        outs = {n: np.empty(self.T) for n in SLIDE_OUTPUTS}
+        st = SlideStats()
+        _check(self.lib, self.lib.pbsm3d_slide_run(self.h, *[_dp(a) for a in ins], *[_dp(outs[n]) for n in SLIDE_OUTPUTS], C.byref(st), 0))
+        return outs, {n: getattr(st, n) for n, _ in st._fields_}
+
+    def slide_get_state(self):
+        s = {n: np.empty(self.T) for n in SLIDE_OUTPUTS[:4]}
+        _check(self.lib, self.lib.pbsm3d_slide_get_state(self.h, *[_dp(s[n]) for n in SLIDE_OUTPUTS[:4]]))
+        return s
+
+    def slide_set_state(self, **arrays):
+        arrs = [None if arrays.get(n) is None else np.ascontiguousarray(arrays[n], dtype=np.float64) for n in SLIDE_OUTPUTS[:4]]
+        _check(self.lib, self.lib.pbsm3d_slide_set_state(self.h, *[_dp(a) for a in arrs]))
 
     # ------------------------------------------------------------------ inspection
     def geometry(self):

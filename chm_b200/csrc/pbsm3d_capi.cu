@@ -26,6 +26,7 @@
 #include "pbsm3d_kernels.cuh"
 #include "pbsm3d_wind.cuh"
 #include "pbsm3d_snobal.cuh"
+#include "pbsm3d_slide.cuh"
 
 using namespace pbsm3d;
 
@@ -214,6 +215,15 @@ struct pbsm3d_handle {
     int pred_n32 = 0;  // leading sweeps of the next solve that may stream fp32 coefficient copies
     bool have_system = false;
     long long n_launch = 0;
+    // snow_slide (pbsm3d_slide_init / _run)
+    double* slope = nullptr;            // [Tp] face slope (rad), computed with the rest of the geometry
+    bool slide_ready = false;
+    pbsm3d_slide_config slide_cfg{};
+    SlideArrays sl{};
+    double *sl_sum_sd = nullptr, *sl_sum_mass = nullptr, *sl_xfer = nullptr, *sl_rev = nullptr, *sl_in = nullptr;
+    int* sl_moved = nullptr;
+    unsigned* sl_bar = nullptr;
+    int sl_grid = 0;
     double* sno_stage = nullptr;  // [23][T] staging of a host-side snowpack (pbsm3d_apply_drift / _avalanche with host buffers)
 
     template <typename U>
@@ -2152,8 +2162,9 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
         TRY(h->alloc(&h->cx, (size_t)Tp + nG));
         TRY(h->alloc(&h->cy, (size_t)Tp + nG));
         TRY(h->alloc(&h->cz, (size_t)Tp + nG));
+        TRY(h->alloc(&h->slope, Tp));
         LAUNCH(h, geometry_kernel, cdiv((size_t)Tp + nG, 256), 256, T, Tp, nG, h->perm, d_verts, d_area_param, h->nx, h->ny, h->elen,
-               h->area, h->cx, h->cy, h->cz);
+               h->area, h->cx, h->cy, h->cz, h->slope);
         TRY(h->alloc(&h->ddiag, Tp));
         TRY(h->alloc(&h->doff, (size_t)3 * Tp));
         TRY(h->alloc(&h->dinv, Tp));
@@ -2540,6 +2551,177 @@ int pbsm3d_apply_avalanche(pbsm3d_handle* h, const pbsm3d_snobal_config* cfg, co
                            const double* delta_avalanche_snowdepth, const double* delta_avalanche_mass, double* swe_out,
                            double* snowdepth_out, int device_ptrs) {
     return adj_snow_call(h, cfg, pack, 1, delta_avalanche_snowdepth, delta_avalanche_mass, swe_out, snowdepth_out, device_ptrs);
+}
+
+// ---- snow_slide (src/modules/snow_slide.cpp) -----------------------------------------------------
+void pbsm3d_slide_config_defaults(pbsm3d_slide_config* c) {
+    if (!c) return;
+    c->avalache_mult = 3178.4;    // snow_slide.cpp:409
+    c->avalache_pow = -1.998;     // :410
+    c->use_vertical_snow = 1;     // :33 (read by the reference's constructor, not used by its run())
+}
+
+int pbsm3d_slide_init(pbsm3d_handle* h, const pbsm3d_slide_config* cfg) {
+    if (!h) return fail(PBSM3D_ERR_INVALID, "null handle");
+    if (h->geographic) return fail(PBSM3D_ERR_UNSUPPORTED, "snow_slide on a geographic (lat/long) mesh is not implemented");
+    CU(cudaSetDevice(h->device));
+    pbsm3d_slide_config local;
+    if (!cfg) { pbsm3d_slide_config_defaults(&local); cfg = &local; }
+    h->slide_cfg = *cfg;
+    const int Tp = h->Tp, S = h->S, nG = h->nG;
+    SlideArrays& a = h->sl;
+    if (!h->slide_ready) {
+        double *maxD = nullptr, *cosf = nullptr, *area = nullptr;
+        TRY(h->alloc(&maxD, Tp));
+        TRY(h->alloc(&cosf, Tp));
+        TRY(h->alloc_zero(&area, S));
+        TRY(h->alloc_zero(&a.sd, Tp));
+        TRY(h->alloc_zero(&a.sdv, S));
+        TRY(h->alloc_zero(&a.swe, Tp));
+        TRY(h->alloc_zero(&a.dsd, Tp));
+        TRY(h->alloc_zero(&a.dmass, Tp));
+        TRY(h->alloc(&a.key, Tp));
+        TRY(h->alloc_zero(&a.gacc, (size_t)std::max(nG, 1) * 4));
+        TRY(h->alloc(&a.stamp, Tp));
+        for (int k = 0; k < 3; ++k) TRY(h->alloc(&a.list[k], Tp));
+        TRY(h->alloc_zero(&a.cnt, 8));
+        TRY(h->alloc_zero(&h->sl_sum_sd, Tp));
+        TRY(h->alloc_zero(&h->sl_sum_mass, Tp));
+        TRY(h->alloc_zero(&h->sl_xfer, (size_t)4 * Tp));
+        TRY(h->alloc_zero(&h->sl_rev, (size_t)std::max(h->n_send, 1) * 4));
+        TRY(h->alloc(&h->sl_in, (size_t)3 * h->T));
+        TRY(h->alloc_zero(&h->sl_moved, 2));
+        TRY(h->alloc_zero(&h->sl_bar, 1));
+        a.T = h->T; a.Tp = Tp; a.S = S;
+        a.perm = h->perm; a.nbs = h->nbs; a.cz = h->cz; a.area = area; a.maxD = maxD; a.cosf = cosf;
+        // face areas, ghost-extended: a ghost's area is its owner's get_area() (the mesh "area" parameter included)
+        CU(cudaMemcpyAsync(area, h->area, (size_t)Tp * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        TRY(halo_exchange(h, area, 1));
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, slide_sweep_kernel, kSlideThreads, 0));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, h->device));
+        h->sl_grid = std::max(1, std::min(nb, 2)) * prop.multiProcessorCount;
+        h->slide_ready = true;
+    } else {  // re-init: the reference's init() zeroes the sums
+        CU(cudaMemsetAsync(h->sl_sum_sd, 0, (size_t)Tp * sizeof(double), h->stream));
+        CU(cudaMemsetAsync(h->sl_sum_mass, 0, (size_t)Tp * sizeof(double), h->stream));
+    }
+    LAUNCH(h, slide_init_kernel, cdiv(Tp, 256), 256, Tp, h->perm, h->slope, h->wv_canopy, cfg->avalache_mult, cfg->avalache_pow,
+           const_cast<double*>(a.maxD), const_cast<double*>(a.cosf));
+    TRY(sync_stream(h));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pbsm3d_slide_run(pbsm3d_handle* h, const double* snowdepthavg, const double* snowdepthavg_vert, const double* swe,
+                     double* delta_avalanche_snowdepth, double* delta_avalanche_mass, double* delta_avalanche_snowdepth_sum,
+                     double* delta_avalanche_mass_sum, double* maxDepth, pbsm3d_slide_stats* stats, int device_ptrs) {
+    if (!h || !snowdepthavg || !snowdepthavg_vert || !swe) return fail(PBSM3D_ERR_INVALID, "null argument");
+    if (!h->slide_ready) return fail(PBSM3D_ERR_INVALID, "call pbsm3d_slide_init first");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int T = h->T, Tp = h->Tp, nG = h->nG;
+    const size_t bytes = (size_t)T * sizeof(double);
+    SlideArrays& a = h->sl;
+    const double *d_sd = snowdepthavg, *d_sdv = snowdepthavg_vert, *d_swe = swe;
+    if (!device_ptrs) {
+        CU(cudaMemcpyAsync(h->sl_in, snowdepthavg, bytes, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->sl_in + T, snowdepthavg_vert, bytes, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->sl_in + 2 * (size_t)T, swe, bytes, cudaMemcpyHostToDevice, s));
+        d_sd = h->sl_in; d_sdv = h->sl_in + T; d_swe = h->sl_in + 2 * (size_t)T;
+    }
+    CU(cudaEventRecord(h->ev[0], s));
+    LAUNCH(h, slide_begin_kernel, cdiv(Tp, 256), 256, Tp, h->perm, d_sd, d_sdv, d_swe, a);
+    int iterations = 0, rounds = 0, fired = 0;
+    int host_cnt[8];
+    for (;;) {
+        // owners -> ghosts: the vertical depth the weights of a partition-edge face read (snow_slide.cpp:166-169, :398-402)
+        TRY(halo_exchange(h, a.sdv, 1));
+        CU(cudaMemsetAsync(a.cnt, 0, 8 * sizeof(int), s));
+        CU(cudaMemsetAsync(h->sl_bar, 0, sizeof(unsigned), s));
+        if (nG > 0) CU(cudaMemsetAsync(a.gacc, 0, (size_t)nG * 4 * sizeof(double), s));
+        void* args[] = {&a, &h->sl_bar};
+        ++h->n_launch;
+        CU(cudaLaunchCooperativeKernel((const void*)slide_sweep_kernel, dim3(h->sl_grid), dim3(kSlideThreads), args, 0, s));
+        // ghosts -> owners (ghost_to_neighbors_communicate_variable): what I routed to faces of other ranks
+        const double* xfer = nullptr;
+        if (h->n_ranks > 1) {
+            CU(cudaMemsetAsync(h->sl_xfer, 0, (size_t)4 * Tp * sizeof(double), s));
+            NC(ncclGroupStart());
+            for (const Partner& p : h->partners) {
+                if (p.recv_cnt > 0) NC(ncclSend(a.gacc + (size_t)p.recv_off * 4, (size_t)p.recv_cnt * 4, ncclDouble, p.rank, h->comm, s));
+                if (p.send_cnt > 0) NC(ncclRecv(h->sl_rev + (size_t)p.send_off * 4, (size_t)p.send_cnt * 4, ncclDouble, p.rank, h->comm, s));
+            }
+            NC(ncclGroupEnd());
+            for (const Partner& p : h->partners)  // ascending rank: the last partner's value stays
+                if (p.send_cnt > 0)
+                    LAUNCH(h, slide_unpack_kernel, cdiv(p.send_cnt, 256), 256, p.send_cnt, h->send_slot + p.send_off,
+                           h->sl_rev + (size_t)p.send_off * 4, h->sl_xfer, Tp);
+            xfer = h->sl_xfer;
+        }
+        CU(cudaMemsetAsync(h->sl_moved, 0, sizeof(int), s));
+        LAUNCH(h, slide_absorb_kernel, cdiv(Tp, 256), 256, a, xfer, h->sl_sum_sd, h->sl_sum_mass, h->sl_moved);
+        int moved = 0;
+        if (h->n_ranks > 1) {  // done = min over ranks of "nobody received transport" (snow_slide.cpp:381-388)
+            NC(ncclAllReduce(h->sl_moved, h->sl_moved + 1, 1, ncclInt, ncclMax, h->comm, s));
+            CU(cudaMemcpyAsync(&moved, h->sl_moved + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+        }
+        CU(cudaMemcpyAsync(host_cnt, a.cnt, sizeof(host_cnt), cudaMemcpyDeviceToHost, s));
+        TRY(sync_stream(h));
+        CU(cudaGetLastError());
+        rounds += host_cnt[4];
+        fired += host_cnt[5];
+        if (host_cnt[6]) return fail(PBSM3D_ERR_INVALID, "Snowslide did not conserve mass");  // snow_slide.cpp:322-328
+        ++iterations;
+        bool done = moved == 0;
+        if (!done && iterations > 25) done = true;  // snow_slide.cpp:391-396
+        if (done) break;
+    }
+    CU(cudaEventRecord(h->ev[1], s));
+    // publish (snow_slide.cpp:352-357, :441): slot order -> CHM order
+    const double* src[5] = {a.dsd, a.dmass, h->sl_sum_sd, h->sl_sum_mass, a.maxD};
+    double* dst[5] = {delta_avalanche_snowdepth, delta_avalanche_mass, delta_avalanche_snowdepth_sum, delta_avalanche_mass_sum, maxDepth};
+    for (int k = 0; k < 5; ++k) {
+        if (!dst[k]) continue;
+        if (device_ptrs) {
+            LAUNCH(h, to_chm_kernel, cdiv(T, 256), 256, 1, T, (size_t)0, h->iperm, src[k], dst[k]);
+        } else {
+            TRY(fetch_chm(h, dst[k], src[k], 1, 0));
+        }
+    }
+    TRY(sync_stream(h));
+    CU(cudaGetLastError());
+    if (stats) {
+        stats->iterations = iterations;
+        stats->wavefront_rounds = rounds;
+        stats->faces_fired = fired;
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        stats->ms_device = ms;
+    }
+    return 0;
+}
+
+int pbsm3d_slide_get_state(pbsm3d_handle* h, double* delta_avalanche_snowdepth, double* delta_avalanche_mass,
+                           double* delta_avalanche_snowdepth_sum, double* delta_avalanche_mass_sum) {
+    if (!h || !h->slide_ready) return fail(PBSM3D_ERR_INVALID, "call pbsm3d_slide_init first");
+    CU(cudaSetDevice(h->device));
+    TRY(fetch_chm(h, delta_avalanche_snowdepth, h->sl.dsd, 1, 0));
+    TRY(fetch_chm(h, delta_avalanche_mass, h->sl.dmass, 1, 0));
+    TRY(fetch_chm(h, delta_avalanche_snowdepth_sum, h->sl_sum_sd, 1, 0));
+    TRY(fetch_chm(h, delta_avalanche_mass_sum, h->sl_sum_mass, 1, 0));
+    return 0;
+}
+int pbsm3d_slide_set_state(pbsm3d_handle* h, const double* delta_avalanche_snowdepth, const double* delta_avalanche_mass,
+                           const double* delta_avalanche_snowdepth_sum, const double* delta_avalanche_mass_sum) {
+    if (!h || !h->slide_ready) return fail(PBSM3D_ERR_INVALID, "call pbsm3d_slide_init first");
+    CU(cudaSetDevice(h->device));
+    TRY(store_chm(h, h->sl.dsd, delta_avalanche_snowdepth));
+    TRY(store_chm(h, h->sl.dmass, delta_avalanche_mass));
+    TRY(store_chm(h, h->sl_sum_sd, delta_avalanche_snowdepth_sum));
+    TRY(store_chm(h, h->sl_sum_mass, delta_avalanche_mass_sum));
+    return 0;
 }
 
 int pbsm3d_time_kernel(pbsm3d_handle* h, int kernel, int reps, float* ms) {

@@ -148,12 +148,13 @@ __global__ void to_chm_u8_kernel(int T, const int* __restrict__ iperm, const uns
 __global__ void geometry_kernel(int T, int Tp, int nG, const int* __restrict__ perm, const double* __restrict__ verts,
                                 const double* __restrict__ area_param, double* __restrict__ nx, double* __restrict__ ny,
                                 double* __restrict__ elen, double* __restrict__ area, double* __restrict__ cx,
-                                double* __restrict__ cy, double* __restrict__ cz) {
+                                double* __restrict__ cy, double* __restrict__ cz, double* __restrict__ slope) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= Tp + nG) return;
     const int i = p < Tp ? perm[p] : T + (p - Tp);
     if (i < 0) {  // pad: a harmless unit triangle
         cx[p] = cy[p] = cz[p] = 0.0;
+        slope[p] = 0.0;
         for (int k = 0; k < 3; ++k) { nx[(size_t)k * Tp + p] = 1.0; ny[(size_t)k * Tp + p] = 0.0; elen[(size_t)k * Tp + p] = 1.0; }
         area[p] = 1.0;
         return;
@@ -169,6 +170,16 @@ __global__ void geometry_kernel(int T, int Tp, int nG, const int* __restrict__ p
     cy[p] = __ddiv_rn(__dadd_rn(__dadd_rn(py[0], py[1]), py[2]), 3.0);
     cz[p] = __ddiv_rn(__dadd_rn(__dadd_rn(pz[0], pz[1]), pz[2]), 3.0);
     if (p >= Tp) return;  // ghosts only need a centroid
+    {   // face::slope (triangulation.hpp:1501-1523): acos(norm_dot(CGAL::unit_normal(v0, v1, v2), (0,0,1))); snow_slide reads it
+        const double ax = __dsub_rn(px[1], px[0]), ay = __dsub_rn(py[1], py[0]), az = __dsub_rn(pz[1], pz[0]);
+        const double bx = __dsub_rn(px[2], px[0]), by = __dsub_rn(py[2], py[0]), bz = __dsub_rn(pz[2], pz[0]);
+        double n_x = __dsub_rn(__dmul_rn(ay, bz), __dmul_rn(az, by)), n_y = __dsub_rn(__dmul_rn(az, bx), __dmul_rn(ax, bz)),
+               n_z = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx));
+        const double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(n_x, n_x), __dmul_rn(n_y, n_y)), __dmul_rn(n_z, n_z)));
+        n_x = __ddiv_rn(n_x, len); n_y = __ddiv_rn(n_y, len); n_z = __ddiv_rn(n_z, len);
+        const double na = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(n_x, n_x), __dmul_rn(n_y, n_y)), __dmul_rn(n_z, n_z)));
+        slope[p] = acos(__ddiv_rn(n_z, na));
+    }
     double ex[3], ey[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {  // edge(k) = v[cw(k)] - v[ccw(k)]

@@ -94,6 +94,19 @@ def uniform_mesh(nx: int = 708, ny: int = 708, h: float = 30.0, order: str = "mo
     return _finish(vertex, elem, order)
 
 
+def alpine_terrain(x, y):
+    """Steep synthetic relief for snow_slide: slopes up to ~55 degrees, ridges ~3-6 km apart plus 1 km-scale gullies."""
+    return (2000.0 + 900.0 * np.sin(x / 900.0) * np.cos(y / 700.0) + 150.0 * np.sin(x / 170.0 + 1.0) * np.sin(y / 210.0)
+            + 40.0 * np.sin((x + 0.7 * y) / 61.0))
+
+
+def with_elevation(mesh: TriMesh, fn=alpine_terrain, x0: float = 488000.0, y0: float = 6710000.0) -> TriMesh:
+    """The same triangulation with vertex elevations fn(x - x0, y - y0) (global, unpartitioned meshes)."""
+    v = mesh.vertex.copy()
+    v[:, 2] = fn(v[:, 0] - x0, v[:, 1] - y0)
+    return TriMesh(v, mesh.elem, mesh.neigh, dict(mesh.params), local_sizes=mesh.local_sizes)
+
+
 def variable_mesh(n_tri_target: int, seed: int = 20250101, area_ratio: float = 10.0,
                   order: str = "morton", x0: float = 488000.0, y0: float = 6710000.0) -> TriMesh:
     """Variable-resolution Delaunay mesh, ≈n_tri_target triangles, areas spanning ≈area_ratio:1.

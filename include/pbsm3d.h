@@ -21,6 +21,7 @@
  *   fetchr::run(face), every face      fetchr.cpp:54-119            pbsm3d_fetchr            } optionally fused into the step
  *                                                                   (pbsm3d_set_providers)
  *   snobal::run, drift_mass hook       snobal.cpp:363-387 -> sno::_adj_snow (sno.cpp:2527-2575)   pbsm3d_apply_drift     } the consumers of
+ *   snow_slide::init / run / checkpoint  snow_slide.cpp:406-446 / :94-404 / :59-93            pbsm3d_slide_init / _run / _get_state / _set_state
  *   snobal::run, avalanche hook        snobal.cpp:389-408 -> sno::_adj_snow                       pbsm3d_apply_avalanche } PBSM3D's / snow_slide's output
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
@@ -40,7 +41,7 @@
 extern "C" {
 #endif
 
-#define PBSM3D_ABI_VERSION 5
+#define PBSM3D_ABI_VERSION 6
 
 enum {
     PBSM3D_OK = 0,
@@ -309,6 +310,40 @@ int pbsm3d_apply_drift(pbsm3d_handle* h, const pbsm3d_snobal_config* cfg, const 
 int pbsm3d_apply_avalanche(pbsm3d_handle* h, const pbsm3d_snobal_config* cfg, const pbsm3d_snowpack* pack,
                            const double* delta_avalanche_snowdepth, const double* delta_avalanche_mass, double* swe_out,
                            double* snowdepth_out, int device_ptrs);
+
+/* ---- snow_slide on the device (src/modules/snow_slide.cpp) ----
+ * Gravitational redistribution: a face whose slope-normal snow depth exceeds maxDepth = max(avalache_mult * slopeDeg^avalache_pow,
+ * CanopyHeight) * max(0.001, cos(slope)) sheds the excess to its lower neighbours, highest snow surface first.  The reference
+ * sweeps the faces SEQUENTIALLY in that order (snow_slide.cpp:171-330); the device runs the same updates as a dependency wavefront
+ * and reproduces the sequential result (pbsm3d_slide.cuh).  Across ranks: forward halo of the vertical depth, the reverse
+ * ghost -> owner exchange of what was routed across a partition edge (triangulation.cpp:2081-2186), and outer iterations while any
+ * rank received transport (<= 26), as in the reference.  Faces with EQUAL sort keys (undefined order in the reference's
+ * tbb::parallel_sort) take their turn in CHM face order.  Vegetation height comes from pbsm3d_mesh.canopy_height. */
+typedef struct pbsm3d_slide_config {
+    double avalache_mult;        /* "avalache_mult", 3178.4 (snow_slide.cpp:409; the reference's spelling) */
+    double avalache_pow;         /* "avalache_pow", -1.998 (:410) */
+    int32_t use_vertical_snow;   /* "use_vertical_snow", true (:33); read by the reference's constructor and never used */
+} pbsm3d_slide_config;
+typedef struct pbsm3d_slide_stats {
+    int32_t iterations;          /* outer iterations (1 on a single rank) */
+    int32_t wavefront_rounds;    /* dependency rounds of the sweeps */
+    int32_t faces_fired;         /* faces that shed snow */
+    float ms_device;             /* CUDA-event time of the run without the copies of the outputs */
+} pbsm3d_slide_stats;
+void pbsm3d_slide_config_defaults(pbsm3d_slide_config* cfg);
+/* snow_slide::init: maxDepth per face; zeroes delta_avalanche_*_sum.  cfg NULL = defaults. */
+int pbsm3d_slide_init(pbsm3d_handle* h, const pbsm3d_slide_config* cfg);
+/* snow_slide::run.  Inputs [n_local] in CHM face order: snowdepthavg (m, slope-normal), snowdepthavg_vert (m, vertical), swe (mm).
+ * Outputs [n_local], any may be NULL: delta_avalanche_snowdepth (m^3), delta_avalanche_mass (m^3 of water), their running sums,
+ * maxDepth.  stats may be NULL.  Fails with PBSM3D_ERR_INVALID ("Snowslide did not conserve mass") like the reference's throw. */
+int pbsm3d_slide_run(pbsm3d_handle* h, const double* snowdepthavg, const double* snowdepthavg_vert, const double* swe,
+                     double* delta_avalanche_snowdepth, double* delta_avalanche_mass, double* delta_avalanche_snowdepth_sum,
+                     double* delta_avalanche_mass_sum, double* maxDepth, pbsm3d_slide_stats* stats, int device_ptrs);
+/* Checkpoint (snow_slide.cpp:59-93): the four arrays the reference persists.  Each [n_local]; NULL = skip. */
+int pbsm3d_slide_get_state(pbsm3d_handle* h, double* delta_avalanche_snowdepth, double* delta_avalanche_mass,
+                           double* delta_avalanche_snowdepth_sum, double* delta_avalanche_mass_sum);
+int pbsm3d_slide_set_state(pbsm3d_handle* h, const double* delta_avalanche_snowdepth, const double* delta_avalanche_mass,
+                           const double* delta_avalanche_snowdepth_sum, const double* delta_avalanche_mass_sum);
 
 /* Stand-alone kernels for measurement (bench.py roofline line, ncu): run `reps` launches of the named kernel on
  * the last assembled system and return the mean CUDA-event time per launch in milliseconds.

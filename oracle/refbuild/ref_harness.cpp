@@ -313,10 +313,10 @@ int chmref_run_fetchr(void* hv, const char* cfg_kv)
 }
 
 // ---- snow_slide (src/modules/snow_slide.cpp, compiled unmodified; USE_MPI undefined, so its exchanges are compiled out) ----
-// Ghost faces for a rank-local view: face k of the nG ghosts hangs off owned face attach_face[k] as neighbour attach_edge[k]
-// (is_ghost = true; not part of domain->face(i)).  vx,vy,vz [nG][3]; area [nG] (NaN = compute from the vertices).
-int chmref_add_ghosts(void* hv, int nG, const double* vx, const double* vy, const double* vz, const double* area,
-                      const int* attach_face, const int* attach_edge)
+// Ghost faces for a rank-local view (is_ghost = true; not part of domain->face(i)): vx,vy,vz [nG][3]; area [nG] (NaN = compute from
+// the vertices); ghost attach_ghost[k] becomes neighbour attach_edge[k] of owned face attach_face[k] (a ghost may touch two faces).
+int chmref_add_ghosts(void* hv, int nG, const double* vx, const double* vy, const double* vz, const double* area, int n_attach,
+                      const int* attach_face, const int* attach_edge, const int* attach_ghost)
 {
     auto h = static_cast<Harness*>(hv);
     for (int k = 0; k < nG; ++k) {
@@ -326,8 +326,8 @@ int chmref_add_ghosts(void* hv, int nG, const double* vx, const double* vy, cons
         for (int j = 0; j < 3; ++j) { f->vx[j] = vx[3 * k + j]; f->vy[j] = vy[3 * k + j]; f->vz[j] = vz[3 * k + j]; }
         if (!std::isnan(area[k])) f->_parameters["area"] = area[k];
         h->domain->_ghosts.emplace_back(f);
-        h->domain->_faces[attach_face[k]]->_neigh[attach_edge[k]] = f;
     }
+    for (int k = 0; k < n_attach; ++k) h->domain->_faces[attach_face[k]]->_neigh[attach_edge[k]] = h->domain->_ghosts[attach_ghost[k]].get();
     return 0;
 }
 int chmref_set_ghost_var(void* hv, const char* name, const double* vals)

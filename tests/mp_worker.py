@@ -28,6 +28,32 @@ def main():
         buf.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
     dist.broadcast(buf, 0)
     uid = bytes(buf.cpu().numpy().tobytes())
+    if meshname.startswith("alpine"):  # snow_slide across ranks: steep terrain, every rank runs init + run on its partition
+        from oracle import slide_oracle as so
+        n = int(meshname[6:])
+        gmesh = synthetic.with_elevation(synthetic.uniform_mesh(n, n))
+        ggeo = gmesh.geometry()
+        slope = so.face_slope(gmesh.face_vertices().reshape(-1, 3, 3))
+        sd, sdv, swe = so.synthetic_snow(ggeo.cx, ggeo.cy, slope, seed=n, deep=float(L) / 2)
+        p = partition_mesh(gmesh, rank, world)
+        T, s = p.n_local, int(p.global_id[0])
+        h = capi.Handle(capi.default_config(nLayer=2), p, device=local, rank=rank, n_ranks=world, unique_id=uid)
+        h.slide_init()
+        gathered = {}
+        for k in range(nsteps):
+            o, st = h.slide_run(sd[s:s + T], sdv[s:s + T], swe[s:s + T])
+            for name, a in o.items():
+                sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+                dist.all_gather(sizes, torch.tensor([T], dtype=torch.int64, device="cuda"))
+                parts = [torch.zeros(int(n_.item()), dtype=torch.float64, device="cuda") for n_ in sizes]
+                dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(a)).cuda())
+                gathered[f"{name}_{k}"] = torch.cat(parts).cpu().numpy()
+            gathered[f"stats_{k}"] = np.array([st["iterations"], st["wavefront_rounds"], st["faces_fired"]])
+        if rank == 0:
+            np.savez(out_path, **gathered)
+        h.close()
+        dist.destroy_process_group()
+        return
     if meshname.startswith("uniform"):
         n = int(meshname[7:])
         gmesh = synthetic.uniform_mesh(n, n)

@@ -87,3 +87,45 @@ def test_max_ranks_on_uniform_mesh(tmp_path):
     u2 = h.scale_wind_vert(F0["U_R"], F0["snowdepthavg"])
     assert np.max(np.abs(g["u2_domain"] - u2) / u2) <= 1e-12
     h.close()
+
+
+def slide_partitioned_oracle(gmesh, world, sd, sdv, swe):
+    """oracle/slide_oracle.py:run_partitioned on CHM's contiguous partition of the global mesh."""
+    from chm_b200.mesh import partition_mesh
+    from oracle import slide_oracle as so
+    geo = gmesh.geometry()
+    parts = [partition_mesh(gmesh, r, world) for r in range(world)]
+    starts = np.concatenate([[0], np.cumsum(parts[0].local_sizes)])
+    states, ins, gown, gloc = [], [], [], []
+    for p in parts:
+        T, gid = p.n_local, p.global_id
+        V = p.face_vertices().reshape(-1, 3, 3)
+        states.append(so.SlideState(V[:T], p.neigh, geo.area[gid[:T]], ghost_vertices=V[T:], ghost_area=geo.area[gid[T:]]))
+        ins.append((sd[gid[:T]], sdv[gid[:T]], swe[gid[:T]]))
+        gown.append(p.ghost_owner)
+        gloc.append(gid[T:] - starts[p.ghost_owner])
+    outs = so.run_partitioned(states, gown, gloc, [i[0] for i in ins], [i[1] for i in ins], [i[2] for i in ins])
+    cat = lambda k: np.concatenate([o[k] for o in outs])
+    return {k: cat(k) for k in capi.SLIDE_OUTPUTS}, outs[0]["iterations"]
+
+
+def test_snow_slide_across_ranks(tmp_path):
+    """snow_slide on a partitioned mesh: forward halo of the vertical depth, reverse ghost -> owner exchange, outer iterations
+    (snow_slide.cpp:166-169, 332-338, 381-402) = the emulation of the reference's MPI composition in the oracle."""
+    n = ngpus()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 4 if n >= 4 else 2
+    from oracle import slide_oracle as so
+    side, deep2 = 70, 2   # 6 / 10 outer iterations on 2 / 4 ranks; deeper snow runs into the reference's 26-iteration bail-out
+    g = run_ranks(tmp_path, world, f"alpine{side}", deep2, 0, 2)
+    gmesh = synthetic.with_elevation(synthetic.uniform_mesh(side, side))
+    geo = gmesh.geometry()
+    slope = so.face_slope(gmesh.face_vertices().reshape(-1, 3, 3))
+    sd, sdv, swe = so.synthetic_snow(geo.cx, geo.cy, slope, seed=side, deep=deep2 / 2)
+    want, iters = slide_partitioned_oracle(gmesh, world, sd, sdv, swe)
+    assert int(g["stats_0"][0]) == iters and 1 < iters < 26
+    for k in capi.SLIDE_OUTPUTS:
+        scale = float(np.max(np.abs(want[k])))
+        assert float(np.max(np.abs(g[f"{k}_0"] - want[k]))) / scale <= 1e-10, k
+    assert np.count_nonzero(want["delta_avalanche_mass"]) > 1000
