@@ -306,6 +306,66 @@ def timed_steps(job, h, dev_in, dev_out, steps, warmup):
     return acc
 
 
+def time_next_rows(h, T, local_rank):
+    """SURVEY §8f ranks 3 and 4 on the bench handle's device (N = 1 only): snobal's drift_mass consumer on the handle's own
+    device-resident drift_mass with a device-resident snowpack (no PCIe), and snow_slide on steep synthetic terrain of the same
+    size.  Extra figures: failures are reported, never fatal."""
+    import ctypes as C
+    import torch
+    from chm_b200 import synthetic
+    out = {}
+    try:
+        rng = np.random.default_rng(5)
+        z_s = rng.uniform(0.0, 1.5, T)
+        rho = rng.uniform(80.0, 500.0, T)
+        two = z_s > 0.1
+        host = {"z_s": z_s, "m_s": rho * z_s, "rho": rho, "layer_count": np.where(two, 2, 1).astype(np.int32),
+                "z_s_0": np.where(two, 0.1, z_s), "z_s_l": np.where(two, z_s - 0.1, 0.0)}
+        host["m_s_0"], host["m_s_l"] = rho * host["z_s_0"], rho * host["z_s_l"]
+        for k in ("cc_s", "cc_s_0", "cc_s_l", "h2o_total", "h2o_vol", "h2o", "h2o_max", "h2o_sat"):
+            host[k] = np.zeros(T)
+        for k in ("T_s", "T_s_0", "T_s_l"):
+            host[k] = np.full(T, 265.0)
+        dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in host.items()}
+        pk = capi.Snowpack()
+        for k in capi.SNOWPACK_FIELDS:
+            setattr(pk, k, C.cast(C.c_void_p(dev[k].data_ptr()), capi.c_int32_p if k == "layer_count" else capi.c_double_p))
+        ts = []
+        for k in range(12):
+            t0 = time.perf_counter()
+            capi._check(h.lib, h.lib.pbsm3d_apply_drift(h.h, None, C.byref(pk), None, None, None, 1))
+            ts.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.median(ts[2:]))
+        nbytes = T * (19 * 8 * 2 - 8 + 8 + 4)  # 18 doubles + 1 int32 read and written, drift_mass + its slot index read
+        out["snobal_apply_drift"] = {"ms": ms, "bytes": nbytes, "GB_per_s": nbytes / (ms * 1e-3) / 1e9,
+                                     "what": "synchronous call, device-resident snowpack (19 SoA fields) and the handle's own drift_mass"}
+    except Exception as e:
+        out["snobal_apply_drift"] = {"error": repr(e)[:200]}
+    try:
+        side = int(round((T / 2) ** 0.5))
+        m = synthetic.with_elevation(synthetic.uniform_mesh(side, side))
+        geo = m.geometry()
+        rng = np.random.default_rng(11)
+        f = 0.5 + 0.25 * (np.sin(geo.cx / 2100.0) * np.cos(geo.cy / 1700.0) + np.sin((geo.cx + geo.cy) / 3900.0))
+        sd = np.abs(1.0 * np.clip(f, 0.02, None) * (1.0 + 0.05 * rng.standard_normal(m.n_local)))
+        hs = capi.Handle(capi.default_config(nLayer=2), m, device=local_rank)
+        hs.slide_init()
+        # the vertical depth is the slope-normal one over cos(slope), from the vertices
+        v = m.vertex[m.elem]
+        nrm = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+        cosf = np.maximum(0.001, np.abs(nrm[:, 2]) / np.linalg.norm(nrm, axis=1))
+        res = [hs.slide_run(sd, sd / cosf, sd * 300.0)[1] for _ in range(5)]
+        z = np.zeros(m.n_local)
+        calm = [hs.slide_run(z, z, z)[1]["ms_device"] for _ in range(4)]
+        out["snow_slide"] = {"triangles": int(m.n_local), "terrain": "synthetic.alpine_terrain (slopes to 68 degrees), 1 m snow cover",
+                             "faces_fired": int(res[-1]["faces_fired"]), "wavefront_rounds": int(res[-1]["wavefront_rounds"]),
+                             "ms_device": float(np.median([r["ms_device"] for r in res[1:]])), "calm_ms_device": float(np.median(calm[1:]))}
+        hs.close()
+    except Exception as e:
+        out["snow_slide"] = {"error": repr(e)[:200]}
+    return out
+
+
 def cached_mesh(job, target):
     """The variable-resolution Delaunay mesh of BASELINE c3/c4 (seed 20250101).  Rank 0 generates it once per box and caches it
     under CACHE_DIR (the driver runs N = 1, 2, 4, 8 back to back on one box); everyone loads the cache."""
@@ -580,6 +640,9 @@ def main():
     except Exception:  # the extra figure must never cost the line
         calm_ms = None
 
+    # ---- the consumers on the far side of the path (N = 1: extra figures, not the headline)
+    next_rows = time_next_rows(h, T, local_rank) if world == 1 and args.workload == "c2" and not args.no_variants else None
+
     # ---- end-to-end arm: pinned host buffers through the reference-facing call
     for k in range(3):
         h.step_ptr(3600.0, dptr(pin_in[k % N_FORCING]), dptr(pin_out), device=False)
@@ -598,8 +661,8 @@ def main():
         import ctypes as C
         cast = lambda t: C.cast(C.c_void_p(t.data_ptr()), capi.c_double_p)
         d0, scratch = dev_in[0], torch.empty(T, dtype=torch.float64, device="cuda")
-        t_sw = t_fe = 0.0
-        for k in range(12):
+        l_sw, l_fe = [], []
+        for k in range(14):
             barrier()
             t0 = time.perf_counter()
             capi._check(h.lib, h.lib.pbsm3d_scale_wind_vert(h.h, None, cast(d0["U_R"]), cast(d0["snowdepthavg"]), cast(scratch), 1))
@@ -607,8 +670,11 @@ def main():
             capi._check(h.lib, h.lib.pbsm3d_fetchr(h.h, None, cast(d0["vw_dir"]), cast(scratch), 1))
             t2 = time.perf_counter()
             if k >= 2:
-                t_sw += (t1 - t0) / 10
-                t_fe += (t2 - t1) / 10
+                l_sw.append(t1 - t0)
+                l_fe.append(t2 - t1)
+        # median over the calls (a rank that leaves the host barrier late makes its partners' halo wait look like kernel time)
+        t_sw, t_fe = float(np.median(l_sw)), float(np.median(l_fe))
+        sw_max = reduce_max(1e3 * float(np.max(l_sw)))
         h.set_providers(capi.default_wind_config())
         part = [{n: p for n, p in dptr(pi).items() if n not in ("U_2m_above_srf", "fetch")} for pi in pin_in]
         for k in range(3):
@@ -621,7 +687,7 @@ def main():
         barrier()
         fused_ms = reduce_max(1e3 * (time.perf_counter() - t0) / args.steps)
         h.set_providers(None)
-        providers = {"scale_wind_vert_ms": reduce_max(1e3 * t_sw), "fetchr_ms": reduce_max(1e3 * t_fe),
+        providers = {"scale_wind_vert_ms": reduce_max(1e3 * t_sw), "fetchr_ms": reduce_max(1e3 * t_fe), "scale_wind_vert_ms_worst_call": sw_max,
                      "e2e_ms_with_providers_fused": fused_ms, "h2d_bytes_per_step_fused": 6 * 8 * T * world,
                      "note": "synchronous device-pointer calls (host wall clock, ranks aligned by a barrier before each call); fused: "
                              "U_2m_above_srf and fetch are derived on the device inside pbsm3d_step (these steps use the derived fields, "
@@ -758,7 +824,7 @@ def main():
                        "halo_exchanges_inside_solver_kernels": st["halo_fused"],
                        "l2_policy": "working set of one step (~1 GB of coefficient streams per rank) exceeds the 126 MB L2; no flush needed",
                        "phases_ms": {k: v / args.steps for k, v in acc["phases"].items()}, "wall_ms_per_step": wall_ms,
-                       "providers": providers, "calm_step_ms": calm_ms, "calm_step_launches": calm_launches,
+                       "providers": providers, "next_rows": next_rows, "calm_step_ms": calm_ms, "calm_step_launches": calm_launches,
                        "variants": variants, "strong_c4": strong,
                        "cpu_baseline_is": "a C++/OpenMP PORT of the reference algorithm, not the CHM binary (DESIGN.md §6)"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * 8 * T * world,
