@@ -258,3 +258,69 @@ class fetchr:
             domain["fetch"] = pbsm.handle.fetchr(domain["vw_dir"], capi.default_wind_config(**self.wind_cfg_kw))
         except capi.Pbsm3dError as e:
             raise module_error(str(e)) from e
+
+
+class snow_slide:
+    """Mirror of the reference module (src/modules/snow_slide.cpp:27-446) on the device kernels of a PBSM3D handle.
+
+    depends snowdepthavg, swe (and reads snowdepthavg_vert without declaring it, :121); provides the ten variables of :35-50
+    (the ghost_ss_* ones are the reference's MPI scratch space: declared for the contract, never filled here — the exchange
+    happens inside pbsm3d_slide_run); config keys ``use_vertical_snow`` (true; read and unused by the reference),
+    ``avalache_mult`` (3178.4), ``avalache_pow`` (-1.998).  parallel::domain."""
+
+    name = "snow_slide"
+    parallel = "domain"
+    OUTPUTS = ("delta_avalanche_snowdepth", "delta_avalanche_mass", "delta_avalanche_snowdepth_sum", "delta_avalanche_mass_sum", "maxDepth")
+
+    def __init__(self, cfg: Optional[dict] = None):
+        cfg = dict(cfg or {})
+        unknown = set(cfg) - {"use_vertical_snow", "avalache_mult", "avalache_pow"}
+        if unknown:
+            raise module_error(f"snow_slide: unknown config key(s) {sorted(unknown)}")
+        c = {k: PBSM3D._coerce(v) for k, v in cfg.items()}
+        self.slide_cfg_kw = dict(avalache_mult=float(c.get("avalache_mult", 3178.4)), avalache_pow=float(c.get("avalache_pow", -1.998)),
+                                 use_vertical_snow=int(bool(c.get("use_vertical_snow", True))))
+        self._depends = ["snowdepthavg", "swe"]
+        self._provides = ["delta_avalanche_mass", "delta_avalanche_snowdepth", "delta_avalanche_mass_sum", "delta_avalanche_snowdepth_sum",
+                          "maxDepth", "ghost_ss_snowdepthavg_vert_copy", "ghost_ss_snowdepthavg_to_xfer", "ghost_ss_swe_to_xfer",
+                          "ghost_ss_delta_avalanche_snowdepth", "ghost_ss_delta_avalanche_swe"]
+        self.stats = None
+
+    def get_depends(self):
+        return list(self._depends)
+
+    def get_provides(self):
+        return list(self._provides)
+
+    def init(self, domain: Domain, pbsm: PBSM3D):
+        if pbsm.handle is None:
+            raise module_error("snow_slide::init needs an initialised PBSM3D handle (it owns the device mesh)")
+        domain.init_face_data(self._provides)
+        try:
+            pbsm.handle.slide_init(**self.slide_cfg_kw)
+        except capi.Pbsm3dError as e:
+            raise module_error(str(e)) from e
+        domain["delta_avalanche_snowdepth_sum"] = 0.0   # snow_slide.cpp:442-443
+        domain["delta_avalanche_mass_sum"] = 0.0
+        self._first = True
+
+    def run(self, domain: Domain, pbsm: PBSM3D):
+        if pbsm.handle is None or not hasattr(self, "_first"):
+            raise module_error("snow_slide::run before init")
+        try:
+            out, self.stats = pbsm.handle.slide_run(domain["snowdepthavg"], domain["snowdepthavg_vert"], domain["swe"])
+        except capi.Pbsm3dError as e:
+            raise module_error(str(e)) from e
+        for n in self.OUTPUTS:
+            domain[n] = out[n]
+
+    def checkpoint(self, domain: Domain, pbsm: PBSM3D) -> Dict[str, np.ndarray]:
+        """snow_slide.cpp:59-76."""
+        s = pbsm.handle.slide_get_state()
+        return {"snow_slide:" + k: v for k, v in s.items()}
+
+    def load_checkpoint(self, domain: Domain, pbsm: PBSM3D, chk: Dict[str, np.ndarray]):
+        """snow_slide.cpp:78-92."""
+        pbsm.handle.slide_set_state(**{k.split(":", 1)[1]: v for k, v in chk.items()})
+        domain["delta_avalanche_snowdepth_sum"] = chk["snow_slide:delta_avalanche_snowdepth_sum"]
+        domain["delta_avalanche_mass_sum"] = chk["snow_slide:delta_avalanche_mass_sum"]

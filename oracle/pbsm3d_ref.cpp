@@ -1,8 +1,8 @@
 // CPU restatement (C++17 + OpenMP) of the reference PBSM3D timestep.   TEST INFRASTRUCTURE / CPU BASELINE ONLY.
 //
-// PARITY UNPINNED: the reference has no PBSM3D test or golden vector and cannot be built here,
-// so this is a restatement, written independently of oracle/pbsm3d_oracle.py and cross-checked against it
-// (tests/test_oracle_cpp.py).  Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference)
+// A restatement written independently of oracle/pbsm3d_oracle.py.  Its assembly is pinned, through that oracle, to the reference's
+// own PBSM3D.cpp compiled unmodified (oracle/_ref/libchmref.so, tests/test_reference_pin.py + tests/test_oracle_cpp.py: 1e-12);
+// its solver (own GMRES(30) + thread-block-local ILUT) is pinned only through the contract ||b - Ax|| <= 1e-8 ||b||.  Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference)
 // may load it; nothing under chm_b200/ does.
 //
 // What it follows:

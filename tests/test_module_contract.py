@@ -55,3 +55,20 @@ def test_provider_mirrors_declare_the_reference_contract():
         module.scale_wind_vert({"ignore_canopi": True})
     with pytest.raises(module.module_error):  # run before the PBSM3D handle exists
         module.fetchr().run(module.Domain.__new__(module.Domain), module.PBSM3D({"nLayer": 5}))
+
+
+def test_snow_slide_mirror_declares_the_reference_contract():
+    """snow_slide.cpp:27-50 (ctor) against the lists read from the compiled reference (tests/golden/golden_slide.npz)."""
+    import os
+    from chm_b200 import module
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "golden_slide.npz"))
+    m = module.snow_slide()
+    assert m.get_depends() == list(g["depends"]) and m.get_provides() == list(g["provides"])
+    assert m.parallel == "domain"
+    assert m.slide_cfg_kw == dict(avalache_mult=3178.4, avalache_pow=-1.998, use_vertical_snow=1)
+    assert module.snow_slide({"avalache_mult": "900", "use_vertical_snow": "false"}).slide_cfg_kw["avalache_mult"] == 900.0
+    with pytest.raises(module.module_error):
+        module.snow_slide({"avalanche_mult": 900})          # the reference's key is spelt "avalache"
+    with pytest.raises(module.module_error):
+        module.snow_slide().run(module.Domain.__new__(module.Domain), module.PBSM3D({"nLayer": 5}))
