@@ -24,7 +24,7 @@ c_uint8_p = C.POINTER(C.c_uint8)
 SOLVER_AUTO, SOLVER_LINE, SOLVER_BICGSTAB = 0, 1, 2
 DEP_AUTO, DEP_CG, DEP_CHEBYSHEV, DEP_SOR = 0, 1, 2, 3
 HALO_NONE, HALO_NCCL, HALO_PEER = 0, 1, 2
-ABI_VERSION = 6  # include/pbsm3d.h PBSM3D_ABI_VERSION
+ABI_VERSION = 7  # include/pbsm3d.h PBSM3D_ABI_VERSION
 ERR_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "NOCONVERGE"}
 
 
@@ -143,6 +143,7 @@ SYMBOLS = {
     "pbsm3d_slide_config_defaults": (None, [C.POINTER(SlideConfig)]),
     "pbsm3d_slide_init": (C.c_int, [C.c_void_p, C.POINTER(SlideConfig)]),
     "pbsm3d_slide_run": (C.c_int, [C.c_void_p] + [c_double_p] * 8 + [C.POINTER(SlideStats), C.c_int]),
+    "pbsm3d_slide_get_constants": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "pbsm3d_slide_get_state": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
     "pbsm3d_slide_set_state": (C.c_int, [C.c_void_p] + [c_double_p] * 4),
     "pbsm3d_snobal_config_defaults": (None, [C.POINTER(SnobalConfig)]),
@@ -381,6 +382,12 @@ class Handle:
         st = SlideStats()
         _check(self.lib, self.lib.pbsm3d_slide_run(self.h, *[_dp(a) for a in ins], *[_dp(outs[n]) for n in SLIDE_OUTPUTS], C.byref(st), 0))
         return outs, {n: getattr(st, n) for n, _ in st._fields_}
+
+    def slide_constants(self):
+        """(maxDepth, max(0.001, cos(slope))) per face as the device computed them in slide_init."""
+        a, b = np.empty(self.T), np.empty(self.T)
+        _check(self.lib, self.lib.pbsm3d_slide_get_constants(self.h, _dp(a), _dp(b)))
+        return a, b
 
     def slide_get_state(self):
         s = {n: np.empty(self.T) for n in SLIDE_OUTPUTS[:4]}

@@ -2703,6 +2703,13 @@ int pbsm3d_slide_run(pbsm3d_handle* h, const double* snowdepthavg, const double*
     return 0;
 }
 
+int pbsm3d_slide_get_constants(pbsm3d_handle* h, double* maxDepth, double* cos_slope) {
+    if (!h || !h->slide_ready) return fail(PBSM3D_ERR_INVALID, "call pbsm3d_slide_init first");
+    CU(cudaSetDevice(h->device));
+    TRY(fetch_chm(h, maxDepth, h->sl.maxD, 1, 0));
+    TRY(fetch_chm(h, cos_slope, h->sl.cosf, 1, 0));
+    return 0;
+}
 int pbsm3d_slide_get_state(pbsm3d_handle* h, double* delta_avalanche_snowdepth, double* delta_avalanche_mass,
                            double* delta_avalanche_snowdepth_sum, double* delta_avalanche_mass_sum) {
     if (!h || !h->slide_ready) return fail(PBSM3D_ERR_INVALID, "call pbsm3d_slide_init first");

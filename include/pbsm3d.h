@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define PBSM3D_ABI_VERSION 6
+#define PBSM3D_ABI_VERSION 7
 
 enum {
     PBSM3D_OK = 0,
@@ -339,6 +339,12 @@ int pbsm3d_slide_init(pbsm3d_handle* h, const pbsm3d_slide_config* cfg);
 int pbsm3d_slide_run(pbsm3d_handle* h, const double* snowdepthavg, const double* snowdepthavg_vert, const double* swe,
                      double* delta_avalanche_snowdepth, double* delta_avalanche_mass, double* delta_avalanche_snowdepth_sum,
                      double* delta_avalanche_mass_sum, double* maxDepth, pbsm3d_slide_stats* stats, int device_ptrs);
+/* Inspection (parity tests): the two per-face constants of init, maxDepth and max(0.001, cos(slope)), each [n_local], NULL = skip.
+ * Under MPI the reference's outer iterations end in a cascade of ever smaller transfers across partition edges; whether a transfer
+ * of one ulp still counts decides a FINITE change down-slope (a receiver's vertical depth is recomputed with the donor's slope,
+ * snow_slide.cpp:297), so a partitioned run is sensitive to the last bit of these constants (libm's pow / cos).  Tests feed the
+ * device's own constants to the oracle to compare the sweeps themselves. */
+int pbsm3d_slide_get_constants(pbsm3d_handle* h, double* maxDepth, double* cos_slope);
 /* Checkpoint (snow_slide.cpp:59-93): the four arrays the reference persists.  Each [n_local]; NULL = skip. */
 int pbsm3d_slide_get_state(pbsm3d_handle* h, double* delta_avalanche_snowdepth, double* delta_avalanche_mass,
                            double* delta_avalanche_snowdepth_sum, double* delta_avalanche_mass_sum);

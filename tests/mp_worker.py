@@ -42,6 +42,7 @@ def main():
         gathered = {}
         for k in range(nsteps):
             o, st = h.slide_run(sd[s:s + T], sdv[s:s + T], swe[s:s + T])
+            o["cos_slope"] = h.slide_constants()[1]
             for name, a in o.items():
                 sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
                 dist.all_gather(sizes, torch.tensor([T], dtype=torch.int64, device="cuda"))
