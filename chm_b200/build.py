@@ -74,8 +74,8 @@ def build_adaptor(force: bool = False) -> str:
     """g++ build of the CHM adaptor (host/PBSM3D_gpu.cpp) over the stand-in CHM types (host/chm_shim.hpp) plus the
     stand-alone driver, linked against libpbsm3d_b200.so.  Inside CHM the same PBSM3D_gpu.cpp is compiled against
     CHM's own headers instead."""
-    srcs = [os.path.join(HOST, f) for f in ("PBSM3D_gpu.cpp", "standalone_driver.cpp")]
-    deps = srcs + [os.path.join(HOST, f) for f in ("PBSM3D_gpu.hpp", "chm_shim.hpp")] + [os.path.join(HERE, "..", "include", "pbsm3d.h"), LIB]
+    srcs = [os.path.join(HOST, f) for f in ("PBSM3D_gpu.cpp", "snow_slide_gpu.cpp", "standalone_driver.cpp")]
+    deps = srcs + [os.path.join(HOST, f) for f in ("PBSM3D_gpu.hpp", "snow_slide_gpu.hpp", "chm_shim.hpp")] + [os.path.join(HERE, "..", "include", "pbsm3d.h"), LIB]
     if not force and os.path.exists(DRIVER) and all(os.path.getmtime(d) <= os.path.getmtime(DRIVER) for d in deps):
         return DRIVER
     cmd = ["g++", "-std=c++17", "-O2", "-fopenmp", "-DPBSM3D_GPU_STANDALONE", "-I", os.path.join(HERE, "..", "include"), "-I", HOST,

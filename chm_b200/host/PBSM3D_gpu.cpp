@@ -16,7 +16,10 @@ void check(int rc)
         CHM_THROW_EXCEPTION(module_error, std::string("PBSM3D_gpu: ") + pbsm3d_last_error());
     }
 }
+pbsm3d_handle* g_shared_handle = nullptr; // one PBSM3D_gpu instance per process (core.cpp creates each module once)
 } // namespace
+
+pbsm3d_handle* PBSM3D_gpu::shared_handle() { return g_shared_handle; }
 
 PBSM3D_gpu::PBSM3D_gpu(config_file cfg) : module_base("PBSM3D_gpu", parallel::domain, cfg)
 {
@@ -250,6 +253,7 @@ void PBSM3D_gpu::init(mesh& domain)
     if (device < 0)
         device = pcomm ? comm.rank % std::max(1, cfg.get("gpus_per_node", 8)) : 0;
     check(pbsm3d_create(&_c, &m, device, pcomm, &_h));
+    g_shared_handle = _h;
     if (_fuse)
     { // the provider modules' own config keys (scale_wind_vert.cpp:161, fetchr.cpp:34-43)
         pbsm3d_wind_config w;
@@ -326,6 +330,8 @@ void PBSM3D_gpu::run(mesh& domain)
 
 PBSM3D_gpu::~PBSM3D_gpu()
 {
+    if (g_shared_handle == _h)
+        g_shared_handle = nullptr;
     pbsm3d_destroy(_h);
     pbsm3d_host_free(_stage);
 }

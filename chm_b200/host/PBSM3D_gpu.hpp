@@ -40,6 +40,8 @@ class PBSM3D_gpu : public module_base
 
     // last step's solver statistics (iterations, residuals, CUDA-event times)
     const pbsm3d_stats& stats() const { return _stats; }
+    // the device mesh of this rank, for the modules that run on it (snow_slide_gpu); nullptr before init()
+    static pbsm3d_handle* shared_handle();
 
   private:
     pbsm3d_config _c;

@@ -4,11 +4,14 @@
 //
 //   standalone_driver <dir> <nsteps>      dir holds meta.txt, vertex.bin, elem.bin, neigh.bin, [area.bin],
 //                                         config.txt (key value per line), forcing_<k>_<name>.bin
+//   with slide_config.txt + slide_{snowdepthavg,snowdepthavg_vert,swe}.bin present, snow_slide_gpu runs twice after the PBSM3D
+//   steps (ctor -> init -> run -> run -> checkpoint) and its provided variables are written as slide_out_<run>_<name>.bin
 #include <cstdio>
 #include <fstream>
 #include <iostream>
 
 #include "PBSM3D_gpu.hpp"
+#include "snow_slide_gpu.hpp"
 
 template <typename T> static std::vector<T> slurp(const std::string& path, bool required = true)
 {
@@ -105,6 +108,41 @@ int main(int argc, char** argv)
         netcdf chk;
         mod.checkpoint(domain, chk);
         dump(dir + "/checkpoint_sum_drift.bin", chk.data.at("PBSM3D:sum_drift"));
+        if (std::ifstream(dir + "/slide_config.txt"))
+        {
+            config_file scfg;
+            std::ifstream c(dir + "/slide_config.txt");
+            std::string k, v;
+            while (c >> k >> v)
+                scfg.kv[k] = v;
+            snow_slide_gpu slide(scfg);
+            slide.init(domain);
+            const char* sin[] = {"snowdepthavg", "snowdepthavg_vert", "swe"};
+            const char* sout[] = {"delta_avalanche_snowdepth", "delta_avalanche_mass", "delta_avalanche_snowdepth_sum",
+                                  "delta_avalanche_mass_sum", "maxDepth"};
+            for (const char* n : sin)
+            {
+                auto a = slurp<double>(dir + "/slide_" + n + ".bin");
+                for (size_t i = 0; i < T; ++i)
+                    (*tri->face(i))[n] = a[i];
+            }
+            for (int run = 0; run < 2; ++run)
+            {
+                slide.run(domain);
+                for (const char* n : sout)
+                {
+                    std::vector<double> a(T);
+                    for (size_t i = 0; i < T; ++i)
+                        a[i] = (*tri->face(i))[n];
+                    dump(dir + "/slide_out_" + std::to_string(run) + "_" + n + ".bin", a);
+                }
+                std::printf("snow_slide run %d: %d iteration(s), %d faces shed snow in %d rounds, %.3f ms\n", run, slide.stats().iterations,
+                            slide.stats().faces_fired, slide.stats().wavefront_rounds, slide.stats().ms_device);
+            }
+            netcdf schk;
+            slide.checkpoint(domain, schk);
+            dump(dir + "/slide_checkpoint_mass_sum.bin", schk.data.at("snow_slide:delta_avalanche_mass_sum"));
+        }
     }
     catch (std::exception& e)
     {

@@ -90,3 +90,39 @@ def test_adaptor_with_fused_providers(tmp_path):
     for v in ("Qsalt", "Qsusp", "Qsubl", "drift_mass"):
         a, b = np.fromfile(plain / f"out_0_{v}.bin"), np.fromfile(fused / f"out_0_{v}.bin")
         assert np.abs(b).max() > 0 and rel_l2(b, a) <= 1e-9, v
+
+
+def test_snow_slide_adaptor_declares_the_reference_contract():
+    """chm_b200/host/snow_slide_gpu.cpp: the depends / provides lists of snow_slide.cpp:30-39 (read from the compiled reference)."""
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "golden_slide.npz"))
+    src = open(os.path.join(build.HOST, "snow_slide_gpu.cpp")).read()
+    for v in g["depends"]:
+        assert f'depends("{v}")' in src
+    for v in g["provides"]:
+        if not v.startswith("ghost_ss_"):       # the reference's MPI scratch variables: the exchange lives in the library
+            assert f'provides("{v}")' in src
+    for key in ("avalache_mult", "avalache_pow", "use_vertical_snow"):
+        assert f'cfg.get("{key}"' in src
+
+
+@pytest.mark.gpu
+def test_snow_slide_adaptor_matches_the_reference_vectors(tmp_path):
+    """snow_slide_gpu driven like a CHM module (ctor -> init -> run -> run -> checkpoint) on granger1m, after PBSM3D_gpu has
+    flattened the mesh: the variables it provides = the reference's own snow_slide.cpp (golden_slide.npz, granger_m900)."""
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "golden_slide.npz"))
+    mesh = load_mesh("granger1m")
+    geo = mesh.geometry()
+    write_case(tmp_path, mesh, ["nLayer 5"], [synthetic.forcing(geo.cx, geo.cy, seed=7, step=0)])
+    (tmp_path / "slide_config.txt").write_text("avalache_mult 900\n")
+    for n, k in (("snowdepthavg", "sd"), ("snowdepthavg_vert", "sdv"), ("swe", "swe")):
+        np.ascontiguousarray(g[f"granger_m900_{k}"]).tofile(tmp_path / f"slide_{n}.bin")
+    res = subprocess.run([build.build_adaptor(), str(tmp_path), "1"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "snow_slide run 1" in res.stdout
+    for run in (0, 1):
+        for v in ("delta_avalanche_snowdepth", "delta_avalanche_mass", "delta_avalanche_snowdepth_sum", "delta_avalanche_mass_sum", "maxDepth"):
+            got, want = np.fromfile(tmp_path / f"slide_out_{run}_{v}.bin"), g[f"granger_m900_run{run + 1}_{v}"]
+            assert np.max(np.abs(got - want)) <= 1e-10 * np.max(np.abs(want)), (run, v)
+    assert np.array_equal(np.fromfile(tmp_path / "slide_checkpoint_mass_sum.bin"), np.fromfile(tmp_path / "slide_out_1_delta_avalanche_mass_sum.bin"))
