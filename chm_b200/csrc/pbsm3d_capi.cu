@@ -2583,6 +2583,7 @@ int pbsm3d_slide_init(pbsm3d_handle* h, const pbsm3d_slide_config* cfg) {
         TRY(h->alloc(&a.key, Tp));
         TRY(h->alloc_zero(&a.gacc, (size_t)std::max(nG, 1) * 4));
         TRY(h->alloc(&a.stamp, Tp));
+        TRY(h->alloc_zero(&a.queued, Tp));
         for (int k = 0; k < 3; ++k) TRY(h->alloc(&a.list[k], Tp));
         TRY(h->alloc_zero(&a.cnt, 8));
         TRY(h->alloc_zero(&h->sl_sum_sd, Tp));

@@ -17,7 +17,8 @@
 //     frontier expansion; everything else is settled from the start (on most hours of a winter the live set is empty and the call
 //     costs two passes over the faces).
 // One persistent cooperative kernel: candidates -> frontier expansion -> wavefront rounds over a compacted work list, a grid barrier
-// per round.  Every load of data another block may have written goes through L2 (__ldcg).  Concurrently firing faces are more than
+// per round; a face waiting for an up-slope neighbour is parked and woken by that neighbour's turn.  Every load of data another
+// block may have written goes through L2 (__ldcg).  Concurrently firing faces are more than
 // two edges apart, so plain stores suffice; the only atomics are the work-list cursors and the ghost accumulators.
 #pragma once
 #include <cuda_runtime.h>
@@ -41,6 +42,7 @@ struct SlideArrays {
     double* key;          // [Tp] sort key of this sweep
     double* gacc;         // [nG][4] ghost accumulators {snowdepth_to_xfer, swe_to_xfer, delta_snowdepth, delta_swe}
     int* stamp;           // [Tp] 1 = not live; 0 = live, turn still to come; r >= 2: took its turn in wavefront round r - 2
+    int* queued;          // [Tp] last round stamp for which the face was put on a work list (one entry per face and round)
     int* list[3];         // [Tp] work lists: live list, and the two alternating round lists
     int* cnt;             // [8] cursors: 0..2 rotating round cursors, 3 = live count, 4 = rounds executed, 5 = fired faces, 6 = mass error flag
 };
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
         a.key[p] = k;
         const bool cand = real && a.sd[p] > a.maxD[p];
         a.stamp[p] = cand ? 0 : 1;
+        a.queued[p] = 0;
         if (cand) {
             a.list[1][atomicAdd(a.cnt + 0, 1)] = p;
             a.list[0][atomicAdd(a.cnt + 3, 1)] = p;
@@ -153,7 +156,9 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
     grid_barrier(bar, target);
     if (tid == 0) a.cnt[0] = a.cnt[1] = a.cnt[2] = 0;
     grid_barrier(bar, target);
-    // ---- wavefront rounds over the live faces whose turn is still to come
+    // ---- wavefront rounds over the live faces whose turn is still to come.  Event-driven: round 0 examines every live face; after
+    // that a face is examined again only when a face within two edges of it has just had its turn (the only event that can unblock
+    // it), so the work is proportional to the faces that take a turn, not to rounds x live faces.
     int n_in = __ldcg(a.cnt + 3);
     const int* in = a.list[0];
     int fired = 0;
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
         int* cur = a.cnt + (w + 1) % 3;
         for (int idx = tid; idx < n_in; idx += nth) {
             const int f = __ldcg(in + idx);
+            if (__ldcg(a.stamp + f) != 0) continue;  // woken twice and already done
             const double kf = a.key[f];
             const int i_f = a.perm[f];
             int nb[3];
@@ -178,11 +184,8 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
                 const int s = __ldcg(a.stamp + n);
                 if ((s == 0 || s == stampv) && slide_earlier(a.key[n], a.perm[n], kf, i_f)) wait = true;
             }
-            if (!wait && !(__ldcg(a.sd + f) > a.maxD[f])) {  // every possible donor has had its turn: this face never fires
-                a.stamp[f] = stampv;
-                continue;
-            }
-            if (!wait) {  // a firing face also needs the earlier faces two edges away to be done
+            const bool active = __ldcg(a.sd + f) > a.maxD[f];
+            if (!wait && active) {  // a firing face also needs the earlier faces two edges away to be done
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int n = nb[j];
@@ -196,13 +199,27 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
                     }
                 }
             }
-            if (wait) {
-                out[atomicAdd(cur, 1)] = f;
-                continue;
-            }
-            if (!slide_fire(a, f)) bad = true;
-            ++fired;
+            if (wait) continue;  // parked: the blocking face wakes it when it has had its turn
+            if (active) {
+                if (!slide_fire(a, f)) bad = true;
+                ++fired;
+            }  // else every possible donor has had its turn: this face never fires
             a.stamp[f] = stampv;
+            // wake the later-ordered live faces within two edges whose turn is still to come
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int n = nb[j];
+                if (n == f || n >= Tp) continue;
+                if (__ldcg(a.stamp + n) == 0 && slide_earlier(kf, i_f, a.key[n], a.perm[n]) && atomicExch(a.queued + n, stampv) != stampv)
+                    out[atomicAdd(cur, 1)] = n;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int m = a.nbs[(size_t)k * Tp + n];
+                    if (m == n || m == f || m >= Tp) continue;
+                    if (__ldcg(a.stamp + m) == 0 && slide_earlier(kf, i_f, a.key[m], a.perm[m]) && atomicExch(a.queued + m, stampv) != stampv)
+                        out[atomicAdd(cur, 1)] = m;
+                }
+            }
         }
         grid_barrier(bar, target);
         n_in = __ldcg(cur);

@@ -1,5 +1,6 @@
-"""numpy model of the device schedule of snow_slide (chm_b200/csrc/pbsm3d_slide.cuh): live-set frontier expansion + wavefront
-rounds with the "every EARLIER face within two edges has had its turn" rule.  Used by tests/test_slide_oracle.py to show, on CPU,
+"""numpy model of the device schedule of snow_slide (chm_b200/csrc/pbsm3d_slide.cuh): live-set frontier expansion + event-driven
+wavefront rounds with the "every EARLIER face within two edges has had its turn" rule (a blocked face is parked and woken when a
+face within two edges of it has had its turn).  Used by tests/test_slide_oracle.py to show, on CPU,
 that the schedule reproduces the reference's sequential sweep bit for bit (same fire() arithmetic, different execution order)."""
 import numpy as np
 
@@ -62,34 +63,44 @@ def run(st, snowdepthavg, snowdepthavg_vert, swe_mm):
                     nxt.append(int(f))
                     live.append(int(f))
         frontier = nxt
-    work, rounds, fired = live, 0, 0
+    work, rounds, fired, examined = live, 0, 0, 0
+    queued = np.zeros(T, dtype=np.int64)
     while work:
         sv = rounds + 2
         before = stamp.copy()          # what "had its turn before this round" means on the device (stamps of this round don't count)
         unsettled = lambda n: before[n] == 0
-        nxt, fire_now = [], []
+        turn_now = []
         for f in work:
-            wait = any(n >= 0 and unsettled(n) and earlier(key, n, f) for n in nb[f])
-            if not wait and not sd[f] > st.maxDepth[f]:
-                stamp[f] = sv
+            if before[f] != 0:
                 continue
-            if not wait:
+            examined += 1
+            wait = any(n >= 0 and unsettled(n) and earlier(key, n, f) for n in nb[f])
+            active = sd[f] > st.maxDepth[f]
+            if not wait and active:
                 for n in nb[f]:
                     if n < 0:
                         continue
                     for m in nb[n]:
                         if m >= 0 and m != f and unsettled(m) and earlier(key, m, f):
                             wait = True
-            if wait:
-                nxt.append(f)
-            else:
-                fire_now.append(f)
-        # faces firing in one round are > 2 edges apart: any order gives the same bits; reverse it to make the point
-        for f in reversed(fire_now):
+            if not wait:                # parked otherwise: the blocking face wakes it when it has had its turn
+                turn_now.append(f)
+        # faces taking their turn in one round are > 2 edges apart if they fire: any order gives the same bits; reverse it
+        nxt = []
+        for f in reversed(turn_now):
             if sd[f] > st.maxDepth[f]:
                 fire(st, f, sd, sdv, swe, dsd, dmass)
                 fired += 1
             stamp[f] = sv
+        for f in turn_now:              # wake the later-ordered live faces within two edges whose turn is still to come
+            for n in nb[f]:
+                if n < 0:
+                    continue
+                for m in [n] + [int(x) for x in nb[n]]:
+                    if m >= 0 and m != f and stamp[m] == 0 and earlier(key, f, m) and queued[m] != sv:
+                        queued[m] = sv
+                        nxt.append(m)
         work = nxt
         rounds += 1
+    assert not np.any(stamp == 0), "a live face never had its turn"
     return dsd, dmass, rounds, len(live), fired
