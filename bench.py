@@ -312,7 +312,7 @@ def time_next_rows(h, T, local_rank):
     size.  Extra figures: failures are reported, never fatal."""
     import ctypes as C
     import torch
-    from chm_b200 import synthetic
+    from chm_b200 import capi, synthetic
     out = {}
     try:
         rng = np.random.default_rng(5)

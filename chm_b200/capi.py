@@ -106,7 +106,8 @@ class SlideConfig(C.Structure):
 
 
 class SlideStats(C.Structure):
-    _fields_ = [("iterations", C.c_int32), ("wavefront_rounds", C.c_int32), ("faces_fired", C.c_int32), ("ms_device", C.c_float)]
+    _fields_ = [("iterations", C.c_int32), ("wavefront_rounds", C.c_int32), ("faces_fired", C.c_int32), ("frontier_rounds", C.c_int32),
+                ("live_faces", C.c_int32), ("ms_device", C.c_float)]
 
 
 SLIDE_OUTPUTS = ("delta_avalanche_snowdepth", "delta_avalanche_mass", "delta_avalanche_snowdepth_sum", "delta_avalanche_mass_sum", "maxDepth")

@@ -2634,7 +2634,7 @@ int pbsm3d_slide_run(pbsm3d_handle* h, const double* snowdepthavg, const double*
     }
     CU(cudaEventRecord(h->ev[0], s));
     LAUNCH(h, slide_begin_kernel, cdiv(Tp, 256), 256, Tp, h->perm, d_sd, d_sdv, d_swe, a);
-    int iterations = 0, rounds = 0, fired = 0;
+    int iterations = 0, rounds = 0, fired = 0, frontier = 0, live = 0;
     int host_cnt[8];
     for (;;) {
         // owners -> ghosts: the vertical depth the weights of a partition-edge face read (snow_slide.cpp:166-169, :398-402)
@@ -2673,6 +2673,8 @@ int pbsm3d_slide_run(pbsm3d_handle* h, const double* snowdepthavg, const double*
         CU(cudaGetLastError());
         rounds += host_cnt[4];
         fired += host_cnt[5];
+        frontier += host_cnt[7];
+        live += host_cnt[3];
         if (host_cnt[6]) return fail(PBSM3D_ERR_INVALID, "Snowslide did not conserve mass");  // snow_slide.cpp:322-328
         ++iterations;
         bool done = moved == 0;
@@ -2697,6 +2699,8 @@ int pbsm3d_slide_run(pbsm3d_handle* h, const double* snowdepthavg, const double*
         stats->iterations = iterations;
         stats->wavefront_rounds = rounds;
         stats->faces_fired = fired;
+        stats->frontier_rounds = frontier;
+        stats->live_faces = live;
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
         stats->ms_device = ms;

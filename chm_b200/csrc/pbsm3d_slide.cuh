@@ -21,6 +21,7 @@
 // block may have written goes through L2 (__ldcg).  Concurrently firing faces are more than
 // two edges apart, so plain stores suffice; the only atomics are the work-list cursors and the ghost accumulators.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include "pbsm3d_kernels.cuh"
 
@@ -44,8 +45,18 @@ struct SlideArrays {
     int* stamp;           // [Tp] 1 = not live; 0 = live, turn still to come; r >= 2: took its turn in wavefront round r - 2
     int* queued;          // [Tp] last round stamp for which the face was put on a work list (one entry per face and round)
     int* list[3];         // [Tp] work lists: live list, and the two alternating round lists
-    int* cnt;             // [8] cursors: 0..2 rotating round cursors, 3 = live count, 4 = rounds executed, 5 = fired faces, 6 = mass error flag
+    int* cnt;             // [8] cursors: 0..2 rotating round cursors, 3 = live count, 4 = wavefront rounds, 5 = fired faces, 6 = mass error flag, 7 = frontier rounds
 };
+
+// Append to a work list with ONE atomic per group of converged lanes (the cursors are single addresses: per-element atomics
+// serialise at the L2 and dominate rounds that append ~1e5 faces).
+__device__ __forceinline__ int slide_reserve(int* cursor) {
+    namespace cg = cooperative_groups;
+    auto g = cg::coalesced_threads();
+    int base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(cursor, (int)g.size());
+    return g.shfl(base, 0) + (int)g.thread_rank();
+}
 
 __device__ __forceinline__ bool slide_earlier(double kg, int ig, double kf, int i_f) { return kg > kf || (kg == kf && ig < i_f); }
 
@@ -121,8 +132,8 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
         a.stamp[p] = cand ? 0 : 1;
         a.queued[p] = 0;
         if (cand) {
-            a.list[1][atomicAdd(a.cnt + 0, 1)] = p;
-            a.list[0][atomicAdd(a.cnt + 3, 1)] = p;
+            a.list[1][slide_reserve(a.cnt + 0)] = p;
+            a.list[0][slide_reserve(a.cnt + 3)] = p;
         }
     }
     grid_barrier(bar, target);
@@ -144,8 +155,8 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
                 if (f == g || f >= Tp) continue;
                 if (!slide_earlier(kg, ig, a.key[f], a.perm[f])) continue;
                 if (atomicCAS(a.stamp + f, 1, 0) == 1) {
-                    out[atomicAdd(a.cnt + (r + 1) % 3, 1)] = f;
-                    a.list[0][atomicAdd(a.cnt + 3, 1)] = f;
+                    out[slide_reserve(a.cnt + (r + 1) % 3)] = f;
+                    a.list[0][slide_reserve(a.cnt + 3)] = f;
                 }
             }
         }
@@ -211,13 +222,13 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
                 const int n = nb[j];
                 if (n == f || n >= Tp) continue;
                 if (__ldcg(a.stamp + n) == 0 && slide_earlier(kf, i_f, a.key[n], a.perm[n]) && atomicExch(a.queued + n, stampv) != stampv)
-                    out[atomicAdd(cur, 1)] = n;
+                    out[slide_reserve(cur)] = n;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int m = a.nbs[(size_t)k * Tp + n];
                     if (m == n || m == f || m >= Tp) continue;
                     if (__ldcg(a.stamp + m) == 0 && slide_earlier(kf, i_f, a.key[m], a.perm[m]) && atomicExch(a.queued + m, stampv) != stampv)
-                        out[atomicAdd(cur, 1)] = m;
+                        out[slide_reserve(cur)] = m;
                 }
             }
         }
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
     }
     if (fired) atomicAdd(a.cnt + 5, fired);
     if (bad) a.cnt[6] = 1;
-    if (tid == 0) a.cnt[4] = w;
+    if (tid == 0) { a.cnt[4] = w; a.cnt[7] = r; }
 }
 
 // snow_slide::init per face (snow_slide.cpp:414-444)

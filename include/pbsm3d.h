@@ -328,6 +328,8 @@ typedef struct pbsm3d_slide_stats {
     int32_t iterations;          /* outer iterations (1 on a single rank) */
     int32_t wavefront_rounds;    /* dependency rounds of the sweeps */
     int32_t faces_fired;         /* faces that shed snow */
+    int32_t frontier_rounds;     /* rounds of the live-set expansion */
+    int32_t live_faces;          /* faces that took part (start candidates and, transitively, their later-ordered neighbours) */
     float ms_device;             /* CUDA-event time of the run without the copies of the outputs */
 } pbsm3d_slide_stats;
 void pbsm3d_slide_config_defaults(pbsm3d_slide_config* cfg);

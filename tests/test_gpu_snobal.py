@@ -78,3 +78,35 @@ def test_missing_state_array_is_refused(handle2048):
     pk = capi.Snowpack()
     rc = h.lib.pbsm3d_apply_drift(h.h, None, pk, None, None, None, 0)
     assert rc == 1 and b"required" in h.lib.pbsm3d_last_error()
+
+
+def test_coupled_loop_pbsm3d_into_the_snowpack(granger):
+    """Config c1's shape (bundled granger1m mesh, nLayer 5, 24 hourly steps) with the loop closed on the device: PBSM3D's
+    drift_mass goes into each face's snowpack (pbsm3d_apply_drift on the handle's own device-resident drift_mass) and the pack's
+    swe / depth are the next hour's inputs.  Checked hour by hour: the pack against the snobal oracle fed the device's drift_mass
+    (bit-exact), PBSM3D's outputs against the PBSM3D oracle fed the same inputs (1e-6)."""
+    from oracle.pbsm3d_oracle import Config, PBSM3DOracle
+    mesh = granger
+    geo = mesh.geometry()
+    T = mesh.n_local
+    h = capi.Handle(capi.default_config(nLayer=5), mesh)
+    o = PBSM3DOracle(Config(nLayer=5), mesh.neigh, geo, mesh.global_id, mesh.n_global, mesh.params)
+    pack = so.synthetic_state(T, seed=12)
+    moved = 0
+    for hour in range(24):
+        F = synthetic.forcing(geo.cx, geo.cy, seed=7, step=hour, calm=(hour % 6 == 5))
+        F["swe"] = pack["m_s"].copy()                 # snobal.cpp:468,491: what snobal hands to the next PBSM3D step
+        F["snowdepthavg"] = pack["z_s"].copy()
+        outs, st = h.step(3600.0, F)
+        r = o.step(F, 3600.0)
+        for v in ("Qsusp", "Qsalt", "drift_mass", "sum_drift"):
+            scale = np.linalg.norm(r[v])
+            assert np.linalg.norm(outs[v] - r[v]) <= 1e-6 * scale + 1e-300, (v, hour)
+        want = so.apply_drift(pack, outs["drift_mass"])
+        got = h.apply_drift(gpu_state(pack), None)    # the handle's own drift_mass, never leaving the device
+        assert_same(got, want)
+        assert np.array_equal(got["swe"], want["m_s"]) and np.array_equal(got["snowdepthavg"], want["z_s"])
+        moved += int(np.count_nonzero(want["m_s"] != pack["m_s"]))
+        pack = want
+    assert moved > 24 * 50 and np.all(pack["m_s"] >= 0)
+    h.close()

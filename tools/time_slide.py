@@ -40,7 +40,7 @@ z = np.zeros(m.n_local)
 h.slide_init()
 calm = [h.slide_run(z, z, z)[1]["ms_device"] for _ in range(4)]
 out["gpu"] = {"triangles": int(m.n_local), "candidates": int(np.count_nonzero(sd > so.max_depth(slope, None))), "faces_fired": st["faces_fired"],
-              "wavefront_rounds": st["wavefront_rounds"], "ms_device": float(np.median([r[1]["ms_device"] for r in runs[1:]])),
+              "wavefront_rounds": st["wavefront_rounds"], "frontier_rounds": st["frontier_rounds"], "live_faces": st["live_faces"], "ms_device": float(np.median([r[1]["ms_device"] for r in runs[1:]])),
               "ms_host_call_with_copies": float(np.median([r[0] for r in runs[1:]]) * 1e3), "calm_ms_device": float(np.median(calm[1:])),
               "moved_m3_water": float(np.abs(o["delta_avalanche_mass"]).sum() / 2)}
 h.close()
