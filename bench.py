@@ -553,7 +553,7 @@ def main():
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--side", type=int, default=0, help="override squares per side (debug)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "c5shard"],
                     help="c2 (default, the driver's line): uniform 1 M triangles per GPU; c3 / c4 / c5: BASELINE's variable-resolution "
                          "5 M / 10 M / 50 M-triangle Delaunay meshes as the HEADLINE workload (strong scaling over the GPUs given; c5 "
                          "with nLayer 20), recorded in profiles/")
@@ -587,8 +587,9 @@ def main():
         gmesh = synthetic.uniform_mesh(side, side)
         wl = f"BASELINE c2 generator: {side}x{side} squares of 30 m"
     else:
-        target = {"c3": 5_000_000, "c4": C4_TARGET, "c5": 50_000_000}[args.workload]
-        if args.workload == "c5":
+        # c5shard: one GPU's share of config c5 (50 M triangles x nLayer 20 over 8 GPUs = 6.25 M x 20 = 125 M unknowns) run on ONE GPU
+        target = {"c3": 5_000_000, "c4": C4_TARGET, "c5": 50_000_000, "c5shard": 6_250_000}[args.workload]
+        if args.workload in ("c5", "c5shard"):
             nl = 20
             cfg_kw["nLayer"] = 20
         gmesh, _ = cached_mesh(job, target)

@@ -44,7 +44,7 @@ struct SlideArrays {
     double* gacc;         // [nG][4] ghost accumulators {snowdepth_to_xfer, swe_to_xfer, delta_snowdepth, delta_swe}
     int* stamp;           // [Tp] 1 = not live; 0 = live, turn still to come; r >= 2: took its turn in wavefront round r - 2
     int* queued;          // [Tp] last round stamp for which the face was put on a work list (one entry per face and round)
-    int* list[3];         // [Tp] work lists: live list, and the two alternating round lists
+    int* list[3];         // [Tp] work lists: the live list (built segment by segment by the frontier expansion), two alternating round lists
     int* cnt;             // [8] cursors: 0..2 rotating round cursors, 3 = live count, 4 = wavefront rounds, 5 = fired faces, 6 = mass error flag, 7 = frontier rounds
 };
 
@@ -119,10 +119,11 @@ __device__ __forceinline__ bool slide_fire(const SlideArrays& a, int f) {
 
 constexpr int kSlideThreads = 256;
 
-__global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArrays a, unsigned* bar) {
+__global__ void __launch_bounds__(kSlideThreads, 1) slide_sweep_kernel(SlideArrays a, unsigned* bar) {
     unsigned target = 0;
     const int Tp = a.Tp;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    int* live = a.list[0];
     // ---- start candidates; every other face is settled until a deposit can reach it
     for (int p = tid; p < Tp; p += nth) {
         const bool real = a.perm[p] >= 0;
@@ -131,47 +132,37 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
         const bool cand = real && a.sd[p] > a.maxD[p];
         a.stamp[p] = cand ? 0 : 1;
         a.queued[p] = 0;
-        if (cand) {
-            a.list[1][slide_reserve(a.cnt + 0)] = p;
-            a.list[0][slide_reserve(a.cnt + 3)] = p;
-        }
+        if (cand) live[slide_reserve(a.cnt + 3)] = p;
     }
     grid_barrier(bar, target);
-    // ---- frontier expansion: the live set = candidates and, transitively, their later-ordered neighbours
+    // ---- frontier expansion: the live set = candidates and, transitively, their later-ordered neighbours.  The frontier of a
+    // round is the segment of the live list the previous round appended, so one cursor serves both.
     int r = 0;
-    for (;; ++r) {
-        const int n_in = __ldcg(a.cnt + r % 3);
-        if (n_in == 0) break;
-        if (tid == 0) a.cnt[(r + 2) % 3] = 0;  // the cursor of round r - 1, free again: round r + 1 appends through it
-        const int* in = a.list[1 + r % 2];
-        int* out = a.list[1 + (r + 1) % 2];
-        for (int idx = tid; idx < n_in; idx += nth) {
-            const int g = __ldcg(in + idx);
+    for (int seg0 = 0, seg1 = __ldcg(a.cnt + 3); seg1 > seg0; ++r) {
+        for (int idx = seg0 + tid; idx < seg1; idx += nth) {
+            const int g = __ldcg(live + idx);
             const double kg = a.key[g];
             const int ig = a.perm[g];
+            int f[3];
+            bool take[3];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int f = a.nbs[(size_t)j * Tp + g];
-                if (f == g || f >= Tp) continue;
-                if (!slide_earlier(kg, ig, a.key[f], a.perm[f])) continue;
-                if (atomicCAS(a.stamp + f, 1, 0) == 1) {
-                    out[slide_reserve(a.cnt + (r + 1) % 3)] = f;
-                    a.list[0][slide_reserve(a.cnt + 3)] = f;
-                }
-            }
+            for (int j = 0; j < 3; ++j) f[j] = a.nbs[(size_t)j * Tp + g];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) take[j] = f[j] != g && f[j] < Tp && slide_earlier(kg, ig, a.key[f[j] < Tp ? f[j] : g], a.perm[f[j] < Tp ? f[j] : g]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (take[j] && atomicCAS(a.stamp + f[j], 1, 0) == 1) live[slide_reserve(a.cnt + 3)] = f[j];
         }
         grid_barrier(bar, target);
+        seg0 = seg1;
+        seg1 = __ldcg(a.cnt + 3);
     }
-    // the loop left cnt[r % 3] == 0 and cnt[(r + 1) % 3] == 0 (zeroed in round r - 1, never appended to); cnt[(r + 2) % 3] may hold
-    // the in-count of round r - 1: clear all three behind a barrier so that nobody is still reading them
-    grid_barrier(bar, target);
-    if (tid == 0) a.cnt[0] = a.cnt[1] = a.cnt[2] = 0;
-    grid_barrier(bar, target);
     // ---- wavefront rounds over the live faces whose turn is still to come.  Event-driven: round 0 examines every live face; after
     // that a face is examined again only when a face within two edges of it has just had its turn (the only event that can unblock
-    // it), so the work is proportional to the faces that take a turn, not to rounds x live faces.
+    // it).  A round costs a few dependent L2 round trips plus the grid barrier, so everything a decision needs is loaded up front,
+    // level by level (the face, its neighbours, their neighbours), and the wake-up atomics are issued together.
     int n_in = __ldcg(a.cnt + 3);
-    const int* in = a.list[0];
+    const int* in = live;
     int fired = 0;
     bool bad = false;
     int w = 0;
@@ -182,33 +173,54 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
         int* cur = a.cnt + (w + 1) % 3;
         for (int idx = tid; idx < n_in; idx += nth) {
             const int f = __ldcg(in + idx);
-            if (__ldcg(a.stamp + f) != 0) continue;  // woken twice and already done
+            // level 1: indexed by the face
+            const int sf = __ldcg(a.stamp + f);
+            int nb[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) nb[j] = a.nbs[(size_t)j * Tp + f];
             const double kf = a.key[f];
             const int i_f = a.perm[f];
-            int nb[3];
-            bool wait = false;
+            const bool active = __ldcg(a.sd + f) > a.maxD[f];
+            if (sf != 0) continue;  // woken twice and already done
+            // level 2: the edge neighbours (a missing / ghost neighbour reads the face itself and is masked out)
+            bool v1[3];
+            int s1[3], p1[3], m2[3][3];
+            double k1[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const int n = a.nbs[(size_t)j * Tp + f];
-                nb[j] = n;
-                if (n == f || n >= Tp) continue;
-                const int s = __ldcg(a.stamp + n);
-                if ((s == 0 || s == stampv) && slide_earlier(a.key[n], a.perm[n], kf, i_f)) wait = true;
+                v1[j] = nb[j] != f && nb[j] < Tp;
+                const int n = v1[j] ? nb[j] : f;
+                s1[j] = __ldcg(a.stamp + n);
+                k1[j] = a.key[n];
+                p1[j] = a.perm[n];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) m2[j][k] = a.nbs[(size_t)k * Tp + n];
             }
-            const bool active = __ldcg(a.sd + f) > a.maxD[f];
+            // level 3: the faces two edges away
+            bool v2[3][3];
+            int s2[3][3], p2[3][3];
+            double k2[3][3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int m = m2[j][k];
+                    v2[j][k] = v1[j] && m != nb[j] && m != f && m < Tp;
+                    const int mm = v2[j][k] ? m : f;
+                    s2[j][k] = __ldcg(a.stamp + mm);
+                    k2[j][k] = a.key[mm];
+                    p2[j][k] = a.perm[mm];
+                }
+            bool wait = false;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (v1[j] && (s1[j] == 0 || s1[j] == stampv) && slide_earlier(k1[j], p1[j], kf, i_f)) wait = true;
             if (!wait && active) {  // a firing face also needs the earlier faces two edges away to be done
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int n = nb[j];
-                    if (n == f || n >= Tp) continue;
+                for (int j = 0; j < 3; ++j)
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int m = a.nbs[(size_t)k * Tp + n];
-                        if (m == n || m == f || m >= Tp) continue;
-                        const int s = __ldcg(a.stamp + m);
-                        if ((s == 0 || s == stampv) && slide_earlier(a.key[m], a.perm[m], kf, i_f)) wait = true;
-                    }
-                }
+                    for (int k = 0; k < 3; ++k)
+                        if (v2[j][k] && (s2[j][k] == 0 || s2[j][k] == stampv) && slide_earlier(k2[j][k], p2[j][k], kf, i_f)) wait = true;
             }
             if (wait) continue;  // parked: the blocking face wakes it when it has had its turn
             if (active) {
@@ -216,19 +228,37 @@ __global__ void __launch_bounds__(kSlideThreads, 2) slide_sweep_kernel(SlideArra
                 ++fired;
             }  // else every possible donor has had its turn: this face never fires
             a.stamp[f] = stampv;
-            // wake the later-ordered live faces within two edges whose turn is still to come
+            // wake the later-ordered live faces within two edges whose turn is still to come.  Their stamps were read above: such
+            // a face cannot have had its turn in this round (this face was in its way), so 0 is still 0.
+            bool w1[3], w2[3][3];
+            int o1[3], o2[3][3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const int n = nb[j];
-                if (n == f || n >= Tp) continue;
-                if (__ldcg(a.stamp + n) == 0 && slide_earlier(kf, i_f, a.key[n], a.perm[n]) && atomicExch(a.queued + n, stampv) != stampv)
-                    out[slide_reserve(cur)] = n;
+                w1[j] = v1[j] && s1[j] == 0 && slide_earlier(kf, i_f, k1[j], p1[j]);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int m = a.nbs[(size_t)k * Tp + n];
-                    if (m == n || m == f || m >= Tp) continue;
-                    if (__ldcg(a.stamp + m) == 0 && slide_earlier(kf, i_f, a.key[m], a.perm[m]) && atomicExch(a.queued + m, stampv) != stampv)
-                        out[slide_reserve(cur)] = m;
+                for (int k = 0; k < 3; ++k) w2[j][k] = v2[j][k] && s2[j][k] == 0 && slide_earlier(kf, i_f, k2[j][k], p2[j][k]);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                o1[j] = w1[j] ? atomicExch(a.queued + nb[j], stampv) : stampv;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) o2[j][k] = w2[j][k] ? atomicExch(a.queued + m2[j][k], stampv) : stampv;
+            }
+            int n_new = 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                n_new += o1[j] != stampv;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) n_new += o2[j][k] != stampv;
+            }
+            if (n_new) {
+                int pos = atomicAdd(cur, n_new);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (o1[j] != stampv) out[pos++] = nb[j];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (o2[j][k] != stampv) out[pos++] = m2[j][k];
                 }
             }
         }

@@ -84,6 +84,16 @@ def main():
     # scale_wind_vert in domain mode on the partition: its neighbour spline needs the partners' point-scaled values (halo)
     Fg = synthetic.forcing(ggeo.cx, ggeo.cy, seed=7, step=0)
     u2 = h.scale_wind_vert(Fg["U_R"][s:s + T], Fg["snowdepthavg"][s:s + T])
+    import time
+    calls = []
+    for _ in range(7):  # the halo of the point-scaled wind must not stall at any rank count (round 1 reported 12 ms at 8 ranks)
+        dist.barrier()
+        t0 = time.perf_counter()
+        h.scale_wind_vert(Fg["U_R"][s:s + T], Fg["snowdepthavg"][s:s + T])
+        calls.append(time.perf_counter() - t0)
+    tmed = torch.tensor([float(np.median(calls[2:]))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tmed, op=dist.ReduceOp.MAX)
+    gathered["scale_wind_vert_call_ms"] = np.array(1e3 * float(tmed.item()))
     sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([T], dtype=torch.int64, device="cuda"))
     parts = [torch.zeros(int(n_.item()), dtype=torch.float64, device="cuda") for n_ in sizes]
