@@ -204,6 +204,8 @@ struct pbsm3d_handle {
     int gs_grid = 0, sor_grid = 0;
     void* gs_fn = nullptr;
     const void* sor_fn = nullptr;
+    bool sor_resident = false;          // sor_resident_kernel: static face data on chip for the whole solve (2 colours, <= 7 faces/thread/colour)
+    size_t sor_smem = 0;
     int sor_threads = 1024;
     int plan_n32 = 0, plan_nx32 = 0;
     float* xf = nullptr;                // [L][S] fp32 storage of the iterate for the sweeps furthest from convergence
@@ -843,6 +845,38 @@ int setup_persistent(pbsm3d_handle* h) {
         h->sor_fn = sf;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sf, h->sor_threads, 0));
         h->sor_grid = std::min(kRedBlocks, std::max(nb, 1) * prop.multiProcessorCount);
+        // the on-chip variant: two colour classes whose faces fit K per thread of a one-CTA-per-SM grid
+        const char* rs = getenv("PBSM3D_SOR_RESIDENT");
+        const char* rv = getenv("PBSM3D_SOR_RES_NT");  // tuning knob: threads per block (K follows: 512 x 7, 384 x 9, 256 x 14)
+        const int rnt = rv ? atoi(rv) : 384;  // measured on c2: 0.60 / 0.68 / 0.75 ms for 384 / 512 / 256 (profiles/r2m_summary.md)
+        int used = 0, maxc = 0;
+        for (int c = 0; c < h->n_colours; ++c)
+            if (h->ccount[c] > 0) { ++used; maxc = std::max(maxc, h->ccount[c]); }
+        const void* rf = rnt == 256 ? (const void*)sor_resident_kernel<14, 256> : rnt == 384 ? (const void*)sor_resident_kernel<9, 384>
+                                                                                                : (const void*)sor_resident_kernel<7, 512>;
+        const int resK = rnt == 256 ? 14 : rnt == 384 ? 9 : 7, resNT = rnt == 256 ? 256 : rnt == 384 ? 384 : 512;
+        const size_t smem = (size_t)2 * resK * (3 * sizeof(int) + 2 * sizeof(double)) * resNT;
+        if (multi) rf = rnt == 512 ? (const void*)sor_resident_halo_kernel<7, 512> : (const void*)sor_resident_halo_kernel<9, 384>;
+        if ((!multi || rnt != 256) && !stream && used <= 2 && !(rs && atoi(rs) == 0) && smem <= (size_t)prop.sharedMemPerBlockOptin) {
+            CU(cudaFuncSetAttribute(rf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int rb = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rb, rf, resNT, smem));
+            const int grid = std::min(kRedBlocks, std::min(rb, 1) * prop.multiProcessorCount);
+            bool fits = rb >= 1 && (long long)maxc <= (long long)resK * grid * resNT;
+            if (multi && fits)  // interior faces of a colour are shared by the blocks that are not its boundary blocks
+                for (int c = 0; c < h->n_colours; ++c) {
+                    if (h->ccount[c] <= 0) continue;
+                    const int nbb = std::max(1, (h->nb[c] + resNT - 1) / resNT);
+                    if (grid - nbb < 1 || (long long)(h->ccount[c] - h->nb[c]) > (long long)resK * (grid - nbb) * resNT) fits = false;
+                }
+            if (fits) {
+                h->sor_resident = true;
+                h->sor_fn = rf;
+                h->sor_threads = resNT;
+                h->sor_grid = grid;
+                h->sor_smem = smem;
+            }
+        }
     }
     if (multi) {  // the boundary columns of a colour must fit the first grid-stride iteration
         for (int c = 0; c < h->n_colours; ++c)
@@ -936,10 +970,10 @@ int sor_enqueue_persistent(pbsm3d_handle* h) {
         for (int c = 0; c < h->n_colours; ++c)
             if (h->ccount[c] > 0) qh.colour_of[k++] = c;
         void* args[] = {&h->dm, &h->offS, &h->drhsS, &h->ddiag, &h->qA, &h->sor_omega, &cr, &h->sc, &h->partial, &h->red, &pl, &bar, &qh};
-        CU(cudaLaunchCooperativeKernel(h->sor_fn, dim3(h->sor_grid), dim3(h->sor_threads), args, 0, h->stream));
+        CU(cudaLaunchCooperativeKernel(h->sor_fn, dim3(h->sor_grid), dim3(h->sor_threads), args, h->sor_resident ? h->sor_smem : 0, h->stream));
     } else {
         void* args[] = {&h->dm, &h->offS, &h->drhsS, &h->ddiag, &h->qA, &h->sor_omega, &cr, &h->sc, &h->partial, &pl, &bar};
-        CU(cudaLaunchCooperativeKernel(h->sor_fn, dim3(h->sor_grid), dim3(h->sor_threads), args, 0, h->stream));
+        CU(cudaLaunchCooperativeKernel(h->sor_fn, dim3(h->sor_grid), dim3(h->sor_threads), args, h->sor_resident ? h->sor_smem : 0, h->stream));
     }
     h->sor_enqueued = maxit;  // replaced by the executed count (Scalars::dep_sweeps) once the step has synchronised
     return 0;

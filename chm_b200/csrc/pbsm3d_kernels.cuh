@@ -17,6 +17,7 @@
 //                                             so a neighbour gather is x[z*S + nbs] with no owned/ghost branch
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include "pbsm3d_physics.cuh"
 #include "pbsm3d_math.cuh"
 
@@ -1014,14 +1015,26 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
     return v;
 }
 // `ctr` is zeroed by the host before the launch; `target` is the block's private running count.
+// Arrival is one `atom.add.release.gpu` by thread 0: the release is cumulative over the block's writes that the preceding bar.sync
+// ordered before it, so no separate fence is needed; departure is an `ld.acquire.gpu` spin followed by bar.sync, which orders every
+// later load of the block after the writes of all blocks that arrived.  (PBSM3D_BARRIER_FENCES=1 at compile time restores the
+// explicit __threadfence() pair around the atomic.)
+__device__ __forceinline__ void atom_add_release_gpu_u32(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();  // release: every write of this block (ordered before thread 0 by the barrier above)
+#ifdef PBSM3D_BARRIER_FENCES
+        __threadfence();
         atomicAdd(ctr, 1u);
         while (ld_acquire_gpu_u32(ctr) < target) {}
-        __threadfence();  // and drop what this SM's L1 still holds of the arrays the other blocks just wrote
+        __threadfence();
+#else
+        atom_add_release_gpu_u32(ctr, 1u);
+        while (ld_acquire_gpu_u32(ctr) < target) {}
+#endif
     }
     __syncthreads();
 }
@@ -1601,6 +1614,96 @@ __global__ void __launch_bounds__(NT, 1) sor_persistent_kernel(DevMesh m, const 
             double z = bS[p] - q[p];
 #pragma unroll
             for (int j = 0; j < 3; ++j) z -= offS[(size_t)j * Tp + p] * q[m.nbs[(size_t)j * Tp + p]];
+            const double r = z * ddiag[p];
+            a += r * r;
+        }
+        a = block_sum(a);
+        if (threadIdx.x == 0) partial[blockIdx.x] = a;
+        grid_barrier(bar, target);
+        rr = fold_partials(partial, gridDim.x);
+        if (rr <= pl.tol2 * bnorm2) { done = 1; break; }
+        if (!(rr == rr) || rr > 1e60 * bnorm2) { done = 2; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->rr = rr;
+        sc->dep_sweeps = it;
+        sc->iters = it;
+        if (done == 1) { sc->done = 1; sc->dep_ok = 1; sc->dep_buf = 0; }
+        else if (done == 2) sc->done = 2;
+    }
+}
+
+// The same solve with the STATIC part of every face resident on chip for the whole launch.  A persistent thread updates the same
+// faces in every sweep, so their neighbour slots and two of the three scaled off-diagonals live in shared memory (28 B per face,
+// laid out [colour][k][field][thread]: conflict-free), the third off-diagonal in registers; a colour pass then costs ONE L2 round
+// trip (the q gathers + bS, all issued at once for the thread's K faces of that colour) plus the grid barrier, instead of two
+// dependent round trips (slots, then gathers) over 84 B per face.  Two colour classes (every structured split mesh), at most K faces
+// per thread and colour; anything else runs sor_persistent_kernel.  Same operations in the same order: identical iterates.
+template <int K, int NT>
+__global__ void __launch_bounds__(NT, 1) sor_resident_kernel(DevMesh m, const double* __restrict__ offS, const double* __restrict__ bS,
+                                                                         const double* __restrict__ ddiag, double* q, double omega,
+                                                                         ColourRanges cr, Scalars* sc, double* __restrict__ partial,
+                                                                         SolvePlan pl, unsigned* bar) {
+    if (!sc->tail_done || !sc->dep_present || sc->done) return;  // uniform: written only after the last grid barrier
+    extern __shared__ unsigned char sor_smem[];
+    int* s_nb = reinterpret_cast<int*>(sor_smem);                                        // [2][K][3][NT]
+    double* s_o = reinterpret_cast<double*>(sor_smem + (size_t)2 * K * 3 * NT * sizeof(int));  // [2][K][2][NT]
+    const int Tp = m.Tp, tid = threadIdx.x;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + tid;
+    double o2[2][K];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int p = (c < cr.n ? cr.start[c] : 0) + t0 + k * stride;
+            const bool ok = c < cr.n && p < cr.end[c];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) s_nb[((c * K + k) * 3 + j) * NT + tid] = ok ? m.nbs[(size_t)j * Tp + p] : 0;
+            s_o[((c * K + k) * 2 + 0) * NT + tid] = ok ? offS[p] : 0.0;
+            s_o[((c * K + k) * 2 + 1) * NT + tid] = ok ? offS[(size_t)Tp + p] : 0.0;
+            o2[c][k] = ok ? offS[(size_t)2 * Tp + p] : 0.0;
+        }
+    const double bnorm2 = sc->bnorm2;
+    unsigned target = 0;
+    int it = 0, done = 0;
+    double rr = bnorm2;
+    while (it < pl.maxit) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (c >= cr.n) break;
+            const int start = cr.start[c], end = cr.end[c];
+            double qp[K], bs[K], g[K][3];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int p = start + t0 + k * stride;
+                if (p < end) {
+                    qp[k] = __ldcg(q + p);
+                    bs[k] = bS[p];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) g[k][j] = __ldcg(q + s_nb[((c * K + k) * 3 + j) * NT + tid]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int p = start + t0 + k * stride;
+                if (p < end) {
+                    double z = bs[k] - qp[k];
+                    z -= s_o[((c * K + k) * 2 + 0) * NT + tid] * g[k][0];
+                    z -= s_o[((c * K + k) * 2 + 1) * NT + tid] * g[k][1];
+                    z -= o2[c][k] * g[k][2];
+                    q[p] = qp[k] + omega * z;
+                }
+            }
+            grid_barrier(bar, target);
+        }
+        ++it;
+        const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
+        if (!check) continue;
+        double a = 0.0;
+        for (int p = t0; p < Tp; p += stride) {
+            double z = bS[p] - __ldcg(q + p);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) z -= offS[(size_t)j * Tp + p] * __ldcg(q + m.nbs[(size_t)j * Tp + p]);
             const double r = z * ddiag[p];
             a += r * r;
         }
@@ -2510,6 +2613,135 @@ __global__ void __launch_bounds__(NT, 1) sor_persistent_halo_kernel(const __grid
 #pragma unroll
                 for (int k = 0; k < B; ++k)
                     if (base + k * strideI < end) q[base + k * strideI] = qp[k] + omega * z[k];
+            }
+            grid_barrier(bar, target);
+        }
+        ++it;
+        const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
+        if (!check) continue;
+        double a = 0.0;
+        for (int p = t0; p < Tp; p += stride) {  // every ghost entry carries tag e after sweep e
+            double z = bS[p] - q[p];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int n = m.nbs[(size_t)j * Tp + p];
+                z -= offS[(size_t)j * Tp + p] * (n < Tp ? q[n] : tagged_read(qh.sl.tl.ghost + (n - Tp), e, qh.sl.tl.pt));
+            }
+            const double r = z * ddiag[p];
+            a += r * r;
+        }
+        a = block_sum(a);
+        if (threadIdx.x == 0) partial[blockIdx.x] = a;
+        grid_barrier(bar, target);
+        const double rloc = fold_partials(partial, gridDim.x);
+        if (blockIdx.x == 0 && threadIdx.x < 32) {
+            if (threadIdx.x == 0) red[0] = rloc;
+            __syncwarp();
+            peer_allreduce_warp(red, 1, 0, qh.sl.tl.pt);
+            __threadfence();
+        }
+        grid_barrier(bar, target);
+        rr = __ldcg(red);
+        if (rr <= pl.tol2 * bnorm2) { done = 1; break; }
+        if (!(rr == rr) || rr > 1e60 * bnorm2) { done = 2; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->rr = rr;
+        sc->dep_sweeps = it;
+        sc->iters = it;
+        if (done == 1) { sc->done = 1; sc->dep_ok = 1; sc->dep_buf = 0; }
+        else if (done == 2) sc->done = 2;
+    }
+}
+
+// sor_persistent_halo_kernel with the interior blocks' static face data resident on chip (sor_resident_kernel): two colour classes,
+// at most K interior faces per thread and colour.
+template <int K, int NT>
+__global__ void __launch_bounds__(NT, 1) sor_resident_halo_kernel(const __grid_constant__ DevMesh m, const double* __restrict__ offS,
+                                                                    const double* __restrict__ bS, const double* __restrict__ ddiag, double* q,
+                                                                    double omega, ColourRanges cr, Scalars* sc, double* __restrict__ partial,
+                                                                    double* red, SolvePlan pl, unsigned* bar, const __grid_constant__ QHalo qh) {
+    if (!sc->tail_done || !sc->dep_present || sc->done) return;
+    const int Tp = m.Tp;
+    // static data of this block's INTERIOR faces on chip (see sor_resident_kernel); boundary faces keep the global-memory path
+    extern __shared__ unsigned char sor_smem[];
+    int* s_nb = reinterpret_cast<int*>(sor_smem);                                               // [2][K][3][NT]
+    double* s_o = reinterpret_cast<double*>(sor_smem + (size_t)2 * K * 3 * NT * sizeof(int));   // [2][K][2][NT]
+    const int tid = threadIdx.x;
+    double o2[2][K];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const bool have = c < cr.n;
+        const int nbc = have ? qh.nb[c] : 0, nbb = max(1, (nbc + NT - 1) / NT);
+        const int strideI = ((int)gridDim.x - nbb) * NT;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int p = (have ? cr.start[c] : 0) + nbc + ((int)blockIdx.x - nbb) * NT + tid + k * strideI;
+            const bool ok = have && (int)blockIdx.x >= nbb && p < cr.end[c];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) s_nb[((c * K + k) * 3 + j) * NT + tid] = ok ? m.nbs[(size_t)j * Tp + p] : 0;
+            s_o[((c * K + k) * 2 + 0) * NT + tid] = ok ? offS[p] : 0.0;
+            s_o[((c * K + k) * 2 + 1) * NT + tid] = ok ? offS[(size_t)Tp + p] : 0.0;
+            o2[c][k] = ok ? offS[(size_t)2 * Tp + p] : 0.0;
+        }
+    }
+    const double bnorm2 = sc->bnorm2;
+    unsigned target = 0;
+    int it = 0, done = 0;
+    double rr = bnorm2;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    while (it < pl.maxit) {
+        const unsigned long long e = qh.e0 + (unsigned long long)it + 1ull;
+        const int first = it == 0 ? 1 : 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (c >= cr.n) break;
+            const int start = cr.start[c], end = cr.end[c], nbc = qh.nb[c];
+            const int my_key = qh.colour_of[c] * qh.n_ranks + qh.rank;
+            // boundary faces (first in the class, the only ones with ghost neighbours) belong to the first nbb blocks, which do
+            // nothing else in this pass; the other blocks split the interior
+            const int nbb = max(1, (nbc + NT - 1) / NT);
+            if ((int)blockIdx.x < nbb)
+            for (int i = blockIdx.x * NT + threadIdx.x; i < nbc; i += nbb * NT) {
+                const int p = start + i;
+                const double qp = q[p];
+                double z = bS[p] - qp;
+                int n[3];
+                double o[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { n[j] = m.nbs[(size_t)j * Tp + p]; o[j] = offS[(size_t)j * Tp + p]; }
+                const int k0 = qh.sl.tl.bptr[qh.boff[c] + i], k1 = qh.sl.tl.bptr[qh.boff[c] + i + 1];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) z -= o[j] * (n[j] < Tp ? q[n[j]] : sor_ghost(qh.sl, n[j] - Tp, my_key, e, first));
+                const double qn = qp + omega * z;
+                q[p] = qn;
+                for (int k = k0; k < k1; ++k) tagged_write(qh.sl.tl.remote[k], qn, e);
+            }
+            const int strideI = ((int)gridDim.x - nbb) * NT;
+            if ((int)blockIdx.x >= nbb) {
+                const int base = start + nbc + ((int)blockIdx.x - nbb) * NT + tid;
+                double qp[K], bs[K], g[K][3];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int p = base + k * strideI;
+                    if (p < end) {
+                        qp[k] = __ldcg(q + p);
+                        bs[k] = bS[p];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) g[k][j] = __ldcg(q + s_nb[((c * K + k) * 3 + j) * NT + tid]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int p = base + k * strideI;
+                    if (p < end) {
+                        double z = bs[k] - qp[k];
+                        z -= s_o[((c * K + k) * 2 + 0) * NT + tid] * g[k][0];
+                        z -= s_o[((c * K + k) * 2 + 1) * NT + tid] * g[k][1];
+                        z -= o2[c][k] * g[k][2];
+                        q[p] = qp[k] + omega * z;
+                    }
+                }
             }
             grid_barrier(bar, target);
         }

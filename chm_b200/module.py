@@ -134,6 +134,10 @@ class PBSM3D:
         domain.init_face_data(self._provides)
         cc = capi.default_config()
         for k, v in self.cfg.items():
+            if k == "smooth_coeff":
+                # the reference reads it as an INT (cfg.get("smooth_coeff", 820), PBSM3D.cpp:235): ptree's stream translator yields the
+                # default when the text does not parse completely as an int ("820.7" -> 820), as PBSM3D_gpu.cpp does
+                v = int(v) if float(v).is_integer() else 820
             setattr(cc, k, type(getattr(cc, k))(v))
         try:
             self.handle = capi.Handle(cc, domain.mesh, device=self.device, rank=self.rank, n_ranks=self.n_ranks,

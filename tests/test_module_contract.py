@@ -72,3 +72,20 @@ def test_snow_slide_mirror_declares_the_reference_contract():
         module.snow_slide({"avalanche_mult": 900})          # the reference's key is spelt "avalache"
     with pytest.raises(module.module_error):
         module.snow_slide().run(module.Domain.__new__(module.Domain), module.PBSM3D({"nLayer": 5}))
+
+
+def test_smooth_coeff_is_read_as_an_int_like_the_reference(monkeypatch):
+    """PBSM3D.cpp:235 cfg.get("smooth_coeff", 820): an int read; ptree returns the default for text that is not an int."""
+    from chm_b200 import capi, module
+    seen = {}
+
+    class FakeHandle:
+        def __init__(self, cc, *a, **k):
+            seen["smooth_coeff"] = cc.smooth_coeff
+
+    monkeypatch.setattr(capi, "Handle", FakeHandle)
+    import conftest
+    for text, want in (("6500", 6500.0), ("820.7", 820.0), (900.0, 900.0)):
+        m = module.PBSM3D({"smooth_coeff": text})
+        m.init(module.Domain(conftest.load_mesh("granger1m")))
+        assert seen["smooth_coeff"] == want, text
