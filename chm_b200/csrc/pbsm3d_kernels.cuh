@@ -1015,10 +1015,12 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
     return v;
 }
 // `ctr` is zeroed by the host before the launch; `target` is the block's private running count.
-// Arrival is one `atom.add.release.gpu` by thread 0: the release is cumulative over the block's writes that the preceding bar.sync
-// ordered before it, so no separate fence is needed; departure is an `ld.acquire.gpu` spin followed by bar.sync, which orders every
-// later load of the block after the writes of all blocks that arrived.  (PBSM3D_BARRIER_FENCES=1 at compile time restores the
-// explicit __threadfence() pair around the atomic.)
+// grid_barrier: arrival is one `red.release.gpu` by thread 0 — the release is cumulative over the block's writes that the preceding
+// bar.sync ordered before it — and departure an `ld.acquire.gpu` spin followed by bar.sync, which orders every later load of the
+// block after the writes of all blocks that arrived.  No separate fences.  Measured against the fenced form below (c2, one B200,
+// profiles/r2m_summary.md): the latency-bound solves (deposition SOR: 148 barriers around 4 us passes; snow_slide) gain 0.35 us per
+// barrier; the bandwidth-bound suspension solve (60 barriers around 30 us passes that stream 200-400 MB each) LOSES 0.4 us per
+// barrier, so it keeps the fenced form.
 __device__ __forceinline__ void atom_add_release_gpu_u32(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -1026,15 +1028,19 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-#ifdef PBSM3D_BARRIER_FENCES
-        __threadfence();
+        atom_add_release_gpu_u32(ctr, 1u);
+        while (ld_acquire_gpu_u32(ctr) < target) {}
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void grid_barrier_fenced(unsigned* ctr, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();  // release: every write of this block (ordered before thread 0 by the barrier above)
         atomicAdd(ctr, 1u);
         while (ld_acquire_gpu_u32(ctr) < target) {}
         __threadfence();
-#else
-        atom_add_release_gpu_u32(ctr, 1u);
-        while (ld_acquire_gpu_u32(ctr) < target) {}
-#endif
     }
     __syncthreads();
 }
@@ -1104,7 +1110,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem
     if (nx32 > 0) {  // x0 = 0 in the fp32 copy (ghost tails included)
         const size_t NS = (size_t)L * m.S;
         for (size_t k = t0; k < NS; k += stride) xf[k] = 0.f;
-        grid_barrier(bar, target);
+        grid_barrier_fenced(bar, target);
     }
     while (it < pl.maxit) {
         const int phase = it < nx32 ? 0 : (it < pl.n32 ? 1 : 2);
@@ -1112,13 +1118,13 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem
             if (phase == 0) for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) gs_column<LT, float, float>(s, m, L, p, xf);
             else if (phase == 1) for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) gs_column<LT, float, double>(s, m, L, p, x);
             else for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) gs_column<LT, double, double>(s, m, L, p, x);
-            grid_barrier(bar, target);
+            grid_barrier_fenced(bar, target);
         }
         ++it;
         if (it == nx32) {  // the iterate moves to fp64
             const size_t NS = (size_t)L * m.S;
             for (size_t k = t0; k < NS; k += stride) x[k] = (double)xf[k];
-            grid_barrier(bar, target);
+            grid_barrier_fenced(bar, target);
         }
         const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
         if (!check) continue;
@@ -1134,7 +1140,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem
         }
         a = block_sum(a);
         if (threadIdx.x == 0) partial[blockIdx.x] = a;
-        grid_barrier(bar, target);
+        grid_barrier_fenced(bar, target);
         rr = fold_partials(partial, gridDim.x);
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             if (n_checks < 16) { sc->rr_hist[n_checks] = rr; sc->it_hist[n_checks] = it; }
@@ -2428,7 +2434,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
     if (nx32 > 0) {
         const size_t NS = (size_t)L * S;
         for (size_t k = t0; k < NS; k += stride) xf[k] = 0.f;
-        grid_barrier(bar, target);
+        grid_barrier_fenced(bar, target);
     }
     while (it < pl.maxit) {
         const int phase = it < nx32 ? 0 : (it < pl.n32 ? 1 : 2);
@@ -2470,13 +2476,13 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
                     else gs_column<LT, double, double>(s, m, L, p, x);
                 }
             }
-            grid_barrier(bar, target);
+            grid_barrier_fenced(bar, target);
         }
         ++it;
         if (it == nx32) {
             const size_t NS = (size_t)L * S;
             for (size_t k = t0; k < NS; k += stride) x[k] = (double)xf[k];
-            grid_barrier(bar, target);
+            grid_barrier_fenced(bar, target);
         }
         const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
         if (!check) continue;
@@ -2509,7 +2515,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
         }
         a = block_sum(a);
         if (threadIdx.x == 0) partial[blockIdx.x] = a;
-        grid_barrier(bar, target);
+        grid_barrier_fenced(bar, target);
         const double rloc = fold_partials(partial, gridDim.x);
         if (blockIdx.x == 0 && threadIdx.x < 32) {  // the sum over ranks
             if (threadIdx.x == 0) red[0] = rloc;
@@ -2517,7 +2523,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
             peer_allreduce_warp(red, 1, 0, xh.pt);
             __threadfence();
         }
-        grid_barrier(bar, target);
+        grid_barrier_fenced(bar, target);
         rr = __ldcg(red);
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             if (n_checks < 16) { sc->rr_hist[n_checks] = rr; sc->it_hist[n_checks] = it; }
