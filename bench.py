@@ -123,9 +123,13 @@ def persistent_solve_bytes(st, T, L):
     three storage phases, 58 B/row per residual check (3 latS + belowS + cp + den + x, + slots/rhs amortised), and 16 B/row
     once for zeroing the fp32 iterate and converting it to fp64."""
     n, n32, nx = st["sweeps_timed"], st["sweeps_timed_fp32"], st["sweeps_fp32_x"]
-    per_row = nx * sweep_bytes_per_row(L, True, True) + (n32 - nx) * sweep_bytes_per_row(L, True) + (n - n32) * sweep_bytes_per_row(L) \
-        + st["residual_checks"] * (56.0 + 20.0 / L) + (16.0 if nx > 0 else 0.0)
-    return per_row * T * L
+    # face-column updates per storage phase: with the solver's active set (pbsm3d_stats.active_set) only the executed ones count
+    cols = (st.get("column_updates_fp32_x", 0), st.get("column_updates_fp32", 0), st.get("column_updates_fp64", 0), st.get("columns_checked", 0))
+    if not st.get("active_set") or sum(cols) == 0:
+        cols = (nx * T, (n32 - nx) * T, (n - n32) * T, st["residual_checks"] * T)
+    per_col = cols[0] * sweep_bytes_per_row(L, True, True) + cols[1] * sweep_bytes_per_row(L, True) + cols[2] * sweep_bytes_per_row(L) \
+        + cols[3] * (56.0 + 20.0 / L)
+    return per_col * L + (16.0 * T * L if nx > 0 else 0.0)
 
 
 def assembly_bytes_per_row(L: int) -> float:
@@ -296,6 +300,8 @@ def timed_steps(job, h, dev_in, dev_out, steps, warmup):
             acc["solve_launches"] += 1
             acc["sweeps_x32"] += st["sweeps_fp32_x"]
             acc["checks"] += st["residual_checks"]
+            acc["col_updates"] = acc.get("col_updates", 0) + st.get("column_updates_fp32_x", 0) + st.get("column_updates_fp32", 0) + st.get("column_updates_fp64", 0)
+            acc["col_sweeps"] = acc.get("col_sweeps", 0) + st["sweeps_timed"] * h.T
         for p in acc["phases"]:
             acc["phases"][p] += st[p]
     job.barrier()
@@ -726,6 +732,11 @@ def main():
                     "traffic_frac_of_peak": (traffic / (sweep_ms / nlch * 1e-3) / 1e9 / peak) if traffic else None,
                     "peak_source": peak_src, "bytes_per_launch": acc["solve_bytes"] / nlch, "avg_launch_ms": sweep_ms / nlch,
                     "launches_timed": int(nlch), "share_of_step": sweep_ms / max(ev_ms, 1e-9),
+                    "active_set": {"on": bool(st.get("active_set")),
+                                   "column_updates_executed": (acc.get("col_updates", 0) / max(acc.get("col_sweeps", 0), 1)) if st.get("active_set") else 1.0,
+                                   "note": "share of sweeps x faces column updates the solver executed: columns whose right-hand side "
+                                           "and whose neighbours' iterates are still exactly zero are skipped (a no-op update, iterates "
+                                           "bit-identical); bytes_per_launch counts the executed updates only"},
                     "per_launch": {"sweeps": sweeps / nlch, "of_which_fp32_coefficients": sweeps32 / nlch,
                                    "of_which_fp32_x": acc["sweeps_x32"] / nlch, "residual_checks": acc["checks"] / nlch},
                     "bytes_per_row": {"fp32_x_sweep": sweep_bytes_per_row(nl, True, True),

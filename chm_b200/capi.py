@@ -24,7 +24,7 @@ c_uint8_p = C.POINTER(C.c_uint8)
 SOLVER_AUTO, SOLVER_LINE, SOLVER_BICGSTAB = 0, 1, 2
 DEP_AUTO, DEP_CG, DEP_CHEBYSHEV, DEP_SOR = 0, 1, 2, 3
 HALO_NONE, HALO_NCCL, HALO_PEER = 0, 1, 2
-ABI_VERSION = 7  # include/pbsm3d.h PBSM3D_ABI_VERSION
+ABI_VERSION = 8  # include/pbsm3d.h PBSM3D_ABI_VERSION
 ERR_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "NOCONVERGE"}
 
 
@@ -74,6 +74,8 @@ class Stats(C.Structure):
         ("sweeps_timed", C.c_int32), ("sweeps_timed_fp32", C.c_int32), ("ms_line_sweeps_fp32", C.c_float), ("n_colours", C.c_int32), ("deposition_solver_used", C.c_int32), ("host_syncs", C.c_int32),
         ("halo_exchanges", C.c_int32), ("halo_transport", C.c_int32), ("halo_fused", C.c_int32),
         ("residual_checks", C.c_int32), ("sweeps_fp32_x", C.c_int32), ("persistent_kernels", C.c_int32),
+        ("active_set", C.c_int32), ("column_updates_fp32_x", C.c_int64), ("column_updates_fp32", C.c_int64),
+        ("column_updates_fp64", C.c_int64), ("columns_checked", C.c_int64),
     ]
 
     def asdict(self):

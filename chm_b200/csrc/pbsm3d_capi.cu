@@ -198,6 +198,7 @@ struct pbsm3d_handle {
     int sweeps_timed = 0, sweeps_timed32 = 0;
     // persistent (cooperative) solver kernels: single rank
     bool persistent = false;
+    bool active_set = true;  // PBSM3D_ACTIVE_SET=0: the persistent line solver updates every column in every sweep
     bool sor_persistent = false;        // the deposition solve too: only while its working set stays in the L2 (else per-pass launches
                                         // stream better: 17 vs 21 ms on 10 M faces, profiles/r2b)
     unsigned* grid_bar = nullptr;       // [2] grid-barrier counters (suspension, deposition)
@@ -797,6 +798,8 @@ ColourRanges colour_ranges(const pbsm3d_handle* h) {
 using GsHaloKernel = void (*)(SuspSystem, DevMesh, int, ColourRanges, double*, float*, Scalars*, double*, double*, SolvePlan, unsigned*, XHalo);
 int setup_persistent(pbsm3d_handle* h) {
     const char* env = getenv("PBSM3D_PERSISTENT");
+    const char* env_as = getenv("PBSM3D_ACTIVE_SET");
+    h->active_set = !(env_as && atoi(env_as) == 0);
     h->persistent = false;
     if (env && atoi(env) == 0) return 0;
     const bool multi = h->n_ranks > 1;
@@ -912,6 +915,7 @@ int line_enqueue_persistent(pbsm3d_handle* h) {
     const char* nox = getenv("PBSM3D_FP32_X");
     pl.nx32 = (h->xf && !(nox && atoi(nox) == 0)) ? std::max(0, std::min(pl.n32, pl.check_first - 10)) : 0;
     pl.maxit = maxit;
+    pl.use_live = h->active_set ? 1 : 0;
     pl.tol2 = h->cfg.tolerance * h->cfg.tolerance;
     h->plan_n32 = pl.n32;
     h->plan_nx32 = pl.nx32;
@@ -949,7 +953,7 @@ int sor_enqueue_persistent(pbsm3d_handle* h) {
     const int maxit = std::min(h->cfg.max_iterations, 6 * h->sor_kest + 64);
     const bool known = h->pred_sor > 0;
     SolvePlan pl;
-    pl.n32 = pl.nx32 = 0;
+    pl.n32 = pl.nx32 = pl.use_live = 0;
     pl.check_first = std::max(1, std::min(maxit, known ? h->pred_sor : h->sor_kest));
     pl.check_every = known ? 1 : 4;
     pl.maxit = maxit;
@@ -1904,6 +1908,13 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
         CU(cudaEventElapsedTime(&st->ms_line_sweeps_fp32, h->ev_sw[0], h->ev_sw[2]));
     }
     st->residual_checks = h->h_sc->n_checks;
+    if (h->persistent && line && h->h_sc->susp_present) {
+        st->column_updates_fp32_x = (int64_t)h->h_sc->col_updates[0];
+        st->column_updates_fp32 = (int64_t)h->h_sc->col_updates[1];
+        st->column_updates_fp64 = (int64_t)h->h_sc->col_updates[2];
+        st->columns_checked = (int64_t)h->h_sc->col_updates[3];
+        st->active_set = h->active_set ? 1 : 0;
+    }
     st->sweeps_fp32_x = h->persistent ? std::min(h->plan_nx32, h->sweeps_timed) : 0;
     st->persistent_kernels = h->persistent ? 1 : 0;
     st->sweeps_timed = h->sweeps_timed;
@@ -2248,6 +2259,7 @@ static int create_impl(pbsm3d_handle* h, const pbsm3d_config* cfg, const pbsm3d_
     TRY(h->alloc_zero(&ss.Qsalt, h->S));
     TRY(h->alloc(&ss.c_salt, Tp));
     TRY(h->alloc(&ss.salt, Tp));
+    TRY(h->alloc_zero(&ss.live, h->S));
     TRY(h->alloc(&ss.prob, Tp));
     TRY(h->alloc_zero(&h->x, h->NS));
     TRY(h->alloc_zero(&h->Qsusp, h->S));

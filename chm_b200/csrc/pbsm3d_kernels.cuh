@@ -68,6 +68,8 @@ struct SuspSystem {
     double *u_z, *csubl;           // [L][Tp]
     double *Qsalt, *c_salt;        // [Tp]
     unsigned char* salt;           // [Tp]
+    unsigned char* live;           // [S] active set of the line solver (gs_persistent_kernel): a superset of the columns whose
+                                   //     right-hand side or iterate is non-zero; the assembly seeds it with b_p != 0
     double* prob;                  // [Tp] blowingsnow_probability (face variable; written on saltating faces with use_PomLi_probability)
     const double* ltab;            // [kTabN][L] per-layer constants of a column with hs = 0 (layer_table_kernel)
 };
@@ -97,6 +99,8 @@ struct Scalars {
     int log_n, log_cap;               // setup only: CG recurrence log for the Lanczos spectrum estimate
     double *log_alpha, *log_beta;
     unsigned ticket[4];
+    unsigned long long col_updates[4];  // persistent line solver: face-column updates executed in each storage phase
+                                        // (fp32 x / fp32 coefficients / fp64) and columns evaluated by the residual checks
     int peer_error;                   // sticky: a peer-memory wait timed out (see PeerTable)
 };
 
@@ -341,7 +345,7 @@ __global__ void assemble_pads_kernel(DevMesh m, SuspSystem s, int L) {
     const int Tp = m.Tp;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= Tp || m.perm[p] >= 0) return;
-    s.Qsalt[p] = 0.0; s.c_salt[p] = 0.0; s.salt[p] = 0; s.rhs0[p] = 0.0; s.rhsS0[p] = 0.0;
+    s.Qsalt[p] = 0.0; s.c_salt[p] = 0.0; s.salt[p] = 0; s.rhs0[p] = 0.0; s.rhsS0[p] = 0.0; s.live[p] = 0;
     for (int z = 0; z < L; ++z) {
         const size_t r = (size_t)z * Tp + p;
         s.den[r] = 1.0; s.cp[r] = 0.0; s.belowS[r] = 0.0;
@@ -737,7 +741,7 @@ assemble_tile_kernel(DevConfig c, DevMesh m, FaceRecs R, SuspSystem s, int i0, i
         if (act) {
             const double den = colA[w * 32 + lane], inv = colB[w * 32 + lane], cp = colC[w * 32 + lane];
             store_row(s, (size_t)w * m.Tp + p, LTp, rc, den, inv, cp);
-            if (w == 0) { s.rhs0[p] = rc.rhs; s.rhsS0[p] = rc.rhs * inv; }
+            if (w == 0) { s.rhs0[p] = rc.rhs; s.rhsS0[p] = rc.rhs * inv; s.live[p] = rc.rhs != 0.0 ? 1 : 0; }
         }
         // no barrier: in the next iteration warp w writes only row w of colA..C before the next barrier
     }
@@ -778,6 +782,7 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(DevConfig c, DevMes
                 if (z == 0) {
                     s.rhs0[p] = rc.rhs;
                     s.rhsS0[p] = rc.rhs * inv;
+                    s.live[p] = rc.rhs != 0.0 ? 1 : 0;  // seed of the line solver's active set
                     mx = fmax(mx, fabs(rc.rhs));
                     ss += rc.rhs * rc.rhs;
                 }
@@ -853,6 +858,7 @@ __global__ void flags_kernel(int stage, Scalars* sc, const double* __restrict__ 
             sc->susp_rr = 0.0;
             sc->n_checks = 0;
             sc->susp_sweeps = 0; sc->susp_stalled = 0; sc->dep_sweeps = 0;
+            sc->col_updates[0] = sc->col_updates[1] = sc->col_updates[2] = sc->col_updates[3] = 0ull;
             sc->dep_present = 0; sc->dep_ok = 0; sc->tail_done = 0; sc->drift_done = 0;
             sc->done = 0; sc->iters = 0; sc->dep_rhs_max = 0.0; sc->rr = 0.0; sc->bnorm2 = 0.0;
         } break;
@@ -926,8 +932,9 @@ __device__ __forceinline__ double halo_gather(const XT* x, const double* ghost, 
     return n < Tp ? (double)x[zS + n] : ghost[zG + (n - Tp)];
 }
 // HALO: neighbour slots >= Tp are ghost faces, read from `ghost` [L][nGp] (fp64 whatever XT is); else every neighbour is in x.
+// Returns whether the new column has a non-zero entry (used by the boundary columns of the active set; dead code elsewhere).
 template <int LT, typename CT, typename XT, bool HALO = false>
-__device__ __forceinline__ void gs_column(const SuspSystem& s, const DevMesh& m, int Lrt, int p, XT* x, const double* ghost = nullptr,
+__device__ __forceinline__ bool gs_column(const SuspSystem& s, const DevMesh& m, int Lrt, int p, XT* x, const double* ghost = nullptr,
                                           int nGp = 0) {
     const int Tp = m.Tp, S = m.S;
     const int L = LT > 0 ? LT : Lrt;
@@ -954,8 +961,10 @@ __device__ __forceinline__ void gs_column(const SuspSystem& s, const DevMesh& m,
 #pragma unroll
         for (int z = 1; z < LT; ++z) { y = g[z] - (double)bl[z] * y; g[z] = y; }
         x[(size_t)(LT - 1) * S + p] = (XT)y;
+        bool nz = y != 0.0;
 #pragma unroll
-        for (int z = LT - 2; z >= 0; --z) { y = g[z] - (double)cu[z] * y; x[(size_t)z * S + p] = (XT)y; }
+        for (int z = LT - 2; z >= 0; --z) { y = g[z] - (double)cu[z] * y; x[(size_t)z * S + p] = (XT)y; nz = nz || y != 0.0; }
+        return nz;
     } else {
         // runtime layer count: the own column of x is the scratch of the forward pass (fp64 x only)
         double y = 0.0;
@@ -972,10 +981,13 @@ __device__ __forceinline__ void gs_column(const SuspSystem& s, const DevMesh& m,
             y = g - (double)c.bl * y;
             x[xr + p] = (XT)y;
         }
+        bool nz = y != 0.0;
         for (int z = L - 2; z >= 0; --z) {
             y = (double)x[(size_t)z * S + p] - (double)load_cp<CT>(s, (size_t)z * Tp + p) * y;
             x[(size_t)z * S + p] = (XT)y;
+            nz = nz || y != 0.0;
         }
+        return nz;
     }
 }
 
@@ -1007,8 +1019,36 @@ struct SolvePlan {
     int check_first;  // first residual check after this many sweeps
     int check_every;
     int maxit;
+    int use_live;     // suspension only: skip the columns outside the active set (SuspSystem::live)
     double tol2;
 };
+
+// ---- the active set of the line solver.
+// Every solve starts from x0 = 0 and b is non-zero only on layer 0 of the saltating faces.  A column update is
+// x_p <- T_p^-1 (b_p - A_lat[p,:] x): with b_p = 0 and three neighbour columns that are still identically zero it yields exactly
+// zero, i.e. what x_p already holds, so it can be skipped without changing one bit of any iterate.  live[] (one byte per slot) is a
+// superset of the columns whose right-hand side or iterate is non-zero: seeded by the assembly with b_p != 0, set when a column is
+// updated while a neighbour is live (the set grows by one ring of faces per colour pass), never cleared within a solve.  A column
+// is updated iff it or one of its neighbours is live; the flags it reads belong to itself and to faces of OTHER colours, which the
+// current pass does not write, so there is no race and the set of updated columns does not depend on scheduling.  The residual
+// check skips the same columns (their residual is exactly zero).  A skipped column costs its flag byte, or its three neighbour
+// slots + their flags while it is not live, instead of 30-58 B per layer.  tests/models/active_set_model.py is the numpy statement.
+// Ghost neighbours (slot >= Tp, boundary columns across ranks) count as live: those columns are always updated, and flagged live
+// only when their new values are not all zero, so the always-updated set does not spread inwards from the partition edges.
+// 0: outside the active set (skip); 1: live already; 2: not live yet, but a neighbour is (update it and flag it).
+__device__ __forceinline__ int column_state(const unsigned char* live, const DevMesh& m, int p) {
+    if (live[p]) return 1;
+    const int Tp = m.Tp;
+    const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
+    if (n0 >= Tp || n1 >= Tp || n2 >= Tp) return 2;
+    return (live[n0] | live[n1] | live[n2]) ? 2 : 0;
+}
+// Adds a warp's count of column updates to Scalars::col_updates[k] and clears it (called by whole warps, outside divergent code).
+__device__ __forceinline__ void flush_col_count(Scalars* sc, int k, unsigned& cnt) {
+    const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&sc->col_updates[k], (unsigned long long)tot);
+    cnt = 0;
+}
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1095,6 +1135,20 @@ __device__ __forceinline__ double residual_column(const SuspSystem& s, const Dev
 // it at the usual rate (tests/models/fp32_x_model.py: the sweep count does not change when the switch is >= 10 sweeps before
 // the end).  All arithmetic, the right-hand side and the stopping rule are fp64 throughout.
 constexpr int kGsThreads = 512;
+// A thread's share of one colour pass: columns p0, p0 + stride, ... < p1, those outside the active set skipped (live != nullptr).
+template <int LT, typename CT, typename XT>
+__device__ __forceinline__ void gs_pass(const SuspSystem& s, const DevMesh& m, int L, int p0, int p1, int stride, XT* x,
+                                        unsigned char* live, unsigned& cnt) {
+    for (int p = p0; p < p1; p += stride) {
+        if (live) {
+            const int st = column_state(live, m, p);
+            if (st == 0) continue;
+            if (st == 2) live[p] = 1;
+        }
+        ++cnt;
+        gs_column<LT, CT, XT>(s, m, L, p, x);
+    }
+}
 template <int LT>
 __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem s, DevMesh m, int Lrt, ColourRanges cr, double* x, float* xf,
                                                                       Scalars* sc, double* __restrict__ partial, SolvePlan pl, unsigned* bar) {
@@ -1107,6 +1161,8 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem
     int prev_it = 0;
     const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int nx32 = (LT > 0 && xf) ? pl.nx32 : 0;
+    unsigned char* const live = pl.use_live ? s.live : nullptr;
+    unsigned cnt = 0;
     if (nx32 > 0) {  // x0 = 0 in the fp32 copy (ghost tails included)
         const size_t NS = (size_t)L * m.S;
         for (size_t k = t0; k < NS; k += stride) xf[k] = 0.f;
@@ -1115,9 +1171,9 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem
     while (it < pl.maxit) {
         const int phase = it < nx32 ? 0 : (it < pl.n32 ? 1 : 2);
         for (int c = 0; c < cr.n; ++c) {
-            if (phase == 0) for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) gs_column<LT, float, float>(s, m, L, p, xf);
-            else if (phase == 1) for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) gs_column<LT, float, double>(s, m, L, p, x);
-            else for (int p = cr.start[c] + t0; p < cr.end[c]; p += stride) gs_column<LT, double, double>(s, m, L, p, x);
+            if (phase == 0) gs_pass<LT, float, float>(s, m, L, cr.start[c] + t0, cr.end[c], stride, xf, live, cnt);
+            else if (phase == 1) gs_pass<LT, float, double>(s, m, L, cr.start[c] + t0, cr.end[c], stride, x, live, cnt);
+            else gs_pass<LT, double, double>(s, m, L, cr.start[c] + t0, cr.end[c], stride, x, live, cnt);
             grid_barrier_fenced(bar, target);
         }
         ++it;
@@ -1127,17 +1183,26 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem
             grid_barrier_fenced(bar, target);
         }
         const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
+        if (check || it == nx32 || it == pl.n32) flush_col_count(sc, phase, cnt);
         if (!check) continue;
         double a = 0.0;
         if (LT > 0) {
-            for (int p = t0; p < m.Tp; p += stride) a += residual_column<(LT > 0 ? LT : 1)>(s, m, x, p);
+            for (int p = t0; p < m.Tp; p += stride) {
+                if (live && !column_state(live, m, p)) continue;  // b_p = 0, x = 0 on p and its neighbours: residual exactly 0
+                ++cnt;
+                a += residual_column<(LT > 0 ? LT : 1)>(s, m, x, p);
+            }
         } else {
-            for (int p = t0; p < m.Tp; p += stride)
+            for (int p = t0; p < m.Tp; p += stride) {
+                if (live && !column_state(live, m, p)) continue;
+                ++cnt;
                 for (int z = 0; z < L; ++z) {
                     const double v = ((z == 0) ? s.rhs0[p] : 0.0) - spmv_row(s, m, L, x, z, p);
                     a += v * v;
                 }
+            }
         }
+        flush_col_count(sc, 3, cnt);
         a = block_sum(a);
         if (threadIdx.x == 0) partial[blockIdx.x] = a;
         grid_barrier_fenced(bar, target);
@@ -2431,6 +2496,8 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
     int prev_it = 0;
     const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int nx32 = (LT > 0 && xf) ? pl.nx32 : 0;
+    unsigned char* const live = pl.use_live ? s.live : nullptr;  // the active set (column_state above)
+    unsigned cnt = 0;
     if (nx32 > 0) {
         const size_t NS = (size_t)L * S;
         for (size_t k = t0; k < NS; k += stride) xf[k] = 0.f;
@@ -2457,9 +2524,12 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
                 link_wait(hl);
                 for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nbc; i += nbb * blockDim.x) {
                     const int p = cr.start[c] + i;
-                    if (phase == 0) gs_column<LT, float, float, true>(s, m, L, p, xf, hl.ghost, hl.nGp);
-                    else if (phase == 1) gs_column<LT, float, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
-                    else gs_column<LT, double, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
+                    bool nz;  // boundary columns are always updated (their ghosts may have become non-zero) and always sent
+                    if (phase == 0) nz = gs_column<LT, float, float, true>(s, m, L, p, xf, hl.ghost, hl.nGp);
+                    else if (phase == 1) nz = gs_column<LT, float, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
+                    else nz = gs_column<LT, double, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
+                    if (live && nz) live[p] = 1;
+                    ++cnt;
                     const int e0 = hl.bptr[xh.boff[c] + i], e1 = hl.bptr[xh.boff[c] + i + 1];
                     for (int k = e0; k < e1; ++k) {
                         double* dst = hl.remote[k];
@@ -2470,11 +2540,10 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
                 link_signal(hl, nbb);
             } else {
                 const int strideI = ((int)gridDim.x - nbb) * blockDim.x;
-                for (int p = cr.start[c] + nbc + ((int)blockIdx.x - nbb) * (int)blockDim.x + (int)threadIdx.x; p < cr.end[c]; p += strideI) {
-                    if (phase == 0) gs_column<LT, float, float>(s, m, L, p, xf);
-                    else if (phase == 1) gs_column<LT, float, double>(s, m, L, p, x);
-                    else gs_column<LT, double, double>(s, m, L, p, x);
-                }
+                const int pI = cr.start[c] + nbc + ((int)blockIdx.x - nbb) * (int)blockDim.x + (int)threadIdx.x;
+                if (phase == 0) gs_pass<LT, float, float>(s, m, L, pI, cr.end[c], strideI, xf, live, cnt);
+                else if (phase == 1) gs_pass<LT, float, double>(s, m, L, pI, cr.end[c], strideI, x, live, cnt);
+                else gs_pass<LT, double, double>(s, m, L, pI, cr.end[c], strideI, x, live, cnt);
             }
             grid_barrier_fenced(bar, target);
         }
@@ -2485,6 +2554,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
             grid_barrier_fenced(bar, target);
         }
         const bool check = (it >= pl.check_first && (it - pl.check_first) % pl.check_every == 0) || it >= pl.maxit;
+        if (check || it == nx32 || it == pl.n32) flush_col_count(sc, phase, cnt);
         if (!check) continue;
         // ---- ||b - A x||^2 with the ghosts the next sweep would read
         {
@@ -2495,6 +2565,8 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
         }
         double a = 0.0;
         for (int p = t0; p < Tp; p += stride) {
+            if (live && !column_state(live, m, p)) continue;  // b_p = 0, x = 0 on p and its neighbours: residual exactly 0
+            ++cnt;
             const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
             double xm = 0.0, xc = x[p], cp_prev = 0.0;
             for (int z = 0; z < L; ++z) {
@@ -2513,6 +2585,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
                 cp_prev = cp;
             }
         }
+        flush_col_count(sc, 3, cnt);
         a = block_sum(a);
         if (threadIdx.x == 0) partial[blockIdx.x] = a;
         grid_barrier_fenced(bar, target);

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define PBSM3D_ABI_VERSION 7
+#define PBSM3D_ABI_VERSION 8
 
 enum {
     PBSM3D_OK = 0,
@@ -203,6 +203,13 @@ typedef struct pbsm3d_stats {
     int32_t sweeps_fp32_x;           /* of sweeps_timed_fp32: the leading ones that also kept the iterate x in fp32 STORAGE */
     int32_t persistent_kernels;      /* 1: each solve ran as one cooperative launch (single rank); then ms_line_sweeps is the
                                         duration of that launch = sweeps_timed sweeps + residual_checks checks */
+    int32_t active_set;              /* 1: the persistent line solver skipped the columns outside its active set (columns whose
+                                        right-hand side and whose neighbours' iterates are still exactly zero: their update is a
+                                        no-op, so every iterate is bit-identical to the full sweep's; PBSM3D_ACTIVE_SET=0 disables) */
+    int64_t column_updates_fp32_x;   /* persistent line solver, this rank: face-column updates executed in the sweeps of each */
+    int64_t column_updates_fp32;     /*   storage phase (fp32 x + fp32 coefficients / fp32 coefficients / all fp64): the sum is */
+    int64_t column_updates_fp64;     /*   sweeps_timed x local faces without the active set, less with it */
+    int64_t columns_checked;         /* face columns evaluated by the residual checks (residual_checks x local faces without it) */
 } pbsm3d_stats;
 
 typedef struct pbsm3d_handle pbsm3d_handle;

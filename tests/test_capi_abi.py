@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pbsm3d.h but not exported"
     assert set(syms) == set(capi.SYMBOLS), "ctypes table and header disagree"
-    assert lib.pbsm3d_abi_version() == capi.ABI_VERSION == 7
+    assert lib.pbsm3d_abi_version() == capi.ABI_VERSION == 8
 
 
 def test_config_defaults_are_the_reference_defaults(lib):

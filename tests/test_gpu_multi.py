@@ -20,12 +20,13 @@ def ngpus():
     return torch.cuda.device_count()
 
 
-def run_ranks(tmp_path, world, meshname, L, solver, nsteps, transport="peer"):
-    out = str(tmp_path / f"mp_{meshname}_{world}_{solver}_{transport}.npz")
+def run_ranks(tmp_path, world, meshname, L, solver, nsteps, transport="peer", extra_env=None, tag=""):
+    out = str(tmp_path / f"mp_{meshname}_{world}_{solver}_{transport}{tag}.npz")
     env = dict(os.environ)
     env.pop("PBSM3D_HALO", None)
     if transport in ("nccl", "staged"):
         env["PBSM3D_HALO"] = transport
+    env.update(extra_env or {})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "mp_worker.py"), out, meshname, str(L), str(solver), str(nsteps)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
@@ -89,6 +90,22 @@ def test_max_ranks_on_uniform_mesh(tmp_path):
     # and its halo does not stall: median synchronous host-buffer call on 3 600 faces per rank, max over ranks
     assert float(g["scale_wind_vert_call_ms"]) < 5.0, float(g["scale_wind_vert_call_ms"])
     h.close()
+
+
+def test_active_set_across_ranks_never_changes_an_iterate(tmp_path):
+    """The active set of the persistent line solver across ranks (boundary columns always updated, flagged live by their values;
+    interior columns by their neighbours' flags): the partitioned iterates must be IDENTICAL with and without it."""
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    L = 10
+    g = {f: run_ranks(tmp_path, 2, "uniform120", L, capi.SOLVER_AUTO, 3, extra_env={"PBSM3D_ACTIVE_SET": f}, tag=f"_as{f}") for f in ("1", "0")}
+    assert int(g["1"]["halo_fused"]) > 0
+    for k in range(3):  # step 1 is a calm hour; step 2 runs the fp32 storage phases
+        assert np.array_equal(g["1"][f"iters_{k}"], g["0"][f"iters_{k}"])
+        for z in range(L):
+            assert np.array_equal(g["1"][f"c{z}_{k}"], g["0"][f"c{z}_{k}"]), (k, z)
+        for v in ("Qsusp", "Qsalt", "Qsubl", "drift_mass"):
+            assert np.array_equal(g["1"][f"{v}_{k}"], g["0"][f"{v}_{k}"]), (v, k)
 
 
 def slide_partitioned_oracle(gmesh, world, sd, sdv, swe, max_depth=None, cos_slope=None):

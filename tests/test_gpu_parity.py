@@ -326,6 +326,53 @@ def test_fp32_sweep_streams_do_not_move_the_answer(slope):
         assert rel_l2(res[1][1][v], res[0][1][v]) <= 1e-8
 
 
+def _patchy(cx, cy, seed=7):
+    """Bench forcing with saltation confined to wind-exposed patches (elsewhere 3 m/s: no saltation, zero right-hand side)."""
+    F = synthetic.forcing(cx, cy, seed=seed)
+    s = synthetic._smooth_field(cx - cx.mean(), cy - cy.mean(), np.random.default_rng(5), scale=1500.0)
+    F["U_R"] = np.where(s > 0.4, F["U_R"], 3.0)
+    sd, z0 = F["snowdepthavg"], 0.01
+    F["U_2m_above_srf"] = np.maximum(0.1, F["U_R"] * np.log((2.0 + sd - (sd + z0)) / z0) / np.log((50.0 - (sd + z0)) / z0))
+    return F
+
+
+@pytest.mark.parametrize("L", [10, 12], ids=["L10", "L12-generic"])
+@pytest.mark.parametrize("meshname", ["uniform", "variable"])
+def test_active_set_never_changes_an_iterate(meshname, L, monkeypatch):
+    """The persistent line solver skips columns whose right-hand side and whose neighbours' iterates are still exactly zero
+    (tests/models/active_set_model.py): that update is a no-op, so the solution, every output and the sweep count must be
+    IDENTICAL to the full sweep's (PBSM3D_ACTIVE_SET=0), on every step of a handle (fp64-only first step, fp32 phases later),
+    while fewer column updates are executed."""
+    mesh = synthetic.uniform_mesh(120, 120) if meshname == "uniform" else synthetic.variable_mesh(30000)
+    geo = mesh.geometry()
+    forc = [_patchy(geo.cx, geo.cy, seed=3), _patchy(geo.cx, geo.cy, seed=4), synthetic.forcing(geo.cx, geo.cy, seed=7)]
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PBSM3D_ACTIVE_SET", flag)
+        h = capi.Handle(capi.default_config(**functest_kw(L)), mesh)
+        res[flag] = []
+        for F in forc + forc[:1]:
+            outs, st = h.step(3600.0, F)
+            res[flag].append((h.solution().copy(), {k: v.copy() for k, v in outs.items()}, st))
+        h.close()
+    T = mesh.n_local
+    saved = []
+    for (x1, o1, s1), (x0, o0, s0) in zip(res["1"], res["0"]):
+        assert s1["persistent_kernels"] == 1 and s1["active_set"] == 1 and s0["active_set"] == 0
+        assert s1["suspension_present"] == 1
+        assert s1["suspension_iterations"] == s0["suspension_iterations"] and s1["suspension_residual"] == s0["suspension_residual"]
+        assert np.array_equal(x1, x0)
+        for v in o1:
+            assert np.array_equal(o1[v], o0[v]), v
+        n1 = s1["column_updates_fp32_x"] + s1["column_updates_fp32"] + s1["column_updates_fp64"]
+        n0 = s0["column_updates_fp32_x"] + s0["column_updates_fp32"] + s0["column_updates_fp64"]
+        assert n0 == s0["sweeps_timed"] * T
+        assert s0["residual_checks"] * T <= s0["columns_checked"] <= s0["residual_checks"] * (T + 256)  # padding slots included
+        assert 0 < n1 <= n0 and s1["columns_checked"] <= s0["columns_checked"]
+        saved.append(1.0 - n1 / n0)
+    assert max(saved[:2]) > 0.10, saved  # the patchy fields leave a good part of the domain untouched
+
+
 @pytest.mark.parametrize("L", [15, 20, 12])
 def test_all_layer_count_specialisations(slope, L):
     """nLayer 15 and 20 have compile-time sweep/residual kernels of their own (config c5 uses 20), 12 takes the generic path; each on
