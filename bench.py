@@ -801,6 +801,38 @@ def main():
             del hv
         except Exception as e:
             variants = {"default_block": {"error": repr(e)}}
+        # ---- saltation on wind-exposed patches only (most hours of a real winter): the line solver's active set against the
+        #      plain sweep on the same fields (PBSM3D_ACTIVE_SET is read when a handle is created)
+        if world == 1:
+            try:
+                Fp = [synthetic.patchy_forcing(geo.cx[:T], geo.cy[:T], seed=7, step=k) for k in range(N_FORCING)]
+                dev_p = [{n: torch.from_numpy(F[n]).cuda() for n in names} for F in Fp]
+                pv = {"what": "synthetic.patchy_forcing: the c2 fields with the reference-height wind cut to 3 m/s outside "
+                              "wind-exposed patches; same mesh and PBSM3D block", "steps": 6}
+                saved_env = os.environ.get("PBSM3D_ACTIVE_SET")
+                for key, env in (("active_set", None), ("plain_sweep", "0")):
+                    if env is None:
+                        os.environ.pop("PBSM3D_ACTIVE_SET", None)
+                    else:
+                        os.environ["PBSM3D_ACTIVE_SET"] = env
+                    hp = capi.Handle(cfg, mesh, device=local_rank, rank=rank, n_ranks=world, unique_id=job.new_uid())
+                    ap_ = timed_steps(job, hp, dev_p, dev_out, 6, 3)
+                    sp = ap_["last"]
+                    nup = sp.get("column_updates_fp32_x", 0) + sp.get("column_updates_fp32", 0) + sp.get("column_updates_fp64", 0)
+                    pv[key] = {"ms_per_step": ap_["ms_step"], "ms_suspension_solve": ap_["phases"]["ms_suspension_solve"] / 6,
+                               "sweeps": ap_["susp_its"][:3], "active_set_used": bool(sp.get("active_set")),
+                               "faces_with_rhs_share": sp.get("faces_with_rhs", 0) / T,
+                               "column_updates_executed": nup / max(sp["sweeps_timed"] * T, 1)}
+                    hp.close()
+                    del hp
+                if saved_env is None:
+                    os.environ.pop("PBSM3D_ACTIVE_SET", None)
+                else:
+                    os.environ["PBSM3D_ACTIVE_SET"] = saved_env
+                variants["patchy_saltation"] = pv
+                del dev_p
+            except Exception as e:
+                variants["patchy_saltation"] = {"error": repr(e)}
     h.close()
     del dev_in, dev_out, pin_in, pin_out
     torch.cuda.empty_cache()

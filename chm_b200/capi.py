@@ -74,7 +74,7 @@ class Stats(C.Structure):
         ("sweeps_timed", C.c_int32), ("sweeps_timed_fp32", C.c_int32), ("ms_line_sweeps_fp32", C.c_float), ("n_colours", C.c_int32), ("deposition_solver_used", C.c_int32), ("host_syncs", C.c_int32),
         ("halo_exchanges", C.c_int32), ("halo_transport", C.c_int32), ("halo_fused", C.c_int32),
         ("residual_checks", C.c_int32), ("sweeps_fp32_x", C.c_int32), ("persistent_kernels", C.c_int32),
-        ("active_set", C.c_int32), ("column_updates_fp32_x", C.c_int64), ("column_updates_fp32", C.c_int64),
+        ("active_set", C.c_int32), ("faces_with_rhs", C.c_int32), ("column_updates_fp32_x", C.c_int64), ("column_updates_fp32", C.c_int64),
         ("column_updates_fp64", C.c_int64), ("columns_checked", C.c_int64),
     ]
 

@@ -19,6 +19,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -198,7 +199,10 @@ struct pbsm3d_handle {
     int sweeps_timed = 0, sweeps_timed32 = 0;
     // persistent (cooperative) solver kernels: single rank
     bool persistent = false;
-    bool active_set = true;  // PBSM3D_ACTIVE_SET=0: the persistent line solver updates every column in every sweep
+    // The persistent line solver's active set (pbsm3d_kernels.cuh): PBSM3D_ACTIVE_SET=0 never, =1 always; default: on the steps
+    // where at most kActiveSetMaxSeeded of the faces have a non-zero right-hand side (beyond that the set covers the mesh within a
+    // few sweeps and the measured gain is ~1 %, profiles/r2ae_summary.md)
+    int active_set = 2;
     bool sor_persistent = false;        // the deposition solve too: only while its working set stays in the L2 (else per-pass launches
                                         // stream better: 17 vs 21 ms on 10 M faces, profiles/r2b)
     unsigned* grid_bar = nullptr;       // [2] grid-barrier counters (suspension, deposition)
@@ -799,7 +803,7 @@ using GsHaloKernel = void (*)(SuspSystem, DevMesh, int, ColourRanges, double*, f
 int setup_persistent(pbsm3d_handle* h) {
     const char* env = getenv("PBSM3D_PERSISTENT");
     const char* env_as = getenv("PBSM3D_ACTIVE_SET");
-    h->active_set = !(env_as && atoi(env_as) == 0);
+    h->active_set = env_as ? (atoi(env_as) == 0 ? 0 : 1) : 2;
     h->persistent = false;
     if (env && atoi(env) == 0) return 0;
     const bool multi = h->n_ranks > 1;
@@ -904,6 +908,10 @@ void fill_boundary(const pbsm3d_handle* h, H& x) {
     for (int c = 0; c < h->n_colours; ++c)
         if (h->ccount[c] > 0) { x.nb[k] = h->nb[c]; x.boff[k] = h->boff[c]; ++k; }
 }
+constexpr double kActiveSetMaxSeeded = 0.4;
+int live_max_seeds(const pbsm3d_handle* h) {
+    return h->active_set == 1 ? INT_MAX : (int)(kActiveSetMaxSeeded * h->T);
+}
 int line_enqueue_persistent(pbsm3d_handle* h) {
     const int maxit = h->cfg.max_iterations;
     const bool known = h->pred_sweeps > 0;
@@ -916,6 +924,7 @@ int line_enqueue_persistent(pbsm3d_handle* h) {
     pl.nx32 = (h->xf && !(nox && atoi(nox) == 0)) ? std::max(0, std::min(pl.n32, pl.check_first - 10)) : 0;
     pl.maxit = maxit;
     pl.use_live = h->active_set ? 1 : 0;
+    pl.live_max_seeds = live_max_seeds(h);
     pl.tol2 = h->cfg.tolerance * h->cfg.tolerance;
     h->plan_n32 = pl.n32;
     h->plan_nx32 = pl.nx32;
@@ -953,7 +962,7 @@ int sor_enqueue_persistent(pbsm3d_handle* h) {
     const int maxit = std::min(h->cfg.max_iterations, 6 * h->sor_kest + 64);
     const bool known = h->pred_sor > 0;
     SolvePlan pl;
-    pl.n32 = pl.nx32 = pl.use_live = 0;
+    pl.n32 = pl.nx32 = pl.use_live = pl.live_max_seeds = 0;
     pl.check_first = std::max(1, std::min(maxit, known ? h->pred_sor : h->sor_kest));
     pl.check_every = known ? 1 : 4;
     pl.maxit = maxit;
@@ -1670,6 +1679,7 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
     CU(cudaEventRecord(h->ev[0], s));
     // x0 = 0 (Belos starts from the zero vector); ghost tails included
     CU(cudaMemsetAsync(h->x, 0, h->NS * sizeof(double), s));
+    CU(cudaMemsetAsync(&h->sc->n_seeds, 0, sizeof(unsigned), s));  // counted by the row kernel
     h->x_first = true;
     // A+B: zeroSystem is implicit (every coefficient is overwritten); saltation + suspension assembly,
     // C: suspension_present = ||rhs||_inf > 1e-12 and ||b||_2^2, reduced inside the assembly kernel
@@ -1913,7 +1923,8 @@ int step_impl(pbsm3d_handle* h, double dt, const DevForcing& f_in, const double*
         st->column_updates_fp32 = (int64_t)h->h_sc->col_updates[1];
         st->column_updates_fp64 = (int64_t)h->h_sc->col_updates[2];
         st->columns_checked = (int64_t)h->h_sc->col_updates[3];
-        st->active_set = h->active_set ? 1 : 0;
+        st->active_set = (h->active_set && h->h_sc->n_seeds_step <= (unsigned)live_max_seeds(h)) ? 1 : 0;
+        st->faces_with_rhs = (int32_t)h->h_sc->n_seeds_step;
     }
     st->sweeps_fp32_x = h->persistent ? std::min(h->plan_nx32, h->sweeps_timed) : 0;
     st->persistent_kernels = h->persistent ? 1 : 0;

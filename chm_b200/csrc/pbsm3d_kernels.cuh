@@ -101,6 +101,8 @@ struct Scalars {
     unsigned ticket[4];
     unsigned long long col_updates[4];  // persistent line solver: face-column updates executed in each storage phase
                                         // (fp32 x / fp32 coefficients / fp64) and columns evaluated by the residual checks
+    unsigned n_seeds;                   // faces with a non-zero right-hand side, counted by the row kernel (zeroed by the host
+    unsigned n_seeds_step;              // at the start of a step); its value when the step's solve starts (FLAGS_SUSP)
     int peer_error;                   // sticky: a peer-memory wait timed out (see PeerTable)
 };
 
@@ -643,6 +645,12 @@ __device__ __forceinline__ void store_row(const SuspSystem& s, size_t r, size_t 
     s.pack32[r] = make_float4((float)l0, (float)l1, (float)l2, (float)bS);
 }
 
+// Faces with b != 0 (the seeds of the line solver's active set), counted per warp into Scalars::n_seeds; whole warps call it.
+__device__ __forceinline__ void count_seeds(Scalars* sc, unsigned n) {
+    const unsigned tot = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&sc->n_seeds, tot);
+}
+
 // Per-face records between the prelude kernel and the row kernels: SoA [kRecD][Tp] doubles + [Tp] ints, SLOT order (so the row
 // kernels read records and write every stream fully coalesced whatever the number of colours).
 constexpr int kRecD = 21;
@@ -703,6 +711,7 @@ assemble_tile_kernel(DevConfig c, DevMesh m, FaceRecs R, SuspSystem s, int i0, i
     const int ntiles = (i1 - i0 + 31) / 32;
     const size_t LTp = (size_t)L * m.Tp;
     double mx = 0.0, ss = 0.0;
+    unsigned nseed = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = i0 + tile * 32 + lane;  // a slot
         const bool act = i < i1 && w < L && (R.i[i] & 16);
@@ -741,10 +750,15 @@ assemble_tile_kernel(DevConfig c, DevMesh m, FaceRecs R, SuspSystem s, int i0, i
         if (act) {
             const double den = colA[w * 32 + lane], inv = colB[w * 32 + lane], cp = colC[w * 32 + lane];
             store_row(s, (size_t)w * m.Tp + p, LTp, rc, den, inv, cp);
-            if (w == 0) { s.rhs0[p] = rc.rhs; s.rhsS0[p] = rc.rhs * inv; s.live[p] = rc.rhs != 0.0 ? 1 : 0; }
+            if (w == 0) {
+                s.rhs0[p] = rc.rhs; s.rhsS0[p] = rc.rhs * inv;
+                s.live[p] = rc.rhs != 0.0 ? 1 : 0;  // seed of the line solver's active set
+                nseed += rc.rhs != 0.0 ? 1u : 0u;
+            }
         }
         // no barrier: in the next iteration warp w writes only row w of colA..C before the next barrier
     }
+    count_seeds(sc, nseed);
     double o0, o1;
     if (grid_fold<2>(mx, ss, 1, 0, partial, pstride, &sc->ticket[0], o0, o1)) {
         if (threadIdx.x == 0) { red[0] = o0; red[1] = o1; }
@@ -758,6 +772,7 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(DevConfig c, DevMes
                                                              double* __restrict__ partial, int pstride, Scalars* sc,
                                                              double* __restrict__ red) {
     double mx = 0.0, ss = 0.0;
+    unsigned nseed = 0;
     const int ntiles = (i1 - i0 + 127) / 128;
     const int L = c.L;
     const size_t LTp = (size_t)L * m.Tp;
@@ -783,12 +798,14 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(DevConfig c, DevMes
                     s.rhs0[p] = rc.rhs;
                     s.rhsS0[p] = rc.rhs * inv;
                     s.live[p] = rc.rhs != 0.0 ? 1 : 0;  // seed of the line solver's active set
+                    nseed += rc.rhs != 0.0 ? 1u : 0u;
                     mx = fmax(mx, fabs(rc.rhs));
                     ss += rc.rhs * rc.rhs;
                 }
             }
         }
     }
+    count_seeds(sc, nseed);
     double o0, o1;
     if (grid_fold<2>(mx, ss, 1, 0, partial, pstride, &sc->ticket[0], o0, o1)) {
         if (threadIdx.x == 0) { red[0] = o0; red[1] = o1; }
@@ -859,6 +876,7 @@ __global__ void flags_kernel(int stage, Scalars* sc, const double* __restrict__ 
             sc->n_checks = 0;
             sc->susp_sweeps = 0; sc->susp_stalled = 0; sc->dep_sweeps = 0;
             sc->col_updates[0] = sc->col_updates[1] = sc->col_updates[2] = sc->col_updates[3] = 0ull;
+            sc->n_seeds_step = sc->n_seeds;
             sc->dep_present = 0; sc->dep_ok = 0; sc->tail_done = 0; sc->drift_done = 0;
             sc->done = 0; sc->iters = 0; sc->dep_rhs_max = 0.0; sc->rr = 0.0; sc->bnorm2 = 0.0;
         } break;
@@ -1019,7 +1037,8 @@ struct SolvePlan {
     int check_first;  // first residual check after this many sweeps
     int check_every;
     int maxit;
-    int use_live;     // suspension only: skip the columns outside the active set (SuspSystem::live)
+    int use_live;     // suspension only: skip the columns outside the active set (SuspSystem::live) ...
+    int live_max_seeds;  // ... when at most this many faces have a non-zero right-hand side (Scalars::n_seeds_step)
     double tol2;
 };
 
@@ -1161,7 +1180,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem
     int prev_it = 0;
     const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int nx32 = (LT > 0 && xf) ? pl.nx32 : 0;
-    unsigned char* const live = pl.use_live ? s.live : nullptr;
+    unsigned char* const live = (pl.use_live && sc->n_seeds_step <= (unsigned)pl.live_max_seeds) ? s.live : nullptr;
     unsigned cnt = 0;
     if (nx32 > 0) {  // x0 = 0 in the fp32 copy (ghost tails included)
         const size_t NS = (size_t)L * m.S;
@@ -2496,7 +2515,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
     int prev_it = 0;
     const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int nx32 = (LT > 0 && xf) ? pl.nx32 : 0;
-    unsigned char* const live = pl.use_live ? s.live : nullptr;  // the active set (column_state above)
+    unsigned char* const live = (pl.use_live && sc->n_seeds_step <= (unsigned)pl.live_max_seeds) ? s.live : nullptr;  // column_state
     unsigned cnt = 0;
     if (nx32 > 0) {
         const size_t NS = (size_t)L * S;

@@ -190,6 +190,19 @@ def forcing(cx: np.ndarray, cy: np.ndarray, seed: int = 7, step: int = 0, calm: 
             "vw_dir": vw_dir, "fetch": fetch}
 
 
+def patchy_forcing(cx: np.ndarray, cy: np.ndarray, seed: int = 7, step: int = 0, scale: float = 2500.0,
+                   threshold: float = 0.5) -> Dict[str, np.ndarray]:
+    """`forcing` with saltation confined to wind-exposed patches, as on most hours of a real winter: where a smooth field
+    of length scale `scale` is below `threshold` the reference-height wind drops to 3 m/s (no saltation, zero right-hand
+    side of the suspension system); about a fifth to a third of the faces keep the stormy wind."""
+    f = forcing(cx, cy, seed=seed, step=step)
+    s = _smooth_field(cx - 488000.0, cy - 6710000.0, np.random.default_rng(5 + seed + 1000 * step), scale=scale)
+    f["U_R"] = np.where(s > threshold, f["U_R"], 3.0)
+    sd, z0 = f["snowdepthavg"], 0.01
+    f["U_2m_above_srf"] = np.maximum(0.1, f["U_R"] * np.log((2.0 + sd - (sd + z0)) / z0) / np.log((50.0 - (sd + z0)) / z0))
+    return f
+
+
 def shrub_params(n: int, frac: float = 0.2, seed: int = 11, canopy: float = 1.0) -> Dict[str, np.ndarray]:
     """Variant with `frac` of faces carrying shrubs (CanopyHeight `canopy`, N 1, dv 0.8), others bare.
     With snow depths of 0.2–1.5 m a 1 m canopy gives all three regimes: buried, partly exposed (lambda > 0)

@@ -205,7 +205,9 @@ typedef struct pbsm3d_stats {
                                         duration of that launch = sweeps_timed sweeps + residual_checks checks */
     int32_t active_set;              /* 1: the persistent line solver skipped the columns outside its active set (columns whose
                                         right-hand side and whose neighbours' iterates are still exactly zero: their update is a
-                                        no-op, so every iterate is bit-identical to the full sweep's; PBSM3D_ACTIVE_SET=0 disables) */
+                                        no-op, so every iterate is bit-identical to the full sweep's).  Used on the steps where at
+                                        most 40 % of the faces have a non-zero right-hand side; PBSM3D_ACTIVE_SET=0 / 1: never / always */
+    int32_t faces_with_rhs;          /* local faces with a non-zero right-hand side in this step (the saltating faces) */
     int64_t column_updates_fp32_x;   /* persistent line solver, this rank: face-column updates executed in the sweeps of each */
     int64_t column_updates_fp32;     /*   storage phase (fp32 x + fp32 coefficients / fp32 coefficients / all fp64): the sum is */
     int64_t column_updates_fp64;     /*   sweeps_timed x local faces without the active set, less with it */

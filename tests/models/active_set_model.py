@@ -74,13 +74,8 @@ def solve(sy, skip, tol=1e-8, maxit=200):
 
 
 def patchy(cx, cy):
-    """Saltation on wind-exposed patches only (a third of the domain), as on a real winter day."""
-    f = synthetic.forcing(cx, cy)
-    s = synthetic._smooth_field(cx - cx.mean(), cy - cy.mean(), np.random.default_rng(5), scale=2500.0)
-    f["U_R"] = np.where(s > 0.5, f["U_R"], 3.0)
-    z0 = 0.01; sd = f["snowdepthavg"]
-    f["U_2m_above_srf"] = np.maximum(0.1, f["U_R"] * np.log((2.0 + sd - (sd + z0)) / z0) / np.log((50.0 - (sd + z0)) / z0))
-    return f
+    """Saltation on wind-exposed patches only, as on a real winter day (synthetic.patchy_forcing)."""
+    return synthetic.patchy_forcing(cx, cy)
 
 
 def run(n=236, step=0):

@@ -328,12 +328,7 @@ def test_fp32_sweep_streams_do_not_move_the_answer(slope):
 
 def _patchy(cx, cy, seed=7):
     """Bench forcing with saltation confined to wind-exposed patches (elsewhere 3 m/s: no saltation, zero right-hand side)."""
-    F = synthetic.forcing(cx, cy, seed=seed)
-    s = synthetic._smooth_field(cx - cx.mean(), cy - cy.mean(), np.random.default_rng(5), scale=1500.0)
-    F["U_R"] = np.where(s > 0.4, F["U_R"], 3.0)
-    sd, z0 = F["snowdepthavg"], 0.01
-    F["U_2m_above_srf"] = np.maximum(0.1, F["U_R"] * np.log((2.0 + sd - (sd + z0)) / z0) / np.log((50.0 - (sd + z0)) / z0))
-    return F
+    return synthetic.patchy_forcing(cx, cy, seed=seed, scale=1500.0, threshold=0.4)
 
 
 @pytest.mark.parametrize("L", [10, 12], ids=["L10", "L12-generic"])
@@ -371,6 +366,31 @@ def test_active_set_never_changes_an_iterate(meshname, L, monkeypatch):
         assert 0 < n1 <= n0 and s1["columns_checked"] <= s0["columns_checked"]
         saved.append(1.0 - n1 / n0)
     assert max(saved[:2]) > 0.10, saved  # the patchy fields leave a good part of the domain untouched
+
+
+def test_active_set_switches_on_by_itself_when_saltation_is_patchy(monkeypatch):
+    """Default (PBSM3D_ACTIVE_SET unset): the active set is used on the steps where at most 40 % of the faces have a non-zero
+    right-hand side, and the plain sweep otherwise; either way the results equal the other mode's bit for bit."""
+    monkeypatch.delenv("PBSM3D_ACTIVE_SET", raising=False)
+    mesh = synthetic.uniform_mesh(120, 120)
+    geo = mesh.geometry()
+    T = mesh.n_local
+    h = capi.Handle(capi.default_config(**functest_kw(10)), mesh)
+    monkeypatch.setenv("PBSM3D_ACTIVE_SET", "0")
+    h0 = capi.Handle(capi.default_config(**functest_kw(10)), mesh)
+    seen = set()
+    for F in (_patchy(geo.cx, geo.cy, seed=4), synthetic.forcing(geo.cx, geo.cy, seed=7), _patchy(geo.cx, geo.cy, seed=3)):
+        outs, st = h.step(3600.0, F)
+        o0, s0 = h0.step(3600.0, F)
+        assert st["faces_with_rhs"] == s0["faces_with_rhs"] == int(np.count_nonzero(h.suspension_system()["rhs0"]))
+        assert st["active_set"] == (1 if st["faces_with_rhs"] <= 0.4 * T else 0) and s0["active_set"] == 0
+        seen.add(st["active_set"])
+        assert np.array_equal(h.solution(), h0.solution())
+        for v in outs:
+            assert np.array_equal(outs[v], o0[v]), v
+    assert seen == {0, 1}
+    h.close()
+    h0.close()
 
 
 @pytest.mark.parametrize("L", [15, 20, 12])
