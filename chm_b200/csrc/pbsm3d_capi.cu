@@ -925,6 +925,10 @@ int line_enqueue_persistent(pbsm3d_handle* h) {
     pl.maxit = maxit;
     pl.use_live = h->active_set ? 1 : 0;
     pl.live_max_seeds = live_max_seeds(h);
+    {
+        const char* e = getenv("PBSM3D_NBS_PREFETCH");
+        pl.prefetch = (e && atoi(e) == 0) ? 0 : 1;
+    }
     pl.tol2 = h->cfg.tolerance * h->cfg.tolerance;
     h->plan_n32 = pl.n32;
     h->plan_nx32 = pl.nx32;
@@ -962,7 +966,7 @@ int sor_enqueue_persistent(pbsm3d_handle* h) {
     const int maxit = std::min(h->cfg.max_iterations, 6 * h->sor_kest + 64);
     const bool known = h->pred_sor > 0;
     SolvePlan pl;
-    pl.n32 = pl.nx32 = pl.use_live = pl.live_max_seeds = 0;
+    pl.n32 = pl.nx32 = pl.use_live = pl.live_max_seeds = pl.prefetch = 0;
     pl.check_first = std::max(1, std::min(maxit, known ? h->pred_sor : h->sor_kest));
     pl.check_every = known ? 1 : 4;
     pl.maxit = maxit;

@@ -951,12 +951,16 @@ __device__ __forceinline__ double halo_gather(const XT* x, const double* ghost, 
 }
 // HALO: neighbour slots >= Tp are ghost faces, read from `ghost` [L][nGp] (fp64 whatever XT is); else every neighbour is in x.
 // Returns whether the new column has a non-zero entry (used by the boundary columns of the active set; dead code elsewhere).
+struct Nbs { int n0, n1, n2; };  // the three neighbour slots of a column
+__device__ __forceinline__ Nbs load_nbs(const DevMesh& m, int p) {
+    return {m.nbs[p], m.nbs[(size_t)m.Tp + p], m.nbs[(size_t)2 * m.Tp + p]};
+}
 template <int LT, typename CT, typename XT, bool HALO = false>
-__device__ __forceinline__ bool gs_column(const SuspSystem& s, const DevMesh& m, int Lrt, int p, XT* x, const double* ghost = nullptr,
-                                          int nGp = 0) {
+__device__ __forceinline__ bool gs_column(const SuspSystem& s, const DevMesh& m, int Lrt, int p, XT* x, const Nbs nb,
+                                          const double* ghost = nullptr, int nGp = 0) {
     const int Tp = m.Tp, S = m.S;
     const int L = LT > 0 ? LT : Lrt;
-    const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
+    const int n0 = nb.n0, n1 = nb.n1, n2 = nb.n2;
     const size_t LTp = (size_t)L * Tp;
     if (LT > 0) {
         double g[LT > 0 ? LT : 1];
@@ -1015,7 +1019,7 @@ __global__ void __launch_bounds__(128, 4) gs_sweep_kernel(SuspSystem s, DevMesh 
     if (sc->susp_done) return;
     const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p1) return;
-    gs_column<LT, CT, double>(s, m, Lrt, p, x);
+    gs_column<LT, CT, double>(s, m, Lrt, p, x, load_nbs(m, p));
 }
 
 __device__ __forceinline__ double spmv_row(const SuspSystem& s, const DevMesh& m, int L, const double* __restrict__ x, int z, int p);
@@ -1039,6 +1043,7 @@ struct SolvePlan {
     int maxit;
     int use_live;     // suspension only: skip the columns outside the active set (SuspSystem::live) ...
     int live_max_seeds;  // ... when at most this many faces have a non-zero right-hand side (Scalars::n_seeds_step)
+    int prefetch;     // suspension only: load a thread's next neighbour slots before it works on the current column (gs_pass)
     double tol2;
 };
 
@@ -1055,12 +1060,14 @@ struct SolvePlan {
 // Ghost neighbours (slot >= Tp, boundary columns across ranks) count as live: those columns are always updated, and flagged live
 // only when their new values are not all zero, so the always-updated set does not spread inwards from the partition edges.
 // 0: outside the active set (skip); 1: live already; 2: not live yet, but a neighbour is (update it and flag it).
-__device__ __forceinline__ int column_state(const unsigned char* live, const DevMesh& m, int p) {
+__device__ __forceinline__ int column_state(const unsigned char* live, const DevMesh& m, int p, const Nbs nb) {
     if (live[p]) return 1;
     const int Tp = m.Tp;
-    const int n0 = m.nbs[p], n1 = m.nbs[(size_t)Tp + p], n2 = m.nbs[(size_t)2 * Tp + p];
-    if (n0 >= Tp || n1 >= Tp || n2 >= Tp) return 2;
-    return (live[n0] | live[n1] | live[n2]) ? 2 : 0;
+    if (nb.n0 >= Tp || nb.n1 >= Tp || nb.n2 >= Tp) return 2;
+    return (live[nb.n0] | live[nb.n1] | live[nb.n2]) ? 2 : 0;
+}
+__device__ __forceinline__ int column_state(const unsigned char* live, const DevMesh& m, int p) {
+    return column_state(live, m, p, load_nbs(m, p));
 }
 // Adds a warp's count of column updates to Scalars::col_updates[k] and clears it (called by whole warps, outside divergent code).
 __device__ __forceinline__ void flush_col_count(Scalars* sc, int k, unsigned& cnt) {
@@ -1157,15 +1164,27 @@ constexpr int kGsThreads = 512;
 // A thread's share of one colour pass: columns p0, p0 + stride, ... < p1, those outside the active set skipped (live != nullptr).
 template <int LT, typename CT, typename XT>
 __device__ __forceinline__ void gs_pass(const SuspSystem& s, const DevMesh& m, int L, int p0, int p1, int stride, XT* x,
-                                        unsigned char* live, unsigned& cnt) {
+                                        unsigned char* live, unsigned& cnt, bool prefetch) {
+    // The neighbour slots of a thread's NEXT column are loaded before it works on the current one: the gathers of a column then
+    // start together with its coefficient loads instead of one round trip later.
+    if (p0 >= p1) return;
+    Nbs cur = load_nbs(m, p0);
     for (int p = p0; p < p1; p += stride) {
+        const int pn = p + stride;
+        Nbs nxt = cur;
+        if (prefetch && pn < p1) nxt = load_nbs(m, pn);
+        bool go = true;
         if (live) {
-            const int st = column_state(live, m, p);
-            if (st == 0) continue;
+            const int st = column_state(live, m, p, cur);
+            go = st != 0;
             if (st == 2) live[p] = 1;
         }
-        ++cnt;
-        gs_column<LT, CT, XT>(s, m, L, p, x);
+        if (go) {
+            ++cnt;
+            gs_column<LT, CT, XT>(s, m, L, p, x, cur);
+        }
+        if (!prefetch && pn < p1) nxt = load_nbs(m, pn);  // PBSM3D_NBS_PREFETCH=0: the slots are loaded when they are needed
+        cur = nxt;
     }
 }
 template <int LT>
@@ -1190,9 +1209,9 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_kernel(SuspSystem
     while (it < pl.maxit) {
         const int phase = it < nx32 ? 0 : (it < pl.n32 ? 1 : 2);
         for (int c = 0; c < cr.n; ++c) {
-            if (phase == 0) gs_pass<LT, float, float>(s, m, L, cr.start[c] + t0, cr.end[c], stride, xf, live, cnt);
-            else if (phase == 1) gs_pass<LT, float, double>(s, m, L, cr.start[c] + t0, cr.end[c], stride, x, live, cnt);
-            else gs_pass<LT, double, double>(s, m, L, cr.start[c] + t0, cr.end[c], stride, x, live, cnt);
+            if (phase == 0) gs_pass<LT, float, float>(s, m, L, cr.start[c] + t0, cr.end[c], stride, xf, live, cnt, pl.prefetch != 0);
+            else if (phase == 1) gs_pass<LT, float, double>(s, m, L, cr.start[c] + t0, cr.end[c], stride, x, live, cnt, pl.prefetch != 0);
+            else gs_pass<LT, double, double>(s, m, L, cr.start[c] + t0, cr.end[c], stride, x, live, cnt, pl.prefetch != 0);
             grid_barrier_fenced(bar, target);
         }
         ++it;
@@ -2544,9 +2563,9 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
                 for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nbc; i += nbb * blockDim.x) {
                     const int p = cr.start[c] + i;
                     bool nz;  // boundary columns are always updated (their ghosts may have become non-zero) and always sent
-                    if (phase == 0) nz = gs_column<LT, float, float, true>(s, m, L, p, xf, hl.ghost, hl.nGp);
-                    else if (phase == 1) nz = gs_column<LT, float, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
-                    else nz = gs_column<LT, double, double, true>(s, m, L, p, x, hl.ghost, hl.nGp);
+                    if (phase == 0) nz = gs_column<LT, float, float, true>(s, m, L, p, xf, load_nbs(m, p), hl.ghost, hl.nGp);
+                    else if (phase == 1) nz = gs_column<LT, float, double, true>(s, m, L, p, x, load_nbs(m, p), hl.ghost, hl.nGp);
+                    else nz = gs_column<LT, double, double, true>(s, m, L, p, x, load_nbs(m, p), hl.ghost, hl.nGp);
                     if (live && nz) live[p] = 1;
                     ++cnt;
                     const int e0 = hl.bptr[xh.boff[c] + i], e1 = hl.bptr[xh.boff[c] + i + 1];
@@ -2560,9 +2579,9 @@ __global__ void __launch_bounds__(kGsThreads, 1) gs_persistent_halo_kernel(SuspS
             } else {
                 const int strideI = ((int)gridDim.x - nbb) * blockDim.x;
                 const int pI = cr.start[c] + nbc + ((int)blockIdx.x - nbb) * (int)blockDim.x + (int)threadIdx.x;
-                if (phase == 0) gs_pass<LT, float, float>(s, m, L, pI, cr.end[c], strideI, xf, live, cnt);
-                else if (phase == 1) gs_pass<LT, float, double>(s, m, L, pI, cr.end[c], strideI, x, live, cnt);
-                else gs_pass<LT, double, double>(s, m, L, pI, cr.end[c], strideI, x, live, cnt);
+                if (phase == 0) gs_pass<LT, float, float>(s, m, L, pI, cr.end[c], strideI, xf, live, cnt, pl.prefetch != 0);
+                else if (phase == 1) gs_pass<LT, float, double>(s, m, L, pI, cr.end[c], strideI, x, live, cnt, pl.prefetch != 0);
+                else gs_pass<LT, double, double>(s, m, L, pI, cr.end[c], strideI, x, live, cnt, pl.prefetch != 0);
             }
             grid_barrier_fenced(bar, target);
         }
