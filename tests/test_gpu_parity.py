@@ -228,6 +228,17 @@ def test_error_paths_on_device(granger):
     mod.close()
 
 
+def test_fetch_is_required_while_a_fetch_option_is_on(granger):
+    """The reference declares depends("fetch") when use_exp_fetch or use_tanh_fetch (the default) is set (PBSM3D.cpp:181-184) and
+    would fail module linking without a provider; here a step without the array is refused instead of running on fetch = 1000 m."""
+    geo = granger.geometry()
+    F = {k: v for k, v in synthetic.forcing(geo.cx, geo.cy).items() if k != "fetch"}
+    h = capi.Handle(capi.default_config(nLayer=5), granger)
+    with pytest.raises(capi.Pbsm3dError, match="forcing array missing"):
+        h.step(3600.0, F)
+    h.close()
+
+
 @pytest.mark.parametrize("which", ["granger1m", "slope_metis", "uniform", "variable"])
 def test_colour_major_layout_is_a_proper_colouring(which):
     """The device order is a permutation of CHM's faces into colour classes in which no two edge-neighbours share
